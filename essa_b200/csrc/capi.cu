@@ -1,0 +1,1042 @@
+// C ABI of the World::update hot path (see include/essa_b200.h for the reference interfaces each
+// entry point replaces).  Host code only: context, transfers, step scheduling, NCCL plumbing.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "ctx.hpp"
+
+using namespace essa;
+
+static thread_local std::string g_create_error;
+
+// Object::deleted() on the host (src/Object.cpp:60-62), same expression as common.cuh body_active.
+static inline bool body_active_host(bool del_flag, int64_t ddate, int64_t cdate, int64_t date) {
+    return !((del_flag && ddate <= date) || cdate > date);
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                              \
+            return ESSA_ERR_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+#define ARG(cond, msg)                                                                                   \
+    do {                                                                                                 \
+        if (!(cond)) {                                                                                   \
+            if (ctx)                                                                                     \
+                ctx->err = msg;                                                                          \
+            return ESSA_ERR_ARG;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen: single-GPU users never need the library; inside a torch process the
+// already loaded libnccl.so.2 is picked up by soname.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NcclId {
+    char internal[ESSA_NCCL_ID_BYTES];
+};
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(ncclComm**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(ncclComm*) = nullptr;
+    int (*AllGather)(void const*, void*, size_t, int, ncclComm*, cudaStream_t) = nullptr;
+    int (*Broadcast)(void const*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
+    int (*AllReduce)(void const*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    char const* (*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+constexpr int kNcclFloat64 = 8, kNcclSum = 0; // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried)
+        return api;
+    tried = true;
+    char const* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (char const* nm : names) {
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib)
+            break;
+    }
+    if (!api.lib) {
+        api.why = std::string("libnccl.so.2 not loadable: ") + dlerror();
+        return api;
+    }
+#define SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, name))
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllGather, "ncclAllGather");
+    SYM(Broadcast, "ncclBroadcast");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    if (!api.GetUniqueId || !api.CommInitRank || !api.Broadcast || !api.GroupStart || !api.GroupEnd || !api.AllReduce) {
+        api.why = "libnccl.so.2 lacks required symbols";
+        dlclose(api.lib);
+        api.lib = nullptr;
+    }
+    return api;
+}
+} // namespace
+
+#define NK(call)                                                                                         \
+    do {                                                                                                 \
+        int r__ = (call);                                                                                \
+        if (r__ != 0) {                                                                                  \
+            ctx->err = std::string(#call) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r__) : "nccl error"); \
+            return ESSA_ERR_NCCL;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+static void free_world(essa_ctx* c) {
+    cudaFree(c->pos[0]);
+    cudaFree(c->pos[1]);
+    cudaFree(c->vel);
+    cudaFree(c->velh);
+    cudaFree(c->acc);
+    cudaFree(c->gf);
+    cudaFree(c->cdate);
+    cudaFree(c->ddate);
+    cudaFree(c->delflag);
+    cudaFree(c->active);
+    cudaFree(c->most);
+    cudaFree(c->old_most);
+    cudaFree(c->maxattr);
+    cudaFree(c->appe);
+    c->pos[0] = c->pos[1] = nullptr;
+    c->vel = c->velh = c->acc = c->gf = c->maxattr = c->appe = nullptr;
+    c->cdate = c->ddate = nullptr;
+    c->delflag = c->active = nullptr;
+    c->most = c->old_most = nullptr;
+    c->cap = 0;
+}
+
+static int reserve_world(essa_ctx* ctx, int cap) {
+    if (cap <= ctx->cap)
+        return ESSA_OK;
+    // Growing keeps nothing: callers re-upload (essa_upload is the only entry that grows).
+    free_world(ctx);
+    cap = (cap + 255) / 256 * 256;
+    size_t n = (size_t)cap;
+    CK(cudaMalloc(&ctx->pos[0], n * sizeof(double4)));
+    CK(cudaMalloc(&ctx->pos[1], n * sizeof(double4)));
+    CK(cudaMalloc(&ctx->vel, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&ctx->velh, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&ctx->acc, 3 * n * sizeof(double)));
+    CK(cudaMalloc(&ctx->gf, n * sizeof(double)));
+    CK(cudaMalloc(&ctx->cdate, n * sizeof(int64_t)));
+    CK(cudaMalloc(&ctx->ddate, n * sizeof(int64_t)));
+    CK(cudaMalloc(&ctx->delflag, n));
+    CK(cudaMalloc(&ctx->active, n));
+    CK(cudaMalloc(&ctx->most, n * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->old_most, n * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->maxattr, n * sizeof(double)));
+    CK(cudaMalloc(&ctx->appe, 4 * n * sizeof(double)));
+    CK(cudaMemsetAsync(ctx->pos[0], 0, n * sizeof(double4), ctx->stream));
+    CK(cudaMemsetAsync(ctx->pos[1], 0, n * sizeof(double4), ctx->stream));
+    CK(cudaMemsetAsync(ctx->acc, 0, 3 * n * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->velh, 0, 3 * n * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->maxattr, 0, n * sizeof(double), ctx->stream));
+    ctx->cap = cap;
+    return ESSA_OK;
+}
+
+static int reserve_pinned(essa_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes)
+        return ESSA_OK;
+    if (ctx->pinned)
+        cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    bytes = (bytes + (1u << 20)) & ~((size_t)(1u << 20) - 1);
+    CK(cudaHostAlloc(&ctx->pinned, bytes, cudaHostAllocDefault));
+    ctx->pinned_bytes = bytes;
+    return ESSA_OK;
+}
+
+extern "C" int essa_abi_version(void) { return ESSA_ABI_VERSION; }
+
+extern "C" int essa_ctx_create(int device, int capacity, essa_ctx** out) {
+    if (!out) {
+        g_create_error = "out is null";
+        return ESSA_ERR_ARG;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return ESSA_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "device ordinal out of range";
+        return ESSA_ERR_ARG;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return ESSA_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return ESSA_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = "device is not sm_100 (this library carries sm_100a code only)";
+        return ESSA_ERR_CUDA;
+    }
+    essa_ctx* ctx = new essa_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    auto fail = [&](char const* what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        essa_ctx_destroy(ctx);
+        return ESSA_ERR_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail("cudaStreamCreate", e);
+    cudaEvent_t* evs[] = { &ctx->ev_begin, &ctx->ev_end, &ctx->ev_f0, &ctx->ev_f1 };
+    for (auto* ev : evs)
+        if ((e = cudaEventCreate(ev)) != cudaSuccess)
+            return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming)) != cudaSuccess)
+        return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming)) != cudaSuccess)
+        return fail("cudaEventCreate", e);
+    if (capacity > 0) {
+        int rc = reserve_world(ctx, capacity);
+        if (rc != ESSA_OK) {
+            g_create_error = ctx->err;
+            essa_ctx_destroy(ctx);
+            return rc;
+        }
+    }
+    *out = ctx;
+    return ESSA_OK;
+}
+
+static void free_recording(essa_ctx* c) {
+    cudaFree(c->hist);
+    cudaFree(c->hist_first);
+    cudaFree(c->hist_start);
+    cudaFree(c->hist_len);
+    cudaFree(c->verts);
+    cudaFree(c->vert_off);
+    cudaFree(c->tcap);
+    cudaFree(c->append_off);
+    cudaFree(c->tlength);
+    cudaFree(c->toff);
+    cudaFree(c->last_angle);
+    c->hist = c->hist_first = nullptr;
+    c->hist_start = c->hist_len = c->tcap = c->append_off = c->tlength = nullptr;
+    c->verts = nullptr;
+    c->vert_off = nullptr;
+    c->toff = c->last_angle = nullptr;
+    c->tracked = 0;
+    c->verts_total = 0;
+    c->trail_cap.clear();
+    c->vert_off_h.clear();
+}
+
+extern "C" void essa_ctx_destroy(essa_ctx* c) {
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    if (c->stream)
+        cudaStreamSynchronize(c->stream);
+    if (c->comm && nccl().CommDestroy)
+        nccl().CommDestroy(c->comm);
+    free_world(c);
+    free_recording(c);
+    cudaFree(c->part);
+    cudaFree(c->part_m);
+    cudaFree(c->part_j);
+    cudaFree(c->counters);
+    cudaFree(c->ens_state);
+    cudaFree(c->ens_gf);
+    cudaFree(c->ens_mind);
+    cudaFree(c->escratch);
+    if (c->pinned)
+        cudaFreeHost(c->pinned);
+    cudaEvent_t evs[] = { c->ev_begin, c->ev_end, c->ev_f0, c->ev_f1, c->ev_gather, c->ev_ready };
+    for (auto ev : evs)
+        if (ev)
+            cudaEventDestroy(ev);
+    for (auto ev : c->force_events)
+        cudaEventDestroy(ev);
+    if (c->stream)
+        cudaStreamDestroy(c->stream);
+    if (c->comm_stream)
+        cudaStreamDestroy(c->comm_stream);
+    delete c;
+}
+
+extern "C" const char* essa_last_error(const essa_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+extern "C" int64_t essa_launch_count(const essa_ctx* c) { return c ? c->launches : 0; }
+extern "C" int64_t essa_pass_count(const essa_ctx* c) { return c ? c->passes : 0; }
+extern "C" double essa_interaction_count(const essa_ctx* c) { return c ? c->interactions : 0; }
+extern "C" double essa_last_step_ms(const essa_ctx* c) { return c ? c->last_step_ms : 0; }
+extern "C" double essa_last_force_ms(const essa_ctx* c) { return c ? c->last_force_ms : 0; }
+extern "C" int essa_last_force_passes(const essa_ctx* c) { return c ? c->last_force_passes : 0; }
+extern "C" int essa_body_count(const essa_ctx* c) { return c ? c->n : 0; }
+extern "C" int64_t essa_get_date(const essa_ctx* c) { return c ? c->date : 0; }
+extern "C" int essa_tracked_count(const essa_ctx* c) { return c ? c->tracked : 0; }
+extern "C" int essa_shard_rank(const essa_ctx* c) { return c ? c->rank : 0; }
+extern "C" int essa_shard_world(const essa_ctx* c) { return c ? c->world : 1; }
+
+extern "C" int essa_sync(essa_ctx* ctx) {
+    ARG(ctx, "ctx is null");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->comm_stream));
+    return ESSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// active mask bookkeeping (Object::deleted(), src/Object.cpp:60-62): the mask flips exactly when
+// the date crosses a creation date, or the deletion date of a body whose m_deleted is set.
+// ---------------------------------------------------------------------------------------------
+static bool mask_changes(essa_ctx const* c, int64_t d_from, int64_t d_to) {
+    if (c->events.empty() || d_from == d_to)
+        return false;
+    int64_t lo = std::min(d_from, d_to), hi = std::max(d_from, d_to);
+    auto it = std::upper_bound(c->events.begin(), c->events.end(), lo); // first t > lo
+    return it != c->events.end() && *it <= hi;
+}
+
+extern "C" int essa_set_date(essa_ctx* ctx, int64_t date) {
+    ARG(ctx, "ctx is null");
+    CK(cudaSetDevice(ctx->device));
+    bool changed = mask_changes(ctx, ctx->date, date);
+    ctx->date = date;
+    if (changed && ctx->n > 0) {
+        CK(launch_refresh_active(ctx, ctx->stream));
+        ctx->acc_valid = false;
+    }
+    return ESSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// upload / download
+// ---------------------------------------------------------------------------------------------
+extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
+    ARG(ctx, "ctx is null");
+    ARG(h && n >= 0, "bad arguments");
+    ARG(n == 0 || (h->x && h->y && h->z && h->vx && h->vy && h->vz && h->gf), "x,y,z,vx,vy,vz,gf are required");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = reserve_world(ctx, n);
+    if (rc != ESSA_OK)
+        return rc;
+    ctx->n = n;
+    ctx->acc_valid = false;
+    ctx->acc_has_most = false;
+    ctx->events.clear();
+    if (n == 0)
+        return ESSA_OK;
+    size_t N = (size_t)n, cap = (size_t)ctx->cap;
+    // staging layout: 7 N doubles | 4 N doubles (ap pe apv pev) | 2 N int64 | N int32 | 2 N bytes
+    size_t bytes = 11 * N * sizeof(double) + 2 * N * sizeof(int64_t) + N * sizeof(int32_t) + 2 * N;
+    rc = reserve_pinned(ctx, bytes);
+    if (rc != ESSA_OK)
+        return rc;
+    double* d = static_cast<double*>(ctx->pinned);
+    double const* src[7] = { h->x, h->y, h->z, h->vx, h->vy, h->vz, h->gf };
+    for (int k = 0; k < 7; k++)
+        memcpy(d + k * N, src[k], N * sizeof(double));
+    double* appe = d + 7 * N;
+    for (size_t i = 0; i < N; i++) {
+        appe[i] = h->ap ? h->ap[i] : 0.0;
+        appe[N + i] = h->pe ? h->pe[i] : DBL_MAX;
+        appe[2 * N + i] = h->ap_vel ? h->ap_vel[i] : 0.0;
+        appe[3 * N + i] = h->pe_vel ? h->pe_vel[i] : 0.0;
+    }
+    int64_t* dates = reinterpret_cast<int64_t*>(d + 11 * N);
+    int32_t* most = reinterpret_cast<int32_t*>(dates + 2 * N);
+    uint8_t* flags = reinterpret_cast<uint8_t*>(most + N);
+    for (size_t i = 0; i < N; i++) {
+        int64_t cd = h->creation_date ? h->creation_date[i] : INT64_MIN;
+        int64_t dd = h->deletion_date ? h->deletion_date[i] : 0;
+        uint8_t del = h->deleted ? (h->deleted[i] != 0) : 0;
+        dates[i] = cd;
+        dates[N + i] = dd;
+        flags[i] = del;
+        flags[N + i] = body_active_host(del, dd, cd, ctx->date) ? 1 : 0;
+        most[i] = h->most ? h->most[i] : -1;
+        if (cd != INT64_MIN)
+            ctx->events.push_back(cd);
+        if (del)
+            ctx->events.push_back(dd);
+    }
+    std::sort(ctx->events.begin(), ctx->events.end());
+    ctx->events.erase(std::unique(ctx->events.begin(), ctx->events.end()), ctx->events.end());
+
+    cudaStream_t st = ctx->stream;
+    // x y z go through velh (scratch between steps) and are packed into 32-byte j-records
+    for (int k = 0; k < 3; k++) {
+        CK(cudaMemcpyAsync(ctx->velh + k * cap, d + k * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->vel + k * cap, d + (3 + k) * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(ctx->gf, d + 6 * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 4; k++)
+        CK(cudaMemcpyAsync(ctx->appe + k * cap, appe + k * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->cdate, dates, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->ddate, dates + N, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->most, most, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->old_most, most, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->delflag, flags, N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->active, flags + N, N, cudaMemcpyHostToDevice, st));
+    CK(launch_pack(ctx, ctx->velh, ctx->velh + cap, ctx->velh + 2 * cap, st));
+    CK(cudaStreamSynchronize(st));
+    return ESSA_OK;
+}
+
+extern "C" int essa_download(essa_ctx* ctx, essa_bodies* h) {
+    ARG(ctx, "ctx is null");
+    ARG(h, "host view is null");
+    CK(cudaSetDevice(ctx->device));
+    size_t N = (size_t)ctx->n, cap = (size_t)ctx->cap;
+    if (N == 0)
+        return ESSA_OK;
+    size_t bytes = 15 * N * sizeof(double) + 2 * N * sizeof(int64_t) + N * sizeof(int32_t) + N;
+    int rc = reserve_pinned(ctx, bytes);
+    if (rc != ESSA_OK)
+        return rc;
+    cudaStream_t st = ctx->stream;
+    double* d = static_cast<double*>(ctx->pinned);
+    if (ctx->world > 1) {
+        // every rank holds all positions (gathered each pass) but only its own targets' v, a, most
+        NK(nccl().GroupStart());
+        for (int r = 0; r < ctx->world; r++) {
+            long long a = (long long)ctx->n * r / ctx->world, b = (long long)ctx->n * (r + 1) / ctx->world;
+            if (b <= a)
+                continue;
+            for (int k = 0; k < 3; k++) {
+                NK(nccl().Broadcast(ctx->vel + k * cap + a, ctx->vel + k * cap + a, (size_t)(b - a), kNcclFloat64, r, ctx->comm, st));
+                NK(nccl().Broadcast(ctx->acc + k * cap + a, ctx->acc + k * cap + a, (size_t)(b - a), kNcclFloat64, r, ctx->comm, st));
+            }
+        }
+        NK(nccl().GroupEnd());
+    }
+    bool want_pos = h->x || h->y || h->z;
+    if (want_pos) {
+        CK(launch_unpack(ctx, ctx->velh, ctx->velh + cap, ctx->velh + 2 * cap, st));
+        for (int k = 0; k < 3; k++)
+            CK(cudaMemcpyAsync(d + k * N, ctx->velh + k * cap, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (h->vx || h->vy || h->vz)
+        for (int k = 0; k < 3; k++)
+            CK(cudaMemcpyAsync(d + (3 + k) * N, ctx->vel + k * cap, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h->ax || h->ay || h->az)
+        for (int k = 0; k < 3; k++)
+            CK(cudaMemcpyAsync(d + (6 + k) * N, ctx->acc + k * cap, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h->gf)
+        CK(cudaMemcpyAsync(d + 9 * N, ctx->gf, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h->max_attraction)
+        CK(cudaMemcpyAsync(d + 10 * N, ctx->maxattr, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h->ap || h->pe || h->ap_vel || h->pe_vel)
+        for (int k = 0; k < 4; k++)
+            CK(cudaMemcpyAsync(d + (11 + k) * N, ctx->appe + k * cap, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    int64_t* dates = reinterpret_cast<int64_t*>(d + 15 * N);
+    int32_t* most = reinterpret_cast<int32_t*>(dates + 2 * N);
+    uint8_t* flags = reinterpret_cast<uint8_t*>(most + N);
+    if (h->creation_date)
+        CK(cudaMemcpyAsync(dates, ctx->cdate, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (h->deletion_date)
+        CK(cudaMemcpyAsync(dates + N, ctx->ddate, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (h->most)
+        CK(cudaMemcpyAsync(most, ctx->most, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (h->deleted)
+        CK(cudaMemcpyAsync(flags, ctx->delflag, N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    double* dst[15] = { h->x, h->y, h->z, h->vx, h->vy, h->vz, h->ax, h->ay, h->az, h->gf, h->max_attraction, h->ap, h->pe, h->ap_vel,
+        h->pe_vel };
+    for (int k = 0; k < 15; k++)
+        if (dst[k])
+            memcpy(dst[k], d + k * N, N * sizeof(double));
+    if (h->creation_date)
+        memcpy(h->creation_date, dates, N * sizeof(int64_t));
+    if (h->deletion_date)
+        memcpy(h->deletion_date, dates + N, N * sizeof(int64_t));
+    if (h->most)
+        memcpy(h->most, most, N * sizeof(int32_t));
+    if (h->deleted)
+        memcpy(h->deleted, flags, N);
+    return ESSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stepping
+// ---------------------------------------------------------------------------------------------
+static cudaEvent_t force_event(essa_ctx* c, size_t idx) {
+    while (c->force_events.size() <= idx) {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess)
+            return nullptr;
+        c->force_events.push_back(ev);
+    }
+    return c->force_events[idx];
+}
+
+// In a sharded context every rank has just written its own targets' records into the `next`
+// position buffer: gather the other ranks' shards (ragged shards -> one broadcast per rank,
+// grouped).  Runs on the comm stream so that the force pass can start on the local shard.
+static int gather_next(essa_ctx* ctx) {
+    if (ctx->world == 1)
+        return ESSA_OK;
+    CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0));
+    double4* buf = ctx->pos[ctx->cur ^ 1];
+    NK(nccl().GroupStart());
+    for (int r = 0; r < ctx->world; r++) {
+        long long a = (long long)ctx->n * r / ctx->world, b = (long long)ctx->n * (r + 1) / ctx->world;
+        if (b > a)
+            NK(nccl().Broadcast(buf + a, buf + a, (size_t)(b - a) * 4, kNcclFloat64, r, ctx->comm, ctx->comm_stream));
+    }
+    NK(nccl().GroupEnd());
+    CK(cudaEventRecord(ctx->ev_gather, ctx->comm_stream));
+    ctx->gather_pending = true;
+    return ESSA_OK;
+}
+
+// One force pass over pos[cur] for this context's targets.  Sharded: local-shard sources first,
+// the other shards once the gather of this buffer has landed.
+static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const& k, double eps2, size_t* ev_idx) {
+    int n = ctx->n;
+    int R;
+    int iblocks = force_iblocks(ctx, &R);
+    cudaEvent_t e0 = force_event(ctx, (*ev_idx)++), e1 = force_event(ctx, (*ev_idx)++);
+    if (!e0 || !e1) {
+        ctx->err = "cudaEventCreate failed";
+        return ESSA_ERR_CUDA;
+    }
+    CK(cudaEventRecord(e0, ctx->stream));
+    if (ctx->world == 1 || !ctx->gather_pending) {
+        int S;
+        choose_split(ctx, iblocks, (n + kTileJ - 1) / kTileJ, &S);
+        CK(launch_force_pass(ctx, 0, n, S, 0, S, argmax, save_old, k, eps2, ctx->stream));
+    } else {
+        int i0 = (int)((long long)n * ctx->rank / ctx->world), i1 = (int)((long long)n * (ctx->rank + 1) / ctx->world);
+        int SA, SB0 = 0, SB1 = 0;
+        choose_split(ctx, iblocks, (i1 - i0 + kTileJ - 1) / kTileJ, &SA);
+        if (i0 > 0)
+            choose_split(ctx, iblocks, (i0 + kTileJ - 1) / kTileJ, &SB0);
+        if (i1 < n)
+            choose_split(ctx, iblocks, (n - i1 + kTileJ - 1) / kTileJ, &SB1);
+        int total = SA + SB0 + SB1;
+        // slot order follows source index so that the ordered reduction is the same on every rank count
+        CK(launch_force_pass(ctx, i0, i1, SA, SB0, total, argmax, save_old, k, eps2, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
+        ctx->gather_pending = false;
+        if (SB0)
+            CK(launch_force_pass(ctx, 0, i0, SB0, 0, total, argmax, save_old, k, eps2, ctx->stream));
+        if (SB1)
+            CK(launch_force_pass(ctx, i1, n, SB1, SB0 + SA, total, argmax, save_old, k, eps2, ctx->stream));
+    }
+    CK(cudaEventRecord(e1, ctx->stream));
+    int i0 = (int)((long long)n * ctx->rank / ctx->world), i1 = (int)((long long)n * (ctx->rank + 1) / ctx->world);
+    ctx->passes++;
+    ctx->interactions += (double)(i1 - i0) * (double)(n - 1);
+    return ESSA_OK;
+}
+
+static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool forces_only) {
+    int const K = forces_only ? 0 : std::abs(steps);
+    double const mul = steps >= 0 ? 1.0 : -1.0;
+    bool const argmax = o.track_most_attracting || o.record;
+    KickArgs base;
+    base.dt = (double)o.dt_seconds;
+    base.h = base.dt / 2.0;
+    base.mul = mul;
+    base.second_kick = 0;
+    base.advance = 0;
+    size_t ev = 0;
+    if (ctx->gather_pending) { // never left pending between calls, defensive
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
+        ctx->gather_pending = false;
+    }
+    if (forces_only) {
+        int rc = force_pass(ctx, argmax, false, base, o.eps2, &ev);
+        if (rc != ESSA_OK)
+            return rc;
+        ctx->acc_valid = true;
+        ctx->acc_has_most = argmax;
+        ctx->acc_exact = false;
+    }
+    bool fused_prev = false;
+    for (int k = 0; k < K; k++) {
+        // update_history_and_date (src/World.cpp:59-84): the date moves before anything else
+        if (!o.forward_simulated) {
+            int64_t nd = ctx->date + (int64_t)(mul > 0 ? 1 : -1) * o.dt_seconds;
+            bool flip = mask_changes(ctx, ctx->date, nd);
+            ctx->date = nd;
+            if (flip) {
+                CK(launch_refresh_active(ctx, ctx->stream));
+                ctx->acc_valid = false;
+            }
+        }
+        bool need_save_old = true;
+        if (!fused_prev) {
+            if (!ctx->acc_valid || o.two_pass || (argmax && !ctx->acc_has_most)) {
+                KickArgs ka = base; // first set_forces() of the step: store only
+                int rc = force_pass(ctx, argmax, need_save_old, ka, o.eps2, &ev);
+                if (rc != ESSA_OK)
+                    return rc;
+                need_save_old = false;
+            }
+            KickArgs kd = base;
+            kd.advance = 1;
+            CK(launch_kick_drift(ctx, kd, ctx->stream));
+            int rc = gather_next(ctx);
+            if (rc != ESSA_OK)
+                return rc;
+        }
+        ctx->cur ^= 1;
+        bool advance = false;
+        if (k + 1 < K && !o.two_pass) {
+            int64_t nd = ctx->date + (int64_t)(mul > 0 ? 1 : -1) * o.dt_seconds;
+            advance = o.forward_simulated || !mask_changes(ctx, ctx->date, nd);
+        }
+        KickArgs ks = base;
+        ks.second_kick = 1;
+        ks.advance = advance ? 1 : 0;
+        int rc = force_pass(ctx, argmax, need_save_old, ks, o.eps2, &ev);
+        if (rc != ESSA_OK)
+            return rc;
+        ctx->acc_valid = true;
+        ctx->acc_has_most = argmax;
+        ctx->acc_exact = false;
+        if (advance) {
+            rc = gather_next(ctx);
+            if (rc != ESSA_OK)
+                return rc;
+        }
+        fused_prev = advance;
+        if (o.record && ctx->tracked > 0)
+            CK(launch_record(ctx, o.offset_trails, o.forward_simulated, ctx->stream));
+    }
+    CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0, total = 0;
+    for (size_t i = 0; i + 1 < ev; i += 2) {
+        CK(cudaEventElapsedTime(&ms, ctx->force_events[i], ctx->force_events[i + 1]));
+        total += ms;
+    }
+    ctx->last_force_ms = total;
+    ctx->last_force_passes = (int)(ev / 2);
+    return ESSA_OK;
+}
+
+static int resident_finish(essa_ctx* ctx, int steps, essa_step_opts const& o, bool forces_only) {
+    if (!forces_only && !o.forward_simulated)
+        ctx->date += (int64_t)steps * o.dt_seconds;
+    ctx->acc_valid = true;
+    ctx->acc_has_most = o.track_most_attracting || o.record || o.exact_order;
+    ctx->acc_exact = o.exact_order != 0;
+    ctx->last_force_ms = 0;
+    return ESSA_OK;
+}
+
+static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, bool forces_only) {
+    ARG(ctx, "ctx is null");
+    ARG(opts, "opts is null");
+    ARG(forces_only || steps != 0, "steps must not be 0 (assert in src/World.cpp:87)");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n == 0) {
+        if (!forces_only && !opts->forward_simulated)
+            ctx->date += (int64_t)steps * opts->dt_seconds;
+        return ESSA_OK;
+    }
+    essa_step_opts o = *opts;
+    if (o.record)
+        o.track_most_attracting = 1;
+    bool resident = o.kernel == ESSA_KERNEL_RESIDENT || (o.kernel == ESSA_KERNEL_AUTO && ctx->n <= ESSA_RESIDENT_MAX);
+    if (ctx->world > 1)
+        resident = false;
+    if (resident && ctx->n > ESSA_RESIDENT_MAX) {
+        ctx->err = "resident kernel takes at most ESSA_RESIDENT_MAX bodies";
+        return ESSA_ERR_ARG;
+    }
+    if (o.exact_order && !resident) {
+        ctx->err = "exact_order is a resident-kernel mode (N <= ESSA_RESIDENT_MAX, unsharded)";
+        return ESSA_ERR_ARG;
+    }
+    if (o.record && ctx->tracked == 0) {
+        ctx->err = "record requested but essa_record_configure was not called";
+        return ESSA_ERR_STATE;
+    }
+    CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    int rc;
+    if (resident) {
+        CK(launch_resident(ctx, steps, o, forces_only, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        rc = resident_finish(ctx, steps, o, forces_only);
+    } else {
+        rc = step_tiled(ctx, steps, o, forces_only);
+    }
+    if (rc != ESSA_OK)
+        return rc;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    ctx->last_step_ms = ms;
+    return ESSA_OK;
+}
+
+extern "C" int essa_step(essa_ctx* ctx, int steps, const essa_step_opts* opts) { return step_common(ctx, steps, opts, false); }
+extern "C" int essa_set_forces(essa_ctx* ctx, const essa_step_opts* opts) { return step_common(ctx, 1, opts, true); }
+
+// ---------------------------------------------------------------------------------------------
+// recording
+// ---------------------------------------------------------------------------------------------
+extern "C" int essa_record_configure(essa_ctx* ctx, int n_tracked, const int32_t* trail_capacity, int keep) {
+    ARG(ctx, "ctx is null");
+    ARG(n_tracked >= 0 && n_tracked <= ctx->n, "n_tracked out of range");
+    ARG(n_tracked == 0 || trail_capacity, "trail_capacity is null");
+    ARG(keep >= 0 && keep <= ctx->tracked && keep <= n_tracked, "keep out of range");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < keep; k++)
+        ARG(trail_capacity[k] == ctx->trail_cap[k], "kept bodies must keep their trail capacity");
+    if (n_tracked == 0) {
+        free_recording(ctx);
+        return ESSA_OK;
+    }
+    std::vector<int64_t> off(n_tracked);
+    int64_t total = 0;
+    for (int k = 0; k < n_tracked; k++) {
+        ARG(trail_capacity[k] >= 3 && trail_capacity[k] <= 0xfffff, "trail capacity must be in [3, 0xfffff] (src/Trail.cpp:19-34)");
+        off[k] = total;
+        total += trail_capacity[k];
+    }
+    // new buffers, old contents of the kept prefix copied over
+    essa_ctx old = *ctx; // shallow: used only for the old device pointers
+    size_t T = (size_t)n_tracked;
+    double *hist, *hfirst;
+    int32_t *hs, *hl, *tc, *ao, *tl;
+    float* verts;
+    int64_t* voff;
+    double *toff, *la;
+    CK(cudaMalloc(&hist, T * ESSA_HISTORY_SEGMENTS * 6 * sizeof(double)));
+    CK(cudaMalloc(&hfirst, T * 6 * sizeof(double)));
+    CK(cudaMalloc(&hs, T * sizeof(int32_t)));
+    CK(cudaMalloc(&hl, T * sizeof(int32_t)));
+    CK(cudaMalloc(&tc, T * sizeof(int32_t)));
+    CK(cudaMalloc(&ao, T * sizeof(int32_t)));
+    CK(cudaMalloc(&tl, T * sizeof(int32_t)));
+    CK(cudaMalloc(&verts, (size_t)total * 3 * sizeof(float)));
+    CK(cudaMalloc(&voff, T * sizeof(int64_t)));
+    CK(cudaMalloc(&toff, T * 3 * sizeof(double)));
+    CK(cudaMalloc(&la, T * sizeof(double)));
+    CK(cudaMemsetAsync(verts, 0, (size_t)total * 3 * sizeof(float), ctx->stream));
+    CK(cudaMemsetAsync(toff, 0, T * 3 * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(la, 0, T * sizeof(double), ctx->stream));
+    if (keep > 0) {
+        size_t Kp = (size_t)keep;
+        cudaStream_t st = ctx->stream;
+        CK(cudaMemcpyAsync(hist, old.hist, Kp * ESSA_HISTORY_SEGMENTS * 6 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(hfirst, old.hist_first, Kp * 6 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(hs, old.hist_start, Kp * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(hl, old.hist_len, Kp * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ao, old.append_off, Kp * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(tl, old.tlength, Kp * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(toff, old.toff, Kp * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(la, old.last_angle, Kp * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        int64_t kv = old.vert_off_h[keep - 1] + old.trail_cap[keep - 1];
+        CK(cudaMemcpyAsync(verts, old.verts, (size_t)kv * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaMemcpyAsync(tc, trail_capacity, T * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(voff, off.data(), T * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_recording(ctx);
+    ctx->hist = hist;
+    ctx->hist_first = hfirst;
+    ctx->hist_start = hs;
+    ctx->hist_len = hl;
+    ctx->tcap = tc;
+    ctx->append_off = ao;
+    ctx->tlength = tl;
+    ctx->verts = verts;
+    ctx->vert_off = voff;
+    ctx->toff = toff;
+    ctx->last_angle = la;
+    ctx->tracked = n_tracked;
+    ctx->verts_total = total;
+    ctx->trail_cap.assign(trail_capacity, trail_capacity + n_tracked);
+    ctx->vert_off_h = off;
+    if (keep < n_tracked) {
+        CK(launch_record_init(ctx, keep, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return ESSA_OK;
+}
+
+extern "C" int essa_record_reset(essa_ctx* ctx, int body, int history, int trail) {
+    ARG(ctx, "ctx is null");
+    ARG(body >= 0 && body < ctx->tracked, "body is not tracked");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (history) { // History::reset(): the list becomes { m_first_entry } (src/History.cpp:55-59)
+        int32_t one = 1, zero = 0;
+        CK(cudaMemcpy(ctx->hist + (size_t)body * ESSA_HISTORY_SEGMENTS * 6, ctx->hist_first + (size_t)body * 6, 6 * sizeof(double),
+            cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(ctx->hist_start + body, &zero, sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->hist_len + body, &one, sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    if (trail) { // Trail::reset(): m_append_offset = 1, m_length = 1 (src/Trail.cpp:77-80)
+        int32_t one = 1;
+        CK(cudaMemcpy(ctx->append_off + body, &one, sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->tlength + body, &one, sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    return ESSA_OK;
+}
+
+extern "C" int essa_history_read(essa_ctx* ctx, int body, double* out) {
+    ARG(ctx, "ctx is null");
+    ARG(body >= 0 && body < ctx->tracked, "body is not tracked");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int32_t start = 0, len = 0;
+    CK(cudaMemcpy(&start, ctx->hist_start + body, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&len, ctx->hist_len + body, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (!out)
+        return len;
+    double const* ring = ctx->hist + (size_t)body * ESSA_HISTORY_SEGMENTS * 6;
+    int first = std::min(len, ESSA_HISTORY_SEGMENTS - start);
+    if (first > 0)
+        CK(cudaMemcpy(out, ring + (size_t)start * 6, (size_t)first * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (len > first)
+        CK(cudaMemcpy(out + (size_t)first * 6, ring, (size_t)(len - first) * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    return len;
+}
+
+extern "C" int essa_history_write(essa_ctx* ctx, int body, const double* entries, int count, int set_first) {
+    ARG(ctx, "ctx is null");
+    ARG(body >= 0 && body < ctx->tracked, "body is not tracked");
+    ARG(entries && count >= 1 && count <= ESSA_HISTORY_SEGMENTS, "count must be in [1, ESSA_HISTORY_SEGMENTS]");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int32_t zero = 0;
+    CK(cudaMemcpy(ctx->hist + (size_t)body * ESSA_HISTORY_SEGMENTS * 6, entries, (size_t)count * 6 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->hist_start + body, &zero, sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->hist_len + body, &count, sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (set_first)
+        CK(cudaMemcpy(ctx->hist_first + (size_t)body * 6, entries, 6 * sizeof(double), cudaMemcpyHostToDevice));
+    return ESSA_OK;
+}
+
+extern "C" int essa_trail_read(essa_ctx* ctx, int body, float* verts, essa_trail_meta* meta) {
+    ARG(ctx, "ctx is null");
+    ARG(body >= 0 && body < ctx->tracked, "body is not tracked");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (meta) {
+        meta->capacity = ctx->trail_cap[body];
+        meta->pad = 0;
+        CK(cudaMemcpy(&meta->append_offset, ctx->append_off + body, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&meta->length, ctx->tlength + body, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(meta->offset, ctx->toff + (size_t)body * 3, 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&meta->last_xy_angle, ctx->last_angle + body, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (verts)
+        CK(cudaMemcpy(verts, ctx->verts + (size_t)ctx->vert_off_h[body] * 3, (size_t)ctx->trail_cap[body] * 3 * sizeof(float),
+            cudaMemcpyDeviceToHost));
+    return ESSA_OK;
+}
+
+extern "C" int essa_trail_write(essa_ctx* ctx, int body, const float* verts, const essa_trail_meta* meta) {
+    ARG(ctx, "ctx is null");
+    ARG(body >= 0 && body < ctx->tracked, "body is not tracked");
+    ARG(meta, "meta is null");
+    ARG(meta->capacity == ctx->trail_cap[body], "capacity differs from essa_record_configure");
+    ARG(meta->append_offset >= 0 && meta->append_offset < meta->capacity && meta->length >= 1 && meta->length <= meta->capacity,
+        "append_offset / length out of range");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->append_off + body, &meta->append_offset, sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->tlength + body, &meta->length, sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->toff + (size_t)body * 3, meta->offset, 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->last_angle + body, &meta->last_xy_angle, sizeof(double), cudaMemcpyHostToDevice));
+    if (verts)
+        CK(cudaMemcpy(ctx->verts + (size_t)ctx->vert_off_h[body] * 3, verts, (size_t)ctx->trail_cap[body] * 3 * sizeof(float),
+            cudaMemcpyHostToDevice));
+    return ESSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------------------------
+extern "C" int essa_energy(essa_ctx* ctx, double* kinetic, double* potential, double momentum[3]) {
+    ARG(ctx, "ctx is null");
+    CK(cudaSetDevice(ctx->device));
+    double out[5] = { 0, 0, 0, 0, 0 };
+    if (ctx->n > 0) {
+        CK(launch_energy(ctx, ctx->stream));
+        CK(cudaMemcpyAsync(out, ctx->escratch, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->world > 1) { // each rank summed its own targets' rows
+            CK(cudaMemcpyAsync(ctx->escratch, out, 5 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            NK(nccl().AllReduce(ctx->escratch, ctx->escratch, 5, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream));
+            CK(cudaMemcpyAsync(out, ctx->escratch, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    if (kinetic)
+        *kinetic = out[0];
+    if (potential)
+        *potential = out[1];
+    if (momentum) {
+        momentum[0] = out[2];
+        momentum[1] = out[3];
+        momentum[2] = out[4];
+    }
+    return ESSA_OK;
+}
+
+extern "C" double essa_measure_fp64_peak(essa_ctx* ctx, double ms) {
+    if (!ctx)
+        return -1;
+    if (cudaSetDevice(ctx->device) != cudaSuccess)
+        return -1;
+    return run_fp64_peak(ctx, ms);
+}
+
+extern "C" int essa_measure_rsqrt_error(essa_ctx* ctx, double* seed_rel_err, double* refined_rel_err) {
+    ARG(ctx, "ctx is null");
+    CK(cudaSetDevice(ctx->device));
+    return run_rsqrt_error(ctx, seed_rel_err, refined_rel_err);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ensemble
+// ---------------------------------------------------------------------------------------------
+extern "C" double essa_ensemble_factor(uint64_t seed, double rel_sigma, int64_t copy, int body, int component) {
+    return ensemble_factor(seed, rel_sigma, (long long)copy, body, component);
+}
+
+extern "C" int essa_ensemble_init(essa_ctx* ctx, const essa_ensemble_opts* o) {
+    ARG(ctx, "ctx is null");
+    ARG(o && o->copies > 0, "copies must be positive");
+    ARG(ctx->n > 0, "upload the template world first");
+    ARG(ctx->n <= kEnsembleMaxBodies, "ensemble template must have at most ESSA_ENSEMBLE_MAX bodies");
+    ARG(!o->closest_approaches || (o->approach_to >= 0 && o->approach_to < ctx->n), "approach_to out of range");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->ens_state);
+    cudaFree(ctx->ens_gf);
+    cudaFree(ctx->ens_mind);
+    ctx->ens_state = ctx->ens_gf = ctx->ens_mind = nullptr;
+    ctx->ens_copies = o->copies;
+    ctx->ens_n = ctx->n;
+    ctx->ens = *o;
+    size_t total = (size_t)o->copies * ctx->n;
+    CK(cudaMalloc(&ctx->ens_state, total * 6 * sizeof(double)));
+    CK(cudaMalloc(&ctx->ens_gf, (size_t)ctx->n * sizeof(double)));
+    CK(cudaMalloc(&ctx->ens_mind, total * sizeof(double)));
+    CK(launch_ensemble_init(ctx, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESSA_OK;
+}
+
+extern "C" int essa_ensemble_step(essa_ctx* ctx, int steps) {
+    ARG(ctx, "ctx is null");
+    ARG(steps != 0, "steps must not be 0");
+    ARG(ctx->ens_copies > 0, "essa_ensemble_init first");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    CK(launch_ensemble_step(ctx, steps, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    ctx->last_step_ms = ms;
+    ctx->last_force_ms = ms;
+    return ESSA_OK;
+}
+
+extern "C" int essa_ensemble_read(essa_ctx* ctx, int first, int count, double* x, double* y, double* z, double* vx, double* vy,
+    double* vz, double* min_distance) {
+    ARG(ctx, "ctx is null");
+    ARG(first >= 0 && count >= 0 && first + count <= ctx->ens_copies, "copy range out of bounds");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t n = (size_t)ctx->ens_n;
+    double* dst[6] = { x, y, z, vx, vy, vz };
+    for (int c = 0; c < count; c++) {
+        double const* src = ctx->ens_state + (size_t)(first + c) * 6 * n;
+        for (int k = 0; k < 6; k++)
+            if (dst[k])
+                CK(cudaMemcpyAsync(dst[k] + (size_t)c * n, src + k * n, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (min_distance)
+        CK(cudaMemcpyAsync(min_distance, ctx->ens_mind + (size_t)first * n, (size_t)count * n * sizeof(double), cudaMemcpyDeviceToHost,
+            ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sharding
+// ---------------------------------------------------------------------------------------------
+extern "C" int essa_nccl_unique_id(uint8_t id[ESSA_NCCL_ID_BYTES]) {
+    if (!id)
+        return ESSA_ERR_ARG;
+    NcclApi& api = nccl();
+    if (!api.lib) {
+        g_create_error = api.why;
+        return ESSA_ERR_NCCL;
+    }
+    NcclId nid;
+    if (api.GetUniqueId(&nid) != 0) {
+        g_create_error = "ncclGetUniqueId failed";
+        return ESSA_ERR_NCCL;
+    }
+    memcpy(id, nid.internal, ESSA_NCCL_ID_BYTES);
+    return ESSA_OK;
+}
+
+extern "C" int essa_shard_attach(essa_ctx* ctx, int rank, int world, const uint8_t id[ESSA_NCCL_ID_BYTES]) {
+    ARG(ctx, "ctx is null");
+    ARG(world >= 1 && rank >= 0 && rank < world && id, "bad rank / world / id");
+    ARG(!ctx->comm, "already attached");
+    CK(cudaSetDevice(ctx->device));
+    if (world == 1)
+        return ESSA_OK;
+    NcclApi& api = nccl();
+    if (!api.lib) {
+        ctx->err = api.why;
+        return ESSA_ERR_NCCL;
+    }
+    NcclId nid;
+    memcpy(nid.internal, id, ESSA_NCCL_ID_BYTES);
+    NK(api.CommInitRank(&ctx->comm, world, nid, rank));
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->acc_valid = false;
+    return ESSA_OK;
+}

@@ -1,0 +1,194 @@
+// Host-side context behind the C ABI (include/essa_b200.h).  Owns every device buffer of one world.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/essa_b200.h"
+
+namespace essa {
+
+constexpr int kTileJ = 256;       // j-records per shared-memory tile (8 KiB)
+constexpr int kStages = 4;        // bulk-copy pipeline depth
+constexpr int kForceThreads = 256;
+constexpr int kEnsembleMaxBodies = 320; // widest template one ensemble CTA takes
+
+// Arguments of the fused kick / drift epilogue (src/World.cpp:106-116,121-127).
+struct KickArgs {
+    double h;      // dt / 2
+    double dt;     // (double)seconds_per_tick
+    double mul;    // +1 / -1
+    int second_kick; // v = vh + (a h) mul    -- finishes the step whose drift produced these positions
+    int advance;     // vh = v + (a h) mul ; x' = x + (vh dt) mul  -> other position buffer
+};
+
+// Device pointers of the world (all arrays have `cap` elements).
+struct WorldPtrs {
+    double4* pos_cur;  // {x, y, z, active ? gf : 0}: the j-record the force pass streams
+    double4* pos_next;
+    double* v[3];      // velocity at the integer step (what Object::vel() shows)
+    double* vh[3];     // velocity after the first half kick
+    double* a[3];      // m_attraction_factor at pos_cur
+    double const* gf;  // m_gravity_factor
+    uint8_t const* active;
+    int32_t* most;
+    int32_t* old_most;
+    double* maxattr;
+};
+
+struct ForceArgs {
+    WorldPtrs w;
+    int n;          // bodies in the world
+    int i0, i1;     // targets owned by this context (whole world unless sharded)
+    int j0, j1;     // sources streamed by this launch
+    int S;          // j-chunks in this launch (gridDim.x = iblocks * S)
+    int slot0;      // first partial slot this launch writes
+    int slots_total; // slots per i-block that must be present before the epilogue runs
+    int ipad;       // iblocks * 256 * R
+    double* part;   // [slots_total][3][ipad]
+    double* part_m; // [slots_total][ipad]   (argmax variant)
+    int* part_j;    // [slots_total][ipad]
+    unsigned* counters; // [iblocks]
+    double eps2;
+    int save_old;   // Object::before_update: old_most = most (first pass of a step)
+    KickArgs k;
+};
+
+// ---- recording state of the tracked bodies (History + Trail + ap/pe) -----------------------
+struct RecordPtrs {
+    int tracked;
+    double* hist;        // [tracked][ESSA_HISTORY_SEGMENTS][6]
+    int32_t* hist_start; // ring start
+    int32_t* hist_len;
+    float* verts;        // concatenated vertex rings, 3 floats per vertex
+    int64_t const* vert_off; // [tracked] first vertex of body k
+    int32_t const* cap;  // [tracked]
+    int32_t* append_off;
+    int32_t* length;
+    double* toff;        // [tracked][3]  Trail::m_offset
+    double* last_angle;  // [tracked]
+    double* ap;
+    double* pe;
+    double* ap_vel;
+    double* pe_vel;
+};
+
+} // namespace essa
+
+struct ncclComm;
+
+struct essa_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_gather = nullptr, ev_ready = nullptr;
+
+    int n = 0;
+    int cap = 0;
+    double4* pos[2] = { nullptr, nullptr };
+    int cur = 0;
+    double* vel = nullptr;  // 3*cap
+    double* velh = nullptr; // 3*cap
+    double* acc = nullptr;  // 3*cap
+    double* gf = nullptr;
+    int64_t* cdate = nullptr;
+    int64_t* ddate = nullptr;
+    uint8_t* delflag = nullptr;
+    uint8_t* active = nullptr;
+    int32_t* most = nullptr;
+    int32_t* old_most = nullptr;
+    double* maxattr = nullptr;
+    double* appe = nullptr; // 4*cap: ap, pe, ap_vel, pe_vel (also used by untracked bodies' upload/download)
+    bool acc_valid = false;     // acc[] holds set_forces() of pos[cur] under the current active mask
+    bool acc_has_most = false;  // ... and most / max_attraction were evaluated with it
+    bool acc_exact = false;     // ... in exact_order arithmetic
+    bool gather_pending = false;
+    std::vector<cudaEvent_t> force_events;
+    int last_force_passes = 0;
+    int64_t date = ESSA_START_DATE;
+    std::vector<int64_t> events; // sorted creation / deletion instants at which the active mask flips
+    bool any_inactive_possible = false;
+
+    // force-pass scratch
+    double* part = nullptr;
+    double* part_m = nullptr;
+    int* part_j = nullptr;
+    size_t part_doubles = 0;
+    size_t part_slots_cap = 0;
+    unsigned* counters = nullptr;
+    int counters_cap = 0;
+
+    // recording
+    int tracked = 0;
+    std::vector<int32_t> trail_cap;
+    std::vector<int64_t> vert_off_h;
+    double* hist = nullptr;
+    double* hist_first = nullptr; // History::m_first_entry, [tracked][6]
+    int32_t* hist_start = nullptr;
+    int32_t* hist_len = nullptr;
+    float* verts = nullptr;
+    int64_t* vert_off = nullptr;
+    int32_t* tcap = nullptr;
+    int32_t* append_off = nullptr;
+    int32_t* tlength = nullptr;
+    double* toff = nullptr;
+    double* last_angle = nullptr;
+    int64_t verts_total = 0;
+
+    // ensemble
+    int ens_copies = 0;
+    int ens_n = 0;
+    essa_ensemble_opts ens {};
+    double* ens_state = nullptr; // [copies][6][n]
+    double* ens_gf = nullptr;    // [n]
+    double* ens_mind = nullptr;  // [copies][n]
+
+    // energy scratch
+    double* escratch = nullptr;
+    size_t escratch_n = 0;
+
+    // sharding
+    int rank = 0, world = 1;
+    ncclComm* comm = nullptr;
+
+    // stats
+    int64_t launches = 0;
+    int64_t passes = 0;
+    double interactions = 0;
+    double last_step_ms = 0;
+    double last_force_ms = 0;
+    std::string err;
+
+    void* pinned = nullptr; // staging for uploads / downloads
+    size_t pinned_bytes = 0;
+};
+
+namespace essa {
+
+// kernels' host launchers (defined in the .cu files)
+cudaError_t launch_force_pass(essa_ctx* c, int j0, int j1, int S, int slot0, int slots_total, bool argmax, bool save_old,
+    KickArgs const& k, double eps2, cudaStream_t st);
+cudaError_t launch_kick_drift(essa_ctx* c, KickArgs const& k, cudaStream_t st);
+cudaError_t launch_refresh_active(essa_ctx* c, cudaStream_t st);
+cudaError_t launch_record(essa_ctx* c, int offset_trails, int forward_simulated, cudaStream_t st);
+cudaError_t launch_record_init(essa_ctx* c, int first, cudaStream_t st);
+cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double const* z, cudaStream_t st);
+cudaError_t launch_unpack(essa_ctx* c, double* x, double* y, double* z, cudaStream_t st);
+int force_iblocks(essa_ctx const* c, int* R_out);
+void choose_split(essa_ctx const* c, int iblocks, int ntiles, int* S_out);
+
+cudaError_t launch_resident(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st);
+cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st);
+cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st);
+cudaError_t launch_energy(essa_ctx* c, cudaStream_t st); // result in c->escratch[0..5)
+double run_fp64_peak(essa_ctx* c, double ms);
+int run_rsqrt_error(essa_ctx* c, double* seed, double* refined);
+
+RecordPtrs record_ptrs(essa_ctx* c);
+WorldPtrs world_ptrs(essa_ctx* c);
+
+} // namespace essa

@@ -1,0 +1,216 @@
+/* ==========================================================================================
+ * essa_b200.h -- C ABI of the B200-native World::update hot path.
+ *
+ * The reference (essa-software/essa) has no plugin / FFI interface: its boundary for this path
+ * is the C++ method `void World::update(int steps)` (src/World.hpp:29, src/World.cpp:86-139)
+ * observed through the Object accessors (src/Object.hpp:72-99).  This header is what the
+ * replacement World::update binds instead of running the loop itself:
+ *
+ *     reference                                            this ABI
+ *     ---------------------------------------------------  ---------------------------------
+ *     World::m_object_list state (src/World.hpp:77,        essa_upload / essa_download
+ *       src/Object.hpp:152-191)                            (SoA, plain double* / int*)
+ *     World::update(int)           src/World.cpp:86-139    essa_step
+ *     World::set_forces()          src/World.cpp:42-57     essa_set_forces
+ *     World::m_date / deleted()    src/World.cpp:59-84,    essa_set_date / essa_get_date
+ *                                  src/Object.cpp:60-62
+ *     Object::m_history            src/History.cpp:6-59    essa_history_read / _write
+ *     Object::m_trail              src/Trail.cpp:19-110    essa_trail_read / _write
+ *     clone_for_forward_simulation src/World.cpp:230-238,  essa_ensemble_init / _step / _read
+ *       + update(ticks)            src/essagui/EssaCreateObject.cpp:166-189
+ *     (none: new diagnostic required by the north star)    essa_energy
+ *
+ * Conventions: plain C types; every array is caller-owned host memory unless the name says
+ * `_device`; int return code (0 = ok, <0 = error, see essa_status) with a message available
+ * from essa_last_error(); no exceptions cross the boundary; one context per host thread;
+ * every call is synchronous on return unless it ends in `_async`.
+ *
+ * There is NO CPU fallback: without a CUDA device essa_ctx_create fails with ESSA_ERR_CUDA.
+ * ========================================================================================== */
+#ifndef ESSA_B200_H
+#define ESSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESSA_ABI_VERSION 1
+
+typedef struct essa_ctx essa_ctx;
+
+typedef enum essa_status {
+    ESSA_OK = 0,
+    ESSA_ERR_ARG = -1,   /* bad argument (null pointer, steps == 0, N out of range ...) */
+    ESSA_ERR_CUDA = -2,  /* CUDA runtime error, incl. "no device" */
+    ESSA_ERR_NCCL = -3,  /* NCCL missing or failed */
+    ESSA_ERR_STATE = -4, /* call not valid in the current state (nothing uploaded ...) */
+    ESSA_ERR_NOMEM = -5
+} essa_status;
+
+/* Util::Constants::Gravity and ::AU as used by the reference (src/Object.cpp:38,
+ * src/Trail.cpp:53); G is pinned by the reference's tests/accuracy.ods. */
+#define ESSA_GRAVITY 6.67408e-11
+#define ESSA_AU 149597870700.0
+/* Util::SimulationTime::create(1990, 4, 20) (src/World.cpp:24-27) as seconds, from the traces. */
+#define ESSA_START_DATE 640566000LL
+/* History(1000, ...) in the Object constructor (src/Object.cpp:34). */
+#define ESSA_HISTORY_SEGMENTS 1000
+/* Largest world the resident single-CTA kernel takes (one thread per body). */
+#define ESSA_RESIDENT_MAX 1024
+/* Widest template world essa_ensemble_init takes (one copy must fit a 320-thread CTA). */
+#define ESSA_ENSEMBLE_MAX 320
+
+/* Which kernel essa_step runs. */
+typedef enum essa_kernel {
+    ESSA_KERNEL_AUTO = 0,     /* N <= ESSA_RESIDENT_MAX: resident, else tiled */
+    ESSA_KERNEL_TILED = 1,    /* K1: j-tiled FP64 force pass + fused kick/drift (any N) */
+    ESSA_KERNEL_RESIDENT = 2  /* K3: one CTA keeps the world in shared memory for all steps */
+} essa_kernel;
+
+/* SoA view of the per-Object state (src/Object.hpp:152-191).  A null member is skipped.
+ * `most` is the list index of Object::m_most_attracting_object, -1 for nullptr. */
+typedef struct essa_bodies {
+    double *x, *y, *z;       /* m_pos */
+    double *vx, *vy, *vz;    /* m_vel */
+    double *ax, *ay, *az;    /* m_attraction_factor (download only) */
+    double *gf;              /* m_gravity_factor = mass * G */
+    int64_t *creation_date;  /* m_creation_date, seconds */
+    int64_t *deletion_date;  /* m_deletion_date, seconds */
+    uint8_t *deleted;        /* m_deleted */
+    int32_t *most;           /* m_most_attracting_object */
+    double *max_attraction;  /* m_max_attraction (download only) */
+    double *ap, *pe, *ap_vel, *pe_vel; /* m_ap, m_pe, m_ap_vel, m_pe_vel */
+} essa_bodies;
+
+/* Options of one essa_step call.  Zero-initialise, then set what differs. */
+typedef struct essa_step_opts {
+    int dt_seconds;            /* World::m_simulation_seconds_per_tick (an int, src/World.hpp:78) */
+    int forward_simulated;     /* World::m_is_forward_simulated: date frozen, no History, trails not offset */
+    int offset_trails;         /* SimulationView::offset_trails() (default true, SimulationView.hpp:182) */
+    int record;                /* run Object::update (History + Trail + ap/pe) for the tracked bodies */
+    int track_most_attracting; /* evaluate Object.cpp:84-94 (forced on by `record`) */
+    int exact_order;           /* reference operation order, IEEE div/sqrt, no FMA: bit-identical to the
+                                  reference restatement; resident kernel only */
+    int two_pass;              /* evaluate both set_forces() calls of every step instead of reusing the
+                                  acceleration left by the previous step (same results, 2x the work) */
+    int kernel;                /* essa_kernel */
+    double eps2;               /* Plummer softening^2; 0 = reference semantics */
+} essa_step_opts;
+
+/* ---- context ----------------------------------------------------------------------------- */
+int essa_abi_version(void);
+/* device: CUDA ordinal.  capacity: bodies to reserve for (grows on demand). */
+int essa_ctx_create(int device, int capacity, essa_ctx** out);
+void essa_ctx_destroy(essa_ctx* ctx);
+/* Message of the last failure on this context (or of the last failed create when ctx is null). */
+const char* essa_last_error(const essa_ctx* ctx);
+/* Kernels launched by this context so far / force passes / directed interactions evaluated. */
+int64_t essa_launch_count(const essa_ctx* ctx);
+int64_t essa_pass_count(const essa_ctx* ctx);
+double essa_interaction_count(const essa_ctx* ctx);
+/* Device-side milliseconds of the last essa_step / essa_ensemble_run (CUDA events on its stream). */
+double essa_last_step_ms(const essa_ctx* ctx);
+/* Milliseconds spent in force-pass kernels during the last essa_step (events around each launch). */
+double essa_last_force_ms(const essa_ctx* ctx);
+/* Force passes the last essa_step / essa_ensemble_step evaluated. */
+int essa_last_force_passes(const essa_ctx* ctx);
+int essa_sync(essa_ctx* ctx);
+
+/* ---- world state --------------------------------------------------------------------------- */
+/* Replace the world by `n` bodies (list order = index order).  x..vz and gf are required; dates
+ * default to "always active", most to -1, ap to 0, pe to DBL_MAX.  Recording state is kept. */
+int essa_upload(essa_ctx* ctx, int n, const essa_bodies* host);
+/* Copy current state out (members that are null are skipped). */
+int essa_download(essa_ctx* ctx, essa_bodies* host);
+/* Pinned-host variants for repeated transfers: identical semantics, the copies run on the
+ * context's stream from/to cudaHostAlloc'ed staging buffers owned by the context. */
+int essa_set_date(essa_ctx* ctx, int64_t date);
+int64_t essa_get_date(const essa_ctx* ctx);
+int essa_body_count(const essa_ctx* ctx);
+
+/* World::update(steps): |steps| KDK iterations, sign = direction (src/World.cpp:86-139). */
+int essa_step(essa_ctx* ctx, int steps, const essa_step_opts* opts);
+/* World::set_forces() alone (src/World.cpp:42-57): refreshes acc / most / max_attraction. */
+int essa_set_forces(essa_ctx* ctx, const essa_step_opts* opts);
+
+/* ---- recording: Object::m_history / m_trail (src/History.cpp, src/Trail.cpp) ---------------- */
+/* Track bodies [0, n_tracked): allocate History rings (ESSA_HISTORY_SEGMENTS entries) and Trail
+ * vertex rings of trail_capacity[k] vertices (already clamped as in src/Object.cpp:33 and
+ * src/Trail.cpp:19-34) and run the constructor-time pushes from the uploaded state.  Bodies
+ * [0, keep) keep their existing rings (an object was appended), the rest are (re)created. */
+int essa_record_configure(essa_ctx* ctx, int n_tracked, const int32_t* trail_capacity, int keep);
+int essa_tracked_count(const essa_ctx* ctx);
+/* Object::reset_history() / Trail::reset() for one body (src/Object.cpp:268-271). */
+int essa_record_reset(essa_ctx* ctx, int body, int history, int trail);
+/* History entries oldest first, 6 doubles each (px py pz vx vy vz).  Returns the entry count
+ * (<= ESSA_HISTORY_SEGMENTS) or <0; `out` may be null to query the count. */
+int essa_history_read(essa_ctx* ctx, int body, double* out);
+/* set_first != 0 also makes entries[0..6) the History's m_first_entry (what History::reset() restores). */
+int essa_history_write(essa_ctx* ctx, int body, const double* entries, int count, int set_first);
+typedef struct essa_trail_meta {
+    int32_t capacity;      /* m_vertexes.size() */
+    int32_t append_offset; /* m_append_offset */
+    int32_t length;        /* m_length */
+    int32_t pad;
+    double offset[3];      /* m_offset */
+    double last_xy_angle;  /* m_last_xy_angle */
+} essa_trail_meta;
+/* verts: 3 * capacity floats (x y z per vertex, already divided by AU); may be null. */
+int essa_trail_read(essa_ctx* ctx, int body, float* verts, essa_trail_meta* meta);
+int essa_trail_write(essa_ctx* ctx, int body, const float* verts, const essa_trail_meta* meta);
+
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+/* Kinetic and potential energy (J) and total momentum (kg m/s) of the active bodies, FP64,
+ * fixed reduction order.  m = gf / ESSA_GRAVITY. */
+int essa_energy(essa_ctx* ctx, double* kinetic, double* potential, double momentum[3]);
+
+/* ---- ensemble: many perturbed copies of the uploaded template -------------------------------- */
+typedef struct essa_ensemble_opts {
+    int copies;            /* number of copies held by THIS context (a rank's share) */
+    int64_t first_copy;    /* global index of this context's copy 0 (keys the perturbation) */
+    int dt_seconds;
+    uint64_t seed;
+    double rel_sigma;      /* every pos/vel component *= 1 + rel_sigma * n,  n ~ Irwin-Hall(12)-6 from
+                              Philox4x32-10 keyed (seed; copy, body, component); global copy 0 unperturbed */
+    int exact_order;       /* as essa_step_opts.exact_order */
+    int closest_approaches;/* Object::update_closest_approaches (src/Object.cpp:405-417): keep the minimum
+                              distance of every body to body `approach_to` over the run */
+    int approach_to;
+} essa_ensemble_opts;
+/* Build the copies on the device from the uploaded template (positions, velocities, gf). */
+int essa_ensemble_init(essa_ctx* ctx, const essa_ensemble_opts* opts);
+/* Advance every copy by |steps| KDK iterations (forward-simulated semantics: no date, no History). */
+int essa_ensemble_step(essa_ctx* ctx, int steps);
+/* State of `count` copies starting at local copy `first`: arrays of count * N doubles, copy-major. */
+int essa_ensemble_read(essa_ctx* ctx, int first, int count, double* x, double* y, double* z,
+                       double* vx, double* vy, double* vz, double* min_distance);
+/* The perturbation factor (1 + rel_sigma * n) for one (copy, body, component 0..5), on the host,
+ * bit-identical to what the device applies: lets a checker rebuild any copy's initial state. */
+double essa_ensemble_factor(uint64_t seed, double rel_sigma, int64_t copy, int body, int component);
+
+/* ---- multi-GPU: targets sharded over ranks, positions all-gathered each force pass ----------- */
+#define ESSA_NCCL_ID_BYTES 128
+/* Rank 0 fills `id` (an ncclUniqueId); the caller broadcasts it (torch.distributed, MPI ...). */
+int essa_nccl_unique_id(uint8_t id[ESSA_NCCL_ID_BYTES]);
+/* Join the communicator.  After this, essa_upload takes the FULL world on every rank and
+ * essa_step integrates bodies [rank*N/world, (rank+1)*N/world) with one all-gather of the
+ * drifted positions per force pass; essa_download returns the full, gathered world. */
+int essa_shard_attach(essa_ctx* ctx, int rank, int world, const uint8_t id[ESSA_NCCL_ID_BYTES]);
+int essa_shard_rank(const essa_ctx* ctx);
+int essa_shard_world(const essa_ctx* ctx);
+
+/* ---- measurement helpers ----------------------------------------------------------------------- */
+/* Register-resident independent-DFMA-chain kernel on every SM for about `ms` milliseconds:
+ * returns the achieved FP64 rate in TFLOP/s (FMA = 2 flops) -- the roofline denominator that
+ * MEASURED_PEAKS.json lacks -- or <0. */
+double essa_measure_fp64_peak(essa_ctx* ctx, double ms);
+/* Maximum relative error of the MUFU.RSQ64H seed and of the refined r^-3 over a log sweep. */
+int essa_measure_rsqrt_error(essa_ctx* ctx, double* seed_rel_err, double* refined_rel_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESSA_B200_H */

@@ -64,6 +64,7 @@ def lib():
         L.ow_get_state.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _ip, _dp, _ip, _dp]
         L.ow_set_object_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_double]
         L.ow_delete_object.argtypes = [C.c_void_p, C.c_int]
+        L.ow_set_dates.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int]
         L.ow_name.argtypes = [C.c_void_p, C.c_int]
         L.ow_name.restype = C.c_char_p
         for f in (L.ow_radius, L.ow_orbit_len, L.ow_eccentrity):
@@ -166,6 +167,9 @@ class World:
         p = None if pos is None else np.ascontiguousarray(pos, dtype=np.float64)
         v = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64)
         self._L.ow_set_object_state(self._h, idx, _d(p), _d(v), gf)
+
+    def set_dates(self, idx, creation, deletion=0, deleted=False):
+        self._L.ow_set_dates(self._h, idx, int(creation), int(deletion), int(deleted))
 
     def delete_object(self, idx):
         self._L.ow_delete_object(self._h, idx)

@@ -272,6 +272,13 @@ void ow_set_object_state(void* w, int idx, double const* pos, double const* vel,
     if (vel) o->m_vel = { vel[0], vel[1], vel[2] };
     if (gf >= 0) o->m_gravity_factor = gf;
 }
+// m_creation_date / m_deletion_date / m_deleted of one object (what add_object / delete_object set).
+void ow_set_dates(void* w, int idx, long long creation, long long deletion, int deleted) {
+    Object* o = static_cast<World*>(w)->object_at(idx);
+    o->m_creation_date = creation;
+    o->m_deletion_date = deletion;
+    o->m_deleted = deleted != 0;
+}
 void ow_delete_object(void* w, int idx) { static_cast<World*>(w)->object_at(idx)->delete_object(); }
 char const* ow_name(void* w, int idx) { return static_cast<World*>(w)->object_at(idx)->m_name.c_str(); }
 double ow_radius(void* w, int idx) { return static_cast<World*>(w)->object_at(idx)->m_radius; }
