@@ -1,0 +1,407 @@
+#!/usr/bin/env python3
+"""Headline benchmark of the World::update hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): synthetic galaxy collision, N = 1,048,576 bodies, FP64, Leapfrog KDK,
+dt = 200,000 s -- BASELINE.json's headline config; it fits one B200 (59 MB of state).  A "step" is
+one World::update iteration over the whole world.  With N > 1 GPUs the targets are sharded over the
+ranks (strong scaling: the world does not grow) and the drifted positions are all-gathered once per
+force pass (NCCL, overlapped with the local-shard tiles).
+
+One JSON line on stdout (rank 0):
+  value     directed pairwise interactions / s, whole job, device-timed (CUDA events on the
+            launching stream, max over ranks), state resident in HBM, L2 flushed between steps;
+  roofline  FP64-pipe roofline of the force kernel: 20 flops per directed interaction
+            (BASELINE.json's convention) / average launch duration measured live, against the
+            FP64 FMA peak measured in the same run (MEASURED_PEAKS.json has no FP64 figure);
+  e2e       the same metric through the public C-ABI call sequence a host program makes per tick
+            with HOST buffers: essa_upload + essa_step + essa_download inside the timed region;
+  cpu_baseline  the CPU oracle (a restatement of the reference's own loop on the reference's own
+            containers) timed on this box's host cores on a bounded slice of the same world;
+  extra     Solar System iterations / s (resident kernel through the World facade, History + Trail
+            recording on) next to the oracle's, the second half of BASELINE.json's metric.
+
+--impl reference times the reference's CPU implementation (oracle port: the reference itself
+cannot be built offline) on the same world; each step is a bounded slice of World::set_forces.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOPS_PER_INTERACTION = 20.0
+NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+METRIC = "pairwise_interactions_per_s"
+UNIT = "interactions/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1 << 20, help="bodies (default: BASELINE.json's 1,048,576)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the Solar System / CPU baseline legs")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "tiled", "paired"])
+    return ap.parse_args()
+
+
+def workload(n):
+    from essa_b200 import synth
+    if n >= (1 << 20):
+        w = synth.galaxy_collision(n)
+        name = "synthetic galaxy collision (2 Plummer spheres) N=%d FP64 Leapfrog KDK" % n
+    else:
+        w = synth.plummer(n)
+        name = "synthetic Plummer sphere N=%d FP64 Leapfrog KDK" % n
+    return w, synth.default_dt(n), name
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ["clocks.sm", "clocks.max.sm", "power.draw", "clocks_event_reasons.hw_slowdown",
+              "clocks_event_reasons.hw_thermal_slowdown", "clocks_event_reasons.sw_thermal_slowdown",
+              "clocks_event_reasons.sw_power_cap"]
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + ",".join(self.FIELDS),
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return model, os.cpu_count()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference's own loop
+# --------------------------------------------------------------------------------------------
+def cpu_world(w):
+    """oracle::World holding the whole synthetic world in the reference's containers
+    (std::list<std::unique_ptr<Object>>, one Trail + History per object)."""
+    import oracle
+    ow = oracle.World()
+    ow.add_bodies(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"] / oracle.GRAVITY)
+    return ow
+
+
+def cpu_slice(ow, n, row0, target_pairs):
+    """Time rows [row0, row0 + r) of World::set_forces's outer loop (pair-shared, list order).
+    Returns (seconds, directed interactions evaluated, rows)."""
+    rows = max(1, int(np.ceil(target_pairs / max(1, n - 1 - row0))))
+    rows = min(rows, n - 1 - row0)
+    secs, pairs = ow.time_force_rows(row0, row0 + rows)
+    return secs, 2.0 * pairs, rows
+
+
+def cpu_baseline(w, n, seconds=12.0):
+    import oracle
+    model, cores = host_info()
+    t0 = time.time()
+    try:
+        ow = cpu_world(w)
+    except MemoryError:
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "could not allocate the oracle world"}
+    build_s = time.time() - t0
+    # calibrate on a short slice, then size the timed slice for ~`seconds`
+    s0, i0, r0 = cpu_slice(ow, n, 0, 2e7)
+    rate = i0 / s0
+    s1, i1, r1 = cpu_slice(ow, n, r0, rate / 2.0 * seconds)
+    # all-cores variant (NOT the reference, which is single-threaded): OpenMP over rows of the same law
+    rows = np.arange(0, n, max(1, n // 256), dtype=np.int32)[:256]
+    t = time.time()
+    _, threads = oracle.forces_rows(w["x"], w["y"], w["z"], w["gf"], rows, mode="omp")
+    omp_s = time.time() - t
+    return {"value": i1 / s1, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "rows [%d, %d) of World::set_forces over the same %d-body world: %.3g directed interactions in %.1f s, "
+                      "1 thread (the reference is single-threaded), oracle built -O2 -ffp-contract=off" % (r0, r0 + r1, n, i1, s1),
+            "host_cpu": model, "host_cores": cores, "oracle_world_build_s": round(build_s, 1),
+            "omp_all_cores": {"value": len(rows) * (n - 1) / omp_s, "unit": UNIT, "threads": threads,
+                              "note": "OpenMP over rows of the same pair law; not the reference"}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.n
+    w, dt, name = workload(n)
+    ow = cpu_world(w)
+    row = 0
+    per_step = 1.5e8  # pair evaluations per step: a few seconds on one core
+    for _ in range(args.warmup):
+        s, i, r = cpu_slice(ow, n, row, per_step / 10)
+        row += r
+    secs, inter, rows0 = 0.0, 0.0, row
+    for _ in range(args.steps):
+        s, i, r = cpu_slice(ow, n, row, per_step)
+        secs += s
+        inter += i
+        row += r
+    model, cores = host_info()
+    value = inter / secs
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "n": n, "dt_seconds": dt,
+                       "step": "bounded slice of one World::set_forces pass (rows [%d, %d) of the pair loop)" % (rows0, row)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "%d rows of the pair-shared loop per step, %d-body world, 1 thread (reference is single-threaded); "
+                                       "the reference itself cannot be built offline, this is its restatement on its own containers" % ((row - rows0) // max(1, args.steps), n),
+                             "host_cpu": model, "host_cores": cores},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# Solar System leg (second half of BASELINE.json's metric)
+# --------------------------------------------------------------------------------------------
+def solar_leg():
+    import oracle
+    from essa_b200 import world
+    path = os.path.join(ROOT, "tests", "golden", "worlds", "solar.essa")
+    out = {}
+    for label, exact, steps in (("fast", False, 1000000), ("exact_order", True, 200000)):
+        pw = world.World.load(path)
+        pw.simulation_seconds_per_tick = 600
+        pw.set_flags(offset_trails=True, exact_order=exact)
+        pw.update(10000)
+        pw.update(steps)
+        out["solar_iters_per_s_" + label] = steps / (pw.last_step_ms * 1e-3)
+        t0 = time.perf_counter()
+        for _ in range(100):
+            pw.update(10)  # the GUI's default: 10 iterations per tick, state read back every tick
+        out["solar_iters_per_s_%s_10_per_call" % label] = 1000 / (time.perf_counter() - t0)
+        pw.close()
+    ow = oracle.World.load(path)
+    ow.dt = 600
+    ow.update(10000)
+    secs = ow.time_update(300000)
+    out["solar_iters_per_s_cpu_oracle"] = 300000 / secs
+    out["solar_note"] = ("worlds/solar.essa, 10 bodies, dt=600 s, History + Trail + ap/pe recording on, offset trails; GPU = one "
+                         "resident CTA, all steps in one launch; CPU = oracle (reference containers, -O2, 1 thread); the README's "
+                         "67,500 it/s (Ryzen 5 5600H, GUI on) is published-not-measured")
+    out["solar_speedup_vs_cpu_oracle"] = out["solar_iters_per_s_fast"] / out["solar_iters_per_s_cpu_oracle"]
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from essa_b200 import capi
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the essa_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world_size == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.n
+    w, dt, name = workload(n)
+    ctx = capi.Context(local_rank, n)
+    if world_size > 1:
+        uid = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.from_numpy(capi.nccl_unique_id()))
+        dist.broadcast(uid, 0)
+        ctx.shard_attach(rank, world_size, uid.cpu().numpy())
+    kernel = {"auto": capi.KERNEL_TILED, "tiled": capi.KERNEL_TILED, "paired": getattr(capi, "KERNEL_PAIRED", capi.KERNEL_TILED)}[args.kernel]
+    opts = capi.Context.opts(dt, kernel=kernel)
+
+    peak = ctx.measure_fp64_peak(300.0) if rank == 0 else 0.0
+    ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
+    e0 = ctx.energy() if n <= (1 << 20) else None
+
+    for _ in range(max(args.warmup, 0)):
+        ctx.step(1, opts=opts)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0, passes0 = ctx.launches, ctx.passes
+    t_wall0 = time.time()
+    dev_ms = force_ms = 0.0
+    force_passes = 0
+    for _ in range(args.steps):
+        ctx.flush_l2()  # outside the event-timed region
+        ctx.step(1, opts=opts)
+        dev_ms += ctx.last_step_ms
+        force_ms += ctx.last_force_ms
+        force_passes += ctx.last_force_passes
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launches - launches0 - args.steps  # the L2 flush is a memset, not a kernel of ours... count kernels only
+    launches = ctx.launches - launches0
+    passes = ctx.passes - passes0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    dev_ms = max_over_ranks(dev_ms)
+    force_ms_max = max_over_ranks(force_ms)
+    total_interactions = float(passes) * n * (n - 1)  # all ranks together evaluate N(N-1) per pass
+    value = total_interactions / (dev_ms * 1e-3)
+
+    # ---- energy drift over everything stepped so far (warm-up + timed) ----
+    drift = None
+    if e0 is not None:
+        e1 = ctx.energy()
+        E0, E1 = e0[0] + e0[1], e1[0] + e1[1]
+        drift = {"steps": args.warmup + args.steps, "E0_J": E0, "E1_J": E1, "rel": abs(E1 - E0) / abs(E0),
+                 "momentum_rel": float(np.abs(e1[2] - e0[2]).max() / (np.abs(w["vx"]).sum() * (w["gf"][0] / capi.GRAVITY)))}
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e_steps = max(1, min(args.steps, 2))
+    barrier()
+    host = {k: np.array(w[k]) for k in ("x", "y", "z", "vx", "vy", "vz", "gf")}
+    p0 = ctx.passes
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.upload(host["x"], host["y"], host["z"], host["vx"], host["vy"], host["vz"], host["gf"])
+        ctx.step(1, opts=opts)
+        got = ctx.download(("x", "y", "z", "vx", "vy", "vz"))
+        for k in ("x", "y", "z", "vx", "vy", "vz"):
+            host[k] = got[k]
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = float(ctx.passes - p0) * n * (n - 1) / e2e_s
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * (11 * 8 + 2 * 8 + 4 + 2)), "d2h_bytes_per_step": int(n * 6 * 8),
+           "steps": e2e_steps, "passes_per_step": (ctx.passes - p0) / e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "note": "essa_upload (host SoA -> pinned staging -> HBM) + essa_step(1) + essa_download per step; an upload invalidates "
+                   "the resident acceleration, so each step evaluates both set_forces() passes, as the reference does"}
+
+    if rank != 0:
+        ctx.close()
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
+
+    ni = n // world_size
+    per_launch_interactions = float(ni) * (n - 1)
+    avg_force_ms = force_ms_max / max(1, force_passes)
+    achieved_tflops = per_launch_interactions * FLOPS_PER_INTERACTION / (avg_force_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch_n%d" % n)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tflops / peak,
+                "traffic": traffic, "kernel": "k_force_tiled", "avg_launch_ms": avg_force_ms, "launches_timed": force_passes,
+                "algorithmic_flops_per_launch": per_launch_interactions * FLOPS_PER_INTERACTION,
+                "peak_source": "measured in this run: register-resident independent DFMA chains on all SMs for 300 ms "
+                               "(MEASURED_PEAKS.json carries no FP64 figure)",
+                "frac_of_nominal": achieved_tflops / NOMINAL_FP64_TFLOPS, "nominal_peak": NOMINAL_FP64_TFLOPS,
+                "note": "the path is FP64-pipe bound (intensity ~0.19*N flop/B), neither HBM nor tensor: 17 FP64 instructions per "
+                        "directed interaction cap this formulation at 10/17 = 58.8% of the 20-flop convention"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": name, "n": n, "dt_seconds": dt, "sharding": "targets/%d + NCCL position all-gather per pass" % world_size
+                       if world_size > 1 else "single GPU", "l2": "flushed (256 MiB memset) between timed steps",
+                       "passes_per_step": passes / args.steps, "timing": "CUDA events on the launching stream around each essa_step, max over ranks"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "energy_drift": drift,
+            "wall_ms_per_step": 1e3 * (t_wall1 - t_wall0) / args.steps}
+    if world_size == 1 and not args.no_extra:
+        line["cpu_baseline"] = cpu_baseline(w, n)
+        try:
+            line["extra"] = solar_leg()
+        except Exception as e:  # the headline must not die on the secondary leg
+            line["extra"] = {"solar_error": repr(e)}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,7 +18,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
            "--fmad=true"]
-HOSTFLAGS = ["-O2", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-ffp-contract=off"]
+CXX = os.environ.get("CXX", "g++")
+HOSTFLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-ffp-contract=off", "-I/usr/local/cuda/include"]
 
 
 def sources():
@@ -49,7 +50,7 @@ def build(force=False, verbose=False):
         jobs.append(([NVCC, *ARCH, *CUFLAGS, "-Xptxas", "-v", "-c", os.path.join(CSRC, f), "-o", obj], obj))
     for f in cpp:
         obj = os.path.join(OBJ_DIR, f + ".o")
-        jobs.append(([NVCC, *HOSTFLAGS, "-x", "c++", "-c", os.path.join(CSRC, f), "-o", obj], obj))
+        jobs.append(([CXX, *HOSTFLAGS, "-c", os.path.join(CSRC, f), "-o", obj], obj))
 
     def run(job):
         cmd, obj = job

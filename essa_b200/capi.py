@@ -85,6 +85,8 @@ SYMBOLS = [
     ("essa_history_write", C.c_int, [_P, C.c_int, _dp, C.c_int, C.c_int]),
     ("essa_trail_read", C.c_int, [_P, C.c_int, _fp, C.POINTER(TrailMeta)]),
     ("essa_trail_write", C.c_int, [_P, C.c_int, _fp, C.POINTER(TrailMeta)]),
+    ("essa_closest_enable", C.c_int, [_P, C.c_int]),
+    ("essa_closest_read", C.c_int, [_P, C.c_int, C.c_int, _dp]),
     ("essa_energy", C.c_int, [_P, _dp, _dp, _dp]),
     ("essa_ensemble_init", C.c_int, [_P, C.POINTER(EnsembleOpts)]),
     ("essa_ensemble_step", C.c_int, [_P, C.c_int]),
@@ -96,6 +98,7 @@ SYMBOLS = [
     ("essa_shard_world", C.c_int, [_P]),
     ("essa_measure_fp64_peak", C.c_double, [_P, C.c_double]),
     ("essa_measure_rsqrt_error", C.c_int, [_P, _dp, _dp]),
+    ("essa_flush_l2", C.c_int, [_P]),
 ]
 
 _lib = None
@@ -275,6 +278,15 @@ class Context:
         verts = _arr(trail["verts"], np.float32)
         self._ck(self._L.essa_trail_write(self._h, body, _ptr(verts, _fp), C.byref(meta)))
 
+    def closest_enable(self, enable=True):
+        self._ck(self._L.essa_closest_enable(self._h, int(enable)))
+
+    def closest_approach(self, body, other):
+        out = np.zeros(7)
+        if self._ck(self._L.essa_closest_read(self._h, body, other, _ptr(out, _dp))) == 0:
+            return None
+        return dict(distance=out[0], this_position=out[1:4].copy(), other_object_position=out[4:7].copy())
+
     # ---- diagnostics ----
     def energy(self):
         ke, pe = C.c_double(0), C.c_double(0)
@@ -316,6 +328,9 @@ class Context:
         a, b = C.c_double(0), C.c_double(0)
         self._ck(self._L.essa_measure_rsqrt_error(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def flush_l2(self):
+        self._ck(self._L.essa_flush_l2(self._h))
 
     # ---- ensemble ----
     def ensemble_init(self, copies, dt, seed=7, rel_sigma=1e-6, first_copy=0, exact_order=False, closest_approaches=False,

@@ -281,6 +281,8 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     cudaFree(c->ens_gf);
     cudaFree(c->ens_mind);
     cudaFree(c->escratch);
+    cudaFree(c->closest);
+    cudaFree(c->l2_scratch);
     if (c->pinned)
         cudaFreeHost(c->pinned);
     cudaEvent_t evs[] = { c->ev_begin, c->ev_end, c->ev_f0, c->ev_f1, c->ev_gather, c->ev_ready };
@@ -1039,4 +1041,49 @@ extern "C" int essa_shard_attach(essa_ctx* ctx, int rank, int world, const uint8
     ctx->world = world;
     ctx->acc_valid = false;
     return ESSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// measurement hygiene: evict the L2 (126 MB) by writing a larger scratch buffer
+// ---------------------------------------------------------------------------------------------
+extern "C" int essa_flush_l2(essa_ctx* ctx) {
+    ARG(ctx, "ctx is null");
+    CK(cudaSetDevice(ctx->device));
+    size_t const bytes = 256u << 20;
+    if (!ctx->l2_scratch)
+        CK(cudaMalloc(&ctx->l2_scratch, bytes));
+    ctx->l2_value++;
+    CK(cudaMemsetAsync(ctx->l2_scratch, ctx->l2_value & 0xff, bytes, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// closest approaches (Object::m_closest_approaches, src/Object.hpp:184-189, src/Object.cpp:405-417)
+// ---------------------------------------------------------------------------------------------
+extern "C" int essa_closest_enable(essa_ctx* ctx, int enable) {
+    ARG(ctx, "ctx is null");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->closest);
+    ctx->closest = nullptr;
+    ctx->closest_n = 0;
+    if (!enable || ctx->n == 0)
+        return ESSA_OK;
+    ARG(ctx->n <= ESSA_RESIDENT_MAX, "closest approaches are tracked by the resident kernel only");
+    size_t bytes = (size_t)ctx->n * ctx->n * 7 * sizeof(double);
+    CK(cudaMalloc(&ctx->closest, bytes));
+    CK(cudaMemset(ctx->closest, 0, bytes));
+    ctx->closest_n = ctx->n;
+    return ESSA_OK;
+}
+
+extern "C" int essa_closest_read(essa_ctx* ctx, int body, int other, double out[7]) {
+    ARG(ctx, "ctx is null");
+    ARG(out, "out is null");
+    ARG(ctx->closest && body >= 0 && other >= 0 && body < ctx->closest_n && other < ctx->closest_n, "closest approaches not enabled / index");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, ctx->closest + ((size_t)body * ctx->closest_n + other) * 7, 7 * sizeof(double), cudaMemcpyDeviceToHost));
+    return out[0] != 0.0 ? 1 : 0;
 }

@@ -89,8 +89,9 @@ __device__ __forceinline__ void fast_interact_argmax(double xi, double yi, doubl
 }
 
 // ------------------------------------------------------------------------------------------
-// exact flavour (reference order; see oracle/essa_oracle.cpp row_force for the equivalence of
-// the per-row form with World::set_forces's pair-shared loop)
+// exact flavour (reference order).  Row k of World::set_forces's pair-shared loop receives its
+// partners in ascending index order (pairs (0,k) .. (k-1,k) from earlier outer iterations, then
+// (k,k+1) .. in its own), so a per-row ascending loop reproduces it exactly.
 // ------------------------------------------------------------------------------------------
 
 // Partner p acting on body k, p != k:   a_k += ((x_p - x_k) / (r2 * sqrt(r2))) * gf_p.

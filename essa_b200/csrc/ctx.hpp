@@ -147,6 +147,10 @@ struct essa_ctx {
     double* ens_gf = nullptr;    // [n]
     double* ens_mind = nullptr;  // [copies][n]
 
+    // closest approaches of a forward-simulated world: [n][n][7]
+    double* closest = nullptr;
+    int closest_n = 0;
+
     // energy scratch
     double* escratch = nullptr;
     size_t escratch_n = 0;
@@ -163,6 +167,8 @@ struct essa_ctx {
     double last_force_ms = 0;
     std::string err;
 
+    void* l2_scratch = nullptr;
+    int l2_value = 0;
     void* pinned = nullptr; // staging for uploads / downloads
     size_t pinned_bytes = 0;
 };

@@ -36,6 +36,7 @@ struct ResidentArgs {
     long long date_step; // signed seconds per step, 0 when forward-simulated
     double eps2;
     int exact, record, offset_trails, forward_sim, argmax, two_pass, acc_valid;
+    double* closest;    // [n][n][7] {distance, this xyz, other xyz} or null (forward-simulated worlds)
 };
 
 template<int MAXT, bool EXACT, bool ARGMAX>
@@ -102,6 +103,24 @@ __global__ void __launch_bounds__(MAXT, 1) k_resident(ResidentArgs const A) {
                     sg[k] = active ? gfk : 0.0;
                 acc_valid = false;
                 __syncthreads();
+            }
+        }
+        if (A.closest && mine) { // Object::update_closest_approaches (src/Object.cpp:405-417), positions at step start
+            for (int j = 0; j < n; j++) {
+                if (j == k)
+                    continue;
+                double* e = A.closest + ((size_t)k * n + j) * 7;
+                double d = length3(__dsub_rn(sx[j], x), __dsub_rn(sy[j], y), __dsub_rn(sz[j], z));
+                double cur = e[0];
+                if (cur == 0.0 || d < cur) {
+                    e[0] = d;
+                    e[1] = x;
+                    e[2] = y;
+                    e[3] = z;
+                    e[4] = sx[j];
+                    e[5] = sy[j];
+                    e[6] = sz[j];
+                }
             }
         }
         old_most = most; // Object::before_update, every object
@@ -260,6 +279,7 @@ cudaError_t launch_resident(essa_ctx* c, int steps, essa_step_opts const& o, boo
     bool argmax = o.track_most_attracting || o.record || o.exact_order;
     A.argmax = argmax;
     A.two_pass = o.two_pass;
+    A.closest = (o.forward_simulated && c->closest && c->closest_n == c->n) ? c->closest : nullptr;
     A.acc_valid = c->acc_valid && (!argmax || c->acc_has_most) && (c->acc_exact == (o.exact_order != 0));
     int threads = (c->n + 31) / 32 * 32;
     // two register budgets: worlds of up to 256 bodies get 255 registers per thread (no spills)

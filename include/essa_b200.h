@@ -162,6 +162,13 @@ typedef struct essa_trail_meta {
 int essa_trail_read(essa_ctx* ctx, int body, float* verts, essa_trail_meta* meta);
 int essa_trail_write(essa_ctx* ctx, int body, const float* verts, const essa_trail_meta* meta);
 
+/* ---- closest approaches of a forward-simulated world (src/Object.cpp:405-417) ------------------ */
+/* Allocate (enable != 0) or drop the N x N table; essa_step with forward_simulated set then keeps,
+ * for every ordered pair, the smallest distance seen at a step's start and both positions there. */
+int essa_closest_enable(essa_ctx* ctx, int enable);
+/* out = {distance, this x y z, other x y z}; returns 1 if the pair was evaluated, 0 if not, <0 on error. */
+int essa_closest_read(essa_ctx* ctx, int body, int other, double out[7]);
+
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 /* Kinetic and potential energy (J) and total momentum (kg m/s) of the active bodies, FP64,
  * fixed reduction order.  m = gf / ESSA_GRAVITY. */
@@ -209,6 +216,8 @@ int essa_shard_world(const essa_ctx* ctx);
 double essa_measure_fp64_peak(essa_ctx* ctx, double ms);
 /* Maximum relative error of the MUFU.RSQ64H seed and of the refined r^-3 over a log sweep. */
 int essa_measure_rsqrt_error(essa_ctx* ctx, double* seed_rel_err, double* refined_rel_err);
+/* Evict the L2 between timed iterations (writes a 256 MiB scratch buffer). */
+int essa_flush_l2(essa_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,8 @@ def lib():
         L.ow_set_object_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_double]
         L.ow_delete_object.argtypes = [C.c_void_p, C.c_int]
         L.ow_set_dates.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int]
+        L.ow_remove_object.argtypes = [C.c_void_p, C.c_int]
+        L.ow_reset_history.argtypes = [C.c_void_p, C.c_int]
         L.ow_name.argtypes = [C.c_void_p, C.c_int]
         L.ow_name.restype = C.c_char_p
         for f in (L.ow_radius, L.ow_orbit_len, L.ow_eccentrity):
@@ -173,6 +175,17 @@ class World:
 
     def delete_object(self, idx):
         self._L.ow_delete_object(self._h, idx)
+
+    def remove_object(self, idx):
+        """World::delete_object_by_ptr (src/World.cpp:208-219)."""
+        self._L.ow_remove_object(self._h, idx)
+
+    def reset_history(self, idx):
+        self._L.ow_reset_history(self._h, idx)
+
+    @property
+    def is_forward_simulated(self):
+        return bool(self._L.ow_is_forward_simulated(self._h))
 
     def name(self, idx):
         return self._L.ow_name(self._h, idx).decode()

@@ -280,6 +280,16 @@ void ow_set_dates(void* w, int idx, long long creation, long long deletion, int 
     o->m_deleted = deleted != 0;
 }
 void ow_delete_object(void* w, int idx) { static_cast<World*>(w)->object_at(idx)->delete_object(); }
+// World::delete_object_by_ptr (src/World.cpp:208-219)
+void ow_remove_object(void* w, int idx) {
+    auto* world = static_cast<World*>(w);
+    Object* ptr = world->object_at(idx);
+    world->m_object_list.remove_if([ptr](std::unique_ptr<Object>& obj) { return obj.get() == ptr; });
+    for (auto& o : world->m_object_list)
+        if (o->m_most_attracting_object == ptr)
+            o->delete_most_attracting_object();
+}
+void ow_reset_history(void* w, int idx) { static_cast<World*>(w)->object_at(idx)->reset_history(); }
 char const* ow_name(void* w, int idx) { return static_cast<World*>(w)->object_at(idx)->m_name.c_str(); }
 double ow_radius(void* w, int idx) { return static_cast<World*>(w)->object_at(idx)->m_radius; }
 double ow_orbit_len(void* w, int idx) { return static_cast<World*>(w)->object_at(idx)->m_orbit_len; }

@@ -1,0 +1,274 @@
+"""GPU parity of the resident kernel (K3), the recording (K6), the World facade and the ensemble
+kernel (K4) against the CPU oracle.
+
+exact_order mode: BIT-IDENTICAL positions, velocities, accelerations, most-attracting links, ap/pe,
+History rings and Trail vertices after K steps of the reference's .essa worlds (SURVEY.md 8c i).
+The one field that may differ is Trail::m_last_xy_angle (CUDA's atan2 vs glibc's, both < 2 ulp);
+it feeds a threshold test, so the vertices themselves must still be equal.
+
+fast mode: relative tolerance 1e-12 * sqrt(K) on positions / velocities (SURVEY.md 8c iii).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from essa_b200 import capi, world
+
+pytestmark = pytest.mark.gpu
+
+WORLDS = {"2body.essa": (600, 400), "8body.essa": (600, 300), "trail_test.essa": (3600, 400), "light_test.essa": (600, 50),
+          "solar.essa": (600, 300), "jupiter_system.essa": (600, 60)}
+
+
+def _pair(worlds_dir, fname, dt, exact=True, offset_trails=True):
+    path = os.path.join(worlds_dir, fname)
+    ow = oracle.World.load(path)
+    pw = world.World.load(path)
+    ow.dt = dt
+    pw.simulation_seconds_per_tick = dt
+    ow.set_flags(offset_trails=offset_trails)
+    pw.set_flags(offset_trails=offset_trails, exact_order=exact)
+    return ow, pw
+
+
+def _assert_same_state(pw, ow, exact=True, rtol=0.0):
+    a, b = pw.state(), ow.state()
+    assert pw.date == ow.date
+    assert np.array_equal(a["active"], b["active"])
+    assert np.array_equal(a["most"], b["most"])
+    for k in ("pos", "vel", "acc", "maxattr", "appe"):
+        if exact:
+            assert np.array_equal(a[k], b[k]), (k, np.abs(a[k] - b[k]).max())
+        else:
+            num = np.abs(a[k] - b[k]).reshape(len(a[k]), -1).max(axis=1)
+            den = np.abs(b[k]).reshape(len(b[k]), -1).max(axis=1) + 1e-300
+            tol = rtol * (1e3 if k in ("acc", "maxattr") else 1.0)
+            assert (num / den).max() <= tol, (k, (num / den).max())
+
+
+def _assert_same_rings(pw, ow, exact=True):
+    for i in range(len(ow)):
+        ha, hb = pw.history(i), ow.history(i)
+        assert ha.shape == hb.shape
+        ta, tb = pw.trail(i), ow.trail(i)
+        assert (ta["capacity"], ta["append_offset"], ta["length"]) == (tb["capacity"], tb["append_offset"], tb["length"]), i
+        if exact:
+            assert np.array_equal(ha, hb), i
+            assert np.array_equal(ta["verts"][:ta["length"]], tb["verts"][:tb["length"]]), i
+            assert np.array_equal(ta["offset"], tb["offset"]), i
+            assert ta["last_xy_angle"] == pytest.approx(tb["last_xy_angle"], rel=0, abs=4 * np.spacing(abs(tb["last_xy_angle"]) + 1e-300))
+
+
+@pytest.mark.parametrize("fname", list(WORLDS))
+def test_exact_order_is_bit_identical(worlds_dir, fname):
+    dt, steps = WORLDS[fname]
+    ow, pw = _pair(worlds_dir, fname, dt)
+    for chunk in (1, 10, steps - 11):   # GUI-like ticks: several update() calls
+        ow.update(chunk)
+        pw.update(chunk)
+        _assert_same_state(pw, ow)
+    _assert_same_rings(pw, ow)
+
+
+def test_exact_default_tick_and_history_wrap(worlds_dir):
+    """World's own default tick (43,200 s) for 1,100 steps: the 1000-entry History ring wraps, short
+    trails wrap (capacity 500) and Mercury's angular decimation kicks in."""
+    ow, pw = _pair(worlds_dir, "solar.essa", 43200)
+    ow.update(1100)
+    pw.update(1100)
+    _assert_same_state(pw, ow)
+    _assert_same_rings(pw, ow)
+    assert pw.history(0).shape == (1000, 6)
+
+
+def test_exact_without_offset_trails(worlds_dir):
+    ow, pw = _pair(worlds_dir, "trail_test.essa", 3600, offset_trails=False)
+    ow.update(200)
+    pw.update(200)
+    _assert_same_state(pw, ow)
+    _assert_same_rings(pw, ow)
+
+
+def test_exact_backward_steps(worlds_dir):
+    ow, pw = _pair(worlds_dir, "solar.essa", 600)
+    for s in (20, -35, 5):
+        ow.update(s)
+        pw.update(s)
+        _assert_same_state(pw, ow)
+    _assert_same_rings(pw, ow)
+
+
+def test_exact_host_mutation_between_updates(worlds_dir):
+    """GUI / Python edits between ticks: set_pos, set_vel, mark deleted, remove, add, reset_history."""
+    ow, pw = _pair(worlds_dir, "solar.essa", 600)
+    ow.update(7)
+    pw.update(7)
+    # move Mars, re-aim Venus
+    ow.set_object_state(4, pos=(2.0e11, 1.0e10, 5.0e8))
+    pw.set_object_state(4, pos=(2.0e11, 1.0e10, 5.0e8))
+    ow.set_object_state(2, vel=(1000.0, -36000.0, 10.0))
+    pw.set_object_state(2, vel=(1000.0, -36000.0, 10.0))
+    ow.update(5)
+    pw.update(5)
+    _assert_same_state(pw, ow)
+    # Object::delete_object on Jupiter: stays in the list, masked from now on
+    ow.delete_object(5)
+    pw.mark_deleted(5)
+    ow.update(6)
+    pw.update(6)
+    _assert_same_state(pw, ow)
+    # a new object appears (creation date = now)
+    ow.add_object(1e26, 1e7, (5e11, 0, 0), (0, 12000.0, 0), "Rogue", 900)
+    pw.add_object(mass=1e26, radius=1e7, pos=(5e11, 0, 0), vel=(0, 12000.0, 0), name="Rogue", period=900)
+    ow.update(9)
+    pw.update(9)
+    _assert_same_state(pw, ow)
+    # World::delete_object_by_ptr on the Moon's parent: the Moon loses its most-attracting object
+    earth = ow.names().index("Earth")
+    ow.remove_object(earth)
+    pw.delete_object(earth)
+    ow.reset_history(1)
+    pw.reset_history(1)
+    ow.update(11)
+    pw.update(11)
+    _assert_same_state(pw, ow)
+    _assert_same_rings(pw, ow)
+
+
+def test_exact_two_pass_and_set_forces(worlds_dir):
+    ow, pw = _pair(worlds_dir, "jupiter_system.essa", 600)
+    pw.set_flags(exact_order=True, two_pass=True)
+    ow.set_forces()
+    pw.set_forces()
+    _assert_same_state(pw, ow)
+    ow.update(12)
+    pw.update(12)
+    _assert_same_state(pw, ow)
+
+
+@pytest.mark.parametrize("fname,steps", [("solar.essa", 2000), ("jupiter_system.essa", 200), ("trail_test.essa", 1000)])
+def test_fast_mode_within_tolerance(worlds_dir, fname, steps):
+    ow, pw = _pair(worlds_dir, fname, 600, exact=False)
+    ow.update(steps)
+    pw.update(steps)
+    _assert_same_state(pw, ow, exact=False, rtol=1e-12 * np.sqrt(steps))
+    _assert_same_rings(pw, ow, exact=False)
+    # trail vertices are float32 of the same positions: equal to a few float ulps
+    for i in range(len(ow)):
+        ta, tb = pw.trail(i), ow.trail(i)
+        n = ta["length"]
+        assert np.allclose(ta["verts"][:n], tb["verts"][:n], rtol=1e-5, atol=1e-7)
+
+
+def test_forward_simulation_clone_and_closest_approaches(worlds_dir):
+    """World::clone_for_forward_simulation + update(ticks) (EssaCreateObject.cpp:166-189)."""
+    ow, pw = _pair(worlds_dir, "solar.essa", 600)
+    ow.update(3)
+    pw.update(3)
+    of, pf = ow.clone_for_forward_simulation(), pw.clone_for_forward_simulation()
+    pf.set_flags(exact_order=True)
+    assert pf.is_forward_simulated and of.is_forward_simulated
+    of.update(250)
+    pf.update(250)
+    _assert_same_state(pf, of)
+    assert pf.date == capi.START_DATE  # the clock of a forward-simulated world does not move
+    for i in range(len(of)):
+        assert pf.history(i).shape == (1, 6)
+        ta, tb = pf.trail(i), of.trail(i)
+        assert (ta["append_offset"], ta["length"]) == (tb["append_offset"], tb["length"])
+        assert np.array_equal(ta["verts"][:ta["length"]], tb["verts"][:tb["length"]])
+        for j in range(len(of)):
+            if i == j:
+                continue
+            ca, cb = pf.closest_approach(i, j), of.closest_approach(i, j)
+            assert ca["distance"] == cb["distance"]
+            assert np.array_equal(ca["this_position"], cb["this_position"])
+            assert np.array_equal(ca["other_object_position"], cb["other_object_position"])
+    # the original world is untouched and still steps
+    ow.update(2)
+    pw.update(2)
+    _assert_same_state(pw, ow)
+
+
+def test_resident_and_tiled_kernels_agree(worlds_dir):
+    """Same world through both kernels of the C ABI, recording on."""
+    ow = oracle.World.load(os.path.join(worlds_dir, "jupiter_system.essa"))
+    st = ow.state()
+    caps = [ow.trail(i)["capacity"] for i in range(len(ow))]
+    out = {}
+    for kern in (capi.KERNEL_RESIDENT, capi.KERNEL_TILED):
+        c = capi.Context(0)
+        c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"],
+                 creation_date=np.full(len(ow), capi.START_DATE, dtype=np.int64))
+        c.record_configure(caps)
+        c.step(40, 600, kernel=kern, record=True)
+        out[kern] = (c.download(), [c.trail(i) for i in range(len(ow))], [c.history(i) for i in range(len(ow))])
+        c.close()
+    a, b = out[capi.KERNEL_RESIDENT], out[capi.KERNEL_TILED]
+    for k in ("x", "y", "z", "vx", "vy", "vz"):
+        assert np.allclose(a[0][k], b[0][k], rtol=1e-11, atol=0), k
+    assert np.array_equal(a[0]["most"], b[0]["most"])
+    for i in range(len(ow)):
+        assert a[2][i].shape == b[2][i].shape == (41, 6)
+        assert (a[1][i]["append_offset"], a[1][i]["length"]) == (b[1][i]["append_offset"], b[1][i]["length"])
+
+
+def _ensemble_reference(st, copy, steps, dt, seed, sigma):
+    """Oracle run of one perturbed copy, initial state rebuilt with the C ABI's host-side factor."""
+    n = len(st["gf"])
+    w = oracle.World()
+    comp = [st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2]]
+    pert = [np.array([comp[q][b] * capi.ensemble_factor(seed, sigma, copy, b, q) for b in range(n)]) for q in range(6)]
+    w.add_bodies(*pert, st["gf"] / oracle.GRAVITY)
+    for b in range(n):
+        w.set_object_state(b, gf=st["gf"][b])
+    w.dt = dt
+    w.update(steps)
+    return w.state()
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_ensemble_copies_match_oracle(worlds_dir, exact):
+    ow = oracle.World.load(os.path.join(worlds_dir, "jupiter_system.essa"))
+    st = ow.state()
+    copies, steps, dt, seed, sigma = 1000, 25, 600, 7, 1e-6
+    c = capi.Context(0)
+    c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"])
+    c.ensemble_init(copies, dt, seed=seed, rel_sigma=sigma, exact_order=exact)
+    c.ensemble_step(10)
+    c.ensemble_step(steps - 10)
+    sample = [0, 1, 2, 3, 499, 500, 998, 999] + list(np.random.default_rng(0).choice(copies, 24, replace=False))
+    for cp in sample:
+        got = c.ensemble_read(int(cp), 1)
+        ref = _ensemble_reference(st, int(cp), steps, dt, seed, sigma)
+        pos = np.stack([got["x"][0], got["y"][0], got["z"][0]], axis=1)
+        vel = np.stack([got["vx"][0], got["vy"][0], got["vz"][0]], axis=1)
+        if exact:
+            assert np.array_equal(pos, ref["pos"]) and np.array_equal(vel, ref["vel"]), cp
+        else:
+            assert np.abs(pos - ref["pos"]).max() <= 1e-11 * np.abs(ref["pos"]).max()
+            assert np.abs(vel - ref["vel"]).max() <= 1e-10 * np.abs(ref["vel"]).max()
+    # copy 0 is the unperturbed template
+    got0 = c.ensemble_read(0, 2)
+    assert not np.array_equal(got0["x"][0], got0["x"][1])
+    c.close()
+
+
+def test_ensemble_closest_approach_to_body(worlds_dir):
+    ow = oracle.World.load(os.path.join(worlds_dir, "solar.essa"))
+    st = ow.state()
+    c = capi.Context(0)
+    c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"])
+    c.ensemble_init(8, 600, seed=1, rel_sigma=0.0, exact_order=True, closest_approaches=True, approach_to=3)
+    c.ensemble_step(100)
+    got = c.ensemble_read(0, 8, min_distance=True)
+    fw = ow.clone_for_forward_simulation()
+    fw.dt = 600
+    fw.update(100)
+    for b in range(len(ow)):
+        if b == 3:
+            continue
+        assert got["min_distance"][5][b] == fw.closest_approach(b, 3)["distance"]
+    c.close()
