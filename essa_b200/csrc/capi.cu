@@ -405,6 +405,20 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
         CK(cudaMemcpyAsync(ctx->vel + k * cap, d + (3 + k) * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
     }
     CK(cudaMemcpyAsync(ctx->gf, d + 6 * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    // m_attraction_factor / m_max_attraction are outputs of set_forces(), except for bodies that
+    // Object::deleted() masks: those keep whatever they held (clear_forces skips them), so a caller
+    // that re-uploads a world with masked bodies may pass them along.  Default 0.
+    double const* acc_in[3] = { h->ax, h->ay, h->az };
+    for (int k = 0; k < 3; k++) {
+        if (acc_in[k])
+            CK(cudaMemcpyAsync(ctx->acc + k * cap, acc_in[k], N * sizeof(double), cudaMemcpyHostToDevice, st));
+        else
+            CK(cudaMemsetAsync(ctx->acc + k * cap, 0, N * sizeof(double), st));
+    }
+    if (h->max_attraction)
+        CK(cudaMemcpyAsync(ctx->maxattr, h->max_attraction, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    else
+        CK(cudaMemsetAsync(ctx->maxattr, 0, N * sizeof(double), st));
     for (int k = 0; k < 4; k++)
         CK(cudaMemcpyAsync(ctx->appe + k * cap, appe + k * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->cdate, dates, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));

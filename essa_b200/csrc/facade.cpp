@@ -453,18 +453,20 @@ void World::sync_to_device() {
             o->m_slot = slot++;
     }
     if (m_list_dirty || m_state_dirty) {
-        std::vector<double> f(11 * n);
+        std::vector<double> f(15 * n);
         std::vector<int64_t> dates(2 * n);
         std::vector<uint8_t> del(n);
         std::vector<int32_t> most(n);
         double *x = f.data(), *y = x + n, *z = y + n, *vx = z + n, *vy = vx + n, *vz = vy + n, *gf = vz + n, *ap = gf + n, *pe = ap + n,
-               *apv = pe + n, *pev = apv + n;
+               *apv = pe + n, *pev = apv + n, *ax = pev + n, *ay = ax + n, *az = ay + n, *mx = az + n;
         size_t k = 0;
         for (auto& o : m_object_list) {
             x[k] = o->m_pos.x; y[k] = o->m_pos.y; z[k] = o->m_pos.z;
             vx[k] = o->m_vel.x; vy[k] = o->m_vel.y; vz[k] = o->m_vel.z;
             gf[k] = o->m_gravity_factor;
             ap[k] = o->m_ap; pe[k] = o->m_pe; apv[k] = o->m_ap_vel; pev[k] = o->m_pe_vel;
+            ax[k] = o->m_attraction_factor.x; ay[k] = o->m_attraction_factor.y; az[k] = o->m_attraction_factor.z;
+            mx[k] = o->m_max_attraction;
             dates[k] = o->m_creation_date;
             dates[n + k] = o->m_deletion_date;
             del[k] = o->m_deleted;
@@ -475,6 +477,7 @@ void World::sync_to_device() {
         std::memset(&b, 0, sizeof(b));
         b.x = x; b.y = y; b.z = z; b.vx = vx; b.vy = vy; b.vz = vz; b.gf = gf;
         b.ap = ap; b.pe = pe; b.ap_vel = apv; b.pe_vel = pev;
+        b.ax = ax; b.ay = ay; b.az = az; b.max_attraction = mx; // kept by bodies that deleted() masks
         b.creation_date = dates.data();
         b.deletion_date = dates.data() + n;
         b.deleted = del.data();

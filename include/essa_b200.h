@@ -75,13 +75,13 @@ typedef enum essa_kernel {
 typedef struct essa_bodies {
     double *x, *y, *z;       /* m_pos */
     double *vx, *vy, *vz;    /* m_vel */
-    double *ax, *ay, *az;    /* m_attraction_factor (download only) */
+    double *ax, *ay, *az;    /* m_attraction_factor (output of set_forces; on upload: optional value kept by masked bodies) */
     double *gf;              /* m_gravity_factor = mass * G */
     int64_t *creation_date;  /* m_creation_date, seconds */
     int64_t *deletion_date;  /* m_deletion_date, seconds */
     uint8_t *deleted;        /* m_deleted */
     int32_t *most;           /* m_most_attracting_object */
-    double *max_attraction;  /* m_max_attraction (download only) */
+    double *max_attraction;  /* m_max_attraction (same remark) */
     double *ap, *pe, *ap_vel, *pe_vel; /* m_ap, m_pe, m_ap_vel, m_pe_vel */
 } essa_bodies;
 
