@@ -19,7 +19,7 @@ RESIDENT_MAX = 1024
 ENSEMBLE_MAX = 320
 NCCL_ID_BYTES = 128
 
-KERNEL_AUTO, KERNEL_TILED, KERNEL_RESIDENT = 0, 1, 2
+KERNEL_AUTO, KERNEL_TILED, KERNEL_RESIDENT, KERNEL_PAIRED = 0, 1, 2, 3
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)

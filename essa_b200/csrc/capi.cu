@@ -137,7 +137,7 @@ static int reserve_world(essa_ctx* ctx, int cap) {
         return ESSA_OK;
     // Growing keeps nothing: callers re-upload (essa_upload is the only entry that grows).
     free_world(ctx);
-    cap = (cap + 255) / 256 * 256;
+    cap = (cap + 1023) / 1024 * 1024; // whole 1024-body blocks (force_paired.cu)
     size_t n = (size_t)cap;
     CK(cudaMalloc(&ctx->pos[0], n * sizeof(double4)));
     CK(cudaMalloc(&ctx->pos[1], n * sizeof(double4)));
@@ -273,6 +273,8 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
         nccl().CommDestroy(c->comm);
     free_world(c);
     free_recording(c);
+    cudaFree(c->pair_slots);
+    cudaFree(c->pair_part);
     cudaFree(c->part);
     cudaFree(c->part_m);
     cudaFree(c->part_j);
@@ -552,7 +554,9 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
         return ESSA_ERR_CUDA;
     }
     CK(cudaEventRecord(e0, ctx->stream));
-    if (ctx->world == 1 || !ctx->gather_pending) {
+    if (ctx->use_paired) {
+        CK(launch_force_paired(ctx, k, eps2, ctx->stream));
+    } else if (ctx->world == 1 || !ctx->gather_pending) {
         int S;
         choose_split(ctx, iblocks, (n + kTileJ - 1) / kTileJ, &S);
         CK(launch_force_pass(ctx, 0, n, S, 0, S, argmax, save_old, k, eps2, ctx->stream));
@@ -585,6 +589,22 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
     int const K = forces_only ? 0 : std::abs(steps);
     double const mul = steps >= 0 ? 1.0 : -1.0;
     bool const argmax = o.track_most_attracting || o.record;
+    {
+        // pair-shared kernel: single context, no argmax bookkeeping, slots must fit comfortably
+        int nb, S;
+        size_t slot_d = 0, part_d = 0;
+        bool can = ctx->world == 1 && !argmax && paired_plan(ctx, &nb, &S, &slot_d, &part_d);
+        if (can && (slot_d + part_d) * sizeof(double) > ctx->pair_slots_n * sizeof(double)) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            can = (slot_d + part_d) * sizeof(double) < free_b / 2 + ctx->pair_slots_n * sizeof(double);
+        }
+        if (o.kernel == ESSA_KERNEL_PAIRED && !can) {
+            ctx->err = "pair-shared kernel needs an unsharded world of >= 2048 bodies without most-attracting tracking, and room for its slots";
+            return ESSA_ERR_ARG;
+        }
+        ctx->use_paired = can && (o.kernel == ESSA_KERNEL_PAIRED || (o.kernel == ESSA_KERNEL_AUTO && ctx->n >= 32768));
+    }
     KickArgs base;
     base.dt = (double)o.dt_seconds;
     base.h = base.dt / 2.0;
@@ -709,7 +729,12 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     int rc;
     if (resident) {
-        CK(launch_resident(ctx, steps, o, forces_only, ctx->stream));
+        // worlds of up to 32 bodies in fast arithmetic: one-warp kernel with a recorder warp (resident_warp.cu)
+        bool const closest = o.forward_simulated && ctx->closest && ctx->closest_n == ctx->n;
+        if (!o.exact_order && ctx->n <= 32 && !closest)
+            CK(launch_resident_warp(ctx, steps, o, forces_only, ctx->stream));
+        else
+            CK(launch_resident(ctx, steps, o, forces_only, ctx->stream));
         CK(cudaEventRecord(ctx->ev_end, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         rc = resident_finish(ctx, steps, o, forces_only);

@@ -107,6 +107,7 @@ struct essa_ctx {
     bool acc_has_most = false;  // ... and most / max_attraction were evaluated with it
     bool acc_exact = false;     // ... in exact_order arithmetic
     bool gather_pending = false;
+    bool use_paired = false;    // this essa_step runs its force passes through force_paired.cu
     std::vector<cudaEvent_t> force_events;
     int last_force_passes = 0;
     int64_t date = ESSA_START_DATE;
@@ -121,6 +122,12 @@ struct essa_ctx {
     size_t part_slots_cap = 0;
     unsigned* counters = nullptr;
     int counters_cap = 0;
+
+    // pair-shared force pass scratch (force_paired.cu)
+    double* pair_slots = nullptr;
+    size_t pair_slots_n = 0;
+    double* pair_part = nullptr;
+    size_t pair_part_n = 0;
 
     // recording
     int tracked = 0;
@@ -184,10 +191,13 @@ cudaError_t launch_record(essa_ctx* c, int offset_trails, int forward_simulated,
 cudaError_t launch_record_init(essa_ctx* c, int first, cudaStream_t st);
 cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double const* z, cudaStream_t st);
 cudaError_t launch_unpack(essa_ctx* c, double* x, double* y, double* z, cudaStream_t st);
+bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles);
+cudaError_t launch_force_paired(essa_ctx* c, KickArgs const& k, double eps2, cudaStream_t st);
 int force_iblocks(essa_ctx const* c, int* R_out);
 void choose_split(essa_ctx const* c, int iblocks, int ntiles, int* S_out);
 
 cudaError_t launch_resident(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st);
+cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st);
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st);
 cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st);
 cudaError_t launch_energy(essa_ctx* c, cudaStream_t st); // result in c->escratch[0..5)

@@ -1,0 +1,402 @@
+// K1p -- pair-shared force pass: every unordered pair is evaluated ONCE and applied to both bodies,
+// as the reference's own loop does (World::set_forces walks i < j and Object::update_forces_against
+// updates both objects, src/World.cpp:48-56, src/Object.cpp:64-79).
+//
+//   d = x_j - x_i ;  u = |d|^-3 ;  a_i += gf_j u d ;  a_j -= gf_i u d
+//
+// 21 FP64-pipe instructions per pair = 10.5 per directed interaction (K1 needs 17), which lifts the
+// ceiling of the 20-flop-per-interaction roofline from 58.8 % to 95 %.
+//
+// Decomposition.  Bodies are cut into blocks of 1024.  Unordered block pairs are enumerated as
+// (I, J = I + d mod nb), d = 0 .. nb/2, so that every block does the same amount of work.  One CTA
+// (8 warps) owns block I for its whole life: warp w keeps targets [128 w, 128 w + 128) of the block
+// in registers (4 per lane).  A J block arrives through the TMA unit (cp.async.bulk + mbarrier) in
+// two 512-record halves; each warp walks it in 64-body subsets, 2 bodies per lane, and ROTATES the
+// subset -- positions, gf and the subset's own accumulators -- around the warp with shuffles, so
+// that after 32 rotations all 128 x 64 pairs of (targets, subset) have been visited with nothing
+// but registers.  The subset's accumulated a_j goes to a per-warp shared-memory array; after a
+// half, the 8 warps' arrays are summed in warp order and written to the slot (I, d) of the J block.
+// No floating-point atomics anywhere: k_pair_finish adds, per body, the I-side partials and the
+// slots in a fixed order, then runs the same kick / drift epilogue as K1.  Deterministic.
+//
+// d = 0 (the block against itself) is evaluated one-sided (a_i only), so ordered pairs are not
+// double counted; it is 1 / (nb + 1) of the work.
+#include "common.cuh"
+#include "ctx.hpp"
+
+namespace essa {
+
+constexpr int kPB = 1024;       // bodies per block
+constexpr int kPThreads = 256;  // 8 warps
+constexpr int kPRI = 4;         // targets per lane
+constexpr int kPRJ = 2;         // visiting bodies per lane
+constexpr int kPHalf = 512;     // records per staged half block
+constexpr int kPSub = 32 * kPRJ;
+constexpr size_t kPSmem = 2 * kPHalf * sizeof(double4) + 8 * 3 * kPHalf * sizeof(double) + 64;
+
+struct PairArgs {
+    double4 const* pos; // padded to a multiple of kPB with {0,0,0,0}
+    int nb;             // blocks in the world
+    int dmax;           // largest block offset evaluated: nb / 2
+    int S;              // chunks of the offset range per I block (gridDim.x = owned blocks * S)
+    int ib0, ib1;       // I blocks owned by this context
+    int npad;           // nb * kPB
+    double* part_i;     // [S][3][npad]       I-side partial accelerations
+    double* slots;      // [ib1-ib0][dmax][3][kPB]  J-side partials of tile (I, d), d = 1 .. dmax
+    double eps2;
+};
+
+__device__ __forceinline__ double rot1(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+template<bool TWO_SIDED>
+__device__ __forceinline__ void pair_interact(double xi, double yi, double zi, double gi, double xj, double yj, double zj, double gj,
+    double eps2, double& aix, double& aiy, double& aiz, double& ajx, double& ajy, double& ajz) {
+    double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    double r2 = fma(dx, dx, eps2);
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    double y0 = rsqrt_seed(r2);
+    double t = r2 * y0;
+    double e = fma(-t, y0, 1.0);
+    double y2 = y0 * y0;
+    double c = y2 * y0;
+    double w = fma(1.875, e, 1.5);
+    double we = w * e;
+    double u = fma(c, we, c); // |d|^-3
+    double si = gj * u;
+    aix = fma(si, dx, aix);
+    aiy = fma(si, dy, aiy);
+    aiz = fma(si, dz, aiz);
+    if (TWO_SIDED) {
+        double sj = gi * u;
+        ajx = fma(-sj, dx, ajx);
+        ajy = fma(-sj, dy, ajy);
+        ajz = fma(-sj, dz, ajz);
+    }
+}
+
+__global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double4* tile = reinterpret_cast<double4*>(smem_raw);                       // [2][kPHalf]
+    double* accj = reinterpret_cast<double*>(smem_raw + 2 * kPHalf * sizeof(double4)); // [8][3][kPHalf]
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(accj + 8 * 3 * kPHalf); // [2]
+
+    int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int const ibl = blockIdx.x / A.S, chunk = blockIdx.x - ibl * A.S;
+    int const I = A.ib0 + ibl;
+    // offsets d = 0 .. dmax, split into S chunks
+    int const ntot = A.dmax + 1;
+    int const dlo = (int)((long long)ntot * chunk / A.S), dhi = (int)((long long)ntot * (chunk + 1) / A.S);
+
+    double xi[kPRI], yi[kPRI], zi[kPRI], gi[kPRI], aix[kPRI], aiy[kPRI], aiz[kPRI];
+#pragma unroll
+    for (int r = 0; r < kPRI; r++) {
+        double4 p = A.pos[(size_t)I * kPB + warp * (32 * kPRI) + r * 32 + lane];
+        xi[r] = p.x;
+        yi[r] = p.y;
+        zi[r] = p.z;
+        gi[r] = p.w;
+        aix[r] = aiy[r] = aiz[r] = 0.0;
+    }
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // tiles of this CTA in order: (d, half); skipped d's never appear
+    auto valid = [&](int d) { return !((A.nb & 1) == 0 && d == A.nb / 2 && I >= A.nb / 2) && d <= A.dmax; };
+    auto issue = [&](int d, int half, int buf) {
+        int J = I + d;
+        if (J >= A.nb)
+            J -= A.nb;
+        unsigned bytes = kPHalf * (unsigned)sizeof(double4);
+        mbar_expect_tx(&full[buf], bytes);
+        bulk_g2s(tile + (size_t)buf * kPHalf, A.pos + (size_t)J * kPB + half * kPHalf, bytes, &full[buf]);
+    };
+
+    int seq = 0; // tiles consumed so far (parity bookkeeping)
+    // prime the pipeline with the first valid tile
+    int nd = dlo;
+    while (nd < dhi && !valid(nd))
+        nd++;
+    if (tid == 0 && nd < dhi)
+        issue(nd, 0, 0);
+
+    for (int d = dlo; d < dhi; d++) {
+        if (!valid(d))
+            continue;
+        int J = I + d;
+        if (J >= A.nb)
+            J -= A.nb;
+        for (int half = 0; half < 2; half++) {
+            int const buf = seq & 1;
+            // prefetch the tile after this one into the other buffer
+            {
+                int pd = d, ph = half + 1;
+                if (ph == 2) {
+                    ph = 0;
+                    pd = d + 1;
+                    while (pd < dhi && !valid(pd))
+                        pd++;
+                }
+                if (tid == 0 && pd < dhi)
+                    issue(pd, ph, buf ^ 1);
+            }
+            mbar_wait(&full[buf], (unsigned)(seq >> 1) & 1u);
+            double4 const* tp = tile + (size_t)buf * kPHalf;
+            double* myacc = accj + (size_t)warp * 3 * kPHalf;
+
+            for (int s = 0; s < kPHalf / kPSub; s++) {
+                int const sub = (s + warp) & (kPHalf / kPSub - 1); // stagger shared-memory traffic between warps
+                double xj[kPRJ], yj[kPRJ], zj[kPRJ], gj[kPRJ], ajx[kPRJ], ajy[kPRJ], ajz[kPRJ];
+#pragma unroll
+                for (int q = 0; q < kPRJ; q++) {
+                    double4 p = tp[sub * kPSub + q * 32 + lane];
+                    xj[q] = p.x;
+                    yj[q] = p.y;
+                    zj[q] = p.z;
+                    gj[q] = p.w;
+                    ajx[q] = ajy[q] = ajz[q] = 0.0;
+                }
+                int const src = (lane + 31) & 31; // take from the previous lane = pass to the next
+                if (d == 0) {
+                    for (int rot = 0; rot < 32; rot++) {
+#pragma unroll
+                        for (int q = 0; q < kPRJ; q++)
+#pragma unroll
+                            for (int r = 0; r < kPRI; r++)
+                                pair_interact<false>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r], aiz[r],
+                                    ajx[q], ajy[q], ajz[q]);
+#pragma unroll
+                        for (int q = 0; q < kPRJ; q++) {
+                            xj[q] = rot1(xj[q], src);
+                            yj[q] = rot1(yj[q], src);
+                            zj[q] = rot1(zj[q], src);
+                            gj[q] = rot1(gj[q], src);
+                        }
+                    }
+                } else {
+                    for (int rot = 0; rot < 32; rot++) {
+#pragma unroll
+                        for (int q = 0; q < kPRJ; q++)
+#pragma unroll
+                            for (int r = 0; r < kPRI; r++)
+                                pair_interact<true>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r], aiz[r],
+                                    ajx[q], ajy[q], ajz[q]);
+#pragma unroll
+                        for (int q = 0; q < kPRJ; q++) {
+                            xj[q] = rot1(xj[q], src);
+                            yj[q] = rot1(yj[q], src);
+                            zj[q] = rot1(zj[q], src);
+                            gj[q] = rot1(gj[q], src);
+                            ajx[q] = rot1(ajx[q], src);
+                            ajy[q] = rot1(ajy[q], src);
+                            ajz[q] = rot1(ajz[q], src);
+                        }
+                    }
+                    // 32 rotations: every visitor is back in its home lane
+#pragma unroll
+                    for (int q = 0; q < kPRJ; q++) {
+                        int j = sub * kPSub + q * 32 + lane;
+                        myacc[j] = ajx[q];
+                        myacc[kPHalf + j] = ajy[q];
+                        myacc[2 * kPHalf + j] = ajz[q];
+                    }
+                }
+            }
+            __syncthreads();
+            if (d > 0) {
+                double* slot = A.slots + ((size_t)ibl * A.dmax + (d - 1)) * 3 * kPB;
+                for (int e = tid; e < 3 * kPHalf; e += kPThreads) {
+                    int c = e / kPHalf, j = e - c * kPHalf;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int w = 0; w < 8; w++)
+                        sum = __dadd_rn(sum, accj[(size_t)w * 3 * kPHalf + e]);
+                    __stcg(slot + (size_t)c * kPB + half * kPHalf + j, sum);
+                }
+            }
+            __syncthreads();
+            seq++;
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < kPRI; r++) {
+        size_t i = (size_t)I * kPB + warp * (32 * kPRI) + r * 32 + lane;
+        double* p = A.part_i + (size_t)chunk * 3 * A.npad + i;
+        __stcg(p, aix[r]);
+        __stcg(p + A.npad, aiy[r]);
+        __stcg(p + 2 * (size_t)A.npad, aiz[r]);
+    }
+}
+
+// Ordered sum of the I-side partials and the J-side slots of one body, then the K1 epilogue.
+struct PairFinishArgs {
+    WorldPtrs w;
+    KickArgs k;
+    int n, i0, i1;
+    int nb, dmax, S, ib0, ib1, npad;
+    double const* part_i;
+    double const* slots;
+};
+
+__global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
+    int g = A.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= A.i1)
+        return;
+    double ax = 0, ay = 0, az = 0;
+    for (int c = 0; c < A.S; c++) {
+        double const* p = A.part_i + (size_t)c * 3 * A.npad + g;
+        ax = __dadd_rn(ax, __ldcg(p));
+        ay = __dadd_rn(ay, __ldcg(p + A.npad));
+        az = __dadd_rn(az, __ldcg(p + 2 * (size_t)A.npad));
+    }
+    int const K = g / kPB, jl = g - K * kPB;
+    for (int d = 1; d <= A.dmax; d++) {
+        int I = K - d;
+        if (I < 0)
+            I += A.nb;
+        if ((A.nb & 1) == 0 && d == A.nb / 2 && I >= A.nb / 2)
+            continue; // that tile belongs to the other half of the ring
+        if (I < A.ib0 || I >= A.ib1)
+            continue;
+        double const* s = A.slots + ((size_t)(I - A.ib0) * A.dmax + (d - 1)) * 3 * kPB + jl;
+        ax = __dadd_rn(ax, __ldcg(s));
+        ay = __dadd_rn(ay, __ldcg(s + kPB));
+        az = __dadd_rn(az, __ldcg(s + 2 * kPB));
+    }
+    // ---- epilogue: identical to force_tiled.cu finish_body (no argmax in this kernel) ----
+    WorldPtrs const& W = A.w;
+    KickArgs const& Kk = A.k;
+    bool act = W.active[g] != 0;
+    double4 p = W.pos_cur[g];
+    double vx = 0, vy = 0, vz = 0;
+    if (act) {
+        W.a[0][g] = ax;
+        W.a[1][g] = ay;
+        W.a[2][g] = az;
+        if (Kk.second_kick) {
+            vx = kick1(W.vh[0][g], ax, Kk.h, Kk.mul);
+            vy = kick1(W.vh[1][g], ay, Kk.h, Kk.mul);
+            vz = kick1(W.vh[2][g], az, Kk.h, Kk.mul);
+            W.v[0][g] = vx;
+            W.v[1][g] = vy;
+            W.v[2][g] = vz;
+        } else if (Kk.advance) {
+            vx = W.v[0][g];
+            vy = W.v[1][g];
+            vz = W.v[2][g];
+        }
+    }
+    if (Kk.advance) {
+        if (act) {
+            vx = kick1(vx, ax, Kk.h, Kk.mul);
+            vy = kick1(vy, ay, Kk.h, Kk.mul);
+            vz = kick1(vz, az, Kk.h, Kk.mul);
+            W.vh[0][g] = vx;
+            W.vh[1][g] = vy;
+            W.vh[2][g] = vz;
+            p.x = __dadd_rn(p.x, __dmul_rn(__dmul_rn(vx, Kk.dt), Kk.mul));
+            p.y = __dadd_rn(p.y, __dmul_rn(__dmul_rn(vy, Kk.dt), Kk.mul));
+            p.z = __dadd_rn(p.z, __dmul_rn(__dmul_rn(vz, Kk.dt), Kk.mul));
+        }
+        W.pos_next[g] = p;
+    }
+}
+
+// Can this world go through the pair-shared kernel?  (single context, no argmax, slots fit)
+bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles) {
+    int n = c->n;
+    int nb = (n + kPB - 1) / kPB;
+    if (nb < 2 || (size_t)nb * kPB > (size_t)c->cap)
+        return false;
+    int dmax = nb / 2;
+    // chunks of the offset range: minimise waves(1 CTA / SM) x offsets per chunk
+    long long slots = c->sm_count;
+    int bestS = 1;
+    long long best = -1;
+    int smax = dmax + 1 < 16 ? dmax + 1 : 16;
+    for (int S = 1; S <= smax; S++) {
+        long long waves = ((long long)nb * S + slots - 1) / slots;
+        long long cost = waves * ((dmax + 1 + S - 1) / S);
+        if (best < 0 || cost < best) {
+            best = cost;
+            bestS = S;
+        }
+    }
+    *nb_out = nb;
+    *S_out = bestS;
+    *slot_doubles = (size_t)nb * dmax * 3 * kPB;
+    *part_doubles = (size_t)bestS * 3 * nb * kPB;
+    return true;
+}
+
+cudaError_t launch_force_paired(essa_ctx* c, KickArgs const& k, double eps2, cudaStream_t st) {
+    int nb, S;
+    size_t slot_d, part_d;
+    if (!paired_plan(c, &nb, &S, &slot_d, &part_d))
+        return cudaErrorInvalidConfiguration;
+    if (slot_d > c->pair_slots_n) {
+        cudaFree(c->pair_slots);
+        c->pair_slots = nullptr;
+        c->pair_slots_n = 0;
+        cudaError_t e = cudaMalloc(&c->pair_slots, slot_d * sizeof(double));
+        if (e != cudaSuccess)
+            return e;
+        c->pair_slots_n = slot_d;
+    }
+    if (part_d > c->pair_part_n) {
+        cudaFree(c->pair_part);
+        c->pair_part = nullptr;
+        c->pair_part_n = 0;
+        cudaError_t e = cudaMalloc(&c->pair_part, part_d * sizeof(double));
+        if (e != cudaSuccess)
+            return e;
+        c->pair_part_n = part_d;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_force_paired, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem);
+        if (e != cudaSuccess)
+            return e;
+        attr_set = true;
+    }
+    PairArgs A;
+    A.pos = c->pos[c->cur];
+    A.nb = nb;
+    A.dmax = nb / 2;
+    A.S = S;
+    A.ib0 = 0;
+    A.ib1 = nb;
+    A.npad = nb * kPB;
+    A.part_i = c->pair_part;
+    A.slots = c->pair_slots;
+    A.eps2 = eps2;
+    k_force_paired<<<nb * S, kPThreads, kPSmem, st>>>(A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return e;
+    PairFinishArgs F;
+    F.w = world_ptrs(c);
+    F.k = k;
+    F.n = c->n;
+    F.i0 = 0;
+    F.i1 = c->n;
+    F.nb = nb;
+    F.dmax = nb / 2;
+    F.S = S;
+    F.ib0 = 0;
+    F.ib1 = nb;
+    F.npad = nb * kPB;
+    F.part_i = c->pair_part;
+    F.slots = c->pair_slots;
+    k_pair_finish<<<(c->n + 255) / 256, 256, 0, st>>>(F);
+    c->launches += 2;
+    return cudaGetLastError();
+}
+
+} // namespace essa

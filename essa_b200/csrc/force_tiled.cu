@@ -228,11 +228,19 @@ __global__ void k_refresh_active(double4* pos, double const* gf, uint8_t* active
     pos[g].w = act ? gf[g] : 0.0;
 }
 
-__global__ void k_pack(double4* pos, double const* x, double const* y, double const* z, double const* gf, uint8_t const* active, int n) {
+// Builds the j-records of the current buffer and clears the padding [n, cap) of BOTH buffers
+// (kernels that stream whole blocks rely on zero-weight records there).
+__global__ void k_pack(double4* pos, double4* other, double const* x, double const* y, double const* z, double const* gf,
+    uint8_t const* active, int n, int cap) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n)
+    if (g >= cap)
         return;
-    pos[g] = make_double4(x[g], y[g], z[g], active[g] ? gf[g] : 0.0);
+    if (g < n) {
+        pos[g] = make_double4(x[g], y[g], z[g], active[g] ? gf[g] : 0.0);
+    } else {
+        pos[g] = make_double4(0, 0, 0, 0);
+        other[g] = make_double4(0, 0, 0, 0);
+    }
 }
 
 __global__ void k_unpack(double4 const* pos, double* x, double* y, double* z, int n) {
@@ -394,7 +402,7 @@ cudaError_t launch_refresh_active(essa_ctx* c, cudaStream_t st) {
 cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double const* z, cudaStream_t st) {
     if (c->n <= 0)
         return cudaSuccess;
-    k_pack<<<(c->n + 255) / 256, 256, 0, st>>>(c->pos[c->cur], x, y, z, c->gf, c->active, c->n);
+    k_pack<<<(c->cap + 255) / 256, 256, 0, st>>>(c->pos[c->cur], c->pos[c->cur ^ 1], x, y, z, c->gf, c->active, c->n, c->cap);
     c->launches++;
     return cudaGetLastError();
 }

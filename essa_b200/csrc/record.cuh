@@ -57,8 +57,19 @@ __device__ __forceinline__ void rec_store(RecordPtrs const& R, int k, BodyRec co
 }
 
 // pos.cast<float>() / AU  (src/Trail.cpp:53,64): narrow first, divide in double, narrow again.
+// The IEEE division is a long software sequence; the quotient is only needed to binary32, so it
+// is formed as f * RN(1/AU) (within 3 double ulps of the correctly rounded quotient) and the slow
+// exact division runs only when that could change the binary32 rounding, i.e. when the double's 29
+// discarded mantissa bits sit within 8 ulps of the rounding boundary.  Bit-identical to the division.
 __device__ __forceinline__ float to_vertex1(double p) {
-    return __double2float_rn(__ddiv_rn((double)__double2float_rn(p), ESSA_AU));
+    double f = (double)__double2float_rn(p);
+    double qf = __dmul_rn(f, 1.0 / ESSA_AU);
+    unsigned lo = (unsigned)__double2loint(qf) & 0x1fffffffu;
+    unsigned ex = ((unsigned)__double2hiint(qf) >> 20) & 0x7ffu;
+    bool risky = f != 0.0 && ((lo - 0x0ffffff8u) <= 16u || ex < 1023u - 120u || ex > 1023u + 120u);
+    if (risky)
+        qf = __ddiv_rn(f, ESSA_AU);
+    return __double2float_rn(qf);
 }
 
 __device__ __forceinline__ void vert_write(RecordPtrs const& R, BodyRec const& b, int slot, float x, float y, float z) {
@@ -118,9 +129,21 @@ __device__ __forceinline__ void trail_push(RecordPtrs const& R, BodyRec& b, doub
     double ang = 0;
     bool have_ang = false;
     if (b.length >= 3 && b.append_off != 0) {
-        ang = atan2(py, px);
-        have_ang = true;
-        if (fabs(__dsub_rn(ang, b.last_angle)) <= __ddiv_rn(2 * 3.14159265358979323846, (double)b.cap)) {
+        // |atan2(y, x) - last| <= 2 pi / capacity decides between moving the newest vertex and appending.
+        // A binary32 estimate (error < 2e-6 rad incl. the narrowing of x, y) settles every case that is
+        // not within 8e-6 rad of the threshold; only those, and appends (which must store the angle),
+        // pay for the binary64 atan2.
+        double const thr = __ddiv_rn(2 * 3.14159265358979323846, (double)b.cap);
+        double est = fabs((double)atan2f((float)py, (float)px) - b.last_angle);
+        bool decimate;
+        if (est < thr - 8e-6 && fabs(px) < 3e38 && fabs(py) < 3e38)
+            decimate = true;
+        else {
+            ang = atan2(py, px);
+            have_ang = true;
+            decimate = fabs(__dsub_rn(ang, b.last_angle)) <= thr;
+        }
+        if (decimate) {
             if (b.append_off == 1)
                 vert_write(R, b, b.length - 1, fx, fy, fz);
             vert_write(R, b, b.append_off - 1, fx, fy, fz);
@@ -167,7 +190,17 @@ __device__ __forceinline__ void record_body(RecordPtrs const& R, int k, BodyRec&
     }
     if (most < 0)
         return;
-    double d = length3(__dsub_rn(px, mx), __dsub_rn(py, my), __dsub_rn(pz, mz));
+    // ap / pe (src/Object.cpp:111-123).  The exact distance (IEEE sqrt) is needed only when it sets a
+    // new extreme; an estimate good to 1e-14 rules that out on most steps.
+    double dx = __dsub_rn(px, mx), dy = __dsub_rn(py, my), dz = __dsub_rn(pz, mz);
+    double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    double y0 = rsqrt_seed(d2);
+    double t = d2 * y0;
+    double e = fma(-t, y0, 1.0);
+    double est = fma(t * e, fma(0.375, e, 0.5), t); // ~ sqrt(d2)
+    if (est * (1.0 + 1e-12) < b.ap && est * (1.0 - 1e-12) > b.pe)
+        return;
+    double d = __dsqrt_rn(d2);
     if (b.ap < d) {
         b.ap = d;
         b.apv = length3(vx, vy, vz);

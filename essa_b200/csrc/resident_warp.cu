@@ -1,0 +1,332 @@
+// K3w -- resident kernel for worlds of up to 32 bodies (the Solar System template has 10): the whole
+// World::update loop (src/World.cpp:86-139) runs inside ONE WARP, so a KDK step never crosses a
+// block barrier, and Object::update's recording (History / Trail / ap-pe, record.cuh) runs on a
+// SECOND warp that consumes per-step snapshots from a shared-memory ring -- off the physics
+// critical path.  Fast arithmetic only; exact_order worlds go through resident.cu.
+//
+// A single trajectory is a dependent chain (each step needs the previous one), so this kernel is
+// bound by dependent-issue latency, not by any throughput roofline.  Two things shorten the chain:
+//   * lane splitting: a world of n bodies uses L = 32 / n lanes per body; lane (k, q) evaluates the
+//     partners p = q, q + L, ... of body k, so each lane's serial work is ceil(n / L) interactions
+//     instead of n, and all L lanes of a body then form the same ordered sum (every lane reads the
+//     L partials in the same order, so the replicated state stays bit-identical across lanes);
+//   * positions are exchanged through shared memory with __syncwarp only.
+#include "common.cuh"
+#include "ctx.hpp"
+#include "record.cuh"
+
+namespace essa {
+
+constexpr int kRing = 16; // snapshots in flight between the physics warp and the recorder warp
+
+struct WarpArgs {
+    WorldPtrs w;
+    RecordPtrs r;
+    long long const* cdate;
+    long long const* ddate;
+    uint8_t const* delflag;
+    uint8_t* active_out;
+    int n, steps;
+    double mul, dt, h;
+    long long date, date_step;
+    double eps2;
+    int record, offset_trails, forward_sim, two_pass, acc_valid;
+};
+
+struct Snapshot {
+    double x[32], y[32], z[32], vx[32], vy[32], vz[32];
+    int most[32], old_most[32];
+    unsigned active_mask;
+    int pad;
+};
+
+template<bool ARGMAX>
+__device__ __forceinline__ void lane_forces(int k, int q, int L, int n, double const* sx, double const* sy, double const* sz,
+    double const* sg, double x, double y, double z, double gfk, double eps2, int base_lane, double& ax, double& ay, double& az,
+    double& maxattr, int& most) {
+    double fx[4] = { 0, 0, 0, 0 }, fy[4] = { 0, 0, 0, 0 }, fz[4] = { 0, 0, 0, 0 }, bm[4] = { 0, 0, 0, 0 };
+    int bj[4] = { -1, -1, -1, -1 };
+    int const stride = 4 * L;
+    for (int p0 = q; p0 < n; p0 += stride) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int p = p0 + u * L;
+            bool in = p < n;
+            int pc = in ? p : k; // out of range -> the self term, which vanishes
+            double4 qv = make_double4(sx[pc], sy[pc], sz[pc], in ? sg[pc] : 0.0);
+            if (ARGMAX)
+                fast_interact_argmax(x, y, z, gfk, qv, pc, eps2, fx[u], fy[u], fz[u], bm[u], bj[u]);
+            else
+                fast_interact(x, y, z, qv, eps2, fx[u], fy[u], fz[u]);
+        }
+    }
+    double px = (fx[0] + fx[1]) + (fx[2] + fx[3]);
+    double py = (fy[0] + fy[1]) + (fy[2] + fy[3]);
+    double pz = (fz[0] + fz[1]) + (fz[2] + fz[3]);
+    double pm = 0;
+    int pj = -1;
+    if (ARGMAX) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (bm[u] > pm || (bm[u] == pm && bj[u] >= 0 && pj >= 0 && bj[u] < pj)) {
+                pm = bm[u];
+                pj = bj[u];
+            }
+    }
+    // every lane of body k forms the same ordered sum over the L partials
+    double sxm = 0, sym = 0, szm = 0, best = 0;
+    int bp = -1;
+    for (int qq = 0; qq < L; qq++) {
+        int src = base_lane + qq * n;
+        sxm += __shfl_sync(0xffffffffu, px, src);
+        sym += __shfl_sync(0xffffffffu, py, src);
+        szm += __shfl_sync(0xffffffffu, pz, src);
+        if (ARGMAX) {
+            double m = __shfl_sync(0xffffffffu, pm, src);
+            int j = __shfl_sync(0xffffffffu, pj, src);
+            if (m > best || (m == best && j >= 0 && bp >= 0 && j < bp)) {
+                best = m;
+                bp = j;
+            }
+        }
+    }
+    ax = sxm;
+    ay = sym;
+    az = szm;
+    if (ARGMAX) {
+        maxattr = best;
+        if (bp >= 0)
+            most = bp;
+    }
+}
+
+template<bool ARGMAX>
+__global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
+    __shared__ double sx[32], sy[32], sz[32], sg[32];
+    __shared__ Snapshot ring[kRing];
+    __shared__ volatile int produced, consumed;
+
+    int const n = A.n;
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int const L = 32 / n;
+    int const k = lane % n, q = lane / n; // (body, split) of a physics lane
+    bool const worker = lane < n * L;
+    bool const leader = lane < n;
+    bool const rec_on = A.record != 0;
+
+    if (threadIdx.x == 0) {
+        produced = 0;
+        consumed = 0;
+    }
+    __syncthreads();
+
+    if (warp == 1) {
+        // ---------------- recorder warp ----------------
+        if (!rec_on)
+            return;
+        bool const mine = lane < n && lane < A.r.tracked;
+        BodyRec b;
+        if (mine)
+            rec_load(A.r, lane, b);
+        for (int s = 0; s < A.steps; s++) {
+            while (produced <= s)
+                __nanosleep(40);
+            __threadfence_block();
+            Snapshot const& sn = ring[s % kRing];
+            if (mine && ((sn.active_mask >> lane) & 1u)) {
+                record_body(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], sn.most[lane],
+                    sn.old_most[lane], A.offset_trails != 0, A.forward_sim != 0, [&](int j, double& ox, double& oy, double& oz) {
+                        ox = sn.x[j];
+                        oy = sn.y[j];
+                        oz = sn.z[j];
+                    });
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                consumed = s + 1;
+            }
+        }
+        if (mine)
+            rec_store(A.r, lane, b);
+        return;
+    }
+
+    // ---------------- physics warp ----------------
+    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0, maxattr = 0;
+    int most = -1, old_most = -1;
+    bool active = false, delf = false;
+    long long cd = 0, dd = 0;
+    if (worker) {
+        double4 p = A.w.pos_cur[k];
+        x = p.x;
+        y = p.y;
+        z = p.z;
+        gfk = A.w.gf[k];
+        vx = A.w.v[0][k];
+        vy = A.w.v[1][k];
+        vz = A.w.v[2][k];
+        ax = A.w.a[0][k];
+        ay = A.w.a[1][k];
+        az = A.w.a[2][k];
+        maxattr = A.w.maxattr[k];
+        most = A.w.most[k];
+        old_most = A.w.old_most[k];
+        active = A.w.active[k] != 0;
+        delf = A.delflag[k] != 0;
+        cd = A.cdate[k];
+        dd = A.ddate[k];
+    }
+    if (leader) {
+        sx[k] = x;
+        sy[k] = y;
+        sz[k] = z;
+        sg[k] = active ? gfk : 0.0;
+    }
+    __syncwarp();
+
+    bool acc_valid = A.acc_valid != 0;
+    long long date = A.date;
+
+    if (A.steps == 0) { // World::set_forces() alone
+        double fx = ax, fy = ay, fz = az;
+        lane_forces<ARGMAX>(k, q, L, n, sx, sy, sz, sg, x, y, z, gfk, A.eps2, k, fx, fy, fz, maxattr, most);
+        if (active) {
+            ax = fx;
+            ay = fy;
+            az = fz;
+        }
+    }
+
+    for (int s = 0; s < A.steps; s++) {
+        if (A.date_step != 0) { // update_history_and_date: the mask may flip with the date
+            date += A.date_step;
+            bool act = worker && body_active(delf, dd, cd, date);
+            bool changed = act != active;
+            active = act;
+            if (__any_sync(0xffffffffu, changed)) {
+                if (leader)
+                    sg[k] = active ? gfk : 0.0;
+                acc_valid = false;
+                __syncwarp();
+            }
+        }
+        old_most = most; // Object::before_update
+        if (!acc_valid || A.two_pass) {
+            double fx, fy, fz, fm = maxattr;
+            int fmost = most;
+            lane_forces<ARGMAX>(k, q, L, n, sx, sy, sz, sg, x, y, z, gfk, A.eps2, k, fx, fy, fz, fm, fmost);
+            if (active) {
+                ax = fx;
+                ay = fy;
+                az = fz;
+                maxattr = fm;
+                most = fmost;
+            }
+        }
+        if (active) {
+            vx = kick1(vx, ax, A.h, A.mul);
+            vy = kick1(vy, ay, A.h, A.mul);
+            vz = kick1(vz, az, A.h, A.mul);
+            x = __dadd_rn(x, __dmul_rn(__dmul_rn(vx, A.dt), A.mul));
+            y = __dadd_rn(y, __dmul_rn(__dmul_rn(vy, A.dt), A.mul));
+            z = __dadd_rn(z, __dmul_rn(__dmul_rn(vz, A.dt), A.mul));
+        }
+        __syncwarp();
+        if (leader) {
+            sx[k] = x;
+            sy[k] = y;
+            sz[k] = z;
+        }
+        __syncwarp();
+        {
+            double fx, fy, fz, fm = maxattr;
+            int fmost = most;
+            lane_forces<ARGMAX>(k, q, L, n, sx, sy, sz, sg, x, y, z, gfk, A.eps2, k, fx, fy, fz, fm, fmost);
+            if (active) {
+                ax = fx;
+                ay = fy;
+                az = fz;
+                maxattr = fm;
+                most = fmost;
+                vx = kick1(vx, ax, A.h, A.mul);
+                vy = kick1(vy, ay, A.h, A.mul);
+                vz = kick1(vz, az, A.h, A.mul);
+            }
+        }
+        acc_valid = true;
+        if (rec_on) {
+            while (s - consumed >= kRing)
+                __nanosleep(40);
+            Snapshot& sn = ring[s % kRing];
+            unsigned amask = __ballot_sync(0xffffffffu, leader && active);
+            if (leader) {
+                sn.x[k] = x;
+                sn.y[k] = y;
+                sn.z[k] = z;
+                sn.vx[k] = vx;
+                sn.vy[k] = vy;
+                sn.vz[k] = vz;
+                sn.most[k] = most;
+                sn.old_most[k] = old_most;
+            }
+            if (lane == 0)
+                sn.active_mask = amask;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                produced = s + 1;
+            }
+        }
+    }
+
+    if (leader) {
+        A.w.pos_cur[k] = make_double4(x, y, z, active ? gfk : 0.0);
+        A.w.v[0][k] = vx;
+        A.w.v[1][k] = vy;
+        A.w.v[2][k] = vz;
+        A.w.a[0][k] = ax;
+        A.w.a[1][k] = ay;
+        A.w.a[2][k] = az;
+        A.w.maxattr[k] = maxattr;
+        A.w.most[k] = most;
+        A.w.old_most[k] = old_most;
+        A.active_out[k] = active ? 1 : 0;
+    }
+}
+
+cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st) {
+    WarpArgs A;
+    A.w = world_ptrs(c);
+    A.r = record_ptrs(c);
+    A.cdate = (long long const*)c->cdate;
+    A.ddate = (long long const*)c->ddate;
+    A.delflag = c->delflag;
+    A.active_out = c->active;
+    A.n = c->n;
+    A.steps = forces_only ? 0 : (steps < 0 ? -steps : steps);
+    A.mul = steps >= 0 ? 1.0 : -1.0;
+    A.dt = (double)o.dt_seconds;
+    A.h = A.dt / 2.0;
+    A.date = (long long)c->date;
+    A.date_step = o.forward_simulated ? 0 : (long long)(steps >= 0 ? 1 : -1) * o.dt_seconds;
+    A.eps2 = o.eps2;
+    A.record = o.record && !forces_only && c->tracked > 0;
+    A.offset_trails = o.offset_trails;
+    A.forward_sim = o.forward_simulated;
+    A.two_pass = o.two_pass;
+    bool argmax = o.track_most_attracting || o.record;
+    A.acc_valid = c->acc_valid && (!argmax || c->acc_has_most) && !c->acc_exact;
+    if (argmax)
+        k_resident_warp<true><<<1, 64, 0, st>>>(A);
+    else
+        k_resident_warp<false><<<1, 64, 0, st>>>(A);
+    c->launches++;
+    int P = A.steps == 0 ? 1 : (o.two_pass ? 2 * A.steps : A.steps + (A.acc_valid ? 0 : 1));
+    c->passes += P;
+    c->interactions += (double)P * (double)c->n * (double)(c->n - 1);
+    c->last_force_passes = P;
+    return cudaGetLastError();
+}
+
+} // namespace essa

@@ -1,0 +1,123 @@
+"""GPU parity of K1p, the pair-shared force pass (each unordered pair evaluated once and applied to
+both bodies, like the reference's own i<j loop), against the CPU oracle.  Same bars as K1
+(tests/test_gpu_tiled.py): single pass within max(1e-13, 4x the oracle's own error vs extended
+precision); 10-step trajectories of unsoftened Plummer spheres within 1e-10."""
+import numpy as np
+import pytest
+
+import oracle
+from essa_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_rows(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _upload(ctx, w):
+    ctx.date = capi.START_DATE
+    ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
+
+
+# block counts nb = 2 (even, d = nb/2 handled by half the ring), 3 (odd), 4, 5, ragged last blocks, many blocks
+@pytest.mark.parametrize("n", [1025, 2048, 3000, 4096, 5000, 20000, 65536])
+def test_paired_force_pass_matches_extended_precision(ctx, n):
+    w = synth.plummer(n, seed=n)
+    _upload(ctx, w)
+    ctx.set_forces(kernel=capi.KERNEL_PAIRED)
+    got = ctx.download(("ax", "ay", "az"))
+    a = np.stack([got["ax"], got["ay"], got["az"]], axis=1)
+    rows = np.unique(np.concatenate([np.random.default_rng(1).choice(n, 192, replace=False), [0, 1023, 1024, n - 1]]))
+    ld = oracle.forces_rows(w["x"], w["y"], w["z"], w["gf"], rows, mode="ld")
+    ref = oracle.forces_rows(w["x"], w["y"], w["z"], w["gf"], rows, mode="ref")
+    err, err_ref = _rel_rows(a[rows], ld), _rel_rows(ref, ld)
+    assert err.max() <= max(1e-13, 4.0 * err_ref.max()), (err.max(), err_ref.max())
+    assert np.all(np.isfinite(a))
+    # pair-shared evaluation conserves momentum to round-off: sum(m a) ~ 0
+    ma = a * w["gf"][:, None]
+    assert np.abs(ma.sum(axis=0)).max() <= 1e-12 * np.abs(ma).sum()
+
+
+def test_paired_agrees_with_tiled(ctx):
+    n = 30000
+    w = synth.plummer(n, seed=2)
+    _upload(ctx, w)
+    ctx.set_forces(kernel=capi.KERNEL_TILED)
+    t = ctx.download(("ax", "ay", "az"))
+    _upload(ctx, w)
+    ctx.set_forces(kernel=capi.KERNEL_PAIRED)
+    p = ctx.download(("ax", "ay", "az"))
+    a = np.stack([t["ax"], t["ay"], t["az"]], axis=1)
+    b = np.stack([p["ax"], p["ay"], p["az"]], axis=1)
+    assert _rel_rows(b, a).max() <= 1e-12
+
+
+def test_paired_unequal_masses_and_masked_bodies(ctx):
+    """gf varies over 6 decades; some bodies are masked by date (gf_eff = 0 records)."""
+    n = 6000
+    w = synth.plummer(n, seed=3)
+    rng = np.random.default_rng(4)
+    w["gf"] = w["gf"] * 10.0 ** rng.uniform(-3, 3, n)
+    t0 = capi.START_DATE
+    cdate = np.full(n, t0, dtype=np.int64)
+    cdate[rng.choice(n, 50, replace=False)] = t0 + 10 ** 9  # not created yet
+    ctx.date = t0
+    ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"], creation_date=cdate)
+    ctx.set_forces(kernel=capi.KERNEL_PAIRED)
+    got = ctx.download(("ax", "ay", "az"))
+    a = np.stack([got["ax"], got["ay"], got["az"]], axis=1)
+    act = cdate <= t0
+    gfe = np.where(act, w["gf"], 0.0)
+    rows = np.where(act)[0][:200]
+    ld = oracle.forces_rows(w["x"], w["y"], w["z"], gfe, rows, mode="ld")
+    ref = oracle.forces_rows(w["x"], w["y"], w["z"], gfe, rows, mode="ref")
+    assert _rel_rows(a[rows], ld).max() <= max(1e-13, 4.0 * _rel_rows(ref, ld).max())
+    assert np.all(a[~act] == 0.0)  # masked bodies keep their (zero) acceleration
+
+
+@pytest.mark.parametrize("n,steps", [(3000, 10), (3000, -6)])
+def test_paired_kdk_trajectory_matches_oracle(ctx, n, steps):
+    w = synth.plummer(n, seed=11)
+    dt = synth.default_dt(n)
+    _upload(ctx, w)
+    ctx.step(steps, dt, kernel=capi.KERNEL_PAIRED)
+    got = ctx.download()
+    (ox, oy, oz, ovx, ovy, ovz), oacc = oracle.step_soa(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"], steps, dt)
+    pos = np.stack([got["x"], got["y"], got["z"]], axis=1)
+    vel = np.stack([got["vx"], got["vy"], got["vz"]], axis=1)
+    assert _rel_rows(pos, np.stack([ox, oy, oz], axis=1)).max() <= 1e-10
+    assert _rel_rows(vel, np.stack([ovx, ovy, ovz], axis=1)).max() <= 1e-10
+    assert ctx.last_force_passes == abs(steps) + 1
+
+
+def test_paired_is_deterministic_and_reuse_is_exact(ctx):
+    n = 9000
+    w = synth.plummer(n, seed=5)
+    dt = synth.default_dt(n)
+    runs = []
+    for two_pass in (False, False, True):
+        _upload(ctx, w)
+        ctx.step(4, dt, kernel=capi.KERNEL_PAIRED, two_pass=two_pass)
+        runs.append(ctx.download())
+    for k in ("x", "y", "z", "vx", "vy", "vz", "ax", "ay", "az"):
+        assert np.array_equal(runs[0][k], runs[1][k]), k   # no atomics: bitwise reproducible
+        assert np.array_equal(runs[0][k], runs[2][k]), k   # reuse == recompute
+
+
+def test_paired_refuses_what_it_cannot_do(ctx):
+    w = synth.plummer(512, seed=1)
+    _upload(ctx, w)
+    with pytest.raises(capi.EssaError):
+        ctx.step(1, 1000, kernel=capi.KERNEL_PAIRED)
+    w = synth.plummer(4096, seed=1)
+    _upload(ctx, w)
+    with pytest.raises(capi.EssaError):
+        ctx.step(1, 1000, kernel=capi.KERNEL_PAIRED, track_most_attracting=True)
