@@ -94,10 +94,12 @@ SYMBOLS = [
     ("essa_ensemble_factor", C.c_double, [C.c_uint64, C.c_double, C.c_int64, C.c_int, C.c_int]),
     ("essa_nccl_unique_id", C.c_int, [_u8p]),
     ("essa_shard_attach", C.c_int, [_P, C.c_int, C.c_int, _u8p]),
+    ("essa_shard_range", C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("essa_shard_rank", C.c_int, [_P]),
     ("essa_shard_world", C.c_int, [_P]),
     ("essa_measure_fp64_peak", C.c_double, [_P, C.c_double]),
     ("essa_measure_rsqrt_error", C.c_int, [_P, _dp, _dp]),
+    ("essa_measure_latency", C.c_int, [_P, _dp]),
     ("essa_flush_l2", C.c_int, [_P]),
 ]
 
@@ -130,6 +132,14 @@ def _ptr(a, ptype):
 
 def ensemble_factor(seed, rel_sigma, copy, body, component):
     return lib().essa_ensemble_factor(seed, rel_sigma, copy, body, component)
+
+
+def shard_range(n, rank, world):
+    a, b = C.c_int(0), C.c_int(0)
+    rc = lib().essa_shard_range(n, rank, world, C.byref(a), C.byref(b))
+    if rc != 0:
+        raise EssaError(rc, "bad shard arguments")
+    return a.value, b.value
 
 
 def nccl_unique_id():
@@ -328,6 +338,11 @@ class Context:
         a, b = C.c_double(0), C.c_double(0)
         self._ck(self._L.essa_measure_rsqrt_error(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def measure_latency(self):
+        out = np.zeros(6)
+        self._ck(self._L.essa_measure_latency(self._h, _ptr(out, _dp)))
+        return dict(zip(("dfma", "dadd", "dmul", "rsqrt_seed", "lds", "shfl_f64"), out.tolist()))
 
     def flush_l2(self):
         self._ck(self._L.essa_flush_l2(self._h))

@@ -1126,3 +1126,22 @@ extern "C" int essa_closest_read(essa_ctx* ctx, int body, int other, double out[
     CK(cudaMemcpy(out, ctx->closest + ((size_t)body * ctx->closest_n + other) * 7, 7 * sizeof(double), cudaMemcpyDeviceToHost));
     return out[0] != 0.0 ? 1 : 0;
 }
+
+// Targets [*i0, *i1) that rank `rank` of `world` integrates in an n-body world (ragged shards allowed).
+extern "C" int essa_shard_range(int n, int rank, int world, int* i0, int* i1) {
+    if (n < 0 || world < 1 || rank < 0 || rank >= world || !i0 || !i1)
+        return ESSA_ERR_ARG;
+    *i0 = (int)((long long)n * rank / world);
+    *i1 = (int)((long long)n * (rank + 1) / world);
+    return ESSA_OK;
+}
+
+namespace essa {
+int run_latency(essa_ctx* c, double* out6);
+}
+extern "C" int essa_measure_latency(essa_ctx* ctx, double out[6]) {
+    ARG(ctx, "ctx is null");
+    ARG(out, "out is null");
+    CK(cudaSetDevice(ctx->device));
+    return run_latency(ctx, out);
+}

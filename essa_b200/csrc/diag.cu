@@ -241,3 +241,88 @@ int run_rsqrt_error(essa_ctx* c, double* seed, double* refined) {
 }
 
 } // namespace essa
+
+// ------------------------------------------------------------------------------------------
+// Dependent-issue latencies (cycles) of the instructions on a single trajectory's critical
+// path: DFMA, DADD, DMUL, MUFU.RSQ64H (+ its guard), LDS.64 pointer chase, warp shuffle of a
+// double.  One warp, one chain, timed with clock64.
+// ------------------------------------------------------------------------------------------
+namespace essa {
+
+__global__ void k_latency(double* out, double a, double b, int iters) {
+    __shared__ int chase[32];
+    chase[threadIdx.x] = (threadIdx.x + 1) & 31;
+    __syncwarp();
+    double r = a;
+    long long t0, t1;
+    // DFMA
+    t0 = clock64();
+    for (int i = 0; i < iters; i++)
+        r = fma(r, a, b);
+    t1 = clock64();
+    double l_fma = double(t1 - t0) / iters;
+    // DADD
+    t0 = clock64();
+    for (int i = 0; i < iters; i++)
+        r = __dadd_rn(r, b);
+    t1 = clock64();
+    double l_add = double(t1 - t0) / iters;
+    // DMUL
+    t0 = clock64();
+    for (int i = 0; i < iters; i++)
+        r = __dmul_rn(r, a);
+    t1 = clock64();
+    double l_mul = double(t1 - t0) / iters;
+    // rsqrt seed (MUFU.RSQ64H + integer guard) chained through a DADD to keep the value in range
+    double s = fabs(r) + 2.0;
+    t0 = clock64();
+    for (int i = 0; i < iters; i++)
+        s = __dadd_rn(rsqrt_seed(s), 2.0);
+    t1 = clock64();
+    double l_rsq = double(t1 - t0) / iters - l_add;
+    // LDS pointer chase
+    int p = threadIdx.x;
+    t0 = clock64();
+    for (int i = 0; i < iters; i++)
+        p = chase[p];
+    t1 = clock64();
+    double l_lds = double(t1 - t0) / iters;
+    // shuffle of a double (2 x SHFL.32)
+    double v = s;
+    t0 = clock64();
+    for (int i = 0; i < iters; i++)
+        v = __shfl_sync(0xffffffffu, v, (threadIdx.x + 1) & 31);
+    t1 = clock64();
+    double l_shfl = double(t1 - t0) / iters;
+    if (threadIdx.x == 0) {
+        out[0] = l_fma;
+        out[1] = l_add;
+        out[2] = l_mul;
+        out[3] = l_rsq;
+        out[4] = l_lds;
+        out[5] = l_shfl;
+        out[6] = r + s + v + p; // keep everything alive
+    }
+}
+
+int run_latency(essa_ctx* c, double* out6) {
+    double* d;
+    if (cudaMalloc(&d, 8 * sizeof(double)) != cudaSuccess)
+        return ESSA_ERR_CUDA;
+    k_latency<<<1, 32, 0, c->stream>>>(d, 0.9999999, 1e-9, 4096);
+    c->launches++;
+    double h[8];
+    cudaError_t e = cudaMemcpyAsync(h, d, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        c->err = cudaGetErrorString(e);
+        return ESSA_ERR_CUDA;
+    }
+    for (int i = 0; i < 6; i++)
+        out6[i] = h[i];
+    return ESSA_OK;
+}
+
+} // namespace essa

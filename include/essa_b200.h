@@ -207,6 +207,8 @@ int essa_nccl_unique_id(uint8_t id[ESSA_NCCL_ID_BYTES]);
  * essa_step integrates bodies [rank*N/world, (rank+1)*N/world) with one all-gather of the
  * drifted positions per force pass; essa_download returns the full, gathered world. */
 int essa_shard_attach(essa_ctx* ctx, int rank, int world, const uint8_t id[ESSA_NCCL_ID_BYTES]);
+/* The target range [*i0, *i1) of a rank (pure function; what every kernel of a sharded context uses). */
+int essa_shard_range(int n, int rank, int world, int* i0, int* i1);
 int essa_shard_rank(const essa_ctx* ctx);
 int essa_shard_world(const essa_ctx* ctx);
 
@@ -217,6 +219,9 @@ int essa_shard_world(const essa_ctx* ctx);
 double essa_measure_fp64_peak(essa_ctx* ctx, double ms);
 /* Maximum relative error of the MUFU.RSQ64H seed and of the refined r^-3 over a log sweep. */
 int essa_measure_rsqrt_error(essa_ctx* ctx, double* seed_rel_err, double* refined_rel_err);
+/* Dependent-issue latencies in SM cycles: {DFMA, DADD, DMUL, MUFU.RSQ64H seed, LDS chase, shuffle of a double}:
+ * what bounds a single small-N trajectory (one step is a dependent chain). */
+int essa_measure_latency(essa_ctx* ctx, double out[6]);
 /* Evict the L2 between timed iterations (writes a 256 MiB scratch buffer). */
 int essa_flush_l2(essa_ctx* ctx);
 
