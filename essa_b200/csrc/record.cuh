@@ -21,6 +21,7 @@ struct BodyRec {
     long long voff;
     double offx, offy, offz;
     double last_angle;
+    double thr; // 2 pi / capacity (src/Trail.cpp:58), one IEEE division per kernel instead of per step
     double ap, pe, apv, pev;
 };
 
@@ -30,6 +31,7 @@ __device__ __forceinline__ void rec_load(RecordPtrs const& R, int k, BodyRec& b)
     b.append_off = R.append_off[k];
     b.length = R.length[k];
     b.cap = R.cap[k];
+    b.thr = __ddiv_rn(2 * 3.14159265358979323846, (double)b.cap);
     b.voff = R.vert_off[k];
     b.offx = R.toff[3 * k];
     b.offy = R.toff[3 * k + 1];
@@ -92,13 +94,11 @@ __device__ __forceinline__ void history_push(RecordPtrs const& R, int k, BodyRec
         slot = b.hist_start;
         b.hist_start = b.hist_start + 1 == ESSA_HISTORY_SEGMENTS ? 0 : b.hist_start + 1;
     }
-    double* e = R.hist + ((size_t)k * ESSA_HISTORY_SEGMENTS + slot) * 6;
-    e[0] = px;
-    e[1] = py;
-    e[2] = pz;
-    e[3] = vx;
-    e[4] = vy;
-    e[5] = vz;
+    // 48-byte entries in a 256-byte aligned ring: three 16-byte stores
+    double2* e = reinterpret_cast<double2*>(R.hist + ((size_t)k * ESSA_HISTORY_SEGMENTS + slot) * 6);
+    e[0] = make_double2(px, py);
+    e[1] = make_double2(pz, vx);
+    e[2] = make_double2(vy, vz);
 }
 
 // Trail::recalculate_with_offset (src/Trail.cpp:82-88)
@@ -133,7 +133,7 @@ __device__ __forceinline__ void trail_push(RecordPtrs const& R, BodyRec& b, doub
         // A binary32 estimate (error < 2e-6 rad incl. the narrowing of x, y) settles every case that is
         // not within 8e-6 rad of the threshold; only those, and appends (which must store the angle),
         // pay for the binary64 atan2.
-        double const thr = __ddiv_rn(2 * 3.14159265358979323846, (double)b.cap);
+        double const thr = b.thr;
         double est = fabs((double)atan2f((float)py, (float)px) - b.last_angle);
         bool decimate;
         if (est < thr - 8e-6 && fabs(px) < 3e38 && fabs(py) < 3e38)

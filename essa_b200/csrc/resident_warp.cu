@@ -1,15 +1,20 @@
 // K3w -- resident kernel for worlds of up to 32 bodies (the Solar System template has 10): the whole
 // World::update loop (src/World.cpp:86-139) runs inside ONE WARP, so a KDK step never crosses a
 // block barrier, and Object::update's recording (History / Trail / ap-pe, record.cuh) runs on a
-// SECOND warp that consumes per-step snapshots from a shared-memory ring -- off the physics
-// critical path.  Fast arithmetic only; exact_order worlds go through resident.cu.
+// SECOND warp that consumes per-step snapshots from a shared-memory ring (mbarrier full / empty
+// hand-off) -- off the physics critical path.  Fast arithmetic only; exact_order worlds go through
+// resident.cu.
 //
 // A single trajectory is a dependent chain (each step needs the previous one), so this kernel is
-// bound by dependent-issue latency, not by any throughput roofline.  Two things shorten the chain:
+// bound by dependent-issue latency (measured on B200: DFMA/DADD/DMUL 8.3 cycles, MUFU.RSQ64H seed
+// 23, LDS 29, shuffle of a double 30), not by any throughput roofline.  What shortens the chain:
 //   * lane splitting: a world of n bodies uses L = 32 / n lanes per body; lane (k, q) evaluates the
-//     partners p = q, q + L, ... of body k, so each lane's serial work is ceil(n / L) interactions
-//     instead of n, and all L lanes of a body then form the same ordered sum (every lane reads the
-//     L partials in the same order, so the replicated state stays bit-identical across lanes);
+//     partners p = q, q + L, ... of body k (P of them, a compile-time bound, all independent), and
+//     every lane of a body then forms the same ordered sum of the L partials, so the replicated
+//     state stays bit-identical across lanes without a broadcast;
+//   * kick and drift use the exact identities (a h) mul == a (h mul) and (v dt) mul == v (dt mul)
+//     (multiplying by +-1 is exact), and the two half kicks around a reused acceleration share one
+//     product: forces -> dv -> v -> v' -> x is five dependent FP64 instructions;
 //   * positions are exchanged through shared memory with __syncwarp only.
 #include "common.cuh"
 #include "ctx.hpp"
@@ -26,8 +31,8 @@ struct WarpArgs {
     long long const* ddate;
     uint8_t const* delflag;
     uint8_t* active_out;
-    int n, steps;
-    double mul, dt, h;
+    int n, steps, L, iters;
+    double hm, dtm; // (dt / 2) * mul, dt * mul
     long long date, date_step;
     double eps2;
     int record, offset_trails, forward_sim, two_pass, acc_valid;
@@ -40,17 +45,26 @@ struct Snapshot {
     int pad;
 };
 
-template<bool ARGMAX>
-__device__ __forceinline__ void lane_forces(int k, int q, int L, int n, double const* sx, double const* sy, double const* sz,
-    double const* sg, double x, double y, double z, double gfk, double eps2, int base_lane, double& ax, double& ay, double& az,
-    double& maxattr, int& most) {
-    double fx[4] = { 0, 0, 0, 0 }, fy[4] = { 0, 0, 0, 0 }, fz[4] = { 0, 0, 0, 0 }, bm[4] = { 0, 0, 0, 0 };
-    int bj[4] = { -1, -1, -1, -1 };
-    int const stride = 4 * L;
-    for (int p0 = q; p0 < n; p0 += stride) {
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Partial force of lane (k, q) over its partners, then the ordered sum over the L lanes of body k.
+template<int P, bool ARGMAX>
+__device__ __forceinline__ void lane_forces(int k, int q, int L, int iters, int n, double const* sx, double const* sy, double const* sz,
+    double const* sg, double x, double y, double z, double gfk, double eps2, double& ax, double& ay, double& az, double& maxattr,
+    int& most) {
+    double fx[P], fy[P], fz[P], bm[P];
+    int bj[P];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            int p = p0 + u * L;
+    for (int u = 0; u < P; u++) {
+        fx[u] = fy[u] = fz[u] = bm[u] = 0.0;
+        bj[u] = -1;
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < P; u++) {
+            int p = q + (it * P + u) * L;
             bool in = p < n;
             int pc = in ? p : k; // out of range -> the self term, which vanishes
             double4 qv = make_double4(sx[pc], sy[pc], sz[pc], in ? sg[pc] : 0.0);
@@ -60,24 +74,22 @@ __device__ __forceinline__ void lane_forces(int k, int q, int L, int n, double c
                 fast_interact(x, y, z, qv, eps2, fx[u], fy[u], fz[u]);
         }
     }
-    double px = (fx[0] + fx[1]) + (fx[2] + fx[3]);
-    double py = (fy[0] + fy[1]) + (fy[2] + fy[3]);
-    double pz = (fz[0] + fz[1]) + (fz[2] + fz[3]);
-    double pm = 0;
-    int pj = -1;
-    if (ARGMAX) {
+    double px = fx[0], py = fy[0], pz = fz[0], pm = bm[0];
+    int pj = bj[0];
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (bm[u] > pm || (bm[u] == pm && bj[u] >= 0 && pj >= 0 && bj[u] < pj)) {
-                pm = bm[u];
-                pj = bj[u];
-            }
+    for (int u = 1; u < P; u++) {
+        px += fx[u];
+        py += fy[u];
+        pz += fz[u];
+        if (ARGMAX && (bm[u] > pm || (bm[u] == pm && bj[u] >= 0 && pj >= 0 && bj[u] < pj))) {
+            pm = bm[u];
+            pj = bj[u];
+        }
     }
-    // every lane of body k forms the same ordered sum over the L partials
     double sxm = 0, sym = 0, szm = 0, best = 0;
     int bp = -1;
     for (int qq = 0; qq < L; qq++) {
-        int src = base_lane + qq * n;
+        int src = k + qq * n;
         sxm += __shfl_sync(0xffffffffu, px, src);
         sym += __shfl_sync(0xffffffffu, py, src);
         szm += __shfl_sync(0xffffffffu, pz, src);
@@ -100,23 +112,25 @@ __device__ __forceinline__ void lane_forces(int k, int q, int L, int n, double c
     }
 }
 
-template<bool ARGMAX>
+template<int P, bool ARGMAX>
 __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
     __shared__ double sx[32], sy[32], sz[32], sg[32];
     __shared__ Snapshot ring[kRing];
-    __shared__ volatile int produced, consumed;
+    __shared__ __align__(8) unsigned long long full[kRing], empty[kRing];
 
-    int const n = A.n;
+    int const n = A.n, L = A.L;
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int const L = 32 / n;
     int const k = lane % n, q = lane / n; // (body, split) of a physics lane
     bool const worker = lane < n * L;
     bool const leader = lane < n;
     bool const rec_on = A.record != 0;
 
     if (threadIdx.x == 0) {
-        produced = 0;
-        consumed = 0;
+        for (int i = 0; i < kRing; i++) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_fence_init();
     }
     __syncthreads();
 
@@ -129,10 +143,9 @@ __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
         if (mine)
             rec_load(A.r, lane, b);
         for (int s = 0; s < A.steps; s++) {
-            while (produced <= s)
-                __nanosleep(40);
-            __threadfence_block();
-            Snapshot const& sn = ring[s % kRing];
+            int const slot = s % kRing;
+            mbar_wait(&full[slot], (unsigned)(s / kRing) & 1u);
+            Snapshot const& sn = ring[slot];
             if (mine && ((sn.active_mask >> lane) & 1u)) {
                 record_body(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], sn.most[lane],
                     sn.old_most[lane], A.offset_trails != 0, A.forward_sim != 0, [&](int j, double& ox, double& oy, double& oz) {
@@ -142,10 +155,8 @@ __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
                     });
             }
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                consumed = s + 1;
-            }
+            if (lane == 0)
+                mbar_arrive(&empty[slot]);
         }
         if (mine)
             rec_store(A.r, lane, b);
@@ -187,16 +198,23 @@ __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
 
     bool acc_valid = A.acc_valid != 0;
     long long date = A.date;
+    double const hm = A.hm, dtm = A.dtm;
 
-    if (A.steps == 0) { // World::set_forces() alone
-        double fx = ax, fy = ay, fz = az;
-        lane_forces<ARGMAX>(k, q, L, n, sx, sy, sz, sg, x, y, z, gfk, A.eps2, k, fx, fy, fz, maxattr, most);
+    auto forces = [&]() {
+        double fx, fy, fz, fm = maxattr;
+        int fmost = most;
+        lane_forces<P, ARGMAX>(k, q, L, A.iters, n, sx, sy, sz, sg, x, y, z, gfk, A.eps2, fx, fy, fz, fm, fmost);
         if (active) {
             ax = fx;
             ay = fy;
             az = fz;
+            maxattr = fm;
+            most = fmost;
         }
-    }
+    };
+
+    if (A.steps == 0) // World::set_forces() alone
+        forces();
 
     for (int s = 0; s < A.steps; s++) {
         if (A.date_step != 0) { // update_history_and_date: the mask may flip with the date
@@ -212,25 +230,15 @@ __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
             }
         }
         old_most = most; // Object::before_update
-        if (!acc_valid || A.two_pass) {
-            double fx, fy, fz, fm = maxattr;
-            int fmost = most;
-            lane_forces<ARGMAX>(k, q, L, n, sx, sy, sz, sg, x, y, z, gfk, A.eps2, k, fx, fy, fz, fm, fmost);
-            if (active) {
-                ax = fx;
-                ay = fy;
-                az = fz;
-                maxattr = fm;
-                most = fmost;
-            }
-        }
-        if (active) {
-            vx = kick1(vx, ax, A.h, A.mul);
-            vy = kick1(vy, ay, A.h, A.mul);
-            vz = kick1(vz, az, A.h, A.mul);
-            x = __dadd_rn(x, __dmul_rn(__dmul_rn(vx, A.dt), A.mul));
-            y = __dadd_rn(y, __dmul_rn(__dmul_rn(vy, A.dt), A.mul));
-            z = __dadd_rn(z, __dmul_rn(__dmul_rn(vz, A.dt), A.mul));
+        if (!acc_valid || A.two_pass)
+            forces();
+        if (active) { // first half kick + drift (src/World.cpp:112,115)
+            vx = __dadd_rn(vx, __dmul_rn(ax, hm));
+            vy = __dadd_rn(vy, __dmul_rn(ay, hm));
+            vz = __dadd_rn(vz, __dmul_rn(az, hm));
+            x = __dadd_rn(x, __dmul_rn(vx, dtm));
+            y = __dadd_rn(y, __dmul_rn(vy, dtm));
+            z = __dadd_rn(z, __dmul_rn(vz, dtm));
         }
         __syncwarp();
         if (leader) {
@@ -239,26 +247,18 @@ __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
             sz[k] = z;
         }
         __syncwarp();
-        {
-            double fx, fy, fz, fm = maxattr;
-            int fmost = most;
-            lane_forces<ARGMAX>(k, q, L, n, sx, sy, sz, sg, x, y, z, gfk, A.eps2, k, fx, fy, fz, fm, fmost);
-            if (active) {
-                ax = fx;
-                ay = fy;
-                az = fz;
-                maxattr = fm;
-                most = fmost;
-                vx = kick1(vx, ax, A.h, A.mul);
-                vy = kick1(vy, ay, A.h, A.mul);
-                vz = kick1(vz, az, A.h, A.mul);
-            }
+        forces();
+        if (active) { // second half kick (src/World.cpp:127)
+            vx = __dadd_rn(vx, __dmul_rn(ax, hm));
+            vy = __dadd_rn(vy, __dmul_rn(ay, hm));
+            vz = __dadd_rn(vz, __dmul_rn(az, hm));
         }
         acc_valid = true;
         if (rec_on) {
-            while (s - consumed >= kRing)
-                __nanosleep(40);
-            Snapshot& sn = ring[s % kRing];
+            int const slot = s % kRing;
+            if (s >= kRing)
+                mbar_wait(&empty[slot], (unsigned)(s / kRing - 1) & 1u);
+            Snapshot& sn = ring[slot];
             unsigned amask = __ballot_sync(0xffffffffu, leader && active);
             if (leader) {
                 sn.x[k] = x;
@@ -273,10 +273,8 @@ __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
             if (lane == 0)
                 sn.active_mask = amask;
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                produced = s + 1;
-            }
+            if (lane == 0)
+                mbar_arrive(&full[slot]);
         }
     }
 
@@ -295,6 +293,14 @@ __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
     }
 }
 
+template<int P>
+static void launch_P(bool argmax, WarpArgs const& A, cudaStream_t st) {
+    if (argmax)
+        k_resident_warp<P, true><<<1, 64, 0, st>>>(A);
+    else
+        k_resident_warp<P, false><<<1, 64, 0, st>>>(A);
+}
+
 cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st) {
     WarpArgs A;
     A.w = world_ptrs(c);
@@ -305,9 +311,9 @@ cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o
     A.active_out = c->active;
     A.n = c->n;
     A.steps = forces_only ? 0 : (steps < 0 ? -steps : steps);
-    A.mul = steps >= 0 ? 1.0 : -1.0;
-    A.dt = (double)o.dt_seconds;
-    A.h = A.dt / 2.0;
+    double const mul = steps >= 0 ? 1.0 : -1.0;
+    A.dtm = (double)o.dt_seconds * mul;
+    A.hm = (double)o.dt_seconds / 2.0 * mul;
     A.date = (long long)c->date;
     A.date_step = o.forward_simulated ? 0 : (long long)(steps >= 0 ? 1 : -1) * o.dt_seconds;
     A.eps2 = o.eps2;
@@ -317,15 +323,24 @@ cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o
     A.two_pass = o.two_pass;
     bool argmax = o.track_most_attracting || o.record;
     A.acc_valid = c->acc_valid && (!argmax || c->acc_has_most) && !c->acc_exact;
-    if (argmax)
-        k_resident_warp<true><<<1, 64, 0, st>>>(A);
+    // lanes per body and partners per lane
+    A.L = 32 / c->n;
+    int per_lane = (c->n + A.L - 1) / A.L;
+    int P = per_lane <= 1 ? 1 : (per_lane <= 2 ? 2 : (per_lane <= 4 ? 4 : 8));
+    A.iters = (per_lane + P - 1) / P;
+    if (P == 1)
+        launch_P<1>(argmax, A, st);
+    else if (P == 2)
+        launch_P<2>(argmax, A, st);
+    else if (P == 4)
+        launch_P<4>(argmax, A, st);
     else
-        k_resident_warp<false><<<1, 64, 0, st>>>(A);
+        launch_P<8>(argmax, A, st);
     c->launches++;
-    int P = A.steps == 0 ? 1 : (o.two_pass ? 2 * A.steps : A.steps + (A.acc_valid ? 0 : 1));
-    c->passes += P;
-    c->interactions += (double)P * (double)c->n * (double)(c->n - 1);
-    c->last_force_passes = P;
+    int passes = A.steps == 0 ? 1 : (o.two_pass ? 2 * A.steps : A.steps + (A.acc_valid ? 0 : 1));
+    c->passes += passes;
+    c->interactions += (double)passes * (double)c->n * (double)(c->n - 1);
+    c->last_force_passes = passes;
     return cudaGetLastError();
 }
 
