@@ -1,12 +1,22 @@
 // K6 building blocks -- Object::update (src/Object.cpp:131-153): History::move_forward
 // (src/History.cpp:11-31), Object::nonphysical_update / recalculate_trails_with_offset
 // (src/Object.cpp:103-124,155-167) and Trail (src/Trail.cpp:49-88,105-110), as device functions
-// over the rings that essa_record_configure lays out.  Used inline by the resident kernel and by
-// the per-step record kernel of the tiled path.
+// over the rings that essa_record_configure lays out.  Used by the resident kernels (inline or on
+// a recorder warp) and by the per-step record kernel of the tiled path.
 //
-// All arithmetic here follows the reference's order exactly (IEEE single / double, no
-// contraction); the only function that is not bit-reproducible against glibc is atan2, which
-// feeds a threshold test and the stored m_last_xy_angle.
+// Results are bit-identical to the reference's order of operations (IEEE single / double, no
+// contraction); the only value that is not bit-reproducible against glibc is atan2, which feeds a
+// threshold test and the stored m_last_xy_angle.  What is NOT done the reference's way is the
+// amount of work per step -- three things are deferred while a kernel runs, because only their
+// last value is observable:
+//   * Trail::change_current overwrites the newest vertex on every decimated step; the vertex
+//     (two float conversions and a division per component) is materialised only when the next
+//     append, an offset change or the end of the kernel needs it;
+//   * m_ap / m_pe move on every step of a monotonic stretch of an orbit; the exact distance
+//     (IEEE sqrt) and |v| (another one) are formed when the stretch ends.  Decisions are taken on
+//     squared distances with a 1e-15 guard band inside which the exact path runs;
+//   * the decimation test |atan2(y, x) - last| <= 2 pi / capacity is settled by a binary32 estimate
+//     unless it lands within 8e-6 rad of the threshold.
 #pragma once
 
 #include "common.cuh"
@@ -21,8 +31,13 @@ struct BodyRec {
     long long voff;
     double offx, offy, offz;
     double last_angle;
-    double thr; // 2 pi / capacity (src/Trail.cpp:58), one IEEE division per kernel instead of per step
+    double thr; // 2 pi / capacity (src/Trail.cpp:58): one IEEE division per kernel, not per step
     double ap, pe, apv, pev;
+    // deferred work
+    int vpend, ap_pend, pe_pend;
+    double vpx, vpy, vpz;              // position of the pending change_current
+    double ap_d2, ap_vx, ap_vy, ap_vz; // squared distance / velocity of the pending apoapsis
+    double pe_d2, pe_vx, pe_vy, pe_vz;
 };
 
 __device__ __forceinline__ void rec_load(RecordPtrs const& R, int k, BodyRec& b) {
@@ -41,21 +56,10 @@ __device__ __forceinline__ void rec_load(RecordPtrs const& R, int k, BodyRec& b)
     b.pe = R.pe[k];
     b.apv = R.ap_vel[k];
     b.pev = R.pe_vel[k];
-}
-
-__device__ __forceinline__ void rec_store(RecordPtrs const& R, int k, BodyRec const& b) {
-    R.hist_start[k] = b.hist_start;
-    R.hist_len[k] = b.hist_len;
-    R.append_off[k] = b.append_off;
-    R.length[k] = b.length;
-    R.toff[3 * k] = b.offx;
-    R.toff[3 * k + 1] = b.offy;
-    R.toff[3 * k + 2] = b.offz;
-    R.last_angle[k] = b.last_angle;
-    R.ap[k] = b.ap;
-    R.pe[k] = b.pe;
-    R.ap_vel[k] = b.apv;
-    R.pe_vel[k] = b.pev;
+    b.vpend = b.ap_pend = b.pe_pend = 0;
+    b.vpx = b.vpy = b.vpz = 0;
+    b.ap_d2 = b.ap_vx = b.ap_vy = b.ap_vz = 0;
+    b.pe_d2 = b.pe_vx = b.pe_vy = b.pe_vz = 0;
 }
 
 // pos.cast<float>() / AU  (src/Trail.cpp:53,64): narrow first, divide in double, narrow again.
@@ -79,6 +83,56 @@ __device__ __forceinline__ void vert_write(RecordPtrs const& R, BodyRec const& b
     v[0] = x;
     v[1] = y;
     v[2] = z;
+}
+
+__device__ __forceinline__ double length3(double x, double y, double z) {
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+}
+
+// Trail::change_current (src/Trail.cpp:105-110) for the position remembered by the last decimated push.
+__device__ __forceinline__ void trail_flush_vertex(RecordPtrs const& R, BodyRec& b) {
+    if (!b.vpend)
+        return;
+    float fx = to_vertex1(b.vpx), fy = to_vertex1(b.vpy), fz = to_vertex1(b.vpz);
+    if (b.append_off == 1)
+        vert_write(R, b, b.length - 1, fx, fy, fz);
+    vert_write(R, b, b.append_off - 1, fx, fy, fz);
+    b.vpend = 0;
+}
+
+__device__ __forceinline__ void ap_flush(BodyRec& b) {
+    if (b.ap_pend) {
+        b.ap = __dsqrt_rn(b.ap_d2);
+        b.apv = length3(b.ap_vx, b.ap_vy, b.ap_vz);
+        b.ap_pend = 0;
+    }
+}
+
+__device__ __forceinline__ void pe_flush(BodyRec& b) {
+    if (b.pe_pend) {
+        b.pe = __dsqrt_rn(b.pe_d2);
+        b.pev = length3(b.pe_vx, b.pe_vy, b.pe_vz);
+        b.pe_pend = 0;
+    }
+}
+
+// Settles everything deferred and writes the per-body state back.
+__device__ __forceinline__ void rec_store(RecordPtrs const& R, int k, BodyRec& b) {
+    trail_flush_vertex(R, b);
+    ap_flush(b);
+    pe_flush(b);
+    R.hist_start[k] = b.hist_start;
+    R.hist_len[k] = b.hist_len;
+    R.append_off[k] = b.append_off;
+    R.length[k] = b.length;
+    R.toff[3 * k] = b.offx;
+    R.toff[3 * k + 1] = b.offy;
+    R.toff[3 * k + 2] = b.offz;
+    R.last_angle[k] = b.last_angle;
+    R.ap[k] = b.ap;
+    R.pe[k] = b.pe;
+    R.ap_vel[k] = b.apv;
+    R.pe_vel[k] = b.pev;
 }
 
 // History::move_forward on the m_side == 0 branch (the only one World::update reaches).
@@ -105,6 +159,7 @@ __device__ __forceinline__ void history_push(RecordPtrs const& R, int k, BodyRec
 __device__ __forceinline__ void trail_recalculate(RecordPtrs const& R, BodyRec& b, double ox, double oy, double oz) {
     if (b.offx == ox && b.offy == oy && b.offz == oz)
         return;
+    trail_flush_vertex(R, b);
     float ax = to_vertex1(b.offx), ay = to_vertex1(b.offy), az = to_vertex1(b.offz);
     float bx = to_vertex1(ox), by = to_vertex1(oy), bz = to_vertex1(oz);
     float* v = R.verts + b.voff * 3;
@@ -120,36 +175,33 @@ __device__ __forceinline__ void trail_recalculate(RecordPtrs const& R, BodyRec& 
 
 // Trail::push_back (src/Trail.cpp:49-75) incl. change_current (:105-110)
 __device__ __forceinline__ void trail_push(RecordPtrs const& R, BodyRec& b, double px, double py, double pz) {
-    float fx = to_vertex1(px), fy = to_vertex1(py), fz = to_vertex1(pz);
     if (b.length == 1) {
-        vert_write(R, b, b.append_off, fx, fy, fz);
+        vert_write(R, b, b.append_off, to_vertex1(px), to_vertex1(py), to_vertex1(pz));
         b.append_off++;
         b.length++;
     }
     double ang = 0;
     bool have_ang = false;
     if (b.length >= 3 && b.append_off != 0) {
-        // |atan2(y, x) - last| <= 2 pi / capacity decides between moving the newest vertex and appending.
-        // A binary32 estimate (error < 2e-6 rad incl. the narrowing of x, y) settles every case that is
-        // not within 8e-6 rad of the threshold; only those, and appends (which must store the angle),
-        // pay for the binary64 atan2.
-        double const thr = b.thr;
         double est = fabs((double)atan2f((float)py, (float)px) - b.last_angle);
         bool decimate;
-        if (est < thr - 8e-6 && fabs(px) < 3e38 && fabs(py) < 3e38)
+        if (est < b.thr - 8e-6 && fabs(px) < 3e38 && fabs(py) < 3e38)
             decimate = true;
         else {
             ang = atan2(py, px);
             have_ang = true;
-            decimate = fabs(__dsub_rn(ang, b.last_angle)) <= thr;
+            decimate = fabs(__dsub_rn(ang, b.last_angle)) <= b.thr;
         }
-        if (decimate) {
-            if (b.append_off == 1)
-                vert_write(R, b, b.length - 1, fx, fy, fz);
-            vert_write(R, b, b.append_off - 1, fx, fy, fz);
+        if (decimate) { // change_current(pos): remembered, written when something can observe it
+            b.vpend = 1;
+            b.vpx = px;
+            b.vpy = py;
+            b.vpz = pz;
             return;
         }
     }
+    trail_flush_vertex(R, b);
+    float fx = to_vertex1(px), fy = to_vertex1(py), fz = to_vertex1(pz);
     vert_write(R, b, b.append_off, fx, fy, fz);
     b.append_off++;
     if (b.length < b.cap)
@@ -161,8 +213,52 @@ __device__ __forceinline__ void trail_push(RecordPtrs const& R, BodyRec& b, doub
     b.last_angle = have_ang ? ang : atan2(py, px);
 }
 
-__device__ __forceinline__ double length3(double x, double y, double z) {
-    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+// m_ap / m_ap_vel (src/Object.cpp:115-118): `if (ap < d) { ap = d; ap_vel = |v| }`, d = RN(sqrt(d2)).
+// RN o sqrt is monotone, so d2 <= (pending d2) means "no update"; a d2 more than 1e-15 (relative)
+// above the reference square means d is strictly greater; in between, the exact path decides.
+__device__ __forceinline__ void apoapsis_step(BodyRec& b, double d2, double vx, double vy, double vz) {
+    double ref2 = b.ap_pend ? b.ap_d2 : __dmul_rn(b.ap, b.ap);
+    double lo = b.ap_pend ? ref2 : ref2 * (1.0 - 1e-15);
+    double hi = ref2 * (1.0 + 1e-15);
+    if (d2 <= lo)
+        return;
+    if (d2 > hi) {
+        b.ap_pend = 1;
+        b.ap_d2 = d2;
+        b.ap_vx = vx;
+        b.ap_vy = vy;
+        b.ap_vz = vz;
+        return;
+    }
+    ap_flush(b);
+    double d = __dsqrt_rn(d2);
+    if (b.ap < d) {
+        b.ap = d;
+        b.apv = length3(vx, vy, vz);
+    }
+}
+
+// m_pe / m_pe_vel (src/Object.cpp:120-123): `if (pe > d) { pe = d; pe_vel = |v| }`
+__device__ __forceinline__ void periapsis_step(BodyRec& b, double d2, double vx, double vy, double vz) {
+    double ref2 = b.pe_pend ? b.pe_d2 : __dmul_rn(b.pe, b.pe);
+    double hi = b.pe_pend ? ref2 : ref2 * (1.0 + 1e-15);
+    double lo = ref2 * (1.0 - 1e-15);
+    if (d2 >= hi)
+        return;
+    if (d2 < lo) {
+        b.pe_pend = 1;
+        b.pe_d2 = d2;
+        b.pe_vx = vx;
+        b.pe_vy = vy;
+        b.pe_vz = vz;
+        return;
+    }
+    pe_flush(b);
+    double d = __dsqrt_rn(d2);
+    if (b.pe > d) {
+        b.pe = d;
+        b.pev = length3(vx, vy, vz);
+    }
 }
 
 // Object::update(speed > 0) for one non-deleted body.  pos_of(j, x, y, z) yields the final
@@ -175,6 +271,7 @@ __device__ __forceinline__ void record_body(RecordPtrs const& R, int k, BodyRec&
     double mx = 0, my = 0, mz = 0;
     if (most >= 0)
         pos_of(most, mx, my, mz);
+    double dx = __dsub_rn(px, mx), dy = __dsub_rn(py, my), dz = __dsub_rn(pz, mz);
     if (offset_trails && most >= 0 && !forward_sim) {
         if (most != old_most)
             trail_recalculate(R, b, mx, my, mz);
@@ -183,32 +280,17 @@ __device__ __forceinline__ void record_body(RecordPtrs const& R, int k, BodyRec&
             b.offy = my;
             b.offz = mz;
         }
-        trail_push(R, b, __dsub_rn(px, mx), __dsub_rn(py, my), __dsub_rn(pz, mz));
+        trail_push(R, b, dx, dy, dz);
     } else {
         trail_recalculate(R, b, 0.0, 0.0, 0.0);
         trail_push(R, b, px, py, pz);
     }
     if (most < 0)
         return;
-    // ap / pe (src/Object.cpp:111-123).  The exact distance (IEEE sqrt) is needed only when it sets a
-    // new extreme; an estimate good to 1e-14 rules that out on most steps.
-    double dx = __dsub_rn(px, mx), dy = __dsub_rn(py, my), dz = __dsub_rn(pz, mz);
+    // ap / pe against the most attracting object (src/Object.cpp:111-123)
     double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    double y0 = rsqrt_seed(d2);
-    double t = d2 * y0;
-    double e = fma(-t, y0, 1.0);
-    double est = fma(t * e, fma(0.375, e, 0.5), t); // ~ sqrt(d2)
-    if (est * (1.0 + 1e-12) < b.ap && est * (1.0 - 1e-12) > b.pe)
-        return;
-    double d = __dsqrt_rn(d2);
-    if (b.ap < d) {
-        b.ap = d;
-        b.apv = length3(vx, vy, vz);
-    }
-    if (b.pe > d) {
-        b.pe = d;
-        b.pev = length3(vx, vy, vz);
-    }
+    apoapsis_step(b, d2, vx, vy, vz);
+    periapsis_step(b, d2, vx, vy, vz);
 }
 
 } // namespace essa
