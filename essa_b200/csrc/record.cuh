@@ -116,11 +116,9 @@ __device__ __forceinline__ void pe_flush(BodyRec& b) {
     }
 }
 
-// Settles everything deferred and writes the per-body state back.
-__device__ __forceinline__ void rec_store(RecordPtrs const& R, int k, BodyRec& b) {
+// Settles everything deferred and writes the per-body state back (trail / history part).
+__device__ __forceinline__ void rec_store_trail(RecordPtrs const& R, int k, BodyRec& b) {
     trail_flush_vertex(R, b);
-    ap_flush(b);
-    pe_flush(b);
     R.hist_start[k] = b.hist_start;
     R.hist_len[k] = b.hist_len;
     R.append_off[k] = b.append_off;
@@ -129,10 +127,21 @@ __device__ __forceinline__ void rec_store(RecordPtrs const& R, int k, BodyRec& b
     R.toff[3 * k + 1] = b.offy;
     R.toff[3 * k + 2] = b.offz;
     R.last_angle[k] = b.last_angle;
+}
+
+// ... and the ap / pe part.
+__device__ __forceinline__ void rec_store_appe(RecordPtrs const& R, int k, BodyRec& b) {
+    ap_flush(b);
+    pe_flush(b);
     R.ap[k] = b.ap;
     R.pe[k] = b.pe;
     R.ap_vel[k] = b.apv;
     R.pe_vel[k] = b.pev;
+}
+
+__device__ __forceinline__ void rec_store(RecordPtrs const& R, int k, BodyRec& b) {
+    rec_store_trail(R, k, b);
+    rec_store_appe(R, k, b);
 }
 
 // History::move_forward on the m_side == 0 branch (the only one World::update reaches).
@@ -261,36 +270,47 @@ __device__ __forceinline__ void periapsis_step(BodyRec& b, double d2, double vx,
     }
 }
 
-// Object::update(speed > 0) for one non-deleted body.  pos_of(j, x, y, z) yields the final
-// position of body j (the drift of every body is finished before any update() runs).
-template<class PosOf>
-__device__ __forceinline__ void record_body(RecordPtrs const& R, int k, BodyRec& b, double px, double py, double pz, double vx, double vy,
-    double vz, int most, int old_most, bool offset_trails, bool forward_sim, PosOf pos_of) {
+// Object::update(speed > 0) for one non-deleted body, in two independent halves so that they can
+// run on different warps.  (mx, my, mz) is the final position of the most attracting object (the
+// drift of every body is finished before any update() runs); ignored when most < 0.
+//
+// Half 1: History::move_forward + recalculate_trails_with_offset / Trail::push_back.
+__device__ __forceinline__ void record_trail(RecordPtrs const& R, int k, BodyRec& b, double px, double py, double pz, double vx, double vy,
+    double vz, double mx, double my, double mz, int most, int old_most, bool offset_trails, bool forward_sim) {
     if (!forward_sim)
         history_push(R, k, b, px, py, pz, vx, vy, vz);
-    double mx = 0, my = 0, mz = 0;
-    if (most >= 0)
-        pos_of(most, mx, my, mz);
-    double dx = __dsub_rn(px, mx), dy = __dsub_rn(py, my), dz = __dsub_rn(pz, mz);
-    if (offset_trails && most >= 0 && !forward_sim) {
-        if (most != old_most)
-            trail_recalculate(R, b, mx, my, mz);
-        else {
-            b.offx = mx;
-            b.offy = my;
-            b.offz = mz;
-        }
-        trail_push(R, b, dx, dy, dz);
+    bool const rel = offset_trails && most >= 0 && !forward_sim;
+    double ox = rel ? mx : 0.0, oy = rel ? my : 0.0, oz = rel ? mz : 0.0;
+    if (rel && most == old_most) { // Trail::set_offset
+        b.offx = ox;
+        b.offy = oy;
+        b.offz = oz;
     } else {
-        trail_recalculate(R, b, 0.0, 0.0, 0.0);
-        trail_push(R, b, px, py, pz);
+        trail_recalculate(R, b, ox, oy, oz);
     }
+    // pos - most.pos, or pos itself (x - 0.0 == x exactly)
+    trail_push(R, b, rel ? __dsub_rn(px, mx) : px, rel ? __dsub_rn(py, my) : py, rel ? __dsub_rn(pz, mz) : pz);
+}
+
+// Half 2: ap / pe against the most attracting object (src/Object.cpp:111-123).
+__device__ __forceinline__ void record_appe(BodyRec& b, double px, double py, double pz, double vx, double vy, double vz, double mx,
+    double my, double mz, int most) {
     if (most < 0)
         return;
-    // ap / pe against the most attracting object (src/Object.cpp:111-123)
+    double dx = __dsub_rn(px, mx), dy = __dsub_rn(py, my), dz = __dsub_rn(pz, mz);
     double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     apoapsis_step(b, d2, vx, vy, vz);
     periapsis_step(b, d2, vx, vy, vz);
+}
+
+template<class PosOf>
+__device__ __forceinline__ void record_body(RecordPtrs const& R, int k, BodyRec& b, double px, double py, double pz, double vx, double vy,
+    double vz, int most, int old_most, bool offset_trails, bool forward_sim, PosOf pos_of) {
+    double mx = 0, my = 0, mz = 0;
+    if (most >= 0)
+        pos_of(most, mx, my, mz);
+    record_trail(R, k, b, px, py, pz, vx, vy, vz, mx, my, mz, most, old_most, offset_trails, forward_sim);
+    record_appe(b, px, py, pz, vx, vy, vz, mx, my, mz, most);
 }
 
 } // namespace essa

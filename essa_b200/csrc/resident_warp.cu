@@ -1,7 +1,7 @@
 // K3w -- resident kernel for worlds of up to 32 bodies (the Solar System template has 10): the whole
 // World::update loop (src/World.cpp:86-139) runs inside ONE WARP, so a KDK step never crosses a
-// block barrier, and Object::update's recording (History / Trail / ap-pe, record.cuh) runs on a
-// SECOND warp that consumes per-step snapshots from a shared-memory ring (mbarrier full / empty
+// block barrier, and Object::update's recording (record.cuh) runs on TWO MORE warps (History +
+// Trail on one, ap / pe on the other) that consume per-step snapshots from a shared-memory ring (mbarrier full / empty
 // hand-off) -- off the physics critical path.  Fast arithmetic only; exact_order worlds go through
 // resident.cu.
 //
@@ -113,7 +113,7 @@ __device__ __forceinline__ void lane_forces(int k, int q, int L, int iters, int 
 }
 
 template<int P, bool ARGMAX>
-__global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
+__global__ void __launch_bounds__(96, 1) k_resident_warp(WarpArgs const A) {
     __shared__ double sx[32], sy[32], sz[32], sg[32];
     __shared__ Snapshot ring[kRing];
     __shared__ __align__(8) unsigned long long full[kRing], empty[kRing];
@@ -128,14 +128,14 @@ __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < kRing; i++) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], 2); // both recorder warps release a slot
         }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == 1) {
-        // ---------------- recorder warp ----------------
+    if (warp >= 1) {
+        // ---------------- recorder warps: 1 = History + Trail, 2 = ap / pe ----------------
         if (!rec_on)
             return;
         bool const mine = lane < n && lane < A.r.tracked;
@@ -147,19 +147,25 @@ __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
             mbar_wait(&full[slot], (unsigned)(s / kRing) & 1u);
             Snapshot const& sn = ring[slot];
             if (mine && ((sn.active_mask >> lane) & 1u)) {
-                record_body(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], sn.most[lane],
-                    sn.old_most[lane], A.offset_trails != 0, A.forward_sim != 0, [&](int j, double& ox, double& oy, double& oz) {
-                        ox = sn.x[j];
-                        oy = sn.y[j];
-                        oz = sn.z[j];
-                    });
+                int const most = sn.most[lane];
+                int const mi = most >= 0 ? most : 0;
+                double const mx = sn.x[mi], my = sn.y[mi], mz = sn.z[mi];
+                if (warp == 1)
+                    record_trail(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], mx, my, mz, most,
+                        sn.old_most[lane], A.offset_trails != 0, A.forward_sim != 0);
+                else
+                    record_appe(b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], mx, my, mz, most);
             }
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&empty[slot]);
         }
-        if (mine)
-            rec_store(A.r, lane, b);
+        if (mine) {
+            if (warp == 1)
+                rec_store_trail(A.r, lane, b);
+            else
+                rec_store_appe(A.r, lane, b);
+        }
         return;
     }
 
@@ -296,9 +302,9 @@ __global__ void __launch_bounds__(64, 1) k_resident_warp(WarpArgs const A) {
 template<int P>
 static void launch_P(bool argmax, WarpArgs const& A, cudaStream_t st) {
     if (argmax)
-        k_resident_warp<P, true><<<1, 64, 0, st>>>(A);
+        k_resident_warp<P, true><<<1, 96, 0, st>>>(A);
     else
-        k_resident_warp<P, false><<<1, 64, 0, st>>>(A);
+        k_resident_warp<P, false><<<1, 96, 0, st>>>(A);
 }
 
 cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st) {
