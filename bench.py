@@ -285,7 +285,7 @@ def run_ours(args):
         dist.broadcast(uid, 0)
         ctx.shard_attach(rank, world_size, uid.cpu().numpy())
     kernel = {"auto": capi.KERNEL_AUTO, "tiled": capi.KERNEL_TILED, "paired": capi.KERNEL_PAIRED}[args.kernel]
-    paired = args.kernel == "paired" or (args.kernel == "auto" and world_size == 1 and n >= 32768)
+    paired = args.kernel == "paired" or (args.kernel == "auto" and n >= 32768 and n % (1024 * world_size) == 0)
     opts = capi.Context.opts(dt, kernel=kernel)
 
     peak = ctx.measure_fp64_peak(300.0) if rank == 0 else 0.0
@@ -382,7 +382,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": name, "n": n, "dt_seconds": dt, "sharding": "targets/%d + NCCL position all-gather per pass" % world_size
+            "config": {"workload": name, "n": n, "dt_seconds": dt, "sharding": "targets/%d: NCCL gather of drifted positions + reduce-scatter of pair-shared partial accelerations per pass" % world_size
                        if world_size > 1 else "single GPU", "l2": "flushed (256 MiB memset) between timed steps",
                        "passes_per_step": passes / args.steps, "timing": "CUDA events on the launching stream around each essa_step, max over ranks"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "energy_drift": drift,

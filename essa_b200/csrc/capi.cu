@@ -54,6 +54,7 @@ struct NcclApi {
     int (*AllGather)(void const*, void*, size_t, int, ncclComm*, cudaStream_t) = nullptr;
     int (*Broadcast)(void const*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
     int (*AllReduce)(void const*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(void const*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     char const* (*GetErrorString)(int) = nullptr;
@@ -84,11 +85,12 @@ NcclApi& nccl() {
     SYM(AllGather, "ncclAllGather");
     SYM(Broadcast, "ncclBroadcast");
     SYM(AllReduce, "ncclAllReduce");
+    SYM(ReduceScatter, "ncclReduceScatter");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
-    if (!api.GetUniqueId || !api.CommInitRank || !api.Broadcast || !api.GroupStart || !api.GroupEnd || !api.AllReduce) {
+    if (!api.GetUniqueId || !api.CommInitRank || !api.Broadcast || !api.GroupStart || !api.GroupEnd || !api.AllReduce || !api.ReduceScatter) {
         api.why = "libnccl.so.2 lacks required symbols";
         dlclose(api.lib);
         api.lib = nullptr;
@@ -555,7 +557,24 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
     }
     CK(cudaEventRecord(e0, ctx->stream));
     if (ctx->use_paired) {
-        CK(launch_force_paired(ctx, k, eps2, ctx->stream));
+        if (ctx->gather_pending) { // the pair kernel walks the whole ring of blocks: all positions must be in
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
+            ctx->gather_pending = false;
+        }
+        double* acc = nullptr;
+        int npad = 0;
+        CK(launch_force_paired_compute(ctx, eps2, ctx->stream, &acc, &npad));
+        if (ctx->world > 1) {
+            // every rank holds J-side sums for every body: reduce-scatter them onto the owners (in place)
+            size_t cnt = (size_t)n / ctx->world;
+            NK(nccl().GroupStart());
+            for (int c3 = 0; c3 < 3; c3++) {
+                double* base = acc + (size_t)c3 * npad;
+                NK(nccl().ReduceScatter(base, base + (size_t)ctx->rank * cnt, cnt, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream));
+            }
+            NK(nccl().GroupEnd());
+        }
+        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc));
     } else if (ctx->world == 1 || !ctx->gather_pending) {
         int S;
         choose_split(ctx, iblocks, (n + kTileJ - 1) / kTileJ, &S);
@@ -593,14 +612,14 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
         // pair-shared kernel: single context, no argmax bookkeeping, slots must fit comfortably
         int nb, S;
         size_t slot_d = 0, part_d = 0;
-        bool can = ctx->world == 1 && !argmax && paired_plan(ctx, &nb, &S, &slot_d, &part_d);
+        bool can = !argmax && paired_plan(ctx, &nb, &S, &slot_d, &part_d);
         if (can && (slot_d + part_d) * sizeof(double) > ctx->pair_slots_n * sizeof(double)) {
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
             can = (slot_d + part_d) * sizeof(double) < free_b / 2 + ctx->pair_slots_n * sizeof(double);
         }
         if (o.kernel == ESSA_KERNEL_PAIRED && !can) {
-            ctx->err = "pair-shared kernel needs an unsharded world of >= 2048 bodies without most-attracting tracking, and room for its slots";
+            ctx->err = "pair-shared kernel needs >= 1025 bodies (a multiple of 1024 x ranks when sharded), no most-attracting tracking, and room for its slots";
             return ESSA_ERR_ARG;
         }
         ctx->use_paired = can && (o.kernel == ESSA_KERNEL_PAIRED || (o.kernel == ESSA_KERNEL_AUTO && ctx->n >= 32768));

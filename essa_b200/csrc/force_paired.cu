@@ -242,7 +242,40 @@ struct PairFinishArgs {
     int nb, dmax, S, ib0, ib1, npad;
     double const* part_i;
     double const* slots;
+    double const* ajred; // sharded: [3][npad] J-side sums already reduced over ranks (slots are skipped)
 };
+
+// J-side contributions to body g from the tiles whose I block lies in [ib0, ib1), in offset order.
+__device__ __forceinline__ void slot_sum(int g, int nb, int dmax, int ib0, int ib1, double const* slots, double& ax, double& ay,
+    double& az) {
+    int const K = g / kPB, jl = g - K * kPB;
+    for (int d = 1; d <= dmax; d++) {
+        int I = K - d;
+        if (I < 0)
+            I += nb;
+        if ((nb & 1) == 0 && d == nb / 2 && I >= nb / 2)
+            continue; // that tile belongs to the other half of the ring
+        if (I < ib0 || I >= ib1)
+            continue;
+        double const* s = slots + ((size_t)(I - ib0) * dmax + (d - 1)) * 3 * kPB + jl;
+        ax = __dadd_rn(ax, __ldcg(s));
+        ay = __dadd_rn(ay, __ldcg(s + kPB));
+        az = __dadd_rn(az, __ldcg(s + 2 * kPB));
+    }
+}
+
+// Sharded worlds: this rank's J-side sums for EVERY body, to be reduce-scattered over the ranks.
+__global__ void __launch_bounds__(256) k_pair_gather_slots(int nb, int dmax, int ib0, int ib1, int npad, double const* slots,
+    double* acc) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= npad)
+        return;
+    double ax = 0, ay = 0, az = 0;
+    slot_sum(g, nb, dmax, ib0, ib1, slots, ax, ay, az);
+    acc[g] = ax;
+    acc[(size_t)npad + g] = ay;
+    acc[2 * (size_t)npad + g] = az;
+}
 
 __global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
     int g = A.i0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,19 +288,12 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
         ay = __dadd_rn(ay, __ldcg(p + A.npad));
         az = __dadd_rn(az, __ldcg(p + 2 * (size_t)A.npad));
     }
-    int const K = g / kPB, jl = g - K * kPB;
-    for (int d = 1; d <= A.dmax; d++) {
-        int I = K - d;
-        if (I < 0)
-            I += A.nb;
-        if ((A.nb & 1) == 0 && d == A.nb / 2 && I >= A.nb / 2)
-            continue; // that tile belongs to the other half of the ring
-        if (I < A.ib0 || I >= A.ib1)
-            continue;
-        double const* s = A.slots + ((size_t)(I - A.ib0) * A.dmax + (d - 1)) * 3 * kPB + jl;
-        ax = __dadd_rn(ax, __ldcg(s));
-        ay = __dadd_rn(ay, __ldcg(s + kPB));
-        az = __dadd_rn(az, __ldcg(s + 2 * kPB));
+    if (A.ajred) {
+        ax = __dadd_rn(ax, __ldcg(A.ajred + g));
+        ay = __dadd_rn(ay, __ldcg(A.ajred + (size_t)A.npad + g));
+        az = __dadd_rn(az, __ldcg(A.ajred + 2 * (size_t)A.npad + g));
+    } else {
+        slot_sum(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots, ax, ay, az);
     }
     // ---- epilogue: identical to force_tiled.cu finish_body (no argmax in this kernel) ----
     WorldPtrs const& W = A.w;
@@ -308,12 +334,18 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
     }
 }
 
-// Can this world go through the pair-shared kernel?  (single context, no argmax, slots fit)
+// Can this world go through the pair-shared kernel?  Whole 1024-body blocks per rank, no argmax,
+// slots must fit.  Sharded: rank g owns I blocks [nb g / G, nb (g+1) / G) = its own targets.
 bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles) {
     int n = c->n;
     int nb = (n + kPB - 1) / kPB;
     if (nb < 2 || (size_t)nb * kPB > (size_t)c->cap)
         return false;
+    if (c->world > 1 && (n % (kPB * c->world)) != 0)
+        return false;
+    int own = nb / c->world;
+    if (c->world == 1)
+        own = nb;
     int dmax = nb / 2;
     // chunks of the offset range: minimise waves(1 CTA / SM) x offsets per chunk
     long long slots = c->sm_count;
@@ -321,7 +353,7 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
     long long best = -1;
     int smax = dmax + 1 < 16 ? dmax + 1 : 16;
     for (int S = 1; S <= smax; S++) {
-        long long waves = ((long long)nb * S + slots - 1) / slots;
+        long long waves = ((long long)own * S + slots - 1) / slots;
         long long cost = waves * ((dmax + 1 + S - 1) / S);
         if (best < 0 || cost < best) {
             best = cost;
@@ -330,12 +362,19 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
     }
     *nb_out = nb;
     *S_out = bestS;
-    *slot_doubles = (size_t)nb * dmax * 3 * kPB;
-    *part_doubles = (size_t)bestS * 3 * nb * kPB;
+    *slot_doubles = (size_t)own * dmax * 3 * kPB;
+    *part_doubles = (size_t)bestS * 3 * nb * kPB + (c->world > 1 ? (size_t)3 * nb * kPB : 0);
     return true;
 }
 
-cudaError_t launch_force_paired(essa_ctx* c, KickArgs const& k, double eps2, cudaStream_t st) {
+static void pair_geometry(essa_ctx const* c, int nb, int* ib0, int* ib1) {
+    *ib0 = (int)((long long)nb * c->rank / c->world);
+    *ib1 = (int)((long long)nb * (c->rank + 1) / c->world);
+}
+
+// Phase 1: the pair kernel over this rank's I blocks; sharded worlds also fold their slots into
+// acc[3][npad] (returned through *acc_out) for the caller to reduce-scatter over the ranks.
+cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out) {
     int nb, S;
     size_t slot_d, part_d;
     if (!paired_plan(c, &nb, &S, &slot_d, &part_d))
@@ -370,32 +409,55 @@ cudaError_t launch_force_paired(essa_ctx* c, KickArgs const& k, double eps2, cud
     A.nb = nb;
     A.dmax = nb / 2;
     A.S = S;
-    A.ib0 = 0;
-    A.ib1 = nb;
+    pair_geometry(c, nb, &A.ib0, &A.ib1);
     A.npad = nb * kPB;
     A.part_i = c->pair_part;
     A.slots = c->pair_slots;
     A.eps2 = eps2;
-    k_force_paired<<<nb * S, kPThreads, kPSmem, st>>>(A);
+    k_force_paired<<<(A.ib1 - A.ib0) * S, kPThreads, kPSmem, st>>>(A);
+    c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         return e;
+    double* acc = nullptr;
+    if (c->world > 1) {
+        acc = c->pair_part + (size_t)S * 3 * A.npad;
+        k_pair_gather_slots<<<(A.npad + 255) / 256, 256, 0, st>>>(nb, A.dmax, A.ib0, A.ib1, A.npad, c->pair_slots, acc);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (acc_out)
+        *acc_out = acc;
+    if (npad_out)
+        *npad_out = A.npad;
+    return e;
+}
+
+// Phase 2: ordered sums + kick / drift epilogue for this rank's targets.
+cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred) {
+    int nb, S;
+    size_t slot_d, part_d;
+    if (!paired_plan(c, &nb, &S, &slot_d, &part_d))
+        return cudaErrorInvalidConfiguration;
     PairFinishArgs F;
     F.w = world_ptrs(c);
     F.k = k;
     F.n = c->n;
-    F.i0 = 0;
-    F.i1 = c->n;
+    F.i0 = (int)((long long)c->n * c->rank / c->world);
+    F.i1 = (int)((long long)c->n * (c->rank + 1) / c->world);
     F.nb = nb;
     F.dmax = nb / 2;
     F.S = S;
-    F.ib0 = 0;
-    F.ib1 = nb;
+    pair_geometry(c, nb, &F.ib0, &F.ib1);
     F.npad = nb * kPB;
     F.part_i = c->pair_part;
     F.slots = c->pair_slots;
-    k_pair_finish<<<(c->n + 255) / 256, 256, 0, st>>>(F);
-    c->launches += 2;
+    F.ajred = ajred;
+    int cnt = F.i1 - F.i0;
+    if (cnt <= 0)
+        return cudaSuccess;
+    k_pair_finish<<<(cnt + 255) / 256, 256, 0, st>>>(F);
+    c->launches++;
     return cudaGetLastError();
 }
 

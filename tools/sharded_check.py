@@ -27,15 +27,16 @@ def main():
         uid.copy_(torch.from_numpy(capi.nccl_unique_id()))
     dist.broadcast(uid, 0)
     ok = True
-    for n, steps in ((4099, 6), (70001, 3)):
+    for n, steps, kern in ((4099, 6, capi.KERNEL_TILED), (70001, 3, capi.KERNEL_TILED), (8192 * world, 4, capi.KERNEL_PAIRED),
+                           (65536, 3, capi.KERNEL_AUTO)):
         w = synth.plummer(n, seed=21)
         dt = synth.default_dt(n)
         ctx = capi.Context(local)
-        ctx.shard_attach(rank, world, uid.cpu().numpy()) if n == 4099 else ctx.shard_attach(rank, world, uid2.cpu().numpy())
+        ctx.shard_attach(rank, world, uid.cpu().numpy())
         ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
         e0 = ctx.energy()
-        ctx.step(steps, dt, kernel=capi.KERNEL_TILED)
-        ctx.step(-2, dt, kernel=capi.KERNEL_TILED)
+        ctx.step(steps, dt, kernel=kern)
+        ctx.step(-2, dt, kernel=kern)
         got = ctx.download()
         e1 = ctx.energy()
         if rank == 0:
@@ -54,14 +55,14 @@ def main():
             e_ok = abs(e0[1] - r0[1]) <= 1e-12 * abs(r0[1]) and abs(e1[0] - r1[0]) <= 1e-10 * abs(r1[0])
             good = worst <= 1e-10 and e_ok and ctx.date == ref.date
             ok = ok and good
-            print("sharded_check n=%d ranks=%d worst_rel=%.3e energy_ok=%s -> %s" % (n, world, worst, e_ok, "PASS" if good else "FAIL"), flush=True)
+            print("sharded_check kernel=%d n=%d ranks=%d worst_rel=%.3e energy_ok=%s -> %s" % (kern, n, world, worst, e_ok, "PASS" if good else "FAIL"), flush=True)
             ref.close()
         ctx.close()
-        if n == 4099:  # a fresh communicator for the second world
-            uid2 = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                uid2.copy_(torch.from_numpy(capi.nccl_unique_id()))
-            dist.broadcast(uid2, 0)
+        # a fresh communicator for the next world
+        uid = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.from_numpy(capi.nccl_unique_id()))
+        dist.broadcast(uid, 0)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
