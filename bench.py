@@ -36,6 +36,9 @@ import time
 
 import numpy as np
 
+# NCCL prints "NCCL version ..." on stdout at NCCL_DEBUG=VERSION and above; stdout carries ONE JSON line.
+os.environ["NCCL_DEBUG"] = os.environ.get("ESSA_NCCL_DEBUG", "WARN")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -309,6 +312,7 @@ def run_ours(args):
         dev_ms += ctx.last_step_ms
         force_ms += ctx.last_force_ms
         force_passes += ctx.last_force_passes
+        breakdown = ctx.last_step_breakdown
     barrier()
     t_wall1 = time.time()
     launches = ctx.launches - launches0 - args.steps  # the L2 flush is a memset, not a kernel of ours... count kernels only
@@ -386,7 +390,7 @@ def run_ours(args):
                        if world_size > 1 else "single GPU", "l2": "flushed (256 MiB memset) between timed steps",
                        "passes_per_step": passes / args.steps, "timing": "CUDA events on the launching stream around each essa_step, max over ranks"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "energy_drift": drift,
-            "wall_ms_per_step": 1e3 * (t_wall1 - t_wall0) / args.steps}
+            "wall_ms_per_step": 1e3 * (t_wall1 - t_wall0) / args.steps, "last_step_breakdown_rank0": breakdown}
     if world_size == 1 and not args.no_extra:
         line["cpu_baseline"] = cpu_baseline(w, n)
         try:

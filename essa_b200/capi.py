@@ -70,6 +70,7 @@ SYMBOLS = [
     ("essa_last_step_ms", C.c_double, [_P]),
     ("essa_last_force_ms", C.c_double, [_P]),
     ("essa_last_force_passes", C.c_int, [_P]),
+    ("essa_last_step_breakdown", C.c_int, [_P, _dp]),
     ("essa_sync", C.c_int, [_P]),
     ("essa_upload", C.c_int, [_P, C.c_int, C.POINTER(Bodies)]),
     ("essa_download", C.c_int, [_P, C.POINTER(Bodies)]),
@@ -327,6 +328,12 @@ class Context:
     @property
     def last_force_passes(self):
         return self._L.essa_last_force_passes(self._h)
+
+    @property
+    def last_step_breakdown(self):
+        out = np.zeros(4)
+        self._L.essa_last_step_breakdown(self._h, _ptr(out, _dp))
+        return dict(zip(("step_ms", "force_ms", "pre_ms", "post_ms"), out.tolist()))
 
     def measure_fp64_peak(self, ms=200.0):
         v = self._L.essa_measure_fp64_peak(self._h, float(ms))

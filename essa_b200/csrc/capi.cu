@@ -309,6 +309,15 @@ extern "C" double essa_interaction_count(const essa_ctx* c) { return c ? c->inte
 extern "C" double essa_last_step_ms(const essa_ctx* c) { return c ? c->last_step_ms : 0; }
 extern "C" double essa_last_force_ms(const essa_ctx* c) { return c ? c->last_force_ms : 0; }
 extern "C" int essa_last_force_passes(const essa_ctx* c) { return c ? c->last_force_passes : 0; }
+extern "C" int essa_last_step_breakdown(const essa_ctx* c, double out[4]) {
+    if (!c || !out)
+        return ESSA_ERR_ARG;
+    out[0] = c->last_step_ms;
+    out[1] = c->last_force_ms;
+    out[2] = c->last_pre_ms;
+    out[3] = c->last_post_ms;
+    return ESSA_OK;
+}
 extern "C" int essa_body_count(const essa_ctx* c) { return c ? c->n : 0; }
 extern "C" int64_t essa_get_date(const essa_ctx* c) { return c ? c->date : 0; }
 extern "C" int essa_tracked_count(const essa_ctx* c) { return c ? c->tracked : 0; }
@@ -613,10 +622,10 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
         int nb, S;
         size_t slot_d = 0, part_d = 0;
         bool can = !argmax && paired_plan(ctx, &nb, &S, &slot_d, &part_d);
-        if (can && (slot_d + part_d) * sizeof(double) > ctx->pair_slots_n * sizeof(double)) {
+        if (can && (slot_d > ctx->pair_slots_n || part_d > ctx->pair_part_n)) { // first use at this size: will it fit?
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
-            can = (slot_d + part_d) * sizeof(double) < free_b / 2 + ctx->pair_slots_n * sizeof(double);
+            can = (slot_d + part_d) * sizeof(double) < free_b / 2 + (ctx->pair_slots_n + ctx->pair_part_n) * sizeof(double);
         }
         if (o.kernel == ESSA_KERNEL_PAIRED && !can) {
             ctx->err = "pair-shared kernel needs >= 1025 bodies (a multiple of 1024 x ranks when sharded), no most-attracting tracking, and room for its slots";
@@ -704,6 +713,13 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
     }
     ctx->last_force_ms = total;
     ctx->last_force_passes = (int)(ev / 2);
+    ctx->last_pre_ms = ctx->last_post_ms = 0;
+    if (ev >= 2) {
+        CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->force_events[0]));
+        ctx->last_pre_ms = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->force_events[ev - 1], ctx->ev_end));
+        ctx->last_post_ms = ms;
+    }
     return ESSA_OK;
 }
 

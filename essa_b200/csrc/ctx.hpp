@@ -172,6 +172,7 @@ struct essa_ctx {
     double interactions = 0;
     double last_step_ms = 0;
     double last_force_ms = 0;
+    double last_pre_ms = 0, last_post_ms = 0; // before the first / after the last force pass of the last essa_step
     std::string err;
 
     void* l2_scratch = nullptr;

@@ -118,6 +118,8 @@ double essa_last_step_ms(const essa_ctx* ctx);
 double essa_last_force_ms(const essa_ctx* ctx);
 /* Force passes the last essa_step / essa_ensemble_step evaluated. */
 int essa_last_force_passes(const essa_ctx* ctx);
+/* out = {step ms, force-pass ms, ms before the first force pass, ms after the last} of the last essa_step. */
+int essa_last_step_breakdown(const essa_ctx* ctx, double out[4]);
 int essa_sync(essa_ctx* ctx);
 
 /* ---- world state --------------------------------------------------------------------------- */
