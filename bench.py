@@ -36,8 +36,9 @@ import time
 
 import numpy as np
 
-# NCCL prints "NCCL version ..." on stdout at NCCL_DEBUG=VERSION and above; stdout carries ONE JSON line.
-os.environ["NCCL_DEBUG"] = os.environ.get("ESSA_NCCL_DEBUG", "WARN")
+# NCCL writes its debug output ("NCCL version ..." at NCCL_DEBUG=VERSION and above) to stdout by default;
+# stdout carries ONE JSON line, so NCCL's goes to stderr.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
