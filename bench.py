@@ -38,6 +38,9 @@ import numpy as np
 
 # NCCL writes its debug output ("NCCL version ..." at NCCL_DEBUG=VERSION and above) to stdout by default;
 # stdout carries ONE JSON line, so NCCL's goes to stderr.
+# (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, hence WARN.)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "NONE", ""):
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
