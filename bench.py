@@ -225,31 +225,52 @@ def run_reference(args):
 # Solar System leg (second half of BASELINE.json's metric)
 # --------------------------------------------------------------------------------------------
 def solar_leg():
+    """Small-world half of BASELINE.json's metric: Solar System iterations/s (single trajectory through
+    the World facade, recording on; and the 65,536-copy ensemble aggregate), jupiter_system.essa as a
+    resident single-CTA kernel and as a 65,536-copy ensemble -- each next to the CPU oracle."""
     import oracle
-    from essa_b200 import world
-    path = os.path.join(ROOT, "tests", "golden", "worlds", "solar.essa")
+    from essa_b200 import capi, world
+    wdir = os.path.join(ROOT, "tests", "golden", "worlds")
     out = {}
-    for label, exact, steps in (("fast", False, 1000000), ("exact_order", True, 200000)):
-        pw = world.World.load(path)
-        pw.simulation_seconds_per_tick = 600
-        pw.set_flags(offset_trails=True, exact_order=exact)
-        pw.update(10000)
-        pw.update(steps)
-        out["solar_iters_per_s_" + label] = steps / (pw.last_step_ms * 1e-3)
-        t0 = time.perf_counter()
-        for _ in range(100):
-            pw.update(10)  # the GUI's default: 10 iterations per tick, state read back every tick
-        out["solar_iters_per_s_%s_10_per_call" % label] = 1000 / (time.perf_counter() - t0)
-        pw.close()
-    ow = oracle.World.load(path)
-    ow.dt = 600
-    ow.update(10000)
-    secs = ow.time_update(300000)
-    out["solar_iters_per_s_cpu_oracle"] = 300000 / secs
-    out["solar_note"] = ("worlds/solar.essa, 10 bodies, dt=600 s, History + Trail + ap/pe recording on, offset trails; GPU = one "
-                         "resident CTA, all steps in one launch; CPU = oracle (reference containers, -O2, 1 thread); the README's "
-                         "67,500 it/s (Ryzen 5 5600H, GUI on) is published-not-measured")
-    out["solar_speedup_vs_cpu_oracle"] = out["solar_iters_per_s_fast"] / out["solar_iters_per_s_cpu_oracle"]
+    for fname, tag, big, small in (("solar.essa", "solar", 1000000, 200000), ("jupiter_system.essa", "jupiter", 100000, 20000)):
+        path = os.path.join(wdir, fname)
+        for label, exact, steps in (("fast", False, big), ("exact_order", True, small)):
+            pw = world.World.load(path)
+            pw.simulation_seconds_per_tick = 600
+            pw.set_flags(offset_trails=True, exact_order=exact)
+            pw.update(10000 if tag == "solar" else 1000)
+            pw.update(steps)
+            out["%s_iters_per_s_%s" % (tag, label)] = steps / (pw.last_step_ms * 1e-3)
+            if tag == "solar":
+                t0 = time.perf_counter()
+                for _ in range(100):
+                    pw.update(10)  # the GUI's default: 10 iterations per tick, state read back every tick
+                out["solar_iters_per_s_%s_10_per_call" % label] = 1000 / (time.perf_counter() - t0)
+            st = pw.state()
+            pw.close()
+        ow = oracle.World.load(path)
+        ow.dt = 600
+        ow.update(1000)
+        nsteps = 300000 if tag == "solar" else 5000
+        out["%s_iters_per_s_cpu_oracle" % tag] = nsteps / ow.time_update(nsteps)
+        out["%s_speedup_vs_cpu_oracle" % tag] = out["%s_iters_per_s_fast" % tag] / out["%s_iters_per_s_cpu_oracle" % tag]
+        # 65,536 perturbed copies (forward-simulation semantics: no History)
+        c = capi.Context(0)
+        n = len(st["gf"])
+        c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"])
+        copies, esteps = 65536, (200 if tag == "solar" else 20)
+        c.ensemble_init(copies, 600, seed=7, rel_sigma=1e-6)
+        c.ensemble_step(2)
+        c.ensemble_step(esteps)
+        ms = c.last_step_ms
+        out["%s_ensemble_copy_iters_per_s" % tag] = copies * esteps / (ms * 1e-3)
+        out["%s_ensemble_interactions_per_s" % tag] = copies * (esteps + 1) * n * (n - 1) / (ms * 1e-3)
+        out["%s_ensemble_aggregate_vs_cpu_oracle" % tag] = out["%s_ensemble_copy_iters_per_s" % tag] / out["%s_iters_per_s_cpu_oracle" % tag]
+        c.close()
+    out["note"] = ("dt=600 s, History + Trail + ap/pe recording on, offset trails, through the World facade; GPU single trajectory = one "
+                   "resident CTA, all steps in one launch (latency-bound: a step is a dependent chain, so >=100x the CPU is reachable only "
+                   "in aggregate -- the ensemble lines); CPU = oracle (reference containers, -O2, 1 thread) on this box; the README's "
+                   "67,500 it/s (Ryzen 5 5600H, GUI on) is published-not-measured")
     return out
 
 

@@ -180,6 +180,16 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                     }
                 } else {
                     for (int rot = 0; rot < 32; rot++) {
+                        // the next rotation's positions do not depend on this rotation's arithmetic:
+                        // fetch them first so that only the accumulators travel on the critical path
+                        double nx[kPRJ], ny[kPRJ], nz[kPRJ], ng[kPRJ];
+#pragma unroll
+                        for (int q = 0; q < kPRJ; q++) {
+                            nx[q] = rot1(xj[q], src);
+                            ny[q] = rot1(yj[q], src);
+                            nz[q] = rot1(zj[q], src);
+                            ng[q] = rot1(gj[q], src);
+                        }
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++)
 #pragma unroll
@@ -188,10 +198,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                                     ajx[q], ajy[q], ajz[q]);
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++) {
-                            xj[q] = rot1(xj[q], src);
-                            yj[q] = rot1(yj[q], src);
-                            zj[q] = rot1(zj[q], src);
-                            gj[q] = rot1(gj[q], src);
+                            xj[q] = nx[q];
+                            yj[q] = ny[q];
+                            zj[q] = nz[q];
+                            gj[q] = ng[q];
                             ajx[q] = rot1(ajx[q], src);
                             ajy[q] = rot1(ajy[q], src);
                             ajz[q] = rot1(ajz[q], src);
