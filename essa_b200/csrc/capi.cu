@@ -139,7 +139,7 @@ static int reserve_world(essa_ctx* ctx, int cap) {
         return ESSA_OK;
     // Growing keeps nothing: callers re-upload (essa_upload is the only entry that grows).
     free_world(ctx);
-    cap = (cap + 1023) / 1024 * 1024; // whole 1024-body blocks (force_paired.cu)
+    cap = (cap + 2047) / 2048 * 2048; // whole blocks of the pair-shared kernel (force_paired.cu)
     size_t n = (size_t)cap;
     CK(cudaMalloc(&ctx->pos[0], n * sizeof(double4)));
     CK(cudaMalloc(&ctx->pos[1], n * sizeof(double4)));
@@ -628,7 +628,7 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
             can = (slot_d + part_d) * sizeof(double) < free_b / 2 + (ctx->pair_slots_n + ctx->pair_part_n) * sizeof(double);
         }
         if (o.kernel == ESSA_KERNEL_PAIRED && !can) {
-            ctx->err = "pair-shared kernel needs >= 1025 bodies (a multiple of 1024 x ranks when sharded), no most-attracting tracking, and room for its slots";
+            ctx->err = "pair-shared kernel needs >= 2049 bodies (a multiple of 2048 x ranks when sharded), no most-attracting tracking, and room for its slots";
             return ESSA_ERR_ARG;
         }
         ctx->use_paired = can && (o.kernel == ESSA_KERNEL_PAIRED || (o.kernel == ESSA_KERNEL_AUTO && ctx->n >= 32768));

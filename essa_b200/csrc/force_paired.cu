@@ -7,15 +7,16 @@
 // 21 FP64-pipe instructions per pair = 10.5 per directed interaction (K1 needs 17), which lifts the
 // ceiling of the 20-flop-per-interaction roofline from 58.8 % to 95 %.
 //
-// Decomposition.  Bodies are cut into blocks of 1024.  Unordered block pairs are enumerated as
+// Decomposition.  Bodies are cut into blocks of 2048.  Unordered block pairs are enumerated as
 // (I, J = I + d mod nb), d = 0 .. nb/2, so that every block does the same amount of work.  One CTA
-// (8 warps) owns block I for its whole life: warp w keeps targets [128 w, 128 w + 128) of the block
-// in registers (4 per lane).  A J block arrives through the TMA unit (cp.async.bulk + mbarrier) in
-// two 512-record halves; each warp walks it in 64-body subsets, 2 bodies per lane, and ROTATES the
+// (8 warps) owns block I for its whole life: warp w keeps targets [256 w, 256 w + 256) of the block
+// in registers (8 per lane).  A J block arrives through the TMA unit (cp.async.bulk + mbarrier) in
+// four 512-record parts; each warp walks a part in 32-body subsets, 1 body per lane, and ROTATES the
 // subset -- positions, gf and the subset's own accumulators -- around the warp with shuffles, so
-// that after 32 rotations all 128 x 64 pairs of (targets, subset) have been visited with nothing
-// but registers.  The subset's accumulated a_j goes to a per-warp shared-memory array; after a
-// half, the 8 warps' arrays are summed in warp order and written to the slot (I, d) of the J block.
+// that after 32 rotations all 256 x 32 pairs of (targets, subset) have been visited with nothing
+// but registers (14 shuffles per 8 pairs).  Measured on B200 at N = 1,048,576: 8 x 1 blocking 755 ms,
+// 4 x 2 blocking 804 ms, 4 x 2 at two CTAs per SM 824 ms per pass.  The subset's accumulated a_j goes to a per-warp shared-memory array; after a
+// part, the 8 warps' arrays are summed in warp order and written to the slot (I, d) of the J block.
 // No floating-point atomics anywhere: k_pair_finish adds, per body, the I-side partials and the
 // slots in a fixed order, then runs the same kick / drift epilogue as K1.  Deterministic.
 //
@@ -26,11 +27,12 @@
 
 namespace essa {
 
-constexpr int kPB = 1024;       // bodies per block
 constexpr int kPThreads = 256;  // 8 warps
-constexpr int kPRI = 4;         // targets per lane
-constexpr int kPRJ = 2;         // visiting bodies per lane
-constexpr int kPHalf = 512;     // records per staged half block
+constexpr int kPRI = 8;         // targets per lane
+constexpr int kPRJ = 1;         // visiting bodies per lane
+constexpr int kPB = kPThreads * kPRI; // bodies per block
+constexpr int kPHalf = 512;     // records per staged part of a J block
+constexpr int kPParts = kPB / kPHalf;
 constexpr int kPSub = 32 * kPRJ;
 constexpr size_t kPSmem = 2 * kPHalf * sizeof(double4) + 8 * 3 * kPHalf * sizeof(double) + 64;
 
@@ -131,12 +133,12 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
         int J = I + d;
         if (J >= A.nb)
             J -= A.nb;
-        for (int half = 0; half < 2; half++) {
+        for (int half = 0; half < kPParts; half++) {
             int const buf = seq & 1;
             // prefetch the tile after this one into the other buffer
             {
                 int pd = d, ph = half + 1;
-                if (ph == 2) {
+                if (ph == kPParts) {
                     ph = 0;
                     pd = d + 1;
                     while (pd < dhi && !valid(pd))
@@ -180,16 +182,6 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                     }
                 } else {
                     for (int rot = 0; rot < 32; rot++) {
-                        // the next rotation's positions do not depend on this rotation's arithmetic:
-                        // fetch them first so that only the accumulators travel on the critical path
-                        double nx[kPRJ], ny[kPRJ], nz[kPRJ], ng[kPRJ];
-#pragma unroll
-                        for (int q = 0; q < kPRJ; q++) {
-                            nx[q] = rot1(xj[q], src);
-                            ny[q] = rot1(yj[q], src);
-                            nz[q] = rot1(zj[q], src);
-                            ng[q] = rot1(gj[q], src);
-                        }
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++)
 #pragma unroll
@@ -198,10 +190,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                                     ajx[q], ajy[q], ajz[q]);
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++) {
-                            xj[q] = nx[q];
-                            yj[q] = ny[q];
-                            zj[q] = nz[q];
-                            gj[q] = ng[q];
+                            xj[q] = rot1(xj[q], src);
+                            yj[q] = rot1(yj[q], src);
+                            zj[q] = rot1(zj[q], src);
+                            gj[q] = rot1(gj[q], src);
                             ajx[q] = rot1(ajx[q], src);
                             ajy[q] = rot1(ajy[q], src);
                             ajz[q] = rot1(ajz[q], src);
@@ -344,7 +336,7 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
     }
 }
 
-// Can this world go through the pair-shared kernel?  Whole 1024-body blocks per rank, no argmax,
+// Can this world go through the pair-shared kernel?  Whole 2048-body blocks per rank, no argmax,
 // slots must fit.  Sharded: rank g owns I blocks [nb g / G, nb (g+1) / G) = its own targets.
 bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles) {
     int n = c->n;
@@ -358,7 +350,7 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
         own = nb;
     int dmax = nb / 2;
     // chunks of the offset range: minimise waves(1 CTA / SM) x offsets per chunk
-    long long slots = c->sm_count;
+    long long slots = c->sm_count; // 1 CTA per SM
     int bestS = 1;
     long long best = -1;
     int smax = dmax + 1 < 16 ? dmax + 1 : 16;

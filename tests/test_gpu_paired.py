@@ -27,15 +27,15 @@ def _upload(ctx, w):
     ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
 
 
-# block counts nb = 2 (even, d = nb/2 handled by half the ring), 3 (odd), 4, 5, ragged last blocks, many blocks
-@pytest.mark.parametrize("n", [1025, 2048, 3000, 4096, 5000, 20000, 65536])
+# blocks of 2048 bodies: nb = 2 (even, d = nb/2 handled by half the ring), 3 (odd), 4, 5, ragged last blocks, many blocks
+@pytest.mark.parametrize("n", [2049, 4096, 6000, 8192, 10000, 20000, 65536])
 def test_paired_force_pass_matches_extended_precision(ctx, n):
     w = synth.plummer(n, seed=n)
     _upload(ctx, w)
     ctx.set_forces(kernel=capi.KERNEL_PAIRED)
     got = ctx.download(("ax", "ay", "az"))
     a = np.stack([got["ax"], got["ay"], got["az"]], axis=1)
-    rows = np.unique(np.concatenate([np.random.default_rng(1).choice(n, 192, replace=False), [0, 1023, 1024, n - 1]]))
+    rows = np.unique(np.concatenate([np.random.default_rng(1).choice(n, 192, replace=False), [0, 2047, 2048, n - 1]]))
     ld = oracle.forces_rows(w["x"], w["y"], w["z"], w["gf"], rows, mode="ld")
     ref = oracle.forces_rows(w["x"], w["y"], w["z"], w["gf"], rows, mode="ref")
     err, err_ref = _rel_rows(a[rows], ld), _rel_rows(ref, ld)
