@@ -195,9 +195,13 @@ def run_reference(args):
     w, dt, name = workload(n)
     ow = cpu_world(w)
     row = 0
-    per_step = 1.5e8  # pair evaluations per step: a few seconds on one core
+    # calibrate (untimed), then size a step so that the whole run stays near two minutes
+    s, i, r = cpu_slice(ow, n, row, 1e7)
+    row += r
+    pairs_per_s = i / 2.0 / s
+    per_step = float(min(5e7, max(2e6, 120.0 * pairs_per_s / max(1, args.steps + args.warmup))))
     for _ in range(args.warmup):
-        s, i, r = cpu_slice(ow, n, row, per_step / 10)
+        s, i, r = cpu_slice(ow, n, row, per_step)
         row += r
     secs, inter, rows0 = 0.0, 0.0, row
     for _ in range(args.steps):
