@@ -1,0 +1,60 @@
+"""BASELINE.json's full sizes (Plummer N = 262,144; galaxy collision N = 1,048,576) through
+size-independent properties: sampled target rows against the oracle's extended-precision evaluation
+over ALL sources (SURVEY.md 8c iv), Newton's third law (sum m a = 0), +K / -K reversibility, and the
+energy diagnostic against the oracle on a sampled sub-problem."""
+import numpy as np
+import pytest
+
+import oracle
+from essa_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_rows(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+
+
+@pytest.mark.parametrize("name,n,kernel", [("plummer", 262144, capi.KERNEL_AUTO), ("plummer", 262144, capi.KERNEL_TILED),
+                                           ("galaxy", 1048576, capi.KERNEL_AUTO)])
+def test_full_size_force_pass_and_reversibility(name, n, kernel):
+    w = synth.plummer(n) if name == "plummer" else synth.galaxy_collision(n)
+    dt = synth.default_dt(n)
+    ctx = capi.Context(0, n)
+    ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
+    ctx.set_forces(kernel=kernel)
+    got = ctx.download(("ax", "ay", "az"))
+    a = np.stack([got["ax"], got["ay"], got["az"]], axis=1)
+    rows = np.sort(np.random.default_rng(7).choice(n, 48, replace=False))
+    ld = oracle.forces_rows(w["x"], w["y"], w["z"], w["gf"], rows, mode="ld")
+    ref, _ = oracle.forces_rows(w["x"], w["y"], w["z"], w["gf"], rows, mode="omp")
+    err, err_ref = _rel_rows(a[rows], ld), _rel_rows(ref, ld)
+    assert err.max() <= max(1e-13, 4.0 * err_ref.max()), (err.max(), err_ref.max())
+    ma = a * w["gf"][:, None]
+    assert np.abs(ma.sum(axis=0)).max() <= 1e-11 * np.abs(ma).sum()
+    # update(+2); update(-2) returns to the start to round-off (close pairs amplify it: 1e-8 bar at this N)
+    ctx.step(2, dt, kernel=kernel)
+    mid = ctx.download(("x",))
+    assert not np.array_equal(mid["x"], w["x"])
+    ctx.step(-2, dt, kernel=kernel)
+    back = ctx.download(("x", "y", "z"))
+    pos = np.stack([back["x"], back["y"], back["z"]], axis=1)
+    start = np.stack([w["x"], w["y"], w["z"]], axis=1)
+    rel = _rel_rows(pos, start)
+    assert np.percentile(rel, 99) <= 1e-12 and rel.max() <= 1e-8, (np.percentile(rel, 99), rel.max())
+    assert ctx.date == capi.START_DATE
+    ctx.close()
+
+
+def test_energy_diagnostic_on_a_subproblem():
+    """K5 against the oracle's long-double energy on the first 20,000 bodies of the 1 M world."""
+    w = synth.galaxy_collision(1048576)
+    m = 20000
+    ctx = capi.Context(0)
+    sub = {k: v[:m] for k, v in w.items()}
+    ctx.upload(sub["x"], sub["y"], sub["z"], sub["vx"], sub["vy"], sub["vz"], sub["gf"])
+    ke, pe, mom = ctx.energy()
+    oke, ope, omom = oracle.energy(sub["x"], sub["y"], sub["z"], sub["vx"], sub["vy"], sub["vz"], sub["gf"])
+    assert ke == pytest.approx(oke, rel=1e-12) and pe == pytest.approx(ope, rel=1e-12)
+    assert np.allclose(mom, omom, rtol=1e-10, atol=1e-12 * np.abs(sub["vx"]).sum() * synth.BODY_MASS)
+    ctx.close()

@@ -21,7 +21,7 @@ def emit(**kw):
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [16384, 65536, 262144, 1048576]
+    sizes = [int(a) for a in sys.argv[1:]] or [4096, 16384, 32768, 65536, 262144, 1048576]
     ctx = capi.Context(0)
     peak = ctx.measure_fp64_peak(300.0)
     emit(what="fp64_peak_tflops", value=peak)
@@ -32,15 +32,20 @@ def main():
         dt = synth.default_dt(n)
         ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
         steps = 3 if n >= (1 << 20) else (5 if n >= 262144 else 20)
-        ctx.step(1, dt, kernel=capi.KERNEL_TILED)  # warm-up (2 passes)
-        t0 = time.time()
-        ctx.step(steps, dt, kernel=capi.KERNEL_TILED)
-        wall = time.time() - t0
-        fms, passes = ctx.last_force_ms, ctx.last_force_passes
-        inter = float(n) * (n - 1) * passes
-        rate = inter / (fms * 1e-3)
-        emit(what="k1", n=n, steps=steps, passes=passes, force_ms_per_pass=fms / passes, step_ms=ctx.last_step_ms, wall_s=wall,
-             interactions_per_s=rate, frac_of_measured_peak=rate * 20 / (peak * 1e12), frac_of_nominal=rate * 20 / 37.2e12)
+        for kname, kern in (("tiled", capi.KERNEL_TILED), ("paired", capi.KERNEL_PAIRED)):
+            if kern == capi.KERNEL_PAIRED and n <= 2048:
+                continue
+            ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
+            ctx.step(1, dt, kernel=kern)  # warm-up (2 passes)
+            t0 = time.time()
+            ctx.step(steps, dt, kernel=kern)
+            wall = time.time() - t0
+            fms, passes = ctx.last_force_ms, ctx.last_force_passes
+            inter = float(n) * (n - 1) * passes
+            rate = inter / (fms * 1e-3)
+            emit(what="force_pass", kernel=kname, n=n, steps=steps, passes=passes, force_ms_per_pass=fms / passes,
+                 step_ms=ctx.last_step_ms, wall_s=wall, interactions_per_s=rate, frac_of_measured_peak=rate * 20 / (peak * 1e12),
+                 frac_of_nominal=rate * 20 / 37.2e12)
 
 
 if __name__ == "__main__":
