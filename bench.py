@@ -317,7 +317,7 @@ def run_ours(args):
         dist.broadcast(uid, 0)
         ctx.shard_attach(rank, world_size, uid.cpu().numpy())
     kernel = {"auto": capi.KERNEL_AUTO, "tiled": capi.KERNEL_TILED, "paired": capi.KERNEL_PAIRED}[args.kernel]
-    paired = args.kernel == "paired" or (args.kernel == "auto" and n >= 32768 and n % (2048 * world_size) == 0)
+    paired = args.kernel == "paired" or (args.kernel == "auto" and n >= 16384 and n % (2048 * world_size) == 0)
     opts = capi.Context.opts(dt, kernel=kernel)
 
     peak = ctx.measure_fp64_peak(300.0) if rank == 0 else 0.0

@@ -628,10 +628,10 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
             can = (slot_d + part_d) * sizeof(double) < free_b / 2 + (ctx->pair_slots_n + ctx->pair_part_n) * sizeof(double);
         }
         if (o.kernel == ESSA_KERNEL_PAIRED && !can) {
-            ctx->err = "pair-shared kernel needs >= 2049 bodies (a multiple of 2048 x ranks when sharded), no most-attracting tracking, and room for its slots";
+            ctx->err = "pair-shared kernel needs >= 1025 bodies (whole 1024- or 2048-body blocks per rank when sharded), no most-attracting tracking, and room for its slots";
             return ESSA_ERR_ARG;
         }
-        ctx->use_paired = can && (o.kernel == ESSA_KERNEL_PAIRED || (o.kernel == ESSA_KERNEL_AUTO && ctx->n >= 32768));
+        ctx->use_paired = can && (o.kernel == ESSA_KERNEL_PAIRED || (o.kernel == ESSA_KERNEL_AUTO && ctx->n >= 16384));
     }
     KickArgs base;
     base.dt = (double)o.dt_seconds;

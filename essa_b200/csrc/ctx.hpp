@@ -192,7 +192,7 @@ cudaError_t launch_record(essa_ctx* c, int offset_trails, int forward_simulated,
 cudaError_t launch_record_init(essa_ctx* c, int first, cudaStream_t st);
 cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double const* z, cudaStream_t st);
 cudaError_t launch_unpack(essa_ctx* c, double* x, double* y, double* z, cudaStream_t st);
-bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles);
+bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles, int* ri_out = nullptr);
 cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out);
 cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred);
 int force_iblocks(essa_ctx const* c, int* R_out);

@@ -22,17 +22,18 @@
 //
 // d = 0 (the block against itself) is evaluated one-sided (a_i only), so ordered pairs are not
 // double counted; it is 1 / (nb + 1) of the work.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ctx.hpp"
 
 namespace essa {
 
 constexpr int kPThreads = 256;  // 8 warps
-constexpr int kPRI = 8;         // targets per lane
 constexpr int kPRJ = 1;         // visiting bodies per lane
-constexpr int kPB = kPThreads * kPRI; // bodies per block
 constexpr int kPHalf = 512;     // records per staged part of a J block
-constexpr int kPParts = kPB / kPHalf;
+// Targets per lane RI is a template parameter: 8 (blocks of 2048 bodies) for large worlds, 4 (blocks
+// of 1024) when 2048-body blocks would leave SMs idle.  Bodies per block = 256 * RI.
 constexpr int kPSub = 32 * kPRJ;
 constexpr size_t kPSmem = 2 * kPHalf * sizeof(double4) + 8 * 3 * kPHalf * sizeof(double) + 64;
 
@@ -77,7 +78,10 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
     }
 }
 
+template<int kPRI>
 __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A) {
+    constexpr int kPB = kPThreads * kPRI;
+    constexpr int kPParts = kPB / kPHalf;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double4* tile = reinterpret_cast<double4*>(smem_raw);                       // [2][kPHalf]
     double* accj = reinterpret_cast<double*>(smem_raw + 2 * kPHalf * sizeof(double4)); // [8][3][kPHalf]
@@ -248,6 +252,7 @@ struct PairFinishArgs {
 };
 
 // J-side contributions to body g from the tiles whose I block lies in [ib0, ib1), in offset order.
+template<int kPB>
 __device__ __forceinline__ void slot_sum(int g, int nb, int dmax, int ib0, int ib1, double const* slots, double& ax, double& ay,
     double& az) {
     int const K = g / kPB, jl = g - K * kPB;
@@ -267,18 +272,20 @@ __device__ __forceinline__ void slot_sum(int g, int nb, int dmax, int ib0, int i
 }
 
 // Sharded worlds: this rank's J-side sums for EVERY body, to be reduce-scattered over the ranks.
+template<int kPB>
 __global__ void __launch_bounds__(256) k_pair_gather_slots(int nb, int dmax, int ib0, int ib1, int npad, double const* slots,
     double* acc) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= npad)
         return;
     double ax = 0, ay = 0, az = 0;
-    slot_sum(g, nb, dmax, ib0, ib1, slots, ax, ay, az);
+    slot_sum<kPB>(g, nb, dmax, ib0, ib1, slots, ax, ay, az);
     acc[g] = ax;
     acc[(size_t)npad + g] = ay;
     acc[2 * (size_t)npad + g] = az;
 }
 
+template<int kPB>
 __global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
     int g = A.i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= A.i1)
@@ -295,7 +302,7 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
         ay = __dadd_rn(ay, __ldcg(A.ajred + (size_t)A.npad + g));
         az = __dadd_rn(az, __ldcg(A.ajred + 2 * (size_t)A.npad + g));
     } else {
-        slot_sum(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots, ax, ay, az);
+        slot_sum<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots, ax, ay, az);
     }
     // ---- epilogue: identical to force_tiled.cu finish_body (no argmax in this kernel) ----
     WorldPtrs const& W = A.w;
@@ -336,18 +343,32 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
     }
 }
 
-// Can this world go through the pair-shared kernel?  Whole 2048-body blocks per rank, no argmax,
-// slots must fit.  Sharded: rank g owns I blocks [nb g / G, nb (g+1) / G) = its own targets.
-bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles) {
+// Can this world go through the pair-shared kernel, and with which block size?  Whole blocks per
+// rank, no argmax, slots must fit.  Sharded: rank g owns I blocks [nb g / G, nb (g+1) / G) = its own targets.
+static int pair_ri_override() {
+    static int v = -1;
+    if (v < 0) {
+        char const* e = getenv("ESSA_PAIR_RI");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles, int* ri_out) {
     int n = c->n;
-    int nb = (n + kPB - 1) / kPB;
-    if (nb < 2 || (size_t)nb * kPB > (size_t)c->cap)
+    // 2048-body blocks (8 targets per lane) are the fastest per pair; 1024-body blocks give mid-sized worlds
+    // enough CTAs.  Measured on B200 (profiles/README.md): 16,384 bodies 1.08e12 interactions/s with 1024-body
+    // blocks vs 3.1e11 with 2048 and 7.1e11 tiled; from 32,768 bodies on 2048-body blocks win.
+    int ri = n >= 32768 * c->world ? 8 : 4;
+    if (pair_ri_override() == 4 || pair_ri_override() == 8)
+        ri = pair_ri_override();
+    int const pb = kPThreads * ri;
+    int nb = (n + pb - 1) / pb;
+    if (nb < 2 || (size_t)nb * pb > (size_t)c->cap)
         return false;
-    if (c->world > 1 && (n % (kPB * c->world)) != 0)
+    if (c->world > 1 && (n % (pb * c->world)) != 0)
         return false;
-    int own = nb / c->world;
-    if (c->world == 1)
-        own = nb;
+    int own = c->world == 1 ? nb : nb / c->world;
     int dmax = nb / 2;
     // chunks of the offset range: minimise waves(1 CTA / SM) x offsets per chunk
     long long slots = c->sm_count; // 1 CTA per SM
@@ -364,8 +385,10 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
     }
     *nb_out = nb;
     *S_out = bestS;
-    *slot_doubles = (size_t)own * dmax * 3 * kPB;
-    *part_doubles = (size_t)bestS * 3 * nb * kPB + (c->world > 1 ? (size_t)3 * nb * kPB : 0);
+    *slot_doubles = (size_t)own * dmax * 3 * pb;
+    *part_doubles = (size_t)bestS * 3 * nb * pb + (c->world > 1 ? (size_t)3 * nb * pb : 0);
+    if (ri_out)
+        *ri_out = ri;
     return true;
 }
 
@@ -374,12 +397,37 @@ static void pair_geometry(essa_ctx const* c, int nb, int* ib0, int* ib1) {
     *ib1 = (int)((long long)nb * (c->rank + 1) / c->world);
 }
 
+template<int RI>
+static cudaError_t launch_pair_kernels(essa_ctx* c, PairArgs const& A, cudaStream_t st, double** acc) {
+    constexpr int PB = kPThreads * RI;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_force_paired<RI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem);
+        if (e != cudaSuccess)
+            return e;
+        attr_set = true;
+    }
+    k_force_paired<RI><<<(A.ib1 - A.ib0) * A.S, kPThreads, kPSmem, st>>>(A);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return e;
+    *acc = nullptr;
+    if (c->world > 1) {
+        *acc = c->pair_part + (size_t)A.S * 3 * A.npad;
+        k_pair_gather_slots<PB><<<(A.npad + 255) / 256, 256, 0, st>>>(A.nb, A.dmax, A.ib0, A.ib1, A.npad, c->pair_slots, *acc);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
 // Phase 1: the pair kernel over this rank's I blocks; sharded worlds also fold their slots into
 // acc[3][npad] (returned through *acc_out) for the caller to reduce-scatter over the ranks.
 cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out) {
-    int nb, S;
+    int nb, S, ri;
     size_t slot_d, part_d;
-    if (!paired_plan(c, &nb, &S, &slot_d, &part_d))
+    if (!paired_plan(c, &nb, &S, &slot_d, &part_d, &ri))
         return cudaErrorInvalidConfiguration;
     if (slot_d > c->pair_slots_n) {
         cudaFree(c->pair_slots);
@@ -399,35 +447,18 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
             return e;
         c->pair_part_n = part_d;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_force_paired, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem);
-        if (e != cudaSuccess)
-            return e;
-        attr_set = true;
-    }
     PairArgs A;
     A.pos = c->pos[c->cur];
     A.nb = nb;
     A.dmax = nb / 2;
     A.S = S;
     pair_geometry(c, nb, &A.ib0, &A.ib1);
-    A.npad = nb * kPB;
+    A.npad = nb * kPThreads * ri;
     A.part_i = c->pair_part;
     A.slots = c->pair_slots;
     A.eps2 = eps2;
-    k_force_paired<<<(A.ib1 - A.ib0) * S, kPThreads, kPSmem, st>>>(A);
-    c->launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess)
-        return e;
     double* acc = nullptr;
-    if (c->world > 1) {
-        acc = c->pair_part + (size_t)S * 3 * A.npad;
-        k_pair_gather_slots<<<(A.npad + 255) / 256, 256, 0, st>>>(nb, A.dmax, A.ib0, A.ib1, A.npad, c->pair_slots, acc);
-        c->launches++;
-        e = cudaGetLastError();
-    }
+    cudaError_t e = ri == 8 ? launch_pair_kernels<8>(c, A, st, &acc) : launch_pair_kernels<4>(c, A, st, &acc);
     if (acc_out)
         *acc_out = acc;
     if (npad_out)
@@ -437,9 +468,9 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
 
 // Phase 2: ordered sums + kick / drift epilogue for this rank's targets.
 cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred) {
-    int nb, S;
+    int nb, S, ri;
     size_t slot_d, part_d;
-    if (!paired_plan(c, &nb, &S, &slot_d, &part_d))
+    if (!paired_plan(c, &nb, &S, &slot_d, &part_d, &ri))
         return cudaErrorInvalidConfiguration;
     PairFinishArgs F;
     F.w = world_ptrs(c);
@@ -451,14 +482,17 @@ cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStrea
     F.dmax = nb / 2;
     F.S = S;
     pair_geometry(c, nb, &F.ib0, &F.ib1);
-    F.npad = nb * kPB;
+    F.npad = nb * kPThreads * ri;
     F.part_i = c->pair_part;
     F.slots = c->pair_slots;
     F.ajred = ajred;
     int cnt = F.i1 - F.i0;
     if (cnt <= 0)
         return cudaSuccess;
-    k_pair_finish<<<(cnt + 255) / 256, 256, 0, st>>>(F);
+    if (ri == 8)
+        k_pair_finish<kPThreads * 8><<<(cnt + 255) / 256, 256, 0, st>>>(F);
+    else
+        k_pair_finish<kPThreads * 4><<<(cnt + 255) / 256, 256, 0, st>>>(F);
     c->launches++;
     return cudaGetLastError();
 }
