@@ -117,10 +117,12 @@ __device__ __forceinline__ void pe_flush(BodyRec& b) {
 }
 
 // Settles everything deferred and writes the per-body state back (trail / history part).
-__device__ __forceinline__ void rec_store_trail(RecordPtrs const& R, int k, BodyRec& b) {
+__device__ __forceinline__ void rec_store_trail(RecordPtrs const& R, int k, BodyRec& b, bool with_history = true) {
     trail_flush_vertex(R, b);
-    R.hist_start[k] = b.hist_start;
-    R.hist_len[k] = b.hist_len;
+    if (with_history) {
+        R.hist_start[k] = b.hist_start;
+        R.hist_len[k] = b.hist_len;
+    }
     R.append_off[k] = b.append_off;
     R.length[k] = b.length;
     R.toff[3 * k] = b.offx;
@@ -276,8 +278,8 @@ __device__ __forceinline__ void periapsis_step(BodyRec& b, double d2, double vx,
 //
 // Half 1: History::move_forward + recalculate_trails_with_offset / Trail::push_back.
 __device__ __forceinline__ void record_trail(RecordPtrs const& R, int k, BodyRec& b, double px, double py, double pz, double vx, double vy,
-    double vz, double mx, double my, double mz, int most, int old_most, bool offset_trails, bool forward_sim) {
-    if (!forward_sim)
+    double vz, double mx, double my, double mz, int most, int old_most, bool offset_trails, bool forward_sim, bool with_history = true) {
+    if (with_history && !forward_sim)
         history_push(R, k, b, px, py, pz, vx, vy, vz);
     bool const rel = offset_trails && most >= 0 && !forward_sim;
     double ox = rel ? mx : 0.0, oy = rel ? my : 0.0, oz = rel ? mz : 0.0;

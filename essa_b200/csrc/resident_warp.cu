@@ -1,9 +1,17 @@
 // K3w -- resident kernel for worlds of up to 32 bodies (the Solar System template has 10): the whole
-// World::update loop (src/World.cpp:86-139) runs inside ONE WARP, so a KDK step never crosses a
-// block barrier, and Object::update's recording (record.cuh) runs on TWO MORE warps (History +
-// Trail on one, ap / pe on the other) that consume per-step snapshots from a shared-memory ring (mbarrier full / empty
-// hand-off) -- off the physics critical path.  Fast arithmetic only; exact_order worlds go through
-// resident.cu.
+// World::update loop (src/World.cpp:86-139) with ONE WARP on the critical path and three more
+// consuming per-step snapshots from a shared-memory ring (mbarrier hand-off), so that nothing but
+// the kick-drift-kick chain itself delays the next step:
+//
+//   warp 0  physics      forces -> kick -> drift -> forces -> kick, no block barrier per step
+//   warp 3  attraction   Object::update_forces_against's most-attracting bookkeeping
+//                        (src/Object.cpp:84-94): it never feeds back into the trajectory, and its
+//                        result after a step depends only on the step's final positions
+//   warp 1  trail        recalculate_trails_with_offset + Trail::push_back (record.cuh)
+//   warp 2  history      History::move_forward + ap / pe
+//
+// Fast arithmetic only; exact_order worlds, set_forces() alone and closest-approach tracking go
+// through resident.cu.
 //
 // A single trajectory is a dependent chain (each step needs the previous one), so this kernel is
 // bound by dependent-issue latency (measured on B200: DFMA/DADD/DMUL 8.3 cycles, MUFU.RSQ64H seed
@@ -13,8 +21,7 @@
 //     every lane of a body then forms the same ordered sum of the L partials, so the replicated
 //     state stays bit-identical across lanes without a broadcast;
 //   * kick and drift use the exact identities (a h) mul == a (h mul) and (v dt) mul == v (dt mul)
-//     (multiplying by +-1 is exact), and the two half kicks around a reused acceleration share one
-//     product: forces -> dv -> v -> v' -> x is five dependent FP64 instructions;
+//     (multiplying by +-1 is exact);
 //   * positions are exchanged through shared memory with __syncwarp only.
 #include "common.cuh"
 #include "ctx.hpp"
@@ -22,7 +29,7 @@
 
 namespace essa {
 
-constexpr int kRing = 16; // snapshots in flight between the physics warp and the recorder warp
+constexpr int kRing = 16; // snapshots in flight
 
 struct WarpArgs {
     WorldPtrs w;
@@ -35,7 +42,7 @@ struct WarpArgs {
     double hm, dtm; // (dt / 2) * mul, dt * mul
     long long date, date_step;
     double eps2;
-    int record, offset_trails, forward_sim, two_pass, acc_valid;
+    int record, argmax, offset_trails, forward_sim, two_pass, acc_valid;
 };
 
 struct Snapshot {
@@ -50,17 +57,13 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 }
 
 // Partial force of lane (k, q) over its partners, then the ordered sum over the L lanes of body k.
-template<int P, bool ARGMAX>
+template<int P>
 __device__ __forceinline__ void lane_forces(int k, int q, int L, int iters, int n, double const* sx, double const* sy, double const* sz,
-    double const* sg, double x, double y, double z, double gfk, double eps2, double& ax, double& ay, double& az, double& maxattr,
-    int& most) {
-    double fx[P], fy[P], fz[P], bm[P];
-    int bj[P];
+    double const* sg, double x, double y, double z, double eps2, double& ax, double& ay, double& az) {
+    double fx[P], fy[P], fz[P];
 #pragma unroll
-    for (int u = 0; u < P; u++) {
-        fx[u] = fy[u] = fz[u] = bm[u] = 0.0;
-        bj[u] = -1;
-    }
+    for (int u = 0; u < P; u++)
+        fx[u] = fy[u] = fz[u] = 0.0;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int u = 0; u < P; u++) {
@@ -68,74 +71,137 @@ __device__ __forceinline__ void lane_forces(int k, int q, int L, int iters, int 
             bool in = p < n;
             int pc = in ? p : k; // out of range -> the self term, which vanishes
             double4 qv = make_double4(sx[pc], sy[pc], sz[pc], in ? sg[pc] : 0.0);
-            if (ARGMAX)
-                fast_interact_argmax(x, y, z, gfk, qv, pc, eps2, fx[u], fy[u], fz[u], bm[u], bj[u]);
-            else
-                fast_interact(x, y, z, qv, eps2, fx[u], fy[u], fz[u]);
+            fast_interact(x, y, z, qv, eps2, fx[u], fy[u], fz[u]);
         }
     }
-    double px = fx[0], py = fy[0], pz = fz[0], pm = bm[0];
-    int pj = bj[0];
+    double px = fx[0], py = fy[0], pz = fz[0];
 #pragma unroll
     for (int u = 1; u < P; u++) {
         px += fx[u];
         py += fy[u];
         pz += fz[u];
-        if (ARGMAX && (bm[u] > pm || (bm[u] == pm && bj[u] >= 0 && pj >= 0 && bj[u] < pj))) {
-            pm = bm[u];
-            pj = bj[u];
-        }
     }
-    double sxm = 0, sym = 0, szm = 0, best = 0;
-    int bp = -1;
+    double sxm = 0, sym = 0, szm = 0;
     for (int qq = 0; qq < L; qq++) {
         int src = k + qq * n;
         sxm += __shfl_sync(0xffffffffu, px, src);
         sym += __shfl_sync(0xffffffffu, py, src);
         szm += __shfl_sync(0xffffffffu, pz, src);
-        if (ARGMAX) {
-            double m = __shfl_sync(0xffffffffu, pm, src);
-            int j = __shfl_sync(0xffffffffu, pj, src);
-            if (m > best || (m == best && j >= 0 && bp >= 0 && j < bp)) {
-                best = m;
-                bp = j;
-            }
-        }
     }
     ax = sxm;
     ay = sym;
     az = szm;
-    if (ARGMAX) {
-        maxattr = best;
-        if (bp >= 0)
-            most = bp;
-    }
 }
 
-template<int P, bool ARGMAX>
-__global__ void __launch_bounds__(96, 1) k_resident_warp(WarpArgs const A) {
+// gf_p / r^4 of partner p as seen from body k (the reference's |ta|^2 / gf_p), to ~1e-15.
+__device__ __forceinline__ double attraction_metric(double xk, double yk, double zk, double xp, double yp, double zp, double gp) {
+    double dx = xp - xk, dy = yp - yk, dz = zp - zk;
+    double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    double y0 = rsqrt_seed(r2);
+    double t = r2 * y0;
+    double e = fma(-t, y0, 1.0);
+    double y = fma(y0 * e, fma(0.375, e, 0.5), y0); // 1 / r
+    double y2 = y * y;
+    return gp * y2 * y2;
+}
+
+template<int P>
+__global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
     __shared__ double sx[32], sy[32], sz[32], sg[32];
+    __shared__ double sgf[32]; // attraction warp: every body's gf (who is heavier than whom)
     __shared__ Snapshot ring[kRing];
-    __shared__ __align__(8) unsigned long long full[kRing], empty[kRing];
+    // full: physics -> attraction;  ready: attraction -> recorders;  empty: consumers -> physics
+    __shared__ __align__(8) unsigned long long full[kRing], ready[kRing], empty[kRing];
 
     int const n = A.n, L = A.L;
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int const k = lane % n, q = lane / n; // (body, split) of a physics lane
+    int const k = lane % n, q = lane / n; // (body, split) of a lane
     bool const worker = lane < n * L;
     bool const leader = lane < n;
     bool const rec_on = A.record != 0;
+    bool const snap_on = rec_on || A.argmax != 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kRing; i++) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 2); // both recorder warps release a slot
+            mbar_init(&ready[i], 1);
+            mbar_init(&empty[i], rec_on ? 2 : 1); // the recorder warps, or the attraction warp alone
         }
         mbar_fence_init();
     }
     __syncthreads();
 
+    if (warp == 3) {
+        // ---------------- attraction warp ----------------
+        if (!snap_on)
+            return;
+        double gfk = 0, maxattr = 0;
+        int most = -1, old_most = -1;
+        if (worker) {
+            gfk = A.w.gf[k];
+            maxattr = A.w.maxattr[k];
+            most = A.w.most[k];
+            old_most = A.w.old_most[k];
+        }
+        if (leader)
+            sgf[k] = gfk;
+        __syncwarp();
+        int const per = (n + L - 1) / L; // partners per lane
+        for (int s = 0; s < A.steps; s++) {
+            int const slot = s % kRing;
+            mbar_wait(&full[slot], (unsigned)(s / kRing) & 1u);
+            Snapshot& sn = ring[slot];
+            unsigned const amask = sn.active_mask;
+            bool const active = worker && ((amask >> k) & 1u);
+            old_most = most; // Object::before_update
+            double best = 0;
+            int bp = -1;
+            double const xk = sn.x[k], yk = sn.y[k], zk = sn.z[k];
+            for (int u = 0; u < per; u++) {
+                int p = q + u * L;
+                if (p < n && p != k && ((amask >> p) & 1u)) {
+                    double gp = sgf[p];
+                    double m = attraction_metric(xk, yk, zk, sn.x[p], sn.y[p], sn.z[p], gp);
+                    if (m > best && gp > gfk) { // ascending p within a lane: the lowest index wins ties
+                        best = m;
+                        bp = p;
+                    }
+                }
+            }
+            double tb = 0;
+            int tp = -1;
+            for (int qq = 0; qq < L; qq++) {
+                int src = k + qq * n;
+                double m = __shfl_sync(0xffffffffu, best, src);
+                int j = __shfl_sync(0xffffffffu, bp, src);
+                if (m > tb || (m == tb && j >= 0 && tp >= 0 && j < tp)) {
+                    tb = m;
+                    tp = j;
+                }
+            }
+            if (active) { // masked bodies keep max_attraction and the link (clear_forces skips them)
+                maxattr = tb;
+                if (tp >= 0)
+                    most = tp;
+            }
+            if (leader) {
+                sn.most[k] = most;
+                sn.old_most[k] = old_most;
+            }
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(rec_on ? &ready[slot] : &empty[slot]);
+        }
+        if (leader) {
+            A.w.maxattr[k] = maxattr;
+            A.w.most[k] = most;
+            A.w.old_most[k] = old_most;
+        }
+        return;
+    }
+
     if (warp >= 1) {
-        // ---------------- recorder warps: 1 = History + Trail, 2 = ap / pe ----------------
+        // ---------------- recorder warps: 1 = Trail, 2 = History + ap / pe ----------------
         if (!rec_on)
             return;
         bool const mine = lane < n && lane < A.r.tracked;
@@ -144,34 +210,39 @@ __global__ void __launch_bounds__(96, 1) k_resident_warp(WarpArgs const A) {
             rec_load(A.r, lane, b);
         for (int s = 0; s < A.steps; s++) {
             int const slot = s % kRing;
-            mbar_wait(&full[slot], (unsigned)(s / kRing) & 1u);
+            mbar_wait(&ready[slot], (unsigned)(s / kRing) & 1u);
             Snapshot const& sn = ring[slot];
             if (mine && ((sn.active_mask >> lane) & 1u)) {
                 int const most = sn.most[lane];
                 int const mi = most >= 0 ? most : 0;
                 double const mx = sn.x[mi], my = sn.y[mi], mz = sn.z[mi];
-                if (warp == 1)
+                if (warp == 1) {
                     record_trail(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], mx, my, mz, most,
-                        sn.old_most[lane], A.offset_trails != 0, A.forward_sim != 0);
-                else
+                        sn.old_most[lane], A.offset_trails != 0, A.forward_sim != 0, false);
+                } else {
+                    if (!A.forward_sim)
+                        history_push(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane]);
                     record_appe(b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], mx, my, mz, most);
+                }
             }
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&empty[slot]);
         }
         if (mine) {
-            if (warp == 1)
-                rec_store_trail(A.r, lane, b);
-            else
+            if (warp == 1) {
+                rec_store_trail(A.r, lane, b, false); // the History ring's cursor belongs to warp 2
+            } else {
                 rec_store_appe(A.r, lane, b);
+                A.r.hist_start[lane] = b.hist_start;
+                A.r.hist_len[lane] = b.hist_len;
+            }
         }
         return;
     }
 
     // ---------------- physics warp ----------------
-    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0, maxattr = 0;
-    int most = -1, old_most = -1;
+    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0;
     bool active = false, delf = false;
     long long cd = 0, dd = 0;
     if (worker) {
@@ -186,9 +257,6 @@ __global__ void __launch_bounds__(96, 1) k_resident_warp(WarpArgs const A) {
         ax = A.w.a[0][k];
         ay = A.w.a[1][k];
         az = A.w.a[2][k];
-        maxattr = A.w.maxattr[k];
-        most = A.w.most[k];
-        old_most = A.w.old_most[k];
         active = A.w.active[k] != 0;
         delf = A.delflag[k] != 0;
         cd = A.cdate[k];
@@ -207,20 +275,14 @@ __global__ void __launch_bounds__(96, 1) k_resident_warp(WarpArgs const A) {
     double const hm = A.hm, dtm = A.dtm;
 
     auto forces = [&]() {
-        double fx, fy, fz, fm = maxattr;
-        int fmost = most;
-        lane_forces<P, ARGMAX>(k, q, L, A.iters, n, sx, sy, sz, sg, x, y, z, gfk, A.eps2, fx, fy, fz, fm, fmost);
+        double fx, fy, fz;
+        lane_forces<P>(k, q, L, A.iters, n, sx, sy, sz, sg, x, y, z, A.eps2, fx, fy, fz);
         if (active) {
             ax = fx;
             ay = fy;
             az = fz;
-            maxattr = fm;
-            most = fmost;
         }
     };
-
-    if (A.steps == 0) // World::set_forces() alone
-        forces();
 
     for (int s = 0; s < A.steps; s++) {
         if (A.date_step != 0) { // update_history_and_date: the mask may flip with the date
@@ -235,7 +297,6 @@ __global__ void __launch_bounds__(96, 1) k_resident_warp(WarpArgs const A) {
                 __syncwarp();
             }
         }
-        old_most = most; // Object::before_update
         if (!acc_valid || A.two_pass)
             forces();
         if (active) { // first half kick + drift (src/World.cpp:112,115)
@@ -260,7 +321,7 @@ __global__ void __launch_bounds__(96, 1) k_resident_warp(WarpArgs const A) {
             vz = __dadd_rn(vz, __dmul_rn(az, hm));
         }
         acc_valid = true;
-        if (rec_on) {
+        if (snap_on) {
             int const slot = s % kRing;
             if (s >= kRing)
                 mbar_wait(&empty[slot], (unsigned)(s / kRing - 1) & 1u);
@@ -273,8 +334,6 @@ __global__ void __launch_bounds__(96, 1) k_resident_warp(WarpArgs const A) {
                 sn.vx[k] = vx;
                 sn.vy[k] = vy;
                 sn.vz[k] = vz;
-                sn.most[k] = most;
-                sn.old_most[k] = old_most;
             }
             if (lane == 0)
                 sn.active_mask = amask;
@@ -292,22 +351,11 @@ __global__ void __launch_bounds__(96, 1) k_resident_warp(WarpArgs const A) {
         A.w.a[0][k] = ax;
         A.w.a[1][k] = ay;
         A.w.a[2][k] = az;
-        A.w.maxattr[k] = maxattr;
-        A.w.most[k] = most;
-        A.w.old_most[k] = old_most;
         A.active_out[k] = active ? 1 : 0;
     }
 }
 
-template<int P>
-static void launch_P(bool argmax, WarpArgs const& A, cudaStream_t st) {
-    if (argmax)
-        k_resident_warp<P, true><<<1, 96, 0, st>>>(A);
-    else
-        k_resident_warp<P, false><<<1, 96, 0, st>>>(A);
-}
-
-cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st) {
+cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st) {
     WarpArgs A;
     A.w = world_ptrs(c);
     A.r = record_ptrs(c);
@@ -316,34 +364,35 @@ cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o
     A.delflag = c->delflag;
     A.active_out = c->active;
     A.n = c->n;
-    A.steps = forces_only ? 0 : (steps < 0 ? -steps : steps);
+    A.steps = steps < 0 ? -steps : steps;
     double const mul = steps >= 0 ? 1.0 : -1.0;
     A.dtm = (double)o.dt_seconds * mul;
     A.hm = (double)o.dt_seconds / 2.0 * mul;
     A.date = (long long)c->date;
     A.date_step = o.forward_simulated ? 0 : (long long)(steps >= 0 ? 1 : -1) * o.dt_seconds;
     A.eps2 = o.eps2;
-    A.record = o.record && !forces_only && c->tracked > 0;
+    A.record = o.record && c->tracked > 0;
+    A.argmax = o.track_most_attracting || o.record;
     A.offset_trails = o.offset_trails;
     A.forward_sim = o.forward_simulated;
     A.two_pass = o.two_pass;
-    bool argmax = o.track_most_attracting || o.record;
-    A.acc_valid = c->acc_valid && (!argmax || c->acc_has_most) && !c->acc_exact;
+    // the acceleration left by an earlier call is reusable whatever most-attracting tracking came with it
+    A.acc_valid = c->acc_valid && !c->acc_exact;
     // lanes per body and partners per lane
     A.L = 32 / c->n;
     int per_lane = (c->n + A.L - 1) / A.L;
     int P = per_lane <= 1 ? 1 : (per_lane <= 2 ? 2 : (per_lane <= 4 ? 4 : 8));
     A.iters = (per_lane + P - 1) / P;
     if (P == 1)
-        launch_P<1>(argmax, A, st);
+        k_resident_warp<1><<<1, 128, 0, st>>>(A);
     else if (P == 2)
-        launch_P<2>(argmax, A, st);
+        k_resident_warp<2><<<1, 128, 0, st>>>(A);
     else if (P == 4)
-        launch_P<4>(argmax, A, st);
+        k_resident_warp<4><<<1, 128, 0, st>>>(A);
     else
-        launch_P<8>(argmax, A, st);
+        k_resident_warp<8><<<1, 128, 0, st>>>(A);
     c->launches++;
-    int passes = A.steps == 0 ? 1 : (o.two_pass ? 2 * A.steps : A.steps + (A.acc_valid ? 0 : 1));
+    int passes = o.two_pass ? 2 * A.steps : A.steps + (A.acc_valid ? 0 : 1);
     c->passes += passes;
     c->interactions += (double)passes * (double)c->n * (double)(c->n - 1);
     c->last_force_passes = passes;
