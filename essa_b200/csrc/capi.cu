@@ -768,6 +768,9 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
         bool const closest = o.forward_simulated && ctx->closest && ctx->closest_n == ctx->n;
         if (!o.exact_order && ctx->n <= 32 && !closest && !forces_only)
             CK(launch_resident_warp(ctx, steps, o, ctx->stream));
+        else if (resident_cta_applicable(ctx, o, forces_only)
+            && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds)))
+            CK(launch_resident_cta(ctx, steps, o, ctx->stream));
         else
             CK(launch_resident(ctx, steps, o, forces_only, ctx->stream));
         CK(cudaEventRecord(ctx->ev_end, ctx->stream));

@@ -200,6 +200,8 @@ void choose_split(essa_ctx const* c, int iblocks, int ntiles, int* S_out);
 
 cudaError_t launch_resident(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st);
 cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
+bool resident_cta_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
+cudaError_t launch_resident_cta(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st);
 cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st);
 cudaError_t launch_energy(essa_ctx* c, cudaStream_t st); // result in c->escratch[0..5)
