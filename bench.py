@@ -417,7 +417,11 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": name, "n": n, "dt_seconds": dt, "sharding": "targets/%d: NCCL gather of drifted positions + reduce-scatter of pair-shared partial accelerations per pass" % world_size
                        if world_size > 1 else "single GPU", "l2": "flushed (256 MiB memset) between timed steps",
-                       "passes_per_step": passes / args.steps, "timing": "CUDA events on the launching stream around each essa_step, max over ranks"},
+                       "passes_per_step": passes / args.steps,
+                       "accounting": "value counts only force passes actually evaluated: N(N-1) directed interactions per pass; the reference's "
+                                     "first set_forces() of a step recomputes the previous step's second one bit for bit, so the resident "
+                                     "acceleration is reused (tests: two_pass == reuse, bitwise) and is NOT counted",
+                       "timing": "CUDA events on the launching stream around each essa_step, max over ranks"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "energy_drift": drift,
             "wall_ms_per_step": 1e3 * (t_wall1 - t_wall0) / args.steps, "last_step_breakdown_rank0": breakdown}
     if world_size == 1 and not args.no_extra:
