@@ -210,3 +210,41 @@ def test_active_mask_by_date(ctx):
     assert _rel_rows(vel, ref["vel"]).max() <= 1e-10
     # body 7 froze after step 1 (date t0+2dt masks it from step 2 on)
     assert not np.array_equal(pos[7], [w["x"][7], w["y"][7], w["z"][7]])
+
+
+def test_tracked_prefix_recording_on_a_large_world(ctx):
+    """Tiled path with recording: only a tracked prefix of a big world gets History / Trail rings
+    (48 kB of History per body would not scale); checked against the oracle, which records every body."""
+    n, tracked, steps = 3000, 8, 12
+    w = synth.plummer(n, seed=13)
+    # make the first body heavy so that the tracked ones have a most-attracting object
+    w["gf"] = w["gf"].copy()
+    w["gf"][0] *= 500.0
+    dt = synth.default_dt(n)
+    t0 = capi.START_DATE
+    ctx.date = t0
+    ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"], creation_date=np.full(n, t0, dtype=np.int64))
+    ctx.record_configure([500] * tracked)
+    ctx.step(steps, dt, kernel=capi.KERNEL_TILED, record=True)
+    got = ctx.download()
+    ow = oracle.World()
+    ow.add_bodies(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"] / oracle.GRAVITY)
+    for b in range(n):
+        if b == 0:
+            ow.set_object_state(0, gf=w["gf"][0])
+    ow.dt = dt
+    ow.update(steps)
+    ref = ow.state()
+    assert np.array_equal(got["most"], ref["most"])
+    assert np.count_nonzero(got["most"][:tracked] == 0) >= tracked - 1
+    for k in range(tracked):
+        h, ho = ctx.history(k), ow.history(k)
+        assert h.shape == ho.shape == (steps + 1, 6)
+        assert np.allclose(h, ho, rtol=1e-10, atol=0)
+        t, to = ctx.trail(k), ow.trail(k)
+        assert (t["append_offset"], t["length"]) == (to["append_offset"], to["length"])
+        assert np.allclose(t["verts"][:t["length"]], to["verts"][:to["length"]], rtol=1e-5, atol=1e-6)
+        assert np.allclose(t["offset"], to["offset"], rtol=1e-10)
+    assert np.allclose(got["ap"][1:tracked], ref["appe"][1:tracked, 0], rtol=1e-10)
+    assert np.allclose(got["pe"][1:tracked], ref["appe"][1:tracked, 1], rtol=1e-10)
+    ctx.record_configure([])
