@@ -766,7 +766,7 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
     if (resident) {
         // worlds of up to 32 bodies in fast arithmetic: one-warp kernel with a recorder warp (resident_warp.cu)
         bool const closest = o.forward_simulated && ctx->closest && ctx->closest_n == ctx->n;
-        if (!o.exact_order && ctx->n <= 32 && !closest && !forces_only)
+        if (ctx->n <= 32 && !closest && !forces_only)
             CK(launch_resident_warp(ctx, steps, o, ctx->stream));
         else if (resident_cta_applicable(ctx, o, forces_only)
             && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds)))

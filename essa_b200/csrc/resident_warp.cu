@@ -10,8 +10,8 @@
 //   warp 1  trail        recalculate_trails_with_offset + Trail::push_back (record.cuh)
 //   warp 2  history      History::move_forward + ap / pe
 //
-// Fast arithmetic only; exact_order worlds, set_forces() alone and closest-approach tracking go
-// through resident.cu.
+// Both arithmetic flavours (exact_order keeps the most-attracting comparison in the physics warp: it
+// needs the exact terms).  set_forces() alone and closest-approach tracking go through resident.cu.
 //
 // A single trajectory is a dependent chain (each step needs the previous one), so this kernel is
 // bound by dependent-issue latency (measured on B200: DFMA/DADD/DMUL 8.3 cycles, MUFU.RSQ64H seed
@@ -93,6 +93,66 @@ __device__ __forceinline__ void lane_forces(int k, int q, int L, int iters, int 
     az = szm;
 }
 
+// exact_order flavour: the expensive part of a term -- three IEEE divisions and a square root -- does not
+// depend on the summation order, so the L lanes of a body evaluate their partners' terms in parallel
+// (common.cuh exact arithmetic); every lane of the body then adds ALL terms in ascending partner order
+// (p = qq + slot * L is ascending in (slot, qq) order), which is the reference's order bit for bit, and
+// runs the most-attracting comparison of src/Object.cpp:84-94 in the same order.
+template<int P>
+__device__ __forceinline__ void lane_forces_exact(int k, int q, int L, int iters, int n, double const* sx, double const* sy,
+    double const* sz, double const* sg, double x, double y, double z, double gfk, double& ax, double& ay, double& az, double& maxattr,
+    int& most) {
+    double fx = 0, fy = 0, fz = 0, best = 0;
+    int bp = -1;
+    for (int it = 0; it < iters; it++) {
+        double tx[P], ty[P], tz[P], mg[P];
+        int ok[P];
+#pragma unroll
+        for (int u = 0; u < P; u++) {
+            int p = q + (it * P + u) * L;
+            bool in = p < n && p != k;
+            int pc = in ? p : (k + 1 < n ? k + 1 : 0); // any other body: keeps the arithmetic finite, result unused
+            double gp = sg[pc];
+            in = in && gp != 0.0;
+            double dx = __dsub_rn(sx[pc], x), dy = __dsub_rn(sy[pc], y), dz = __dsub_rn(sz[pc], z);
+            double den = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            den = __dmul_rn(den, __dsqrt_rn(den));
+            tx[u] = __dmul_rn(__ddiv_rn(dx, den), gp);
+            ty[u] = __dmul_rn(__ddiv_rn(dy, den), gp);
+            tz[u] = __dmul_rn(__ddiv_rn(dz, den), gp);
+            mg[u] = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(tx[u], tx[u]), __dmul_rn(ty[u], ty[u])), __dmul_rn(tz[u], tz[u])), gp);
+            ok[u] = in ? 1 : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < P; u++) {
+            for (int qq = 0; qq < L; qq++) {
+                int src = k + qq * n;
+                double vx = __shfl_sync(0xffffffffu, tx[u], src);
+                double vy = __shfl_sync(0xffffffffu, ty[u], src);
+                double vz = __shfl_sync(0xffffffffu, tz[u], src);
+                double vm = __shfl_sync(0xffffffffu, mg[u], src);
+                int vok = __shfl_sync(0xffffffffu, ok[u], src);
+                int p = qq + (it * P + u) * L;
+                if (vok) {
+                    fx = __dadd_rn(fx, vx);
+                    fy = __dadd_rn(fy, vy);
+                    fz = __dadd_rn(fz, vz);
+                    if (vm > best && sg[p] > gfk) {
+                        best = vm;
+                        bp = p;
+                    }
+                }
+            }
+        }
+    }
+    ax = fx;
+    ay = fy;
+    az = fz;
+    maxattr = best;
+    if (bp >= 0)
+        most = bp;
+}
+
 // gf_p / r^4 of partner p as seen from body k (the reference's |ta|^2 / gf_p), to ~1e-15.
 __device__ __forceinline__ double attraction_metric(double xk, double yk, double zk, double xp, double yp, double zp, double gp) {
     double dx = xp - xk, dy = yp - yk, dz = zp - zk;
@@ -105,7 +165,7 @@ __device__ __forceinline__ double attraction_metric(double xk, double yk, double
     return gp * y2 * y2;
 }
 
-template<int P>
+template<int P, bool EXACT>
 __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
     __shared__ double sx[32], sy[32], sz[32], sg[32];
     __shared__ double sgf[32]; // attraction warp: every body's gf (who is heavier than whom)
@@ -119,7 +179,9 @@ __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
     bool const worker = lane < n * L;
     bool const leader = lane < n;
     bool const rec_on = A.record != 0;
-    bool const snap_on = rec_on || A.argmax != 0;
+    // exact_order keeps the most-attracting comparison in the physics warp (it needs the exact terms), so
+    // the attraction warp is idle and snapshots exist for the recorders only
+    bool const snap_on = EXACT ? rec_on : (rec_on || A.argmax != 0);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kRing; i++) {
@@ -133,7 +195,7 @@ __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
 
     if (warp == 3) {
         // ---------------- attraction warp ----------------
-        if (!snap_on)
+        if (!snap_on || EXACT)
             return;
         double gfk = 0, maxattr = 0;
         int most = -1, old_most = -1;
@@ -242,7 +304,8 @@ __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
     }
 
     // ---------------- physics warp ----------------
-    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0;
+    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0, maxattr = 0;
+    int most = -1, old_most = -1; // exact_order only
     bool active = false, delf = false;
     long long cd = 0, dd = 0;
     if (worker) {
@@ -261,6 +324,11 @@ __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
         delf = A.delflag[k] != 0;
         cd = A.cdate[k];
         dd = A.ddate[k];
+        if (EXACT) {
+            maxattr = A.w.maxattr[k];
+            most = A.w.most[k];
+            old_most = A.w.old_most[k];
+        }
     }
     if (leader) {
         sx[k] = x;
@@ -275,12 +343,18 @@ __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
     double const hm = A.hm, dtm = A.dtm;
 
     auto forces = [&]() {
-        double fx, fy, fz;
-        lane_forces<P>(k, q, L, A.iters, n, sx, sy, sz, sg, x, y, z, A.eps2, fx, fy, fz);
+        double fx, fy, fz, fm = maxattr;
+        int fmost = most;
+        if (EXACT)
+            lane_forces_exact<P>(k, q, L, A.iters, n, sx, sy, sz, sg, x, y, z, gfk, fx, fy, fz, fm, fmost);
+        else
+            lane_forces<P>(k, q, L, A.iters, n, sx, sy, sz, sg, x, y, z, A.eps2, fx, fy, fz);
         if (active) {
             ax = fx;
             ay = fy;
             az = fz;
+            maxattr = fm;
+            most = fmost;
         }
     };
 
@@ -297,6 +371,7 @@ __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
                 __syncwarp();
             }
         }
+        old_most = most; // Object::before_update (exact_order; the attraction warp does it otherwise)
         if (!acc_valid || A.two_pass)
             forces();
         if (active) { // first half kick + drift (src/World.cpp:112,115)
@@ -334,12 +409,16 @@ __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
                 sn.vx[k] = vx;
                 sn.vy[k] = vy;
                 sn.vz[k] = vz;
+                if (EXACT) {
+                    sn.most[k] = most;
+                    sn.old_most[k] = old_most;
+                }
             }
             if (lane == 0)
                 sn.active_mask = amask;
             __syncwarp();
             if (lane == 0)
-                mbar_arrive(&full[slot]);
+                mbar_arrive(EXACT ? &ready[slot] : &full[slot]);
         }
     }
 
@@ -352,7 +431,20 @@ __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
         A.w.a[1][k] = ay;
         A.w.a[2][k] = az;
         A.active_out[k] = active ? 1 : 0;
+        if (EXACT) {
+            A.w.maxattr[k] = maxattr;
+            A.w.most[k] = most;
+            A.w.old_most[k] = old_most;
+        }
     }
+}
+
+template<int P>
+static void launch_warp_P(bool exact, WarpArgs const& A, cudaStream_t st) {
+    if (exact)
+        k_resident_warp<P, true><<<1, 128, 0, st>>>(A);
+    else
+        k_resident_warp<P, false><<<1, 128, 0, st>>>(A);
 }
 
 cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st) {
@@ -377,20 +469,21 @@ cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o
     A.forward_sim = o.forward_simulated;
     A.two_pass = o.two_pass;
     // the acceleration left by an earlier call is reusable whatever most-attracting tracking came with it
-    A.acc_valid = c->acc_valid && !c->acc_exact;
+    bool const exact = o.exact_order != 0;
+    A.acc_valid = exact ? (c->acc_valid && c->acc_exact && c->acc_has_most) : (c->acc_valid && !c->acc_exact);
     // lanes per body and partners per lane
     A.L = 32 / c->n;
     int per_lane = (c->n + A.L - 1) / A.L;
     int P = per_lane <= 1 ? 1 : (per_lane <= 2 ? 2 : (per_lane <= 4 ? 4 : 8));
     A.iters = (per_lane + P - 1) / P;
     if (P == 1)
-        k_resident_warp<1><<<1, 128, 0, st>>>(A);
+        launch_warp_P<1>(exact, A, st);
     else if (P == 2)
-        k_resident_warp<2><<<1, 128, 0, st>>>(A);
+        launch_warp_P<2>(exact, A, st);
     else if (P == 4)
-        k_resident_warp<4><<<1, 128, 0, st>>>(A);
+        launch_warp_P<4>(exact, A, st);
     else
-        k_resident_warp<8><<<1, 128, 0, st>>>(A);
+        launch_warp_P<8>(exact, A, st);
     c->launches++;
     int passes = o.two_pass ? 2 * A.steps : A.steps + (A.acc_valid ? 0 : 1);
     c->passes += passes;
