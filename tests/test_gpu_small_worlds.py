@@ -57,9 +57,9 @@ def _compare(pw, ow, exact, rtol):
             assert np.array_equal(pw.history(i), ow.history(i)), i
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 200, 300])
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 200, 300, 1024])
 def test_exact_order_boundary_sizes(n):
-    steps = 120 if n <= 33 else 25
+    steps = 120 if n <= 33 else (25 if n <= 300 else 4)
     ow, pw = _pair(n, 100 + n, exact=True)
     for chunk in (1, steps - 1):
         ow.update(chunk)

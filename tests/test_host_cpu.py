@@ -164,6 +164,19 @@ def test_pyssa_surface_on_host():
         w.update(0)
 
 
+def test_empty_world_update_moves_only_the_clock():
+    """World::update on an empty list: update_history_and_date still runs (src/World.cpp:59-84); no device needed."""
+    w = world.World()
+    w.simulation_seconds_per_tick = 600
+    w.update(7)
+    assert w.date == capi.START_DATE + 7 * 600 and len(w) == 0
+    w.update(-3)
+    assert w.date == capi.START_DATE + 4 * 600
+    ow = oracle.World()
+    ow.dt = 600
+    # (the reference dereferences m_object_list.back() on an empty list here; the oracle is not asked to)
+
+
 def test_host_clone_for_forward_simulation(worlds_dir):
     pw = world.World.load(os.path.join(worlds_dir, "solar.essa"))
     pw.mark_deleted(3)
