@@ -374,7 +374,7 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
     long long slots = c->sm_count; // 1 CTA per SM
     int bestS = 1;
     long long best = -1;
-    int smax = dmax + 1 < 16 ? dmax + 1 : 16;
+    int smax = dmax + 1 < 64 ? dmax + 1 : 64; // finer chunks let sharded worlds (few I blocks per rank) fill whole waves
     for (int S = 1; S <= smax; S++) {
         long long waves = ((long long)own * S + slots - 1) / slots;
         long long cost = waves * ((dmax + 1 + S - 1) / S);
