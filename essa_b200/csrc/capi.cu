@@ -403,6 +403,11 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
         flags[i] = del;
         flags[N + i] = body_active_host(del, dd, cd, ctx->date) ? 1 : 0;
         most[i] = h->most ? h->most[i] : -1;
+        if (most[i] < -1 || most[i] >= n) {
+            ctx->err = "most[] must hold list indices in [0, n) or -1";
+            ctx->n = 0; // nothing was uploaded
+            return ESSA_ERR_ARG;
+        }
         if (cd != INT64_MIN)
             ctx->events.push_back(cd);
         if (del)

@@ -107,6 +107,7 @@ struct essa_ctx {
     bool acc_has_most = false;  // ... and most / max_attraction were evaluated with it
     bool acc_exact = false;     // ... in exact_order arithmetic
     bool gather_pending = false;
+    bool attr_pair4 = false, attr_pair8 = false, attr_cta = false; // opt-in shared-memory sizes set on this device
     bool use_paired = false;    // this essa_step runs its force passes through force_paired.cu
     std::vector<cudaEvent_t> force_events;
     int last_force_passes = 0;

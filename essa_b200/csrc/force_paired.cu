@@ -400,7 +400,7 @@ static void pair_geometry(essa_ctx const* c, int nb, int* ib0, int* ib1) {
 template<int RI>
 static cudaError_t launch_pair_kernels(essa_ctx* c, PairArgs const& A, cudaStream_t st, double** acc) {
     constexpr int PB = kPThreads * RI;
-    static bool attr_set = false;
+    bool& attr_set = RI == 8 ? c->attr_pair8 : c->attr_pair4; // per context: the attribute is per device
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_force_paired<RI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem);
         if (e != cudaSuccess)

@@ -359,7 +359,7 @@ cudaError_t launch_resident_cta(essa_ctx* c, int steps, essa_step_opts const& o,
     A.rec_warps = (c->n + 31) / 32;
     int threads = A.phys_threads + 2 * 32 * A.rec_warps;
     size_t smem = sizeof(CtaShared);
-    static bool attr_set = false;
+    bool& attr_set = c->attr_cta; // per context: the attribute is per device
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_resident_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
