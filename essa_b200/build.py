@@ -17,7 +17,7 @@ LIB = os.path.join(OUT_DIR, "libessa_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
-           "--fmad=true"]
+           "--fmad=true"] + os.environ.get("ESSA_NVCC_EXTRA", "").split()  # e.g. -DESSA_STAGE_CLOCKS (diagnostics)
 CXX = os.environ.get("CXX", "g++")
 HOSTFLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-ffp-contract=off", "-I/usr/local/cuda/include"]
 

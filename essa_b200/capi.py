@@ -347,9 +347,9 @@ class Context:
         return a.value, b.value
 
     def measure_latency(self):
-        out = np.zeros(6)
+        out = np.zeros(8)
         self._ck(self._L.essa_measure_latency(self._h, _ptr(out, _dp)))
-        return dict(zip(("dfma", "dadd", "dmul", "rsqrt_seed", "lds", "shfl_f64"), out.tolist()))
+        return dict(zip(("dfma", "dadd", "dmul", "rsqrt_seed", "lds", "shfl_f64", "dfma_issue_4chains", "dfma_issue_8chains"), out.tolist()))
 
     def flush_l2(self):
         self._ck(self._L.essa_flush_l2(self._h))

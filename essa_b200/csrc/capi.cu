@@ -772,7 +772,8 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
         // worlds of up to 32 bodies in fast arithmetic: one-warp kernel with a recorder warp (resident_warp.cu)
         bool const closest = o.forward_simulated && ctx->closest && ctx->closest_n == ctx->n;
         if (ctx->n <= 32 && !closest && !forces_only)
-            CK(launch_resident_warp(ctx, steps, o, ctx->stream));
+            CK(launch_resident_warp(ctx, steps, o,
+                !o.forward_simulated && mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds), ctx->stream));
         else if (resident_cta_applicable(ctx, o, forces_only)
             && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds)))
             CK(launch_resident_cta(ctx, steps, o, ctx->stream));
@@ -1182,7 +1183,7 @@ extern "C" int essa_shard_range(int n, int rank, int world, int* i0, int* i1) {
 namespace essa {
 int run_latency(essa_ctx* c, double* out6);
 }
-extern "C" int essa_measure_latency(essa_ctx* ctx, double out[6]) {
+extern "C" int essa_measure_latency(essa_ctx* ctx, double out[8]) {
     ARG(ctx, "ctx is null");
     ARG(out, "out is null");
     CK(cudaSetDevice(ctx->device));

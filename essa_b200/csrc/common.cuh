@@ -151,6 +151,44 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "r"(parity)
         : "memory");
 }
+// ---- thread-block cluster / distributed shared memory ----
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(void const* local, unsigned rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 8-byte store into a peer CTA's shared memory that completes `bar` (a peer mbarrier) by 8 transaction bytes
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(v)), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_u64(uint32_t remote_addr, unsigned long long v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(v),
+                 "r"(remote_bar)
+                 : "memory");
+}
+// progress counter in a peer CTA.  Relaxed on purpose: a release here would wait for the caller's
+// outstanding GLOBAL stores (ring writes nobody in the cluster reads); what the peer must not overtake are
+// the caller's shared-memory LOADS, which have returned their values before this store can issue.
+__device__ __forceinline__ void st_relaxed_cluster_u32(uint32_t remote_addr, unsigned v) {
+    asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_cluster_u32(void const* local) {
+    unsigned v;
+    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(local)) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, void const* src_gmem, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))

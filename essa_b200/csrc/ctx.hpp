@@ -200,7 +200,7 @@ int force_iblocks(essa_ctx const* c, int* R_out);
 void choose_split(essa_ctx const* c, int iblocks, int ntiles, int* S_out);
 
 cudaError_t launch_resident(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st);
-cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
+cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool mask_may_change, cudaStream_t st);
 bool resident_cta_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
 cudaError_t launch_resident_cta(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st);

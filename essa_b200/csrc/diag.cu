@@ -294,7 +294,34 @@ __global__ void k_latency(double* out, double a, double b, int iters) {
         v = __shfl_sync(0xffffffffu, v, (threadIdx.x + 1) & 31);
     t1 = clock64();
     double l_shfl = double(t1 - t0) / iters;
+    // single-warp FP64 issue rate: 4 and 8 independent DFMA chains (cycles per instruction)
+    double c0 = a, c1 = a + 1, c2 = a + 2, c3 = a + 3, c4 = a + 4, c5 = a + 5, c6 = a + 6, c7 = a + 7;
+    t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+        c0 = fma(c0, a, b);
+        c1 = fma(c1, a, b);
+        c2 = fma(c2, a, b);
+        c3 = fma(c3, a, b);
+    }
+    t1 = clock64();
+    double thr4 = double(t1 - t0) / (4.0 * iters);
+    t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+        c0 = fma(c0, a, b);
+        c1 = fma(c1, a, b);
+        c2 = fma(c2, a, b);
+        c3 = fma(c3, a, b);
+        c4 = fma(c4, a, b);
+        c5 = fma(c5, a, b);
+        c6 = fma(c6, a, b);
+        c7 = fma(c7, a, b);
+    }
+    t1 = clock64();
+    double thr8 = double(t1 - t0) / (8.0 * iters);
     if (threadIdx.x == 0) {
+        out[7] = thr4;
+        out[8] = thr8;
+        out[9] = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
         out[0] = l_fma;
         out[1] = l_add;
         out[2] = l_mul;
@@ -307,12 +334,12 @@ __global__ void k_latency(double* out, double a, double b, int iters) {
 
 int run_latency(essa_ctx* c, double* out6) {
     double* d;
-    if (cudaMalloc(&d, 8 * sizeof(double)) != cudaSuccess)
+    if (cudaMalloc(&d, 16 * sizeof(double)) != cudaSuccess)
         return ESSA_ERR_CUDA;
     k_latency<<<1, 32, 0, c->stream>>>(d, 0.9999999, 1e-9, 4096);
     c->launches++;
-    double h[8];
-    cudaError_t e = cudaMemcpyAsync(h, d, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    double h[16];
+    cudaError_t e = cudaMemcpyAsync(h, d, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(c->stream);
     cudaFree(d);
@@ -322,6 +349,8 @@ int run_latency(essa_ctx* c, double* out6) {
     }
     for (int i = 0; i < 6; i++)
         out6[i] = h[i];
+    out6[6] = h[7];
+    out6[7] = h[8];
     return ESSA_OK;
 }
 

@@ -15,8 +15,12 @@
 //   * m_ap / m_pe move on every step of a monotonic stretch of an orbit; the exact distance
 //     (IEEE sqrt) and |v| (another one) are formed when the stretch ends.  Decisions are taken on
 //     squared distances with a 1e-15 guard band inside which the exact path runs;
-//   * the decimation test |atan2(y, x) - last| <= 2 pi / capacity is settled by a binary32 estimate
-//     unless it lands within 8e-6 rad of the threshold.
+//   * the decimation test |atan2(y, x) - last| <= 2 pi / capacity is settled without an arctangent
+//     against the unit vector of the last appended direction: "decimate" when the new direction is
+//     within (threshold - 1e-9 rad) of it and the two cannot lie on opposite sides of the +-pi cut
+//     (|cross| < tan(threshold - 1e-9) dot), "append" when it is more than (threshold + 1e-9 rad)
+//     away; m_last_xy_angle itself (an atan2) is formed when the narrow band in between, a cut
+//     crossing or the end of the kernel needs its value.
 #pragma once
 
 #include "common.cuh"
@@ -32,6 +36,10 @@ struct BodyRec {
     double offx, offy, offz;
     double last_angle;
     double thr; // 2 pi / capacity (src/Trail.cpp:58): one IEEE division per kernel, not per step
+    double tthr_lo, tthr_hi; // tan(thr -+ 1e-9); -1 / +inf when the shortcuts are not usable
+    double dir_c, dir_s;     // unit vector of last_angle; both 0 when last_angle is not an atan2 value
+    int ang_pend;            // last_angle = atan2(ang_y, ang_x) not formed yet
+    double ang_x, ang_y;
     double ap, pe, apv, pev;
     // deferred work
     int vpend, ap_pend, pe_pend;
@@ -39,6 +47,37 @@ struct BodyRec {
     double ap_d2, ap_vx, ap_vy, ap_vz; // squared distance / velocity of the pending apoapsis
     double pe_d2, pe_vx, pe_vy, pe_vz;
 };
+
+__device__ __forceinline__ void trail_set_angle(BodyRec& b, double ang) {
+    b.last_angle = ang;
+    b.ang_pend = 0;
+    if (fabs(ang) <= 3.14159265358979323846)
+        sincos(ang, &b.dir_s, &b.dir_c);
+    else
+        b.dir_s = b.dir_c = 0.0;
+}
+
+// m_last_xy_angle = atan2(y, x), postponed; the unit vector the shortcuts need comes from a normalisation
+// (rsqrt seed + two Newton steps: ~1e-16).  Overflow / underflow / zero give NaN, which fails both shortcuts.
+__device__ __forceinline__ void trail_set_direction(BodyRec& b, double px, double py) {
+    b.ang_pend = 1;
+    b.ang_x = px;
+    b.ang_y = py;
+    double r2 = fma(px, px, py * py);
+    double y0 = rsqrt_seed(r2);
+    y0 = y0 * fma(-0.5 * r2, y0 * y0, 1.5);
+    y0 = y0 * fma(-0.5 * r2, y0 * y0, 1.5);
+    b.dir_c = px * y0;
+    b.dir_s = py * y0;
+}
+
+__device__ __forceinline__ double trail_last_angle(BodyRec& b) {
+    if (b.ang_pend) {
+        b.last_angle = atan2(b.ang_y, b.ang_x);
+        b.ang_pend = 0;
+    }
+    return b.last_angle;
+}
 
 __device__ __forceinline__ void rec_load(RecordPtrs const& R, int k, BodyRec& b) {
     b.hist_start = R.hist_start[k];
@@ -51,7 +90,10 @@ __device__ __forceinline__ void rec_load(RecordPtrs const& R, int k, BodyRec& b)
     b.offx = R.toff[3 * k];
     b.offy = R.toff[3 * k + 1];
     b.offz = R.toff[3 * k + 2];
-    b.last_angle = R.last_angle[k];
+    trail_set_angle(b, R.last_angle[k]);
+    bool const usable = b.thr > 2e-9 && b.thr < 1.5;
+    b.tthr_lo = usable ? tan(b.thr - 1e-9) : -1.0;
+    b.tthr_hi = usable ? tan(b.thr + 1e-9) : __longlong_as_double(0x7ff0000000000000LL);
     b.ap = R.ap[k];
     b.pe = R.pe[k];
     b.apv = R.ap_vel[k];
@@ -128,7 +170,7 @@ __device__ __forceinline__ void rec_store_trail(RecordPtrs const& R, int k, Body
     R.toff[3 * k] = b.offx;
     R.toff[3 * k + 1] = b.offy;
     R.toff[3 * k + 2] = b.offz;
-    R.last_angle[k] = b.last_angle;
+    R.last_angle[k] = trail_last_angle(b);
 }
 
 // ... and the ap / pe part.
@@ -149,16 +191,13 @@ __device__ __forceinline__ void rec_store(RecordPtrs const& R, int k, BodyRec& b
 // History::move_forward on the m_side == 0 branch (the only one World::update reaches).
 __device__ __forceinline__ void history_push(RecordPtrs const& R, int k, BodyRec& b, double px, double py, double pz, double vx,
     double vy, double vz) {
-    int slot;
-    if (b.hist_len < ESSA_HISTORY_SEGMENTS) {
-        slot = b.hist_start + b.hist_len;
-        if (slot >= ESSA_HISTORY_SEGMENTS)
-            slot -= ESSA_HISTORY_SEGMENTS;
-        b.hist_len++;
-    } else {
-        slot = b.hist_start;
-        b.hist_start = b.hist_start + 1 == ESSA_HISTORY_SEGMENTS ? 0 : b.hist_start + 1;
-    }
+    // growing: append behind the newest entry; full: overwrite the oldest and advance the start
+    bool const grow = b.hist_len < ESSA_HISTORY_SEGMENTS;
+    int slot = grow ? b.hist_start + b.hist_len : b.hist_start;
+    slot = slot >= ESSA_HISTORY_SEGMENTS ? slot - ESSA_HISTORY_SEGMENTS : slot;
+    int const next = b.hist_start + 1 == ESSA_HISTORY_SEGMENTS ? 0 : b.hist_start + 1;
+    b.hist_len = grow ? b.hist_len + 1 : b.hist_len;
+    b.hist_start = grow ? b.hist_start : next;
     // 48-byte entries in a 256-byte aligned ring: three 16-byte stores
     double2* e = reinterpret_cast<double2*>(R.hist + ((size_t)k * ESSA_HISTORY_SEGMENTS + slot) * 6);
     e[0] = make_double2(px, py);
@@ -186,24 +225,30 @@ __device__ __forceinline__ void trail_recalculate(RecordPtrs const& R, BodyRec& 
 
 // Trail::push_back (src/Trail.cpp:49-75) incl. change_current (:105-110)
 __device__ __forceinline__ void trail_push(RecordPtrs const& R, BodyRec& b, double px, double py, double pz) {
+    // The common step -- still within the decimation angle of the last appended vertex -- is branch free:
+    // change_current(pos) is only remembered (written when something can observe it).
+    // same_side: both directions in one open half plane that the +-pi cut does not cross
+    bool const same_side = (px > 0.0 && b.dir_c > 0.0) || (py > 0.0 && b.dir_s > 0.0) || (py < 0.0 && b.dir_s < 0.0);
+    double const dot = fma(px, b.dir_c, py * b.dir_s);
+    double const crs = fabs(fma(px, b.dir_s, -(py * b.dir_c)));
+    bool const tested = b.length >= 3 && b.append_off != 0;
+    bool const quick = tested && same_side && crs < b.tthr_lo * dot;
+    b.vpend = quick ? 1 : b.vpend;
+    b.vpx = quick ? px : b.vpx;
+    b.vpy = quick ? py : b.vpy;
+    b.vpz = quick ? pz : b.vpz;
+    if (quick)
+        return;
+
     if (b.length == 1) {
         vert_write(R, b, b.append_off, to_vertex1(px), to_vertex1(py), to_vertex1(pz));
         b.append_off++;
         b.length++;
     }
-    double ang = 0;
-    bool have_ang = false;
     if (b.length >= 3 && b.append_off != 0) {
-        double est = fabs((double)atan2f((float)py, (float)px) - b.last_angle);
-        bool decimate;
-        if (est < b.thr - 8e-6 && fabs(px) < 3e38 && fabs(py) < 3e38)
-            decimate = true;
-        else {
-            ang = atan2(py, px);
-            have_ang = true;
-            decimate = fabs(__dsub_rn(ang, b.last_angle)) <= b.thr;
-        }
-        if (decimate) { // change_current(pos): remembered, written when something can observe it
+        // farther than the threshold for sure (a cut crossing only makes |difference| larger)?  else the real thing
+        bool const apart = b.tthr_lo > 0.0 && (dot <= 0.0 ? (crs > 0.0 || dot < 0.0) : crs > b.tthr_hi * dot);
+        if (!apart && fabs(__dsub_rn(atan2(py, px), trail_last_angle(b))) <= b.thr) {
             b.vpend = 1;
             b.vpx = px;
             b.vpy = py;
@@ -221,55 +266,53 @@ __device__ __forceinline__ void trail_push(RecordPtrs const& R, BodyRec& b, doub
         vert_write(R, b, 0, fx, fy, fz);
         b.append_off = 1;
     }
-    b.last_angle = have_ang ? ang : atan2(py, px);
+    trail_set_direction(b, px, py);
 }
 
 // m_ap / m_ap_vel (src/Object.cpp:115-118): `if (ap < d) { ap = d; ap_vel = |v| }`, d = RN(sqrt(d2)).
 // RN o sqrt is monotone, so d2 <= (pending d2) means "no update"; a d2 more than 1e-15 (relative)
 // above the reference square means d is strictly greater; in between, the exact path decides.
 __device__ __forceinline__ void apoapsis_step(BodyRec& b, double d2, double vx, double vy, double vz) {
-    double ref2 = b.ap_pend ? b.ap_d2 : __dmul_rn(b.ap, b.ap);
-    double lo = b.ap_pend ? ref2 : ref2 * (1.0 - 1e-15);
-    double hi = ref2 * (1.0 + 1e-15);
-    if (d2 <= lo)
-        return;
-    if (d2 > hi) {
-        b.ap_pend = 1;
-        b.ap_d2 = d2;
-        b.ap_vx = vx;
-        b.ap_vy = vy;
-        b.ap_vz = vz;
+    double const ref2 = b.ap_pend ? b.ap_d2 : __dmul_rn(b.ap, b.ap);
+    double const lo = b.ap_pend ? ref2 : ref2 * (1.0 - 1e-15);
+    double const hi = ref2 * (1.0 + 1e-15);
+    bool const up = d2 > hi;             // strictly farther: remember, settle later
+    if (d2 > lo && !up) {                // inside the guard band (rare): the reference's own comparison
+        ap_flush(b);
+        double d = __dsqrt_rn(d2);
+        if (b.ap < d) {
+            b.ap = d;
+            b.apv = length3(vx, vy, vz);
+        }
         return;
     }
-    ap_flush(b);
-    double d = __dsqrt_rn(d2);
-    if (b.ap < d) {
-        b.ap = d;
-        b.apv = length3(vx, vy, vz);
-    }
+    b.ap_pend = up ? 1 : b.ap_pend;
+    b.ap_d2 = up ? d2 : b.ap_d2;
+    b.ap_vx = up ? vx : b.ap_vx;
+    b.ap_vy = up ? vy : b.ap_vy;
+    b.ap_vz = up ? vz : b.ap_vz;
 }
 
 // m_pe / m_pe_vel (src/Object.cpp:120-123): `if (pe > d) { pe = d; pe_vel = |v| }`
 __device__ __forceinline__ void periapsis_step(BodyRec& b, double d2, double vx, double vy, double vz) {
-    double ref2 = b.pe_pend ? b.pe_d2 : __dmul_rn(b.pe, b.pe);
-    double hi = b.pe_pend ? ref2 : ref2 * (1.0 + 1e-15);
-    double lo = ref2 * (1.0 - 1e-15);
-    if (d2 >= hi)
-        return;
-    if (d2 < lo) {
-        b.pe_pend = 1;
-        b.pe_d2 = d2;
-        b.pe_vx = vx;
-        b.pe_vy = vy;
-        b.pe_vz = vz;
+    double const ref2 = b.pe_pend ? b.pe_d2 : __dmul_rn(b.pe, b.pe);
+    double const hi = b.pe_pend ? ref2 : ref2 * (1.0 + 1e-15);
+    double const lo = ref2 * (1.0 - 1e-15);
+    bool const down = d2 < lo;
+    if (d2 < hi && !down) {
+        pe_flush(b);
+        double d = __dsqrt_rn(d2);
+        if (b.pe > d) {
+            b.pe = d;
+            b.pev = length3(vx, vy, vz);
+        }
         return;
     }
-    pe_flush(b);
-    double d = __dsqrt_rn(d2);
-    if (b.pe > d) {
-        b.pe = d;
-        b.pev = length3(vx, vy, vz);
-    }
+    b.pe_pend = down ? 1 : b.pe_pend;
+    b.pe_d2 = down ? d2 : b.pe_d2;
+    b.pe_vx = down ? vx : b.pe_vx;
+    b.pe_vy = down ? vy : b.pe_vy;
+    b.pe_vz = down ? vz : b.pe_vz;
 }
 
 // Object::update(speed > 0) for one non-deleted body, in two independent halves so that they can
@@ -282,14 +325,13 @@ __device__ __forceinline__ void record_trail(RecordPtrs const& R, int k, BodyRec
     if (with_history && !forward_sim)
         history_push(R, k, b, px, py, pz, vx, vy, vz);
     bool const rel = offset_trails && most >= 0 && !forward_sim;
-    double ox = rel ? mx : 0.0, oy = rel ? my : 0.0, oz = rel ? mz : 0.0;
-    if (rel && most == old_most) { // Trail::set_offset
-        b.offx = ox;
-        b.offy = oy;
-        b.offz = oz;
-    } else {
-        trail_recalculate(R, b, ox, oy, oz);
-    }
+    double const ox = rel ? mx : 0.0, oy = rel ? my : 0.0, oz = rel ? mz : 0.0;
+    bool const follow = rel && most == old_most; // Trail::set_offset: the offset just follows the same body
+    if (!follow && (b.offx != ox || b.offy != oy || b.offz != oz))
+        trail_recalculate(R, b, ox, oy, oz); // the reference point changed: re-base every vertex
+    b.offx = ox;
+    b.offy = oy;
+    b.offz = oz;
     // pos - most.pos, or pos itself (x - 0.0 == x exactly)
     trail_push(R, b, rel ? __dsub_rn(px, mx) : px, rel ? __dsub_rn(py, my) : py, rel ? __dsub_rn(pz, mz) : pz);
 }

@@ -214,7 +214,7 @@ __global__ void k_record_init(WorldPtrs const W, RecordPtrs const R, double* his
     b.append_off = 1;
     b.length = 1;
     b.offx = b.offy = b.offz = 0;
-    b.last_angle = 0;
+    trail_set_angle(b, 0.0);
     trail_push(R, b, p.x, p.y, p.z);
     rec_store(R, k, b);
 }

@@ -221,9 +221,10 @@ int essa_shard_world(const essa_ctx* ctx);
 double essa_measure_fp64_peak(essa_ctx* ctx, double ms);
 /* Maximum relative error of the MUFU.RSQ64H seed and of the refined r^-3 over a log sweep. */
 int essa_measure_rsqrt_error(essa_ctx* ctx, double* seed_rel_err, double* refined_rel_err);
-/* Dependent-issue latencies in SM cycles: {DFMA, DADD, DMUL, MUFU.RSQ64H seed, LDS chase, shuffle of a double}:
- * what bounds a single small-N trajectory (one step is a dependent chain). */
-int essa_measure_latency(essa_ctx* ctx, double out[6]);
+/* Dependent-issue latencies in SM cycles: {DFMA, DADD, DMUL, MUFU.RSQ64H seed, LDS chase, shuffle of a double}, then
+ * the single-warp FP64 issue interval with 4 and 8 independent chains (cycles per instruction):
+ * what bounds a single small-N trajectory (one step is a dependent chain issued by one warp). */
+int essa_measure_latency(essa_ctx* ctx, double out[8]);
 /* Evict the L2 between timed iterations (writes a 256 MiB scratch buffer). */
 int essa_flush_l2(essa_ctx* ctx);
 
