@@ -37,9 +37,8 @@ struct BodyRec {
     double last_angle;
     double thr; // 2 pi / capacity (src/Trail.cpp:58): one IEEE division per kernel, not per step
     double tthr_lo, tthr_hi; // tan(thr -+ 1e-9); -1 / +inf when the shortcuts are not usable
-    double dir_c, dir_s;     // unit vector of last_angle; both 0 when last_angle is not an atan2 value
-    int ang_pend;            // last_angle = atan2(ang_y, ang_x) not formed yet
-    double ang_x, ang_y;
+    double dir_c, dir_s;     // a vector along last_angle; both 0 when last_angle is not an atan2 value
+    int ang_pend;            // last_angle = atan2(dir_s, dir_c) not formed yet
     double ap, pe, apv, pev;
     // deferred work
     int vpend, ap_pend, pe_pend;
@@ -57,23 +56,18 @@ __device__ __forceinline__ void trail_set_angle(BodyRec& b, double ang) {
         b.dir_s = b.dir_c = 0.0;
 }
 
-// m_last_xy_angle = atan2(y, x), postponed; the unit vector the shortcuts need comes from a normalisation
-// (rsqrt seed + two Newton steps: ~1e-16).  Overflow / underflow / zero give NaN, which fails both shortcuts.
+// m_last_xy_angle = atan2(y, x), postponed.  The shortcuts compare directions only (both sides of
+// |cross| < tan * dot scale with the reference vector's length), so the position itself serves as the
+// reference vector.  Overflow / zero give inf / NaN / 0, which fail both shortcuts.
 __device__ __forceinline__ void trail_set_direction(BodyRec& b, double px, double py) {
     b.ang_pend = 1;
-    b.ang_x = px;
-    b.ang_y = py;
-    double r2 = fma(px, px, py * py);
-    double y0 = rsqrt_seed(r2);
-    y0 = y0 * fma(-0.5 * r2, y0 * y0, 1.5);
-    y0 = y0 * fma(-0.5 * r2, y0 * y0, 1.5);
-    b.dir_c = px * y0;
-    b.dir_s = py * y0;
+    b.dir_c = px;
+    b.dir_s = py;
 }
 
 __device__ __forceinline__ double trail_last_angle(BodyRec& b) {
     if (b.ang_pend) {
-        b.last_angle = atan2(b.ang_y, b.ang_x);
+        b.last_angle = atan2(b.dir_s, b.dir_c);
         b.ang_pend = 0;
     }
     return b.last_angle;
@@ -109,6 +103,9 @@ __device__ __forceinline__ void rec_load(RecordPtrs const& R, int k, BodyRec& b)
 // is formed as f * RN(1/AU) (within 3 double ulps of the correctly rounded quotient) and the slow
 // exact division runs only when that could change the binary32 rounding, i.e. when the double's 29
 // discarded mantissa bits sit within 8 ulps of the rounding boundary.  Bit-identical to the division.
+// (kept out of line so that the compiler cannot if-convert it into the common path)
+static __device__ __noinline__ double divide_by_au_exact(double f) { return __ddiv_rn(f, ESSA_AU); }
+
 __device__ __forceinline__ float to_vertex1(double p) {
     double f = (double)__double2float_rn(p);
     double qf = __dmul_rn(f, 1.0 / ESSA_AU);
@@ -116,7 +113,7 @@ __device__ __forceinline__ float to_vertex1(double p) {
     unsigned ex = ((unsigned)__double2hiint(qf) >> 20) & 0x7ffu;
     bool risky = f != 0.0 && ((lo - 0x0ffffff8u) <= 16u || ex < 1023u - 120u || ex > 1023u + 120u);
     if (risky)
-        qf = __ddiv_rn(f, ESSA_AU);
+        qf = divide_by_au_exact(f);
     return __double2float_rn(qf);
 }
 
@@ -223,8 +220,11 @@ __device__ __forceinline__ void trail_recalculate(RecordPtrs const& R, BodyRec& 
     b.offz = oz;
 }
 
-// Trail::push_back (src/Trail.cpp:49-75) incl. change_current (:105-110)
-__device__ __forceinline__ void trail_push(RecordPtrs const& R, BodyRec& b, double px, double py, double pz) {
+// Trail::push_back (src/Trail.cpp:49-75) incl. change_current (:105-110), in two halves so that a warp
+// can convert the vertices of an append cooperatively (resident_warp.cu) between them.
+//
+// First half: everything up to the decision.  Returns true when a vertex has to be appended.
+__device__ __forceinline__ bool trail_decide(RecordPtrs const& R, BodyRec& b, double px, double py, double pz) {
     // The common step -- still within the decimation angle of the last appended vertex -- is branch free:
     // change_current(pos) is only remembered (written when something can observe it).
     // same_side: both directions in one open half plane that the +-pi cut does not cross
@@ -238,7 +238,7 @@ __device__ __forceinline__ void trail_push(RecordPtrs const& R, BodyRec& b, doub
     b.vpy = quick ? py : b.vpy;
     b.vpz = quick ? pz : b.vpz;
     if (quick)
-        return;
+        return false;
 
     if (b.length == 1) {
         vert_write(R, b, b.append_off, to_vertex1(px), to_vertex1(py), to_vertex1(pz));
@@ -253,20 +253,42 @@ __device__ __forceinline__ void trail_push(RecordPtrs const& R, BodyRec& b, doub
             b.vpx = px;
             b.vpy = py;
             b.vpz = pz;
-            return;
+            return false;
         }
     }
-    trail_flush_vertex(R, b);
-    float fx = to_vertex1(px), fy = to_vertex1(py), fz = to_vertex1(pz);
-    vert_write(R, b, b.append_off, fx, fy, fz);
+    return true;
+}
+
+// Second half: the append.  v[0..2] = the pending change_current vertex (used only if there is one),
+// v[3..5] = the new vertex, both already converted with to_vertex1.
+__device__ __forceinline__ void trail_append(RecordPtrs const& R, BodyRec& b, float const* v, double px, double py) {
+    if (b.vpend) {
+        if (b.append_off == 1)
+            vert_write(R, b, b.length - 1, v[0], v[1], v[2]);
+        vert_write(R, b, b.append_off - 1, v[0], v[1], v[2]);
+        b.vpend = 0;
+    }
+    vert_write(R, b, b.append_off, v[3], v[4], v[5]);
     b.append_off++;
     if (b.length < b.cap)
         b.length++;
     if (b.append_off == b.cap) {
-        vert_write(R, b, 0, fx, fy, fz);
+        vert_write(R, b, 0, v[3], v[4], v[5]);
         b.append_off = 1;
     }
     trail_set_direction(b, px, py);
+}
+
+__device__ __forceinline__ void trail_push(RecordPtrs const& R, BodyRec& b, double px, double py, double pz) {
+    if (!trail_decide(R, b, px, py, pz))
+        return;
+    float v[6] = { 0.f, 0.f, 0.f, to_vertex1(px), to_vertex1(py), to_vertex1(pz) };
+    if (b.vpend) {
+        v[0] = to_vertex1(b.vpx);
+        v[1] = to_vertex1(b.vpy);
+        v[2] = to_vertex1(b.vpz);
+    }
+    trail_append(R, b, v, px, py);
 }
 
 // m_ap / m_ap_vel (src/Object.cpp:115-118): `if (ap < d) { ap = d; ap_vel = |v| }`, d = RN(sqrt(d2)).
@@ -320,8 +342,10 @@ __device__ __forceinline__ void periapsis_step(BodyRec& b, double d2, double vx,
 // drift of every body is finished before any update() runs); ignored when most < 0.
 //
 // Half 1: History::move_forward + recalculate_trails_with_offset / Trail::push_back.
-__device__ __forceinline__ void record_trail(RecordPtrs const& R, int k, BodyRec& b, double px, double py, double pz, double vx, double vy,
-    double vz, double mx, double my, double mz, int most, int old_most, bool offset_trails, bool forward_sim, bool with_history = true) {
+// (returns whether a vertex has to be appended for the trail-relative position (rx, ry, rz))
+__device__ __forceinline__ bool record_trail_decide(RecordPtrs const& R, int k, BodyRec& b, double px, double py, double pz, double vx,
+    double vy, double vz, double mx, double my, double mz, int most, int old_most, bool offset_trails, bool forward_sim, bool with_history,
+    double& rx, double& ry, double& rz) {
     if (with_history && !forward_sim)
         history_push(R, k, b, px, py, pz, vx, vy, vz);
     bool const rel = offset_trails && most >= 0 && !forward_sim;
@@ -333,7 +357,25 @@ __device__ __forceinline__ void record_trail(RecordPtrs const& R, int k, BodyRec
     b.offy = oy;
     b.offz = oz;
     // pos - most.pos, or pos itself (x - 0.0 == x exactly)
-    trail_push(R, b, rel ? __dsub_rn(px, mx) : px, rel ? __dsub_rn(py, my) : py, rel ? __dsub_rn(pz, mz) : pz);
+    rx = rel ? __dsub_rn(px, mx) : px;
+    ry = rel ? __dsub_rn(py, my) : py;
+    rz = rel ? __dsub_rn(pz, mz) : pz;
+    return trail_decide(R, b, rx, ry, rz);
+}
+
+__device__ __forceinline__ void record_trail(RecordPtrs const& R, int k, BodyRec& b, double px, double py, double pz, double vx, double vy,
+    double vz, double mx, double my, double mz, int most, int old_most, bool offset_trails, bool forward_sim, bool with_history = true) {
+    double rx, ry, rz;
+    if (!record_trail_decide(R, k, b, px, py, pz, vx, vy, vz, mx, my, mz, most, old_most, offset_trails, forward_sim, with_history, rx, ry,
+            rz))
+        return;
+    float v[6] = { 0.f, 0.f, 0.f, to_vertex1(rx), to_vertex1(ry), to_vertex1(rz) };
+    if (b.vpend) {
+        v[0] = to_vertex1(b.vpx);
+        v[1] = to_vertex1(b.vpy);
+        v[2] = to_vertex1(b.vpz);
+    }
+    trail_append(R, b, v, rx, ry);
 }
 
 // Half 2: ap / pe against the most attracting object (src/Object.cpp:111-123).

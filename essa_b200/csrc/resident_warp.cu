@@ -460,14 +460,16 @@ __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
 //                     costs the physics warps seven stores and no handshake.
 //   CTA 1  warps 0-2  attraction: most-attracting links, steps dealt round-robin (a step's link depends
 //                     only on that step's final positions)
-//          warp 3     Trail
-//          warp 4     link bookkeeping + History + ap / pe
-//                     The two consumers report progress with a release store into CTA 0's shared memory;
+//          warps 3, 5 Trail (even / odd bodies)
+//          warp 4     link bookkeeping + History
+//          warp 6     ap / pe
+//                     The consumers report progress with a release store into CTA 0's shared memory;
 //                     the physics warps look at it only when their cached copy says the ring could be full.
 // ------------------------------------------------------------------------------------------------
 constexpr int kQuadWarps = 4;
 constexpr int kAttrWarps = 3;
-constexpr int kQuadThreads = 32 * 5;
+constexpr int kHistWarp = 4, kConsumerEnd = 7; // CTA 1: warps 3 .. 6 consume
+constexpr int kQuadThreads = 32 * kConsumerEnd;
 
 template<int T, int LOG2L>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_resident_quad(WarpArgs const A) {
@@ -476,7 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
     __shared__ double sgf[32];                            // CTA 1
     __shared__ __align__(16) Snapshot ring[kRing];        // CTA 1
     __shared__ __align__(8) unsigned long long full[kRing], ready[kRing]; // CTA 1
-    __shared__ unsigned done[2];                          // CTA 0: steps consumed by CTA 1's warps 3 and 4
+    __shared__ unsigned done[4];                          // CTA 0: steps consumed by CTA 1's warps 3 .. 6
 
     int const n = A.n, L = A.L; // attraction / recorder warps: L = 32 / n lanes per body, lane = k + q n
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -498,7 +500,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
             for (int i = 0; i < kRing; i++)
                 mbar_expect_tx(&full[i], snap_bytes);
         } else {
-            done[0] = done[1] = 0;
+            done[0] = done[1] = done[2] = done[3] = 0;
         }
     }
     __syncthreads();
@@ -584,15 +586,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
         if (lane == 0)
             printf("attraction warp %d: %lld busy clk per step of its own\n", warp, abusy / (A.steps / kAttrWarps + 1));
 #endif
-    } else if (cta == 1 && snap_on && (warp == 4 || rec_on)) {
-        // ---------------- consumer warps: 3 = Trail, 4 = link bookkeeping + History + ap / pe ----------------
+    } else if (cta == 1 && snap_on && warp < kConsumerEnd && (warp == kHistWarp || rec_on)) {
+        // ---------------- consumer warps ----------------
+        //   3, 5  Trail (bodies with even / odd index: an append is ~4x the cost of a decimated step and stalls
+        //         the whole warp, so two warps halve how often that happens to each)
+        //   4     link bookkeeping + History
+        //   6     ap / pe
+        // Every consumer follows the most-attracting links itself (a few integer instructions per step).
         bool const body = lane < n;
-        bool const mine = rec_on && body && lane < A.r.tracked;
+        bool const is_trail = warp == 3 || warp == 5;
+        bool const mine = rec_on && body && lane < A.r.tracked && (!is_trail || (lane & 1) == (warp == 5 ? 1 : 0));
         uint32_t const done_remote = mapa_u32(&done[warp - 3], 0);
         BodyRec b;
         if (mine)
             rec_load(A.r, lane, b);
         int most = body ? A.w.most[lane] : -1, old_most = body ? A.w.old_most[lane] : -1;
+        bool const offset_trails = A.offset_trails != 0, forward_sim = A.forward_sim != 0;
 #ifdef ESSA_STAGE_CLOCKS
         long long busy = 0;
 #endif
@@ -611,16 +620,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
             if (mine && act) {
                 int const mi = most >= 0 ? most : 0;
                 double const mx = sn.x[mi], my = sn.y[mi], mz = sn.z[mi];
-                if (warp == 3) {
+                if (is_trail)
                     record_trail(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], mx, my, mz, most,
-                        old_most, A.offset_trails != 0, A.forward_sim != 0, false);
-                } else {
-                    if (!A.forward_sim)
+                        old_most, offset_trails, forward_sim, false);
+                else if (warp == kHistWarp) {
+                    if (!forward_sim)
                         history_push(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane]);
+                } else
                     record_appe(b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], mx, my, mz, most);
-                }
             }
-            if (warp == 4 && s == A.steps - 1 && act) {
+            if (warp == kHistWarp && s == A.steps - 1 && act) {
                 // max_attraction as the last force pass left it: the winner's gf / r^4 to full precision, or 0
                 A.w.maxattr[lane] = winner >= 0 ? attraction_metric(sn.x[lane], sn.y[lane], sn.z[lane], sn.x[winner], sn.y[winner],
                                                       sn.z[winner], A.w.gf[winner])
@@ -637,17 +646,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
         if (lane == 0)
             printf("consumer warp %d: %lld busy clk/step\n", warp, busy / A.steps);
 #endif
-        if (warp == 4 && body) {
+        if (warp == kHistWarp && body) {
             A.w.most[lane] = most;
             A.w.old_most[lane] = old_most;
         }
         if (mine) {
-            if (warp == 3) {
+            if (is_trail) {
                 rec_store_trail(A.r, lane, b, false);
-            } else {
-                rec_store_appe(A.r, lane, b);
+            } else if (warp == kHistWarp) {
                 A.r.hist_start[lane] = b.hist_start;
                 A.r.hist_len[lane] = b.hist_len;
+            } else {
+                rec_store_appe(A.r, lane, b);
             }
         }
     } else if (cta == 0 && warp < kQuadWarps) {
@@ -818,9 +828,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                 int const slot = s % kRing;
                 if (s - consumed >= kRing) { // the slot may still be in use: look at CTA 1's progress
                     do {
-                        int d1 = (int)ld_acquire_cluster_u32(&done[1]);
-                        int d0 = rec_on ? (int)ld_acquire_cluster_u32(&done[0]) : d1;
-                        consumed = d0 < d1 ? d0 : d1;
+                        consumed = (int)ld_acquire_cluster_u32(&done[kHistWarp - 3]);
+                        if (rec_on) {
+                            int const d0 = (int)ld_acquire_cluster_u32(&done[0]), d2 = (int)ld_acquire_cluster_u32(&done[2]),
+                                      d3 = (int)ld_acquire_cluster_u32(&done[3]);
+                            consumed = min(min(consumed, d0), min(d2, d3));
+                        }
                     } while (s - consumed >= kRing);
                 }
                 uint32_t const dst = snap_remote + (uint32_t)slot * (uint32_t)sizeof(Snapshot);
