@@ -6,7 +6,7 @@
 // (src/Object.cpp:405-417).  Instead of one clone stepped inline on the GUI thread, `copies`
 // clones are resident in shared memory, several per CTA, for all steps of a launch.
 //
-// Layout: state[copy][6][n] (x y z vx vy vz), copy-major, so a CTA's copies are contiguous.
+// Layout in HBM: state[copy][6][n] (x y z vx vy vz), copy-major, so a CTA's copies are contiguous.
 // Thread t of a CTA owns (copy = t / n, body = t % n); all copies of a CTA step in lock step
 // behind the same two __syncthreads per KDK iteration.
 #include "common.cuh"
@@ -44,18 +44,56 @@ struct EnsembleArgs {
     int approaches, approach_to;
 };
 
+// Fast-arithmetic row: the n - 1 partners of body k in ring order p = k + 1, k + 2, ... (mod n) -- no self
+// term, no padding.  Every copy's arrays are stored twice back to back (entries [0, n) and [n, 2n - 1)), so the
+// ring needs no wrap-around arithmetic: the pointers passed in are the arrays offset by k + 1, and the loop is
+// loads at immediate offsets plus FP64 work only (integer address arithmetic was costing a third of the issue
+// slots).  The per-copy stride is congruent to n modulo 16, which keeps a warp's consecutive (copy, body)
+// lanes on distinct 8-byte bank pairs, exactly as if the copies were packed.
+__device__ __forceinline__ int ring_stride(int n) {
+    int s = 2 * n - 1;
+    return s + ((n - s) % 16 + 16) % 16;
+}
+
+__device__ __forceinline__ void ring_forces(int n, double const* px, double const* py, double const* pz, double const* pg, double x,
+    double y, double z, double& ax, double& ay, double& az) {
+    double fx[4] = { 0, 0, 0, 0 }, fy[4] = { 0, 0, 0, 0 }, fz[4] = { 0, 0, 0, 0 };
+    int j = 0;
+    for (; j + 4 <= n - 1; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            double4 q = make_double4(px[j + u], py[j + u], pz[j + u], pg[j + u]);
+            fast_interact(x, y, z, q, 0.0, fx[u], fy[u], fz[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        if (j + u < n - 1) {
+            double4 q = make_double4(px[j + u], py[j + u], pz[j + u], pg[j + u]);
+            fast_interact(x, y, z, q, 0.0, fx[u], fy[u], fz[u]);
+        }
+    }
+    ax = (fx[0] + fx[1]) + (fx[2] + fx[3]);
+    ay = (fy[0] + fy[1]) + (fy[2] + fy[3]);
+    az = (fz[0] + fz[1]) + (fz[2] + fz[3]);
+}
+
+// Shared memory: sx[per_cta S] sy[..] sz[..] sg[..], copy-major inside each array (copy lc owns [lc S, lc S + S),
+// S = ring_stride(n) for the fast flavour (doubled arrays), n for exact_order).
 template<bool EXACT>
 __global__ void __launch_bounds__(kEnsThreadsMax, 2) k_ensemble(EnsembleArgs const A) {
-    extern __shared__ double smem[]; // per copy: sx[npad] sy[npad] sz[npad] sg[npad]
-    int const n = A.n, npad = (n + 3) & ~3;
+    extern __shared__ double smem[];
+    int const n = A.n;
     int const t = threadIdx.x;
     int const lc = t / n, k = t - lc * n;
     int const copy = blockIdx.x * A.per_cta + lc;
     bool const live = lc < A.per_cta && copy < A.copies;
-    double* sx = smem + (size_t)(lc < A.per_cta ? lc : 0) * 4 * npad;
-    double* sy = sx + npad;
-    double* sz = sy + npad;
-    double* sg = sz + npad;
+    int const S = EXACT ? n : ring_stride(n);
+    size_t const plane = (size_t)A.per_cta * S;
+    double* sx = smem + (size_t)(lc < A.per_cta ? lc : 0) * S;
+    double* sy = sx + plane;
+    double* sz = sy + plane;
+    double* sg = sz + plane;
 
     double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0, md = 0, dummy_m = 0;
     int dummy_most = -1;
@@ -69,50 +107,184 @@ __global__ void __launch_bounds__(kEnsThreadsMax, 2) k_ensemble(EnsembleArgs con
         vz = s[5 * (size_t)n + k];
         gfk = A.gf[k];
         md = A.mind[(size_t)copy * n + k];
-    }
-    // zero-weight padding so that the 4-way unrolled row loop may run to npad
-    for (int i = t; i < A.per_cta * 4 * npad; i += blockDim.x)
-        smem[i] = 0.0;
-    __syncthreads();
-    if (live) {
         sx[k] = x;
         sy[k] = y;
         sz[k] = z;
         sg[k] = gfk;
+        if (!EXACT && k < n - 1) {
+            sx[n + k] = x;
+            sy[n + k] = y;
+            sz[n + k] = z;
+            sg[n + k] = gfk;
+        }
     }
     __syncthreads();
     bool const on = live && gfk != 0.0; // a body that deleted() masks is neither attracted nor moved
+    auto forces = [&]() {
+        if (EXACT)
+            row_forces<true, false>(k, n, n, sx, sy, sz, sg, x, y, z, gfk, 0.0, ax, ay, az, dummy_m, dummy_most);
+        else
+            ring_forces(n, sx + k + 1, sy + k + 1, sz + k + 1, sg + k + 1, x, y, z, ax, ay, az);
+    };
     if (on)
-        row_forces<EXACT, false>(k, n, npad, sx, sy, sz, sg, x, y, z, gfk, 0.0, ax, ay, az, dummy_m, dummy_most);
+        forces();
+    // (a h) mul == a (h mul) and (v dt) mul == v (dt mul) exactly: mul is +-1
+    double const hm = A.h * A.mul, dtm = A.dt * A.mul;
+    // Object::update_closest_approaches (src/Object.cpp:405-417) keeps min over steps of RN(sqrt(d2)); RN o sqrt
+    // is monotone, so the minimum of d2 is tracked and the root taken once.  m2 < 0: nothing seen since the
+    // last restart; a distance of exactly zero stores 0 == "unset" in the reference, i.e. restarts the search.
+    double m2 = -1.0;
+    bool const approaches = A.approaches && live && k != A.approach_to;
+    int const to = A.approach_to;
 
     for (int st = 0; st < A.steps; st++) {
-        if (A.approaches && live && k != A.approach_to) { // Object::update_closest_approaches, at the step's start
-            double dx = __dsub_rn(sx[A.approach_to], x), dy = __dsub_rn(sy[A.approach_to], y), dz = __dsub_rn(sz[A.approach_to], z);
-            double d = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-            if (md == 0.0 || d < md)
-                md = d;
+        if (approaches) { // at the step's start
+            double dx = __dsub_rn(sx[to], x), dy = __dsub_rn(sy[to], y), dz = __dsub_rn(sz[to], z);
+            double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (d2 == 0.0) {
+                md = 0.0;
+                m2 = -1.0;
+            } else if (m2 < 0.0 || d2 < m2) {
+                m2 = d2;
+            }
         }
         if (on) {
-            vx = kick1(vx, ax, A.h, A.mul);
-            vy = kick1(vy, ay, A.h, A.mul);
-            vz = kick1(vz, az, A.h, A.mul);
-            x = __dadd_rn(x, __dmul_rn(__dmul_rn(vx, A.dt), A.mul));
-            y = __dadd_rn(y, __dmul_rn(__dmul_rn(vy, A.dt), A.mul));
-            z = __dadd_rn(z, __dmul_rn(__dmul_rn(vz, A.dt), A.mul));
+            vx = __dadd_rn(vx, __dmul_rn(ax, hm));
+            vy = __dadd_rn(vy, __dmul_rn(ay, hm));
+            vz = __dadd_rn(vz, __dmul_rn(az, hm));
+            x = __dadd_rn(x, __dmul_rn(vx, dtm));
+            y = __dadd_rn(y, __dmul_rn(vy, dtm));
+            z = __dadd_rn(z, __dmul_rn(vz, dtm));
         }
         __syncthreads();
         if (live) {
             sx[k] = x;
             sy[k] = y;
             sz[k] = z;
+            if (!EXACT && k < n - 1) {
+                sx[n + k] = x;
+                sy[n + k] = y;
+                sz[n + k] = z;
+            }
         }
         __syncthreads();
         if (on) {
-            row_forces<EXACT, false>(k, n, npad, sx, sy, sz, sg, x, y, z, gfk, 0.0, ax, ay, az, dummy_m, dummy_most);
-            vx = kick1(vx, ax, A.h, A.mul);
-            vy = kick1(vy, ay, A.h, A.mul);
-            vz = kick1(vz, az, A.h, A.mul);
+            forces();
+            vx = __dadd_rn(vx, __dmul_rn(ax, hm));
+            vy = __dadd_rn(vy, __dmul_rn(ay, hm));
+            vz = __dadd_rn(vz, __dmul_rn(az, hm));
         }
+    }
+    if (approaches && m2 >= 0.0) {
+        double d = __dsqrt_rn(m2);
+        if (md == 0.0 || d < md)
+            md = d;
+    }
+    if (live) {
+        s[k] = x;
+        s[(size_t)n + k] = y;
+        s[2 * (size_t)n + k] = z;
+        s[3 * (size_t)n + k] = vx;
+        s[4 * (size_t)n + k] = vy;
+        s[5 * (size_t)n + k] = vz;
+        A.mind[(size_t)copy * n + k] = md;
+    }
+}
+
+// Warp-synchronous flavour for templates of up to 32 bodies (fast arithmetic): a warp owns 32 / n whole
+// copies and steps them with __syncwarp only.  Warps never wait for each other, so the SM's schedulers
+// always find a warp whose dependent FP64 chain is ready -- with block-wide barriers every warp of a CTA
+// sits in the same phase of the step and the FP64 pipe idles nearly half of the time (measured).
+constexpr int kEnsWarpsPerCta = 4;
+
+__global__ void __launch_bounds__(32 * kEnsWarpsPerCta, 5) k_ensemble_warp(EnsembleArgs const A) {
+    extern __shared__ double smem[]; // per warp: sx[cw n] sy[..] sz[..] sg[..]
+    int const n = A.n, cw = 32 / n;
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int const lc = lane / n, k = lane - lc * n;
+    long long const gw = (long long)blockIdx.x * kEnsWarpsPerCta + warp;
+    long long const copy = gw * cw + lc;
+    bool const live = lc < cw && copy < A.copies;
+    int const S = ring_stride(n), plane = cw * S;
+    double* sx = smem + (size_t)warp * 4 * plane + (lc < cw ? lc : 0) * S;
+    double* sy = sx + plane;
+    double* sz = sy + plane;
+    double* sg = sz + plane;
+
+    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0, md = 0;
+    double* s = A.state + (size_t)(live ? copy : 0) * 6 * n;
+    if (live) {
+        x = s[k];
+        y = s[(size_t)n + k];
+        z = s[2 * (size_t)n + k];
+        vx = s[3 * (size_t)n + k];
+        vy = s[4 * (size_t)n + k];
+        vz = s[5 * (size_t)n + k];
+        gfk = A.gf[k];
+        md = A.mind[(size_t)copy * n + k];
+        sx[k] = x;
+        sy[k] = y;
+        sz[k] = z;
+        sg[k] = gfk;
+        if (k < n - 1) {
+            sx[n + k] = x;
+            sy[n + k] = y;
+            sz[n + k] = z;
+            sg[n + k] = gfk;
+        }
+    }
+    __syncwarp();
+    bool const on = live && gfk != 0.0;
+    double const *const px = sx + k + 1, *const py = sy + k + 1, *const pz = sz + k + 1, *const pg = sg + k + 1;
+    if (on)
+        ring_forces(n, px, py, pz, pg, x, y, z, ax, ay, az);
+    double const hm = A.h * A.mul, dtm = A.dt * A.mul;
+    double m2 = -1.0; // see k_ensemble
+    bool const approaches = A.approaches && live && k != A.approach_to;
+    int const to = A.approach_to;
+
+    for (int st = 0; st < A.steps; st++) {
+        if (approaches) {
+            double dx = __dsub_rn(sx[to], x), dy = __dsub_rn(sy[to], y), dz = __dsub_rn(sz[to], z);
+            double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (d2 == 0.0) {
+                md = 0.0;
+                m2 = -1.0;
+            } else if (m2 < 0.0 || d2 < m2) {
+                m2 = d2;
+            }
+        }
+        if (on) {
+            vx = __dadd_rn(vx, __dmul_rn(ax, hm));
+            vy = __dadd_rn(vy, __dmul_rn(ay, hm));
+            vz = __dadd_rn(vz, __dmul_rn(az, hm));
+            x = __dadd_rn(x, __dmul_rn(vx, dtm));
+            y = __dadd_rn(y, __dmul_rn(vy, dtm));
+            z = __dadd_rn(z, __dmul_rn(vz, dtm));
+        }
+        __syncwarp();
+        if (live) {
+            sx[k] = x;
+            sy[k] = y;
+            sz[k] = z;
+            if (k < n - 1) {
+                sx[n + k] = x;
+                sy[n + k] = y;
+                sz[n + k] = z;
+            }
+        }
+        __syncwarp();
+        if (on) {
+            ring_forces(n, px, py, pz, pg, x, y, z, ax, ay, az);
+            vx = __dadd_rn(vx, __dmul_rn(ax, hm));
+            vy = __dadd_rn(vy, __dmul_rn(ay, hm));
+            vz = __dadd_rn(vz, __dmul_rn(az, hm));
+        }
+    }
+    if (approaches && m2 >= 0.0) {
+        double d = __dsqrt_rn(m2);
+        if (md == 0.0 || d < md)
+            md = d;
     }
     if (live) {
         s[k] = x;
@@ -135,7 +307,7 @@ cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st) {
 }
 
 cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
-    int n = c->ens_n, npad = (n + 3) & ~3;
+    int n = c->ens_n;
     EnsembleArgs A;
     A.state = c->ens_state;
     A.gf = c->ens_gf;
@@ -153,13 +325,19 @@ cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
         per_cta = c->ens_copies;
     A.per_cta = per_cta;
     int threads = (per_cta * n + 31) / 32 * 32;
-    size_t smem = (size_t)per_cta * 4 * npad * sizeof(double);
+    int const ring_s = [&] { int s2 = 2 * n - 1; return s2 + ((n - s2) % 16 + 16) % 16; }(); // = ring_stride(n)
+    size_t smem = (size_t)per_cta * 4 * (c->ens.exact_order ? n : ring_s) * sizeof(double);
     int blocks = (c->ens_copies + per_cta - 1) / per_cta;
     cudaError_t e;
     if (c->ens.exact_order) {
         if (threads > kEnsThreadsMax) // a template wider than one ensemble CTA: one copy per CTA at full width
             return cudaErrorInvalidConfiguration;
         k_ensemble<true><<<blocks, threads, smem, st>>>(A);
+    } else if (n <= 32) {
+        int cw = 32 / n;
+        long long warps = ((long long)c->ens_copies + cw - 1) / cw;
+        int wblocks = (int)((warps + kEnsWarpsPerCta - 1) / kEnsWarpsPerCta);
+        k_ensemble_warp<<<wblocks, 32 * kEnsWarpsPerCta, (size_t)kEnsWarpsPerCta * 4 * cw * ring_s * sizeof(double), st>>>(A);
     } else {
         if (threads > kEnsThreadsMax)
             return cudaErrorInvalidConfiguration;
