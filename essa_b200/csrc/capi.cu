@@ -775,9 +775,17 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
             CK(launch_resident_warp(ctx, steps, o,
                 !o.forward_simulated && mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds), ctx->stream));
         else if (resident_cta_applicable(ctx, o, forces_only)
-            && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds)))
-            CK(launch_resident_cta(ctx, steps, o, ctx->stream));
-        else
+            && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds))) {
+            // 33 .. 128 bodies: a cluster of 8 / 16 SMs (resident_cluster.cu); one SM if the cluster cannot be placed
+            bool clustered = false;
+            if (resident_cluster_applicable(ctx, o, forces_only)) {
+                clustered = launch_resident_cluster(ctx, steps, o, ctx->stream) == cudaSuccess;
+                if (!clustered)
+                    (void)cudaGetLastError();
+            }
+            if (!clustered)
+                CK(launch_resident_cta(ctx, steps, o, ctx->stream));
+        } else
             CK(launch_resident(ctx, steps, o, forces_only, ctx->stream));
         CK(cudaEventRecord(ctx->ev_end, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

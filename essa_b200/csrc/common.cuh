@@ -172,6 +172,11 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
                  "l"(__double_as_longlong(v)), "r"(remote_bar)
                  : "memory");
 }
+__device__ __forceinline__ void st_async_v2_f64(uint32_t remote_addr, double a, double b, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr), "d"(a),
+                 "d"(b), "r"(remote_bar)
+                 : "memory");
+}
 __device__ __forceinline__ void st_async_u64(uint32_t remote_addr, unsigned long long v, uint32_t remote_bar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(v),
                  "r"(remote_bar)

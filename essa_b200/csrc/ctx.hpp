@@ -108,6 +108,7 @@ struct essa_ctx {
     bool acc_exact = false;     // ... in exact_order arithmetic
     bool gather_pending = false;
     bool attr_pair4 = false, attr_pair8 = false, attr_cta = false; // opt-in shared-memory sizes set on this device
+    bool attr_cluster16[5] = { false, false, false, false, false }; // non-portable cluster size allowed for K3x<PER>
     bool use_paired = false;    // this essa_step runs its force passes through force_paired.cu
     std::vector<cudaEvent_t> force_events;
     int last_force_passes = 0;
@@ -203,6 +204,8 @@ cudaError_t launch_resident(essa_ctx* c, int steps, essa_step_opts const& o, boo
 cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool mask_may_change, cudaStream_t st);
 bool resident_cta_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
 cudaError_t launch_resident_cta(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
+bool resident_cluster_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
+cudaError_t launch_resident_cluster(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st);
 cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st);
 cudaError_t launch_energy(essa_ctx* c, cudaStream_t st); // result in c->escratch[0..5)
