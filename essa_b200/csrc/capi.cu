@@ -738,6 +738,8 @@ static int resident_finish(essa_ctx* ctx, int steps, essa_step_opts const& o, bo
     return ESSA_OK;
 }
 
+constexpr int kResidentAutoMax = 320;
+
 static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, bool forces_only) {
     ARG(ctx, "ctx is null");
     ARG(opts, "opts is null");
@@ -751,7 +753,12 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
     essa_step_opts o = *opts;
     if (o.record)
         o.track_most_attracting = 1;
-    bool resident = o.kernel == ESSA_KERNEL_RESIDENT || (o.kernel == ESSA_KERNEL_AUTO && ctx->n <= ESSA_RESIDENT_MAX);
+    // AUTO: one resident launch for all steps up to ESSA_RESIDENT_MAX bodies -- except that from ~350 bodies on a
+    // single SM (K3) takes longer per step than the tiled path's launches do (measured on B200: 384 bodies 27.7 vs
+    // 23.7 us, 1024 bodies 176 vs 24 us per step), so plain fast-arithmetic calls above that size go tiled.
+    bool const needs_resident = o.exact_order || (o.forward_simulated && ctx->closest && ctx->closest_n == ctx->n);
+    bool resident = o.kernel == ESSA_KERNEL_RESIDENT
+        || (o.kernel == ESSA_KERNEL_AUTO && ctx->n <= ESSA_RESIDENT_MAX && (ctx->n <= kResidentAutoMax || needs_resident));
     if (ctx->world > 1)
         resident = false;
     if (resident && ctx->n > ESSA_RESIDENT_MAX) {

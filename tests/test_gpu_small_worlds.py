@@ -67,7 +67,9 @@ def test_exact_order_boundary_sizes(n):
     _compare(pw, ow, True, 0.0)
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 16, 31, 32, 33, 100])
+# 1 .. 32: K3q (two-SM cluster); 33 .. 128: K3x (16-SM cluster; 64 | 65 and 96 | 97 switch the partners per lane,
+# 33, 49, 113 the bodies per CTA); 129: the single-CTA kernel
+@pytest.mark.parametrize("n", [1, 2, 5, 16, 31, 32, 33, 49, 64, 65, 96, 97, 100, 113, 128, 129])
 def test_fast_boundary_sizes(n):
     steps = 400
     ow, pw = _pair(n, 200 + n, exact=False)
@@ -75,6 +77,37 @@ def test_fast_boundary_sizes(n):
         ow.update(chunk)
         pw.update(chunk)
     _compare(pw, ow, False, 1e-12 * np.sqrt(steps))
+
+
+@pytest.mark.parametrize("n", [10, 77])
+def test_fast_masked_bodies_and_backward_steps(n):
+    """Fast-arithmetic cluster kernels (K3q / K3x), recording on: backward steps, then bodies that deleted() masks
+    for a whole call -- two created in the future, two marked deleted."""
+    ow, pw = _pair(n, 300 + n, exact=False)
+    t0 = pw.date
+    for w in (ow, pw):
+        w.date = t0 + 10 ** 8  # World::add_object stamps the creation date with the world's date
+    ow.add_object(1e25, 1e6, (3e11, 1e11, 0.0), (0.0, 2e4, 0.0), "late0", 300)
+    pw.add_object(mass=1e25, radius=1e6, pos=(3e11, 1e11, 0.0), vel=(0.0, 2e4, 0.0), name="late0", period=300)
+    ow.add_object(1e20, 1e6, (-4e11, 0.0, 1e9), (0.0, -1.8e4, 0.0), "late1", 500)
+    pw.add_object(mass=1e20, radius=1e6, pos=(-4e11, 0.0, 1e9), vel=(0.0, -1.8e4, 0.0), name="late1", period=500)
+    for w in (ow, pw):
+        w.date = t0
+    late = [n, n + 1]
+    for steps in (100, -60):
+        ow.update(steps)
+        pw.update(steps)
+    ow.delete_object(2)
+    pw.mark_deleted(2)
+    ow.delete_object(n - 1)
+    pw.mark_deleted(n - 1)
+    for steps in (150, 30):
+        ow.update(steps)
+        pw.update(steps)
+    a, b = pw.state(), ow.state()
+    assert np.array_equal(a["active"], b["active"]) and not a["active"][late + [2, n - 1]].any()
+    assert np.array_equal(a["pos"][late], b["pos"][late])  # masked bodies do not move
+    _compare(pw, ow, False, 1e-12 * np.sqrt(340) * 4)
 
 
 def test_warp_kernel_long_run_wraps_rings():

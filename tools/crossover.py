@@ -1,0 +1,21 @@
+#!/usr/bin/env python3
+"""Where the per-step-launch tiled path overtakes the resident kernels: us per step for Plummer spheres of
+n bodies, 200 steps per call, fast arithmetic, no recording."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from essa_b200 import capi, synth  # noqa: E402
+
+c = capi.Context(0)
+for n in (40, 64, 96, 128, 160, 192, 256, 384, 512, 768, 1024):
+    w = synth.plummer(n, seed=n)
+    row = []
+    for kern in (capi.KERNEL_RESIDENT, capi.KERNEL_TILED):
+        c.date = capi.START_DATE
+        c.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
+        c.step(20, 1000, kernel=kern)
+        c.step(200, 1000, kernel=kern)
+        row.append(c.last_step_ms * 1e3 / 200)
+    print("n=%5d  resident %8.2f us/step   tiled %8.2f us/step" % (n, row[0], row[1]), flush=True)
+c.close()
