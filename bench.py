@@ -231,7 +231,7 @@ def run_reference(args):
 def solar_leg():
     """Small-world half of BASELINE.json's metric: Solar System iterations/s (single trajectory through
     the World facade, recording on; and the 65,536-copy ensemble aggregate), jupiter_system.essa as a
-    resident single-CTA kernel and as a 65,536-copy ensemble -- each next to the CPU oracle."""
+    resident cluster kernel and as a 65,536-copy ensemble -- each next to the CPU oracle."""
     import oracle
     from essa_b200 import capi, world
     wdir = os.path.join(ROOT, "tests", "golden", "worlds")
