@@ -107,6 +107,12 @@ struct essa_ctx {
     bool acc_has_most = false;  // ... and most / max_attraction were evaluated with it
     bool acc_exact = false;     // ... in exact_order arithmetic
     bool gather_pending = false;
+    // paired_plan's last answer (a pure function of n, the sharding and the SM count)
+    mutable struct {
+        int n = -1, world = 0, rank = 0, cap = 0, nb = 0, S = 0, ri = 0;
+        bool ok = false;
+        size_t slot_doubles = 0, part_doubles = 0;
+    } plan;
     bool attr_pair4 = false, attr_pair8 = false, attr_cta = false; // opt-in shared-memory sizes set on this device
     bool attr_cluster16[5] = { false, false, false, false, false }; // non-portable cluster size allowed for K3x<PER>
     bool use_paired = false;    // this essa_step runs its force passes through force_paired.cu

@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
     int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int const ibl = blockIdx.x / A.S, chunk = blockIdx.x - ibl * A.S;
     int const I = A.ib0 + ibl;
-    // offsets d = 0 .. dmax, split into S chunks
-    int const ntot = A.dmax + 1;
-    int const dlo = (int)((long long)ntot * chunk / A.S), dhi = (int)((long long)ntot * (chunk + 1) / A.S);
+    // work units of block I: (offset d = 0 .. dmax) x (kPParts parts of the J block), split into S chunks
+    int const nunits = (A.dmax + 1) * kPParts;
+    int const ulo = (int)((long long)nunits * chunk / A.S), uhi = (int)((long long)nunits * (chunk + 1) / A.S);
 
     double xi[kPRI], yi[kPRI], zi[kPRI], gi[kPRI], aix[kPRI], aiy[kPRI], aiz[kPRI];
 #pragma unroll
@@ -125,31 +125,25 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
 
     int seq = 0; // tiles consumed so far (parity bookkeeping)
     // prime the pipeline with the first valid tile
-    int nd = dlo;
-    while (nd < dhi && !valid(nd))
-        nd++;
-    if (tid == 0 && nd < dhi)
-        issue(nd, 0, 0);
+    int nu = ulo;
+    while (nu < uhi && !valid(nu / kPParts))
+        nu++;
+    if (tid == 0 && nu < uhi)
+        issue(nu / kPParts, nu % kPParts, 0);
 
-    for (int d = dlo; d < dhi; d++) {
+    for (int u = ulo; u < uhi; u++) {
+        int const d = u / kPParts, half = u - d * kPParts;
         if (!valid(d))
             continue;
-        int J = I + d;
-        if (J >= A.nb)
-            J -= A.nb;
-        for (int half = 0; half < kPParts; half++) {
+        {
             int const buf = seq & 1;
             // prefetch the tile after this one into the other buffer
             {
-                int pd = d, ph = half + 1;
-                if (ph == kPParts) {
-                    ph = 0;
-                    pd = d + 1;
-                    while (pd < dhi && !valid(pd))
-                        pd++;
-                }
-                if (tid == 0 && pd < dhi)
-                    issue(pd, ph, buf ^ 1);
+                int pu = u + 1;
+                while (pu < uhi && !valid(pu / kPParts))
+                    pu++;
+                if (tid == 0 && pu < uhi)
+                    issue(pu / kPParts, pu % kPParts, buf ^ 1);
             }
             mbar_wait(&full[buf], (unsigned)(seq >> 1) & 1u);
             double4 const* tp = tile + (size_t)buf * kPHalf;
@@ -354,41 +348,91 @@ static int pair_ri_override() {
     return v;
 }
 
+// Picks the block size (2048 or 1024 bodies) and the number of chunks S per I block.  A CTA works through
+// whole units -- (offset d) x (512-record part of the J block) -- of equal size, one CTA per SM, so the
+// estimate is  waves of working CTAs x units in the longest chunk x time per unit;  the 1024-body kernel
+// amortises its shuffles over 4 instead of 8 targets per lane and is ~20 % slower per pair (measured),
+// but its units are half as large.  Splitting by parts rather than by whole offsets is what fills the
+// machine at mid sizes: 16,384 bodies become 8 blocks x 20 units = 144 working CTAs of one 2048 x 512
+// unit each (one wave) instead of 144 CTAs of one 1024 x 1024 unit at the slower rate.
 bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles, int* ri_out) {
     int n = c->n;
-    // 2048-body blocks (8 targets per lane) are the fastest per pair; 1024-body blocks give mid-sized worlds
-    // enough CTAs.  Measured on B200 (profiles/README.md): 16,384 bodies 1.08e12 interactions/s with 1024-body
-    // blocks vs 3.1e11 with 2048 and 7.1e11 tiled; from 32,768 bodies on 2048-body blocks win.
-    int ri = n >= 32768 * c->world ? 8 : 4;
-    if (pair_ri_override() == 4 || pair_ri_override() == 8)
-        ri = pair_ri_override();
-    int const pb = kPThreads * ri;
-    int nb = (n + pb - 1) / pb;
-    if (nb < 2 || (size_t)nb * pb > (size_t)c->cap)
-        return false;
-    if (c->world > 1 && (n % (pb * c->world)) != 0)
-        return false;
-    int own = c->world == 1 ? nb : nb / c->world;
-    int dmax = nb / 2;
-    // chunks of the offset range: minimise waves(1 CTA / SM) x offsets per chunk
-    long long slots = c->sm_count; // 1 CTA per SM
-    int bestS = 1;
-    long long best = -1;
-    int smax = dmax + 1 < 64 ? dmax + 1 : 64; // finer chunks let sharded worlds (few I blocks per rank) fill whole waves
-    for (int S = 1; S <= smax; S++) {
-        long long waves = ((long long)own * S + slots - 1) / slots;
-        long long cost = waves * ((dmax + 1 + S - 1) / S);
-        if (best < 0 || cost < best) {
-            best = cost;
-            bestS = S;
+    if (c->plan.n == n && c->plan.world == c->world && c->plan.rank == c->rank && c->plan.cap == c->cap) { // same world as last time
+        if (!c->plan.ok)
+            return false;
+        *nb_out = c->plan.nb;
+        *S_out = c->plan.S;
+        *slot_doubles = c->plan.slot_doubles;
+        *part_doubles = c->plan.part_doubles;
+        if (ri_out)
+            *ri_out = c->plan.ri;
+        return true;
+    }
+    c->plan.n = n;
+    c->plan.world = c->world;
+    c->plan.rank = c->rank;
+    c->plan.cap = c->cap;
+    c->plan.ok = false;
+    long long const slots = c->sm_count; // 1 CTA per SM
+    double best = -1;
+    int best_ri = 0, best_S = 1, best_nb = 0;
+    for (int ri = 8; ri >= 4; ri -= 4) {
+        if ((pair_ri_override() == 4 || pair_ri_override() == 8) && ri != pair_ri_override())
+            continue;
+        int const pb = kPThreads * ri, parts = pb / kPHalf;
+        int const nb = (n + pb - 1) / pb;
+        if (nb < 2 || (size_t)nb * pb > (size_t)c->cap)
+            continue;
+        if (c->world > 1 && (n % (pb * c->world)) != 0)
+            continue;
+        int const own = c->world == 1 ? nb : nb / c->world;
+        int const ib0 = (int)((long long)nb * c->rank / c->world);
+        int const dmax = nb / 2;
+        int const U = (dmax + 1) * parts;
+        double const unit_time = ri == 8 ? 2.0 : 1.2;
+        int const smax = U < 64 ? U : 64;
+        for (int S = 1; S <= smax; S++) {
+            // working CTAs and the longest chunk, counting only valid units (for an even block count the
+            // offset nb / 2 belongs to the lower half of the I blocks)
+            long long working = 0;
+            int longest = 0;
+            long long const upper = (nb & 1) == 0 ? (ib0 + own > nb / 2 ? ib0 + own - (ib0 > nb / 2 ? ib0 : nb / 2) : 0) : 0;
+            for (int half = 0; half < 2; half++) { // I blocks with / without the last offset
+                long long const blocks = half ? upper : own - upper;
+                if (blocks == 0)
+                    continue;
+                int const uvalid = half ? dmax * parts : U; // units [uvalid, U) are skipped
+                for (int ch = 0; ch < S; ch++) {
+                    int lo = (int)((long long)U * ch / S), hi = (int)((long long)U * (ch + 1) / S);
+                    hi = hi < uvalid ? hi : uvalid;
+                    if (hi > lo) {
+                        working += blocks;
+                        longest = hi - lo > longest ? hi - lo : longest;
+                    }
+                }
+            }
+            long long const waves = (working + slots - 1) / slots;
+            double const cost = (double)waves * longest * unit_time;
+            if (best < 0 || cost < best) {
+                best = cost;
+                best_ri = ri;
+                best_S = S;
+                best_nb = nb;
+            }
         }
     }
-    *nb_out = nb;
-    *S_out = bestS;
-    *slot_doubles = (size_t)own * dmax * 3 * pb;
-    *part_doubles = (size_t)bestS * 3 * nb * pb + (c->world > 1 ? (size_t)3 * nb * pb : 0);
+    if (best < 0)
+        return false;
+    int const pb = kPThreads * best_ri;
+    int const own = c->world == 1 ? best_nb : best_nb / c->world;
+    c->plan.ok = true;
+    c->plan.nb = *nb_out = best_nb;
+    c->plan.S = *S_out = best_S;
+    c->plan.slot_doubles = *slot_doubles = (size_t)own * (best_nb / 2) * 3 * pb;
+    c->plan.part_doubles = *part_doubles = (size_t)best_S * 3 * best_nb * pb + (c->world > 1 ? (size_t)3 * best_nb * pb : 0);
+    c->plan.ri = best_ri;
     if (ri_out)
-        *ri_out = ri;
+        *ri_out = best_ri;
     return true;
 }
 
