@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1 << 20, help="bodies (default: BASELINE.json's 1,048,576)")
+    ap.add_argument("--n", "--bodies", dest="n", type=int, default=1 << 20, help="bodies (default: BASELINE.json's 1,048,576)")
     ap.add_argument("--no-extra", action="store_true", help="skip the Solar System / CPU baseline legs")
     ap.add_argument("--kernel", default="auto", choices=["auto", "tiled", "paired"])
     return ap.parse_args()
