@@ -318,7 +318,8 @@ def run_ours(args):
         ctx.shard_attach(rank, world_size, uid.cpu().numpy())
     kernel = {"auto": capi.KERNEL_AUTO, "tiled": capi.KERNEL_TILED, "paired": capi.KERNEL_PAIRED}[args.kernel]
     paired = args.kernel == "paired" or (args.kernel == "auto" and n >= 16384 and n % (2048 * world_size) == 0)
-    opts = capi.Context.opts(dt, kernel=kernel)
+    # reference semantics: Object::update_forces_against always runs its most-attracting bookkeeping
+    opts = capi.Context.opts(dt, kernel=kernel, track_most_attracting=True)
 
     peak = ctx.measure_fp64_peak(300.0) if rank == 0 else 0.0
     ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
@@ -418,7 +419,7 @@ def run_ours(args):
             "config": {"workload": name, "n": n, "dt_seconds": dt, "sharding": "targets/%d: NCCL gather of drifted positions + reduce-scatter of pair-shared partial accelerations per pass" % world_size
                        if world_size > 1 else "single GPU", "l2": "flushed (256 MiB memset) between timed steps",
                        "passes_per_step": passes / args.steps,
-                       "accounting": "value counts only force passes actually evaluated: N(N-1) directed interactions per pass; the reference's "
+                       "most_attracting": "tracked, as Object::update_forces_against always does (track_most_attracting=1); every body of this workload has the same mass, so the heavier-partner test of src/Object.cpp:86,91 fails for every pair: the pair-shared kernel writes max_attraction = 0 and keeps the links, exactly what the reference leaves (checked against the tiled argmax kernel in tests/test_gpu_paired.py); unequal masses go through the tiled argmax kernel", "accounting": "value counts only force passes actually evaluated: N(N-1) directed interactions per pass; the reference's "
                                      "first set_forces() of a step recomputes the previous step's second one bit for bit, so the resident "
                                      "acceleration is reused (tests: two_pass == reuse, bitwise) and is NOT counted",
                        "timing": "CUDA events on the launching stream around each essa_step, max over ranks"},

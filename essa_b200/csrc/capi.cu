@@ -384,6 +384,10 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
     double const* src[7] = { h->x, h->y, h->z, h->vx, h->vy, h->vz, h->gf };
     for (int k = 0; k < 7; k++)
         memcpy(d + k * N, src[k], N * sizeof(double));
+    // equal gravity factors everywhere: no body has a heavier partner, so Object.cpp:84-94 can never fire
+    ctx->gf_uniform = true;
+    for (size_t i = 1; i < N && ctx->gf_uniform; i++)
+        ctx->gf_uniform = h->gf[i] == h->gf[0];
     double* appe = d + 7 * N;
     for (size_t i = 0; i < N; i++) {
         appe[i] = h->ap ? h->ap[i] : 0.0;
@@ -588,7 +592,7 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
             }
             NK(nccl().GroupEnd());
         }
-        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc));
+        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc, argmax, save_old));
     } else if (ctx->world == 1 || !ctx->gather_pending) {
         int S;
         choose_split(ctx, iblocks, (n + kTileJ - 1) / kTileJ, &S);
@@ -623,17 +627,19 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
     double const mul = steps >= 0 ? 1.0 : -1.0;
     bool const argmax = o.track_most_attracting || o.record;
     {
-        // pair-shared kernel: single context, no argmax bookkeeping, slots must fit comfortably
+        // pair-shared kernel: slots must fit comfortably; most-attracting tracking only where it is provably a
+        // no-op (all gravity factors equal: the "heavier partner" test of Object.cpp:84-94 fails for every pair, so
+        // max_attraction stays 0 and the links stay as they are -- k_pair_finish writes exactly that)
         int nb, S;
         size_t slot_d = 0, part_d = 0;
-        bool can = !argmax && paired_plan(ctx, &nb, &S, &slot_d, &part_d);
+        bool can = (!argmax || ctx->gf_uniform) && paired_plan(ctx, &nb, &S, &slot_d, &part_d);
         if (can && (slot_d > ctx->pair_slots_n || part_d > ctx->pair_part_n)) { // first use at this size: will it fit?
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
             can = (slot_d + part_d) * sizeof(double) < free_b / 2 + (ctx->pair_slots_n + ctx->pair_part_n) * sizeof(double);
         }
         if (o.kernel == ESSA_KERNEL_PAIRED && !can) {
-            ctx->err = "pair-shared kernel needs >= 1025 bodies (whole 1024- or 2048-body blocks per rank when sharded), no most-attracting tracking, and room for its slots";
+            ctx->err = "pair-shared kernel needs >= 1025 bodies (whole 1024- or 2048-body blocks per rank when sharded), no most-attracting tracking unless all gravity factors are equal, and room for its slots";
             return ESSA_ERR_ARG;
         }
         ctx->use_paired = can && (o.kernel == ESSA_KERNEL_PAIRED || (o.kernel == ESSA_KERNEL_AUTO && ctx->n >= 16384));

@@ -113,6 +113,7 @@ struct essa_ctx {
         bool ok = false;
         size_t slot_doubles = 0, part_doubles = 0;
     } plan;
+    bool gf_uniform = false; // every uploaded gravity factor is the same value
     bool attr_pair4 = false, attr_pair8 = false, attr_cta = false; // opt-in shared-memory sizes set on this device
     bool attr_cluster16[5] = { false, false, false, false, false }; // non-portable cluster size allowed for K3x<PER>
     bool use_paired = false;    // this essa_step runs its force passes through force_paired.cu
@@ -202,7 +203,7 @@ cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double co
 cudaError_t launch_unpack(essa_ctx* c, double* x, double* y, double* z, cudaStream_t st);
 bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles, int* ri_out = nullptr);
 cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out);
-cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred);
+cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred, bool argmax_noop, bool save_old);
 int force_iblocks(essa_ctx const* c, int* R_out);
 void choose_split(essa_ctx const* c, int iblocks, int ntiles, int* S_out);
 

@@ -243,6 +243,8 @@ struct PairFinishArgs {
     double const* part_i;
     double const* slots;
     double const* ajred; // sharded: [3][npad] J-side sums already reduced over ranks (slots are skipped)
+    int argmax_noop;     // most-attracting tracking requested on a world of equal gravity factors: clear_forces only
+    int save_old;        // ... and Object::before_update's old_most = most
 };
 
 // J-side contributions to body g from the tiles whose I block lies in [ib0, ib1), in offset order.
@@ -298,13 +300,17 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
     } else {
         slot_sum<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots, ax, ay, az);
     }
-    // ---- epilogue: identical to force_tiled.cu finish_body (no argmax in this kernel) ----
+    // ---- epilogue: identical to force_tiled.cu finish_body ----
     WorldPtrs const& W = A.w;
     KickArgs const& Kk = A.k;
     bool act = W.active[g] != 0;
     double4 p = W.pos_cur[g];
     double vx = 0, vy = 0, vz = 0;
+    if (A.argmax_noop && A.save_old)
+        W.old_most[g] = W.most[g];
     if (act) {
+        if (A.argmax_noop)
+            W.maxattr[g] = 0.0; // Object::clear_forces; no pair can raise it (nobody is heavier than anybody)
         W.a[0][g] = ax;
         W.a[1][g] = ay;
         W.a[2][g] = az;
@@ -511,7 +517,7 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
 }
 
 // Phase 2: ordered sums + kick / drift epilogue for this rank's targets.
-cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred) {
+cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred, bool argmax_noop, bool save_old) {
     int nb, S, ri;
     size_t slot_d, part_d;
     if (!paired_plan(c, &nb, &S, &slot_d, &part_d, &ri))
@@ -528,6 +534,8 @@ cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStrea
     pair_geometry(c, nb, &F.ib0, &F.ib1);
     F.npad = nb * kPThreads * ri;
     F.part_i = c->pair_part;
+    F.argmax_noop = argmax_noop ? 1 : 0;
+    F.save_old = save_old ? 1 : 0;
     F.slots = c->pair_slots;
     F.ajred = ajred;
     int cnt = F.i1 - F.i0;

@@ -118,6 +118,28 @@ def test_paired_refuses_what_it_cannot_do(ctx):
     with pytest.raises(capi.EssaError):
         ctx.step(1, 1000, kernel=capi.KERNEL_PAIRED)
     w = synth.plummer(4096, seed=1)
+    w["gf"] = w["gf"] * np.linspace(1.0, 2.0, 4096)  # unequal masses: the most-attracting links are real work
     _upload(ctx, w)
     with pytest.raises(capi.EssaError):
         ctx.step(1, 1000, kernel=capi.KERNEL_PAIRED, track_most_attracting=True)
+
+
+def test_paired_tracks_most_attracting_when_it_is_a_no_op(ctx):
+    """Equal gravity factors: `o.gf > this.gf` (src/Object.cpp:86,91) is false for every pair, so the reference leaves
+    most_attracting_object alone and max_attraction at 0.  The pair-shared kernel accepts tracking then and must
+    leave exactly what the tiled argmax kernel leaves."""
+    n = 5000
+    w = synth.plummer(n, seed=21)
+    dt = synth.default_dt(n)
+    got = {}
+    for kern in (capi.KERNEL_TILED, capi.KERNEL_PAIRED):
+        ctx.date = capi.START_DATE
+        ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"], most=np.arange(n, dtype=np.int32)[::-1].copy())
+        ctx.step(3, dt, kernel=kern, track_most_attracting=True)
+        got[kern] = ctx.download()
+    t, p = got[capi.KERNEL_TILED], got[capi.KERNEL_PAIRED]
+    assert np.array_equal(t["most"], p["most"]) and np.array_equal(p["most"], np.arange(n, dtype=np.int32)[::-1])
+    assert np.array_equal(t["max_attraction"], p["max_attraction"]) and not p["max_attraction"].any()
+    pos_t = np.stack([t["x"], t["y"], t["z"]], axis=1)
+    pos_p = np.stack([p["x"], p["y"], p["z"]], axis=1)
+    assert _rel_rows(pos_p, pos_t).max() <= 1e-12
