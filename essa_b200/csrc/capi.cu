@@ -454,6 +454,8 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
     return ESSA_OK;
 }
 
+constexpr size_t kDownloadSmallMax = 4096; // bodies: one packing kernel instead of one copy per field
+
 extern "C" int essa_download(essa_ctx* ctx, essa_bodies* h) {
     ARG(ctx, "ctx is null");
     ARG(h, "host view is null");
@@ -481,35 +483,38 @@ extern "C" int essa_download(essa_ctx* ctx, essa_bodies* h) {
         }
         NK(nccl().GroupEnd());
     }
-    bool want_pos = h->x || h->y || h->z;
+    int64_t* dates = reinterpret_cast<int64_t*>(d + 15 * N);
+    int32_t* most = reinterpret_cast<int32_t*>(dates + 2 * N);
+    uint8_t* flags = reinterpret_cast<uint8_t*>(most + N);
+    bool const small = ctx->world == 1 && N <= kDownloadSmallMax;
+    if (small)
+        CK(launch_download_small(ctx, ctx->pinned, st)); // one kernel writes the whole staging area
+    bool want_pos = !small && (h->x || h->y || h->z);
     if (want_pos) {
         CK(launch_unpack(ctx, ctx->velh, ctx->velh + cap, ctx->velh + 2 * cap, st));
         for (int k = 0; k < 3; k++)
             CK(cudaMemcpyAsync(d + k * N, ctx->velh + k * cap, N * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
-    if (h->vx || h->vy || h->vz)
+    if (!small && (h->vx || h->vy || h->vz))
         for (int k = 0; k < 3; k++)
             CK(cudaMemcpyAsync(d + (3 + k) * N, ctx->vel + k * cap, N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (h->ax || h->ay || h->az)
+    if (!small && (h->ax || h->ay || h->az))
         for (int k = 0; k < 3; k++)
             CK(cudaMemcpyAsync(d + (6 + k) * N, ctx->acc + k * cap, N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (h->gf)
+    if (!small && h->gf)
         CK(cudaMemcpyAsync(d + 9 * N, ctx->gf, N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (h->max_attraction)
+    if (!small && h->max_attraction)
         CK(cudaMemcpyAsync(d + 10 * N, ctx->maxattr, N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (h->ap || h->pe || h->ap_vel || h->pe_vel)
+    if (!small && (h->ap || h->pe || h->ap_vel || h->pe_vel))
         for (int k = 0; k < 4; k++)
             CK(cudaMemcpyAsync(d + (11 + k) * N, ctx->appe + k * cap, N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    int64_t* dates = reinterpret_cast<int64_t*>(d + 15 * N);
-    int32_t* most = reinterpret_cast<int32_t*>(dates + 2 * N);
-    uint8_t* flags = reinterpret_cast<uint8_t*>(most + N);
-    if (h->creation_date)
+    if (!small && h->creation_date)
         CK(cudaMemcpyAsync(dates, ctx->cdate, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    if (h->deletion_date)
+    if (!small && h->deletion_date)
         CK(cudaMemcpyAsync(dates + N, ctx->ddate, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    if (h->most)
+    if (!small && h->most)
         CK(cudaMemcpyAsync(most, ctx->most, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (h->deleted)
+    if (!small && h->deleted)
         CK(cudaMemcpyAsync(flags, ctx->delflag, N, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     double* dst[15] = { h->x, h->y, h->z, h->vx, h->vy, h->vz, h->ax, h->ay, h->az, h->gf, h->max_attraction, h->ap, h->pe, h->ap_vel,

@@ -211,6 +211,7 @@ cudaError_t launch_resident(essa_ctx* c, int steps, essa_step_opts const& o, boo
 cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool mask_may_change, cudaStream_t st);
 bool resident_cta_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
 cudaError_t launch_resident_cta(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
+cudaError_t launch_download_small(essa_ctx* c, void* pinned_out, cudaStream_t st);
 bool resident_cluster_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
 cudaError_t launch_resident_cluster(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st);

@@ -407,6 +407,45 @@ cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double co
     return cudaGetLastError();
 }
 
+// Small worlds: every field essa_download can return, written by ONE kernel straight into pinned host
+// memory (device-visible under unified addressing) in the staging layout of capi.cu -- instead of ~16
+// device-to-host copies of a few hundred bytes each, which cost ~50 us of a 10-step GUI tick.
+__global__ void k_download_small(WorldPtrs const W, double const* __restrict__ appe, size_t cap, long long const* __restrict__ cdate,
+    long long const* __restrict__ ddate, uint8_t const* __restrict__ delflag, double* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    size_t const N = (size_t)n;
+    double4 p = W.pos_cur[i];
+    out[i] = p.x;
+    out[N + i] = p.y;
+    out[2 * N + i] = p.z;
+    for (int k = 0; k < 3; k++) {
+        out[(3 + k) * N + i] = W.v[k][i];
+        out[(6 + k) * N + i] = W.a[k][i];
+    }
+    out[9 * N + i] = W.gf[i];
+    out[10 * N + i] = W.maxattr[i];
+    for (int k = 0; k < 4; k++)
+        out[(11 + k) * N + i] = appe[(size_t)k * cap + i];
+    long long* dates = reinterpret_cast<long long*>(out + 15 * N);
+    dates[i] = cdate[i];
+    dates[N + i] = ddate[i];
+    int* most = reinterpret_cast<int*>(dates + 2 * N);
+    most[i] = W.most[i];
+    uint8_t* flags = reinterpret_cast<uint8_t*>(most + N);
+    flags[i] = delflag[i];
+}
+
+cudaError_t launch_download_small(essa_ctx* c, void* pinned_out, cudaStream_t st) {
+    if (c->n <= 0)
+        return cudaSuccess;
+    k_download_small<<<(c->n + 127) / 128, 128, 0, st>>>(world_ptrs(c), c->appe, (size_t)c->cap, (long long const*)c->cdate,
+        (long long const*)c->ddate, c->delflag, static_cast<double*>(pinned_out), c->n);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_unpack(essa_ctx* c, double* x, double* y, double* z, cudaStream_t st) {
     if (c->n <= 0)
         return cudaSuccess;
