@@ -764,12 +764,16 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
     essa_step_opts o = *opts;
     if (o.record)
         o.track_most_attracting = 1;
-    // AUTO: one resident launch for all steps up to ESSA_RESIDENT_MAX bodies -- except that from ~350 bodies on a
-    // single SM (K3) takes longer per step than the tiled path's launches do (measured on B200: 384 bodies 27.7 vs
-    // 23.7 us, 1024 bodies 176 vs 24 us per step), so plain fast-arithmetic calls above that size go tiled.
+    // AUTO: one resident launch for all steps up to ESSA_RESIDENT_MAX bodies.  Plain fast-arithmetic calls run on a
+    // 16-SM cluster (K3x / K3xw: 0.7 .. 20 us per step, always below the tiled path's ~24 us of launches per step);
+    // what the cluster kernels do not take (a mask that flips during the call, two_pass) goes to the single-CTA K3
+    // only up to ~320 bodies -- beyond that one SM takes longer per step than the tiled launches do (measured on
+    // B200: 384 bodies 27.7 vs 23.7 us, 1024 bodies 176 vs 24 us per step).
     bool const needs_resident = o.exact_order || (o.forward_simulated && ctx->closest && ctx->closest_n == ctx->n);
+    bool const wide_ok = ctx->world == 1 && ctx->n > kResidentAutoMax && resident_cluster_wide_applicable(ctx, o, forces_only)
+        && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds));
     bool resident = o.kernel == ESSA_KERNEL_RESIDENT
-        || (o.kernel == ESSA_KERNEL_AUTO && ctx->n <= ESSA_RESIDENT_MAX && (ctx->n <= kResidentAutoMax || needs_resident));
+        || (o.kernel == ESSA_KERNEL_AUTO && ctx->n <= ESSA_RESIDENT_MAX && (ctx->n <= kResidentAutoMax || needs_resident || wide_ok));
     if (ctx->world > 1)
         resident = false;
     if (resident && ctx->n > ESSA_RESIDENT_MAX) {
@@ -803,8 +807,19 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
             }
             if (!clustered)
                 CK(launch_resident_cta(ctx, steps, o, ctx->stream));
-        } else
-            CK(launch_resident(ctx, steps, o, forces_only, ctx->stream));
+        } else {
+            // 129 .. 1024 bodies in plain fast arithmetic: the wide cluster kernel; everything else (and a cluster
+            // that cannot be placed): the single-CTA kernel
+            bool clustered = false;
+            if (resident_cluster_wide_applicable(ctx, o, forces_only)
+                && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds))) {
+                clustered = launch_resident_cluster_wide(ctx, steps, o, ctx->stream) == cudaSuccess;
+                if (!clustered)
+                    (void)cudaGetLastError();
+            }
+            if (!clustered)
+                CK(launch_resident(ctx, steps, o, forces_only, ctx->stream));
+        }
         CK(cudaEventRecord(ctx->ev_end, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         rc = resident_finish(ctx, steps, o, forces_only);

@@ -115,6 +115,7 @@ struct essa_ctx {
     } plan;
     bool gf_uniform = false; // every uploaded gravity factor is the same value
     bool attr_pair4 = false, attr_pair8 = false, attr_cta = false; // opt-in shared-memory sizes set on this device
+    bool attr_cluster_wide[2] = { false, false };
     bool attr_cluster16[5] = { false, false, false, false, false }; // non-portable cluster size allowed for K3x<PER>
     bool use_paired = false;    // this essa_step runs its force passes through force_paired.cu
     std::vector<cudaEvent_t> force_events;
@@ -212,6 +213,8 @@ cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o
 bool resident_cta_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
 cudaError_t launch_resident_cta(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
 cudaError_t launch_download_small(essa_ctx* c, void* pinned_out, cudaStream_t st);
+bool resident_cluster_wide_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
+cudaError_t launch_resident_cluster_wide(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
 bool resident_cluster_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
 cudaError_t launch_resident_cluster(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st);

@@ -68,10 +68,10 @@ def test_exact_order_boundary_sizes(n):
 
 
 # 1 .. 32: K3q (two-SM cluster); 33 .. 128: K3x (16-SM cluster; 64 | 65 and 96 | 97 switch the partners per lane,
-# 33, 49, 113 the bodies per CTA); 129: the single-CTA kernel
-@pytest.mark.parametrize("n", [1, 2, 5, 16, 31, 32, 33, 49, 64, 65, 96, 97, 100, 113, 128, 129])
+# 33, 49, 113 the bodies per CTA); 129 .. 512: K3xw with 16 lanes per body, 513 .. 1024: 8 lanes per body
+@pytest.mark.parametrize("n", [1, 2, 5, 16, 31, 32, 33, 49, 64, 65, 96, 97, 100, 113, 128, 129, 200, 300, 512, 513, 1000, 1024])
 def test_fast_boundary_sizes(n):
-    steps = 400
+    steps = 400 if n <= 129 else (60 if n <= 512 else 12)
     ow, pw = _pair(n, 200 + n, exact=False)
     for chunk in (3, steps - 3):
         ow.update(chunk)

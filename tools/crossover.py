@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from essa_b200 import capi, synth  # noqa: E402
 
 c = capi.Context(0)
-for n in (40, 64, 96, 128, 160, 192, 256, 384, 512, 768, 1024):
+for n in (40, 64, 96, 128, 160, 192, 256, 384, 512, 513, 768, 1024):
     w = synth.plummer(n, seed=n)
     row = []
     for kern in (capi.KERNEL_RESIDENT, capi.KERNEL_TILED):
