@@ -115,7 +115,7 @@ struct essa_ctx {
     } plan;
     bool gf_uniform = false; // every uploaded gravity factor is the same value
     bool attr_pair4 = false, attr_pair8 = false, attr_cta = false; // opt-in shared-memory sizes set on this device
-    bool attr_cluster_wide[2] = { false, false };
+    bool attr_cluster_wide[3] = { false, false, false };
     bool attr_cluster16[5] = { false, false, false, false, false }; // non-portable cluster size allowed for K3x<PER>
     bool use_paired = false;    // this essa_step runs its force passes through force_paired.cu
     std::vector<cudaEvent_t> force_events;

@@ -3,8 +3,12 @@
 // bodies per warp:
 //
 //   bodies      lanes per body (LB)   bodies per CTA   physics warps per CTA   ring slots
-//   129 .. 512        16                 <= 32              <= 16                  8
-//   513 .. 1024        8                 <= 64              <= 16                  4
+//   129 .. 256        16                 <= 16               <= 8                  8
+//   257 .. 512         8                 <= 32               <= 8                  8
+//   513 .. 1024        4                 <= 64               <= 8                  4
+//
+// (eight physics warps at most, so that the kernel may use 128 registers per thread: with 24 warps the
+// compiler serialised the partner chains to fit 80)
 //
 // Lane q of a body's group takes the partners p = q, q + LB, ... in a four-way unrolled loop over 32-byte
 // records {x, y, z, gf} (the ring is padded with zero-weight records to a multiple of 4 LB), a log2(LB)-level
@@ -29,7 +33,7 @@ constexpr int kWMaxBodies = 1024;
 constexpr int kWLocalMax = 64; // bodies per CTA
 constexpr int kWRoles = 4;     // consumer roles, each on ceil(local bodies / 32) warps
 constexpr int kWCtas = 16;
-constexpr int kWMaxWarps = 16 + 2 * kWRoles;
+constexpr int kWMaxWarps = 8 + 2 * kWRoles; // 8 physics warps + consumers: 512 threads, 128 registers each
 constexpr int kWDone = kWRoles * 2 * kWCtas;
 
 struct WArgs {
@@ -85,7 +89,7 @@ __device__ __forceinline__ double w_metric(double4 const& pk, double4 const& pp,
 }
 
 template<int LB, bool ARGMAX>
-__global__ void __launch_bounds__(LB == 16 ? 32 * (16 + kWRoles) : 32 * kWMaxWarps, 1) k_resident_cluster_wide(WArgs const A) {
+__global__ void __launch_bounds__(32 * kWMaxWarps, 1) k_resident_cluster_wide(WArgs const A) {
     extern __shared__ __align__(16) unsigned char w_smem[];
     constexpr int BW = 32 / LB; // bodies per warp
     int const n = A.n, npad = A.npad, nbl = A.nbl, ring = A.ring;
@@ -140,28 +144,45 @@ __global__ void __launch_bounds__(LB == 16 ? 32 * (16 + kWRoles) : 32 * kWMaxWar
             double fx[4] = { 0, 0, 0, 0 }, fy[4] = { 0, 0, 0, 0 }, fz[4] = { 0, 0, 0, 0 }, bm[4] = { 0, 0, 0, 0 };
             int bj[4] = { -1, -1, -1, -1 };
             for (int j = 0; j < per; j += 4) {
+                // written stage by stage over the four partners so that the four dependent chains interleave
+                // (as one block per partner the compiler ran them back to back to save registers: 47 % of the
+                // FP64 pipe at 1024 bodies, measured)
+                double4 qv[4];
+                double dx[4], dy[4], dz[4], r2[4], y0[4], e[4], c0[4], sc[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    qv[u] = pp[(j + u) * LB];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    double4 const qv = pp[(j + u) * LB];
-                    double dx = qv.x - x, dy = qv.y - y, dz = qv.z - z;
-                    double r2 = fma(dx, dx, A.eps2);
-                    r2 = fma(dy, dy, r2);
-                    r2 = fma(dz, dz, r2);
-                    double y0 = rsqrt_seed(r2);
-                    double t = r2 * y0;
-                    double e = fma(-t, y0, 1.0);
-                    double y2 = y0 * y0;
-                    double gy = qv.w * y0;
-                    double c0 = gy * y2;
-                    double w = fma(1.875, e, 1.5);
-                    double we = w * e;
-                    double s = fma(c0, we, c0);
-                    fx[u] = fma(s, dx, fx[u]);
-                    fy[u] = fma(s, dy, fy[u]);
-                    fz[u] = fma(s, dz, fz[u]);
-                    if (ARGMAX) {
-                        double m = c0 * y0; // gf_p y0^4 ~ gf_p / r^4 (ranking only); 0 for the self term
-                        if (qv.w > gfk && m > bm[u]) { // ascending p within a chain: the lowest index wins ties
+                    dx[u] = qv[u].x - x;
+                    dy[u] = qv[u].y - y;
+                    dz[u] = qv[u].z - z;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    r2[u] = fma(dz[u], dz[u], fma(dy[u], dy[u], fma(dx[u], dx[u], A.eps2)));
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    y0[u] = rsqrt_seed(r2[u]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    e[u] = fma(-(r2[u] * y0[u]), y0[u], 1.0);
+                    c0[u] = (qv[u].w * y0[u]) * (y0[u] * y0[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    sc[u] = fma(c0[u], fma(1.875, e[u], 1.5) * e[u], c0[u]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    fx[u] = fma(sc[u], dx[u], fx[u]);
+                    fy[u] = fma(sc[u], dy[u], fy[u]);
+                    fz[u] = fma(sc[u], dz[u], fz[u]);
+                }
+                if (ARGMAX) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        double m = c0[u] * y0[u]; // gf_p y0^4 ~ gf_p / r^4 (ranking only); 0 for the self term
+                        if (qv[u].w > gfk && m > bm[u]) { // ascending p within a chain: the lowest index wins ties
                             bm[u] = m;
                             bj[u] = q + (j + u) * LB;
                         }
@@ -348,7 +369,7 @@ __global__ void __launch_bounds__(LB == 16 ? 32 * (16 + kWRoles) : 32 * kWMaxWar
 
 template<int LB>
 static cudaError_t launch_w(essa_ctx* c, cudaLaunchConfig_t const& cfg, WArgs const& A) {
-    int const idx = LB == 16 ? 0 : 1;
+    int const idx = LB == 16 ? 0 : (LB == 8 ? 1 : 2);
     if (!c->attr_cluster_wide[idx]) {
         cudaError_t e = cudaSuccess;
         void const* fns[2] = { (void const*)k_resident_cluster_wide<LB, true>, (void const*)k_resident_cluster_wide<LB, false> };
@@ -389,7 +410,7 @@ cudaError_t launch_resident_cluster_wide(essa_ctx* c, int steps, essa_step_opts 
     A.offset_trails = o.offset_trails;
     A.forward_sim = o.forward_simulated;
     A.acc_valid = c->acc_valid && (!A.argmax || c->acc_has_most) && !c->acc_exact;
-    int const lb = c->n <= 512 ? 16 : 8;
+    int const lb = c->n <= 256 ? 16 : (c->n <= 512 ? 8 : 4);
     A.ring = c->n <= 512 ? 8 : 4;
     A.npad = (c->n + 4 * lb - 1) / (4 * lb) * (4 * lb);
     A.nbl = (c->n + kWCtas - 1) / kWCtas;
@@ -409,7 +430,7 @@ cudaError_t launch_resident_cluster_wide(essa_ctx* c, int steps, essa_step_opts 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = lb == 16 ? launch_w<16>(c, cfg, A) : launch_w<8>(c, cfg, A);
+    cudaError_t e = lb == 16 ? launch_w<16>(c, cfg, A) : (lb == 8 ? launch_w<8>(c, cfg, A) : launch_w<4>(c, cfg, A));
     if (e != cudaSuccess)
         return e;
     c->launches++;
