@@ -78,6 +78,7 @@ SYMBOLS = [
     ("essa_get_date", C.c_int64, [_P]),
     ("essa_body_count", C.c_int, [_P]),
     ("essa_step", C.c_int, [_P, C.c_int, C.POINTER(StepOpts)]),
+    ("essa_step_async", C.c_int, [_P, C.c_int, C.POINTER(StepOpts)]),
     ("essa_set_forces", C.c_int, [_P, C.POINTER(StepOpts)]),
     ("essa_record_configure", C.c_int, [_P, C.c_int, _i32p, C.c_int]),
     ("essa_tracked_count", C.c_int, [_P]),

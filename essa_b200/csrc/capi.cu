@@ -306,12 +306,26 @@ extern "C" const char* essa_last_error(const essa_ctx* c) { return c ? c->err.c_
 extern "C" int64_t essa_launch_count(const essa_ctx* c) { return c ? c->launches : 0; }
 extern "C" int64_t essa_pass_count(const essa_ctx* c) { return c ? c->passes : 0; }
 extern "C" double essa_interaction_count(const essa_ctx* c) { return c ? c->interactions : 0; }
-extern "C" double essa_last_step_ms(const essa_ctx* c) { return c ? c->last_step_ms : 0; }
+// essa_step_async leaves the end event unread: settle it the first time anybody asks
+static void settle_timing(essa_ctx const* cc) {
+    essa_ctx* c = const_cast<essa_ctx*>(cc);
+    if (!c || !c->timing_pending)
+        return;
+    c->timing_pending = false;
+    float ms = 0;
+    if (cudaEventSynchronize(c->ev_end) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess)
+        c->last_step_ms = ms;
+}
+extern "C" double essa_last_step_ms(const essa_ctx* c) {
+    settle_timing(c);
+    return c ? c->last_step_ms : 0;
+}
 extern "C" double essa_last_force_ms(const essa_ctx* c) { return c ? c->last_force_ms : 0; }
 extern "C" int essa_last_force_passes(const essa_ctx* c) { return c ? c->last_force_passes : 0; }
 extern "C" int essa_last_step_breakdown(const essa_ctx* c, double out[4]) {
     if (!c || !out)
         return ESSA_ERR_ARG;
+    settle_timing(c);
     out[0] = c->last_step_ms;
     out[1] = c->last_force_ms;
     out[2] = c->last_pre_ms;
@@ -751,11 +765,12 @@ static int resident_finish(essa_ctx* ctx, int steps, essa_step_opts const& o, bo
 
 constexpr int kResidentAutoMax = 320;
 
-static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, bool forces_only) {
+static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, bool forces_only, bool async = false) {
     ARG(ctx, "ctx is null");
     ARG(opts, "opts is null");
     ARG(forces_only || steps != 0, "steps must not be 0 (assert in src/World.cpp:87)");
     CK(cudaSetDevice(ctx->device));
+    settle_timing(ctx); // the events are about to be reused
     if (ctx->n == 0) {
         if (!forces_only && !opts->forward_simulated)
             ctx->date += (int64_t)steps * opts->dt_seconds;
@@ -821,6 +836,10 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
                 CK(launch_resident(ctx, steps, o, forces_only, ctx->stream));
         }
         CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+        if (async) { // host-side bookkeeping does not need the results; the next synchronising call settles the rest
+            ctx->timing_pending = true;
+            return resident_finish(ctx, steps, o, forces_only);
+        }
         CK(cudaStreamSynchronize(ctx->stream));
         rc = resident_finish(ctx, steps, o, forces_only);
     } else {
@@ -836,6 +855,7 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
 
 extern "C" int essa_step(essa_ctx* ctx, int steps, const essa_step_opts* opts) { return step_common(ctx, steps, opts, false); }
 extern "C" int essa_set_forces(essa_ctx* ctx, const essa_step_opts* opts) { return step_common(ctx, 1, opts, true); }
+extern "C" int essa_step_async(essa_ctx* ctx, int steps, const essa_step_opts* opts) { return step_common(ctx, steps, opts, false, true); }
 
 // ---------------------------------------------------------------------------------------------
 // recording

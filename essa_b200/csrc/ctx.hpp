@@ -114,6 +114,7 @@ struct essa_ctx {
         size_t slot_doubles = 0, part_doubles = 0;
     } plan;
     bool gf_uniform = false; // every uploaded gravity factor is the same value
+    bool timing_pending = false; // essa_step_async: ev_end recorded, elapsed time not read yet
     bool attr_pair4 = false, attr_pair8 = false, attr_cta = false; // opt-in shared-memory sizes set on this device
     bool attr_cluster_wide[3] = { false, false, false };
     bool attr_cluster16[5] = { false, false, false, false, false }; // non-portable cluster size allowed for K3x<PER>

@@ -601,7 +601,7 @@ void World::update(int steps) {
     }
     sync_to_device();
     essa_step_opts o = step_opts();
-    check(essa_step(m_ctx, steps, &o), "essa_step");
+    check(essa_step_async(m_ctx, steps, &o), "essa_step"); // the read-back below is the synchronisation point
     m_date = essa_get_date(m_ctx);
     sync_from_device();
 }

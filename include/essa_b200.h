@@ -136,6 +136,10 @@ int essa_body_count(const essa_ctx* ctx);
 
 /* World::update(steps): |steps| KDK iterations, sign = direction (src/World.cpp:86-139). */
 int essa_step(essa_ctx* ctx, int steps, const essa_step_opts* opts);
+/* The same, but a call that one resident kernel serves returns after the launch: the next synchronising call on the
+ * context (essa_download, essa_sync, essa_last_step_ms, the next step ...) waits for it and reports its errors.
+ * What the GUI's tick needs: update(steps) immediately followed by a read-back pays for one synchronisation. */
+int essa_step_async(essa_ctx* ctx, int steps, const essa_step_opts* opts);
 /* World::set_forces() alone (src/World.cpp:42-57): refreshes acc / most / max_attraction. */
 int essa_set_forces(essa_ctx* ctx, const essa_step_opts* opts);
 
