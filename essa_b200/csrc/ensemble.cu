@@ -9,6 +9,8 @@
 // Layout in HBM: state[copy][6][n] (x y z vx vy vz), copy-major, so a CTA's copies are contiguous.
 // Thread t of a CTA owns (copy = t / n, body = t % n); all copies of a CTA step in lock step
 // behind the same two __syncthreads per KDK iteration.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ctx.hpp"
 #include "rows.cuh"
@@ -297,6 +299,153 @@ __global__ void __launch_bounds__(32 * kEnsWarpsPerCta, 5) k_ensemble_warp(Ensem
     }
 }
 
+// Fast-arithmetic ensembles, two bodies per thread.  With one body per thread every interaction costs four
+// 8-byte shared-memory loads per lane, and shared-memory bandwidth (63 % of its peak, ncu) holds the FP64 pipe
+// at 67 %.  Here a thread owns bodies h and h + ceil(n / 2) of its copy and walks ALL n partners (the self term
+// vanishes: the rsqrt seed of 0 is 0), two at a time: one 32-byte record {x, y, z, gf} per partner, read at the
+// same address by every thread of the copy (a broadcast), feeds two interactions, and the four chains of an
+// iteration are independent.  WARP = true: templates of up to 64 bodies, a warp owns 32 / ceil(n / 2) whole
+// copies and steps them with __syncwarp only; otherwise 256 / ceil(n / 2) copies per CTA behind __syncthreads.
+constexpr int kDuoWarps = 4;
+constexpr int kDuoCtaThreads = 256;
+
+template<bool WARP>
+__global__ void __launch_bounds__(WARP ? 32 * kDuoWarps : kDuoCtaThreads, WARP ? 4 : 2) k_ensemble_duo(EnsembleArgs const A) {
+    extern __shared__ __align__(16) unsigned char duo_smem[];
+    int const n = A.n, half = (n + 1) >> 1, rs = n + 1; // records per copy: n bodies + one zero-weight pad
+    int lc, h, group_copies;
+    long long copy;
+    double4* rec;
+    if (WARP) {
+        int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        group_copies = 32 / half;
+        lc = lane / half;
+        h = lane - lc * half;
+        copy = ((long long)blockIdx.x * kDuoWarps + warp) * group_copies + lc;
+        rec = reinterpret_cast<double4*>(duo_smem) + ((size_t)warp * group_copies + (lc < group_copies ? lc : 0)) * rs;
+    } else {
+        group_copies = A.per_cta;
+        lc = threadIdx.x / half;
+        h = threadIdx.x - lc * half;
+        copy = (long long)blockIdx.x * group_copies + lc;
+        rec = reinterpret_cast<double4*>(duo_smem) + (size_t)(lc < group_copies ? lc : 0) * rs;
+    }
+    bool const live = lc < group_copies && copy < A.copies;
+    auto sync = [&]() {
+        if (WARP)
+            __syncwarp();
+        else
+            __syncthreads();
+    };
+
+    int const kb[2] = { h, h + half };
+    bool own[2] = { live, live && h + half < n };
+    double x[2], y[2], z[2], vx[2], vy[2], vz[2], ax[2], ay[2], az[2], gf[2], md[2], m2[2];
+    double* s = A.state + (size_t)(live ? copy : 0) * 6 * n;
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        x[b] = y[b] = z[b] = vx[b] = vy[b] = vz[b] = ax[b] = ay[b] = az[b] = gf[b] = md[b] = 0.0;
+        m2[b] = -1.0; // see k_ensemble: minimum of d2, the root is taken once
+        if (own[b]) {
+            int const k = kb[b];
+            x[b] = s[k];
+            y[b] = s[(size_t)n + k];
+            z[b] = s[2 * (size_t)n + k];
+            vx[b] = s[3 * (size_t)n + k];
+            vy[b] = s[4 * (size_t)n + k];
+            vz[b] = s[5 * (size_t)n + k];
+            gf[b] = A.gf[k];
+            md[b] = A.mind[(size_t)copy * n + k];
+            rec[k] = make_double4(x[b], y[b], z[b], gf[b]);
+        }
+    }
+    if (live && h == 0)
+        rec[n] = make_double4(0, 0, 0, 0);
+    sync();
+    bool const on[2] = { own[0] && gf[0] != 0.0, own[1] && gf[1] != 0.0 }; // deleted() bodies are neither attracted nor moved
+
+    auto forces = [&]() {
+        double fx[2][2] = { { 0, 0 }, { 0, 0 } }, fy[2][2] = { { 0, 0 }, { 0, 0 } }, fz[2][2] = { { 0, 0 }, { 0, 0 } };
+        for (int p = 0; p < n; p += 2) { // p + 1 == n reads the pad
+            double4 const q0 = rec[p], q1 = rec[p + 1];
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                fast_interact(x[b], y[b], z[b], q0, 0.0, fx[b][0], fy[b][0], fz[b][0]);
+                fast_interact(x[b], y[b], z[b], q1, 0.0, fx[b][1], fy[b][1], fz[b][1]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+            if (on[b]) {
+                ax[b] = fx[b][0] + fx[b][1];
+                ay[b] = fy[b][0] + fy[b][1];
+                az[b] = fz[b][0] + fz[b][1];
+            }
+    };
+    forces();
+    double const hm = A.h * A.mul, dtm = A.dt * A.mul;
+    int const to = A.approach_to;
+
+    for (int st = 0; st < A.steps; st++) {
+        if (A.approaches) { // Object::update_closest_approaches, at the step's start
+            double4 const t = rec[to];
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+                if (own[b] && kb[b] != to) {
+                    double dx = __dsub_rn(t.x, x[b]), dy = __dsub_rn(t.y, y[b]), dz = __dsub_rn(t.z, z[b]);
+                    double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    if (d2 == 0.0) {
+                        md[b] = 0.0;
+                        m2[b] = -1.0;
+                    } else if (m2[b] < 0.0 || d2 < m2[b]) {
+                        m2[b] = d2;
+                    }
+                }
+        }
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+            if (on[b]) {
+                vx[b] = __dadd_rn(vx[b], __dmul_rn(ax[b], hm));
+                vy[b] = __dadd_rn(vy[b], __dmul_rn(ay[b], hm));
+                vz[b] = __dadd_rn(vz[b], __dmul_rn(az[b], hm));
+                x[b] = __dadd_rn(x[b], __dmul_rn(vx[b], dtm));
+                y[b] = __dadd_rn(y[b], __dmul_rn(vy[b], dtm));
+                z[b] = __dadd_rn(z[b], __dmul_rn(vz[b], dtm));
+            }
+        sync();
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+            if (on[b])
+                rec[kb[b]] = make_double4(x[b], y[b], z[b], gf[b]);
+        sync();
+        forces();
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+            if (on[b]) {
+                vx[b] = __dadd_rn(vx[b], __dmul_rn(ax[b], hm));
+                vy[b] = __dadd_rn(vy[b], __dmul_rn(ay[b], hm));
+                vz[b] = __dadd_rn(vz[b], __dmul_rn(az[b], hm));
+            }
+    }
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+        if (own[b]) {
+            int const k = kb[b];
+            if (A.approaches && k != to && m2[b] >= 0.0) {
+                double d = __dsqrt_rn(m2[b]);
+                if (md[b] == 0.0 || d < md[b])
+                    md[b] = d;
+            }
+            s[k] = x[b];
+            s[(size_t)n + k] = y[b];
+            s[2 * (size_t)n + k] = z[b];
+            s[3 * (size_t)n + k] = vx[b];
+            s[4 * (size_t)n + k] = vy[b];
+            s[5 * (size_t)n + k] = vz[b];
+            A.mind[(size_t)copy * n + k] = md[b];
+        }
+}
+
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st) {
     long long total = (long long)c->ens_copies * c->ens_n;
     int blocks = (int)((total + 255) / 256);
@@ -304,6 +453,14 @@ cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st) {
         (unsigned long long)c->ens.seed, c->ens.rel_sigma, c->ens_state, c->ens_gf, c->ens_mind);
     c->launches++;
     return cudaGetLastError();
+}
+
+static bool ens_duo_enabled() {
+    static int const v = [] {
+        char const* e = getenv("ESSA_ENSEMBLE_DUO"); // diagnostics: 0 = one body per thread (k_ensemble_warp / k_ensemble)
+        return e ? atoi(e) : 1;
+    }();
+    return v != 0;
 }
 
 cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
@@ -333,6 +490,21 @@ cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
         if (threads > kEnsThreadsMax) // a template wider than one ensemble CTA: one copy per CTA at full width
             return cudaErrorInvalidConfiguration;
         k_ensemble<true><<<blocks, threads, smem, st>>>(A);
+    } else if (ens_duo_enabled()) {
+        int const half = (n + 1) / 2;
+        size_t const rec_bytes = (size_t)(n + 1) * sizeof(double4);
+        if (half <= 32) { // up to 64 bodies: whole copies per warp
+            int const cw = 32 / half;
+            long long const warps = ((long long)c->ens_copies + cw - 1) / cw;
+            int const wblocks = (int)((warps + kDuoWarps - 1) / kDuoWarps);
+            k_ensemble_duo<true><<<wblocks, 32 * kDuoWarps, (size_t)kDuoWarps * cw * rec_bytes, st>>>(A);
+        } else {
+            A.per_cta = kDuoCtaThreads / half;
+            if (A.per_cta < 1)
+                return cudaErrorInvalidConfiguration;
+            int const dblocks = (c->ens_copies + A.per_cta - 1) / A.per_cta;
+            k_ensemble_duo<false><<<dblocks, kDuoCtaThreads, (size_t)A.per_cta * rec_bytes, st>>>(A);
+        }
     } else if (n <= 32) {
         int cw = 32 / n;
         long long warps = ((long long)c->ens_copies + cw - 1) / cw;
