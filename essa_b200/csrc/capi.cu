@@ -60,7 +60,7 @@ struct NcclApi {
     char const* (*GetErrorString)(int) = nullptr;
     std::string why;
 };
-constexpr int kNcclFloat64 = 8, kNcclSum = 0; // ncclDataType_t / ncclRedOp_t values (nccl.h)
+constexpr int kNcclFloat64 = 8, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2; // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
 NcclApi& nccl() {
     static NcclApi api;
@@ -277,6 +277,8 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     free_recording(c);
     cudaFree(c->pair_slots);
     cudaFree(c->pair_part);
+    cudaFree(c->pair_kslots);
+    cudaFree(c->pair_kpart);
     cudaFree(c->part);
     cudaFree(c->part_m);
     cudaFree(c->part_j);
@@ -599,19 +601,24 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
             ctx->gather_pending = false;
         }
         double* acc = nullptr;
+        unsigned long long* kacc = nullptr;
         int npad = 0;
-        CK(launch_force_paired_compute(ctx, eps2, ctx->stream, &acc, &npad));
+        // most-attracting tracking: real candidate keys, unless every gravity factor is equal (then it is a no-op)
+        bool const keys = argmax && !ctx->gf_uniform;
+        CK(launch_force_paired_compute(ctx, eps2, ctx->stream, &acc, &npad, keys, &kacc));
         if (ctx->world > 1) {
-            // every rank holds J-side sums for every body: reduce-scatter them onto the owners (in place)
+            // every rank holds J-side sums (and candidate keys) for every body: reduce-scatter them onto the owners (in place)
             size_t cnt = (size_t)n / ctx->world;
             NK(nccl().GroupStart());
             for (int c3 = 0; c3 < 3; c3++) {
                 double* base = acc + (size_t)c3 * npad;
                 NK(nccl().ReduceScatter(base, base + (size_t)ctx->rank * cnt, cnt, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream));
             }
+            if (keys)
+                NK(nccl().ReduceScatter(kacc, kacc + (size_t)ctx->rank * cnt, cnt, kNcclUint64, kNcclMax, ctx->comm, ctx->stream));
             NK(nccl().GroupEnd());
         }
-        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc, argmax, save_old));
+        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc, argmax && !keys, save_old, keys, kacc));
     } else if (ctx->world == 1 || !ctx->gather_pending) {
         int S;
         choose_split(ctx, iblocks, (n + kTileJ - 1) / kTileJ, &S);
@@ -646,19 +653,20 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
     double const mul = steps >= 0 ? 1.0 : -1.0;
     bool const argmax = o.track_most_attracting || o.record;
     {
-        // pair-shared kernel: slots must fit comfortably; most-attracting tracking only where it is provably a
-        // no-op (all gravity factors equal: the "heavier partner" test of Object.cpp:84-94 fails for every pair, so
-        // max_attraction stays 0 and the links stay as they are -- k_pair_finish writes exactly that)
+        // pair-shared kernel: slots must fit comfortably.  Most-attracting tracking rides along as sortable candidate
+        // keys (worlds of up to 2^21 bodies), or costs nothing where it is provably a no-op (all gravity factors
+        // equal: the "heavier partner" test of Object.cpp:84-94 fails for every pair, so max_attraction stays 0 and
+        // the links stay as they are -- k_pair_finish writes exactly that)
         int nb, S;
         size_t slot_d = 0, part_d = 0;
-        bool can = (!argmax || ctx->gf_uniform) && paired_plan(ctx, &nb, &S, &slot_d, &part_d);
+        bool can = (!argmax || ctx->gf_uniform || ctx->n <= (1 << 21)) && paired_plan(ctx, &nb, &S, &slot_d, &part_d);
         if (can && (slot_d > ctx->pair_slots_n || part_d > ctx->pair_part_n)) { // first use at this size: will it fit?
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
             can = (slot_d + part_d) * sizeof(double) < free_b / 2 + (ctx->pair_slots_n + ctx->pair_part_n) * sizeof(double);
         }
         if (o.kernel == ESSA_KERNEL_PAIRED && !can) {
-            ctx->err = "pair-shared kernel needs >= 1025 bodies (whole 1024- or 2048-body blocks per rank when sharded), no most-attracting tracking unless all gravity factors are equal, and room for its slots";
+            ctx->err = "pair-shared kernel needs >= 1025 bodies (whole 1024- or 2048-body blocks per rank when sharded), at most 2^21 bodies when the most-attracting links are tracked, and room for its slots";
             return ESSA_ERR_ARG;
         }
         ctx->use_paired = can && (o.kernel == ESSA_KERNEL_PAIRED || (o.kernel == ESSA_KERNEL_AUTO && ctx->n >= 16384));

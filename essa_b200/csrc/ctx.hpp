@@ -115,7 +115,8 @@ struct essa_ctx {
     } plan;
     bool gf_uniform = false; // every uploaded gravity factor is the same value
     bool timing_pending = false; // essa_step_async: ev_end recorded, elapsed time not read yet
-    bool attr_pair4 = false, attr_pair8 = false, attr_cta = false; // opt-in shared-memory sizes set on this device
+    bool attr_pair[4] = { false, false, false, false };
+    bool attr_cta = false; // opt-in shared-memory sizes set on this device
     bool attr_cluster_wide[3] = { false, false, false };
     bool attr_cluster16[5] = { false, false, false, false, false }; // non-portable cluster size allowed for K3x<PER>
     bool use_paired = false;    // this essa_step runs its force passes through force_paired.cu
@@ -139,6 +140,10 @@ struct essa_ctx {
     size_t pair_slots_n = 0;
     double* pair_part = nullptr;
     size_t pair_part_n = 0;
+    unsigned long long* pair_kslots = nullptr; // most-attracting candidate keys (pair-shared kernel with tracking)
+    size_t pair_kslots_bytes = 0;
+    unsigned long long* pair_kpart = nullptr;
+    size_t pair_kpart_bytes = 0;
 
     // recording
     int tracked = 0;
@@ -204,8 +209,10 @@ cudaError_t launch_record_init(essa_ctx* c, int first, cudaStream_t st);
 cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double const* z, cudaStream_t st);
 cudaError_t launch_unpack(essa_ctx* c, double* x, double* y, double* z, cudaStream_t st);
 bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles, int* ri_out = nullptr);
-cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out);
-cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred, bool argmax_noop, bool save_old);
+cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out, bool argmax,
+    unsigned long long** kacc_out);
+cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred, bool argmax_noop, bool save_old,
+    bool argmax, unsigned long long const* akred);
 int force_iblocks(essa_ctx const* c, int* R_out);
 void choose_split(essa_ctx const* c, int iblocks, int ntiles, int* S_out);
 

@@ -36,6 +36,19 @@ constexpr int kPHalf = 512;     // records per staged part of a J block
 // of 1024) when 2048-body blocks would leave SMs idle.  Bodies per block = 256 * RI.
 constexpr int kPSub = 32 * kPRJ;
 constexpr size_t kPSmem = 2 * kPHalf * sizeof(double4) + 8 * 3 * kPHalf * sizeof(double) + 64;
+constexpr size_t kPSmemKeys = 8 * kPHalf * sizeof(unsigned long long); // + per-warp J-side candidate keys (ARGMAX)
+
+// Most-attracting candidates (src/Object.cpp:84-94) travel as sortable 64-bit keys: the bit pattern of the ranking
+// metric gf_p |d|^-3 y0 ~ gf_p / r^4 (positive doubles order like unsigned integers; y0 = rsqrt seed, relative
+// error < 1e-6: enough unless two heavier bodies attract within 1 ppm of each other) with its kKeyIdxBits lowest
+// mantissa bits replaced by (mask - index), so that max() picks the largest metric and, among equal ones, the
+// lowest index -- integer-pipe work instead of FP64 compare / select chains.  0 = no candidate.
+constexpr int kKeyIdxBits = 21; // worlds of up to 2,097,152 bodies
+constexpr unsigned long long kKeyIdxMask = (1ull << kKeyIdxBits) - 1ull;
+__device__ __forceinline__ unsigned long long pack_key(double m, int idx) {
+    return ((unsigned long long)__double_as_longlong(m) & ~kKeyIdxMask) | (kKeyIdxMask - (unsigned long long)idx);
+}
+__device__ __forceinline__ unsigned long long key_max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
 struct PairArgs {
     double4 const* pos; // padded to a multiple of kPB with {0,0,0,0}
@@ -46,14 +59,17 @@ struct PairArgs {
     int npad;           // nb * kPB
     double* part_i;     // [S][3][npad]       I-side partial accelerations
     double* slots;      // [ib1-ib0][dmax][3][kPB]  J-side partials of tile (I, d), d = 1 .. dmax
+    unsigned long long* part_k;  // [S][npad]              I-side candidate keys (ARGMAX)
+    unsigned long long* slots_k; // [ib1-ib0][dmax][kPB]   J-side candidate keys of tile (I, d)
     double eps2;
 };
 
 __device__ __forceinline__ double rot1(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-template<bool TWO_SIDED>
+template<bool TWO_SIDED, bool ARGMAX>
 __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, double gi, double xj, double yj, double zj, double gj,
-    double eps2, double& aix, double& aiy, double& aiz, double& ajx, double& ajy, double& ajz) {
+    double eps2, double& aix, double& aiy, double& aiz, double& ajx, double& ajy, double& ajz, int iidx, int jidx,
+    unsigned long long& bi, unsigned long long& bj) {
     double dx = xj - xi, dy = yj - yi, dz = zj - zi;
     double r2 = fma(dx, dx, eps2);
     r2 = fma(dy, dy, r2);
@@ -70,15 +86,23 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
     aix = fma(si, dx, aix);
     aiy = fma(si, dy, aiy);
     aiz = fma(si, dz, aiz);
+    if (ARGMAX) {
+        unsigned long long k = pack_key(si * y0, jidx);
+        bi = key_max(bi, gj > gi ? k : 0ull);
+    }
     if (TWO_SIDED) {
         double sj = gi * u;
         ajx = fma(-sj, dx, ajx);
         ajy = fma(-sj, dy, ajy);
         ajz = fma(-sj, dz, ajz);
+        if (ARGMAX) {
+            unsigned long long k = pack_key(sj * y0, iidx);
+            bj = key_max(bj, gi > gj ? k : 0ull);
+        }
     }
 }
 
-template<int kPRI>
+template<int kPRI, bool ARGMAX>
 __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A) {
     constexpr int kPB = kPThreads * kPRI;
     constexpr int kPParts = kPB / kPHalf;
@@ -86,6 +110,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
     double4* tile = reinterpret_cast<double4*>(smem_raw);                       // [2][kPHalf]
     double* accj = reinterpret_cast<double*>(smem_raw + 2 * kPHalf * sizeof(double4)); // [8][3][kPHalf]
     unsigned long long* full = reinterpret_cast<unsigned long long*>(accj + 8 * 3 * kPHalf); // [2]
+    unsigned long long* acck = full + 8;                                                        // [8][kPHalf] (ARGMAX)
 
     int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int const ibl = blockIdx.x / A.S, chunk = blockIdx.x - ibl * A.S;
@@ -104,6 +129,11 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
         gi[r] = p.w;
         aix[r] = aiy[r] = aiz[r] = 0.0;
     }
+    unsigned long long bi[kPRI]; // best candidate key per target
+#pragma unroll
+    for (int r = 0; r < kPRI; r++)
+        bi[r] = 0ull;
+    int const ibase = I * kPB + warp * (32 * kPRI) + lane; // + r * 32
 
     if (tid == 0) {
         mbar_init(&full[0], 1);
@@ -135,6 +165,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
         int const d = u / kPParts, half = u - d * kPParts;
         if (!valid(d))
             continue;
+        int J = I + d;
+        if (J >= A.nb)
+            J -= A.nb;
         {
             int const buf = seq & 1;
             // prefetch the tile after this one into the other buffer
@@ -161,6 +194,11 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                     gj[q] = p.w;
                     ajx[q] = ajy[q] = ajz[q] = 0.0;
                 }
+                unsigned long long bjk[kPRJ]; // the visitors' own candidate keys travel with them
+#pragma unroll
+                for (int q = 0; q < kPRJ; q++)
+                    bjk[q] = 0ull;
+                int const jbase = J * kPB + half * kPHalf + sub * kPSub; // + q * 32 + home lane of the visitor
                 int const src = (lane + 31) & 31; // take from the previous lane = pass to the next
                 if (d == 0) {
                     for (int rot = 0; rot < 32; rot++) {
@@ -168,8 +206,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                         for (int q = 0; q < kPRJ; q++)
 #pragma unroll
                             for (int r = 0; r < kPRI; r++)
-                                pair_interact<false>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r], aiz[r],
-                                    ajx[q], ajy[q], ajz[q]);
+                                pair_interact<false, ARGMAX>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
+                                    aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q]);
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++) {
                             xj[q] = rot1(xj[q], src);
@@ -184,8 +222,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                         for (int q = 0; q < kPRJ; q++)
 #pragma unroll
                             for (int r = 0; r < kPRI; r++)
-                                pair_interact<true>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r], aiz[r],
-                                    ajx[q], ajy[q], ajz[q]);
+                                pair_interact<true, ARGMAX>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
+                                    aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q]);
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++) {
                             xj[q] = rot1(xj[q], src);
@@ -195,6 +233,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                             ajx[q] = rot1(ajx[q], src);
                             ajy[q] = rot1(ajy[q], src);
                             ajz[q] = rot1(ajz[q], src);
+                            if (ARGMAX)
+                                bjk[q] = __shfl_sync(0xffffffffu, bjk[q], src);
                         }
                     }
                     // 32 rotations: every visitor is back in its home lane
@@ -204,6 +244,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                         myacc[j] = ajx[q];
                         myacc[kPHalf + j] = ajy[q];
                         myacc[2 * kPHalf + j] = ajz[q];
+                        if (ARGMAX)
+                            acck[(size_t)warp * kPHalf + j] = bjk[q];
                     }
                 }
             }
@@ -218,6 +260,16 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                         sum = __dadd_rn(sum, accj[(size_t)w * 3 * kPHalf + e]);
                     __stcg(slot + (size_t)c * kPB + half * kPHalf + j, sum);
                 }
+                if (ARGMAX) {
+                    unsigned long long* slotk = A.slots_k + ((size_t)ibl * A.dmax + (d - 1)) * kPB + half * kPHalf;
+                    for (int j = tid; j < kPHalf; j += kPThreads) {
+                        unsigned long long k = 0ull;
+#pragma unroll
+                        for (int w = 0; w < 8; w++)
+                            k = key_max(k, acck[(size_t)w * kPHalf + j]);
+                        __stcg(slotk + j, k);
+                    }
+                }
             }
             __syncthreads();
             seq++;
@@ -231,6 +283,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
         __stcg(p, aix[r]);
         __stcg(p + A.npad, aiy[r]);
         __stcg(p + 2 * (size_t)A.npad, aiz[r]);
+        if (ARGMAX)
+            __stcg(A.part_k + (size_t)chunk * A.npad + i, bi[r]);
     }
 }
 
@@ -243,6 +297,10 @@ struct PairFinishArgs {
     double const* part_i;
     double const* slots;
     double const* ajred; // sharded: [3][npad] J-side sums already reduced over ranks (slots are skipped)
+    unsigned long long const* part_k;  // ARGMAX: I-side candidate keys [S][npad]
+    unsigned long long const* slots_k; // ARGMAX: J-side candidate keys per tile
+    unsigned long long const* akred;   // sharded ARGMAX: [npad] J-side keys already max-reduced over ranks
+    int argmax;          // most-attracting tracking with real candidates (keys)
     int argmax_noop;     // most-attracting tracking requested on a world of equal gravity factors: clear_forces only
     int save_old;        // ... and Object::before_update's old_most = most
 };
@@ -267,10 +325,28 @@ __device__ __forceinline__ void slot_sum(int g, int nb, int dmax, int ib0, int i
     }
 }
 
+// J-side candidate keys of body g from the tiles whose I block lies in [ib0, ib1).
+template<int kPB>
+__device__ __forceinline__ unsigned long long slot_key(int g, int nb, int dmax, int ib0, int ib1, unsigned long long const* slots_k) {
+    int const K = g / kPB, jl = g - K * kPB;
+    unsigned long long k = 0ull;
+    for (int d = 1; d <= dmax; d++) {
+        int I = K - d;
+        if (I < 0)
+            I += nb;
+        if (I < ib0 || I >= ib1)
+            continue;
+        if ((nb & 1) == 0 && d == nb / 2 && I >= nb / 2)
+            continue;
+        k = key_max(k, __ldcg(slots_k + ((size_t)(I - ib0) * dmax + (d - 1)) * kPB + jl));
+    }
+    return k;
+}
+
 // Sharded worlds: this rank's J-side sums for EVERY body, to be reduce-scattered over the ranks.
 template<int kPB>
 __global__ void __launch_bounds__(256) k_pair_gather_slots(int nb, int dmax, int ib0, int ib1, int npad, double const* slots,
-    double* acc) {
+    double* acc, unsigned long long const* slots_k, unsigned long long* kacc) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= npad)
         return;
@@ -279,6 +355,8 @@ __global__ void __launch_bounds__(256) k_pair_gather_slots(int nb, int dmax, int
     acc[g] = ax;
     acc[(size_t)npad + g] = ay;
     acc[2 * (size_t)npad + g] = az;
+    if (kacc)
+        kacc[g] = slot_key<kPB>(g, nb, dmax, ib0, ib1, slots_k);
 }
 
 template<int kPB>
@@ -306,11 +384,32 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
     bool act = W.active[g] != 0;
     double4 p = W.pos_cur[g];
     double vx = 0, vy = 0, vz = 0;
-    if (A.argmax_noop && A.save_old)
+    if ((A.argmax_noop || A.argmax) && A.save_old)
         W.old_most[g] = W.most[g];
     if (act) {
         if (A.argmax_noop)
             W.maxattr[g] = 0.0; // Object::clear_forces; no pair can raise it (nobody is heavier than anybody)
+        if (A.argmax) {
+            unsigned long long key = A.akred ? __ldcg(A.akred + g) : slot_key<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots_k);
+            for (int c = 0; c < A.S; c++)
+                key = key_max(key, __ldcg(A.part_k + (size_t)c * A.npad + g));
+            double m = 0.0; // Object::clear_forces
+            if (key != 0ull) {
+                // the winner's gf / r^4 (the reference's |ta|^2 / gf) to full precision
+                int const wj = (int)(kKeyIdxMask - (key & kKeyIdxMask));
+                double4 const q = W.pos_cur[wj];
+                double dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+                double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                double y0 = rsqrt_seed(r2);
+                double t = r2 * y0;
+                double e = fma(-t, y0, 1.0);
+                double y = fma(y0 * e, fma(0.375, e, 0.5), y0); // 1 / r
+                double y2 = y * y;
+                m = q.w * y2 * y2;
+                W.most[g] = wj;
+            }
+            W.maxattr[g] = m;
+        }
         W.a[0][g] = ax;
         W.a[1][g] = ay;
         W.a[2][g] = az;
@@ -447,34 +546,52 @@ static void pair_geometry(essa_ctx const* c, int nb, int* ib0, int* ib1) {
     *ib1 = (int)((long long)nb * (c->rank + 1) / c->world);
 }
 
-template<int RI>
-static cudaError_t launch_pair_kernels(essa_ctx* c, PairArgs const& A, cudaStream_t st, double** acc) {
+template<int RI, bool ARGMAX>
+static cudaError_t launch_pair_kernels(essa_ctx* c, PairArgs const& A, cudaStream_t st, double** acc, unsigned long long** kacc) {
     constexpr int PB = kPThreads * RI;
-    bool& attr_set = RI == 8 ? c->attr_pair8 : c->attr_pair4; // per context: the attribute is per device
+    constexpr size_t smem = kPSmem + (ARGMAX ? kPSmemKeys : 0);
+    bool& attr_set = c->attr_pair[(RI == 8 ? 0 : 1) + (ARGMAX ? 2 : 0)]; // per context: the attribute is per device
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_force_paired<RI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_force_paired<RI, ARGMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
         attr_set = true;
     }
-    k_force_paired<RI><<<(A.ib1 - A.ib0) * A.S, kPThreads, kPSmem, st>>>(A);
+    k_force_paired<RI, ARGMAX><<<(A.ib1 - A.ib0) * A.S, kPThreads, smem, st>>>(A);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         return e;
     *acc = nullptr;
+    *kacc = nullptr;
     if (c->world > 1) {
         *acc = c->pair_part + (size_t)A.S * 3 * A.npad;
-        k_pair_gather_slots<PB><<<(A.npad + 255) / 256, 256, 0, st>>>(A.nb, A.dmax, A.ib0, A.ib1, A.npad, c->pair_slots, *acc);
+        if (ARGMAX)
+            *kacc = c->pair_kpart + (size_t)A.S * A.npad;
+        k_pair_gather_slots<PB><<<(A.npad + 255) / 256, 256, 0, st>>>(A.nb, A.dmax, A.ib0, A.ib1, A.npad, c->pair_slots, *acc,
+            c->pair_kslots, *kacc);
         c->launches++;
         e = cudaGetLastError();
     }
     return e;
 }
 
+static cudaError_t grow(void** p, size_t* have, size_t want_bytes) {
+    if (want_bytes <= *have)
+        return cudaSuccess;
+    cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(p, want_bytes);
+    if (e == cudaSuccess)
+        *have = want_bytes;
+    return e;
+}
+
 // Phase 1: the pair kernel over this rank's I blocks; sharded worlds also fold their slots into
 // acc[3][npad] (returned through *acc_out) for the caller to reduce-scatter over the ranks.
-cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out) {
+cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out, bool argmax,
+    unsigned long long** kacc_out) {
     int nb, S, ri;
     size_t slot_d, part_d;
     if (!paired_plan(c, &nb, &S, &slot_d, &part_d, &ri))
@@ -497,6 +614,13 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
             return e;
         c->pair_part_n = part_d;
     }
+    if (argmax) { // candidate keys: one per slot body / per partial body (a third of the acceleration buffers)
+        cudaError_t e = grow((void**)&c->pair_kslots, &c->pair_kslots_bytes, slot_d / 3 * sizeof(unsigned long long));
+        if (e == cudaSuccess)
+            e = grow((void**)&c->pair_kpart, &c->pair_kpart_bytes, (part_d / 3 + 1) * sizeof(unsigned long long));
+        if (e != cudaSuccess)
+            return e;
+    }
     PairArgs A;
     A.pos = c->pos[c->cur];
     A.nb = nb;
@@ -506,18 +630,25 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
     A.npad = nb * kPThreads * ri;
     A.part_i = c->pair_part;
     A.slots = c->pair_slots;
+    A.part_k = c->pair_kpart;
+    A.slots_k = c->pair_kslots;
     A.eps2 = eps2;
     double* acc = nullptr;
-    cudaError_t e = ri == 8 ? launch_pair_kernels<8>(c, A, st, &acc) : launch_pair_kernels<4>(c, A, st, &acc);
+    unsigned long long* kacc = nullptr;
+    cudaError_t e = ri == 8 ? (argmax ? launch_pair_kernels<8, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<8, false>(c, A, st, &acc, &kacc))
+                            : (argmax ? launch_pair_kernels<4, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<4, false>(c, A, st, &acc, &kacc));
     if (acc_out)
         *acc_out = acc;
+    if (kacc_out)
+        *kacc_out = kacc;
     if (npad_out)
         *npad_out = A.npad;
     return e;
 }
 
 // Phase 2: ordered sums + kick / drift epilogue for this rank's targets.
-cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred, bool argmax_noop, bool save_old) {
+cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred, bool argmax_noop, bool save_old,
+    bool argmax, unsigned long long const* akred) {
     int nb, S, ri;
     size_t slot_d, part_d;
     if (!paired_plan(c, &nb, &S, &slot_d, &part_d, &ri))
@@ -535,6 +666,10 @@ cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStrea
     F.npad = nb * kPThreads * ri;
     F.part_i = c->pair_part;
     F.argmax_noop = argmax_noop ? 1 : 0;
+    F.argmax = argmax ? 1 : 0;
+    F.part_k = c->pair_kpart;
+    F.slots_k = c->pair_kslots;
+    F.akred = akred;
     F.save_old = save_old ? 1 : 0;
     F.slots = c->pair_slots;
     F.ajred = ajred;

@@ -117,11 +117,44 @@ def test_paired_refuses_what_it_cannot_do(ctx):
     _upload(ctx, w)
     with pytest.raises(capi.EssaError):
         ctx.step(1, 1000, kernel=capi.KERNEL_PAIRED)
-    w = synth.plummer(4096, seed=1)
-    w["gf"] = w["gf"] * np.linspace(1.0, 2.0, 4096)  # unequal masses: the most-attracting links are real work
-    _upload(ctx, w)
-    with pytest.raises(capi.EssaError):
-        ctx.step(1, 1000, kernel=capi.KERNEL_PAIRED, track_most_attracting=True)
+
+
+@pytest.mark.parametrize("n", [4096, 6000, 20000])
+def test_paired_most_attracting_links_match_tiled_and_oracle(ctx, n):
+    """Unequal masses: the pair-shared kernel carries the most-attracting candidates as sortable keys
+    (src/Object.cpp:84-94: the heavier partner with the largest gf / r^4, lowest index on ties)."""
+    w = synth.plummer(n, seed=31)
+    rng = np.random.default_rng(n)
+    gf = w["gf"] * 10.0 ** rng.uniform(-2, 2, n)
+    t0 = capi.START_DATE
+    cdate = np.full(n, t0, dtype=np.int64)
+    cdate[rng.choice(n, 40, replace=False)] = t0 + 10 ** 9  # masked bodies are neither candidates nor targets
+    dt = synth.default_dt(n)
+    got = {}
+    for kern in (capi.KERNEL_TILED, capi.KERNEL_PAIRED):
+        ctx.date = t0
+        ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], gf, creation_date=cdate,
+                   most=np.full(n, -1, dtype=np.int32))
+        ctx.step(2, dt, kernel=kern, track_most_attracting=True)
+        got[kern] = ctx.download()
+    t, p = got[capi.KERNEL_TILED], got[capi.KERNEL_PAIRED]
+    assert np.array_equal(t["most"], p["most"])
+    act = cdate <= t0
+    assert (p["most"][~act] == -1).all() and (p["most"][act] >= 0).sum() >= act.sum() - 1  # all but the heaviest have a link
+    m_t, m_p = t["max_attraction"], p["max_attraction"]
+    assert np.abs(m_p - m_t).max() <= 1e-12 * np.abs(m_t).max() and np.all(np.abs(m_p[act] - m_t[act]) <= 1e-11 * np.abs(m_t[act]))
+    # the links against a direct evaluation of the rule on the final positions
+    x, y, z = p["x"], p["y"], p["z"]
+    for i in rng.choice(np.where(act)[0], 64, replace=False):
+        r2 = (x - x[i]) ** 2 + (y - y[i]) ** 2 + (z - z[i]) ** 2
+        cand = act & (gf > gf[i])
+        cand[i] = False
+        if not cand.any():
+            continue
+        r2[i] = np.inf
+        metric = np.where(cand, gf / r2 ** 2, 0.0)
+        assert p["most"][i] == int(np.argmax(metric)), i
+        assert m_p[i] == pytest.approx(metric.max(), rel=1e-9)
 
 
 def test_paired_tracks_most_attracting_when_it_is_a_no_op(ctx):

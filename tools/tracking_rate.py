@@ -1,0 +1,26 @@
+#!/usr/bin/env python3
+"""Force-pass rate at N = 262,144 with the most-attracting bookkeeping on: equal masses (pair-shared kernel, the
+bookkeeping is provably a no-op) vs unequal masses (tiled argmax kernel)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from essa_b200 import capi, synth  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+c = capi.Context(0, n)
+peak = c.measure_fp64_peak()
+w = synth.plummer(n, seed=5)
+dt = synth.default_dt(n)
+for label, gf in (("equal masses", w["gf"]), ("unequal masses", w["gf"] * np.random.default_rng(1).uniform(0.5, 2.0, n))):
+    for track in (False, True):
+        c.date = capi.START_DATE
+        c.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], gf)
+        c.step(2, dt, track_most_attracting=track)
+        c.step(3, dt, track_most_attracting=track)
+        ms = c.last_step_ms / 3
+        rate = n * (n - 1) / (ms * 1e-3)
+        print("%-15s tracking=%d  %.3e interactions/s  %.2f ms/step  %.1f %% of FP64 peak" % (label, track, rate, ms, 100 * rate * 20 / (peak * 1e12)), flush=True)
+c.close()
