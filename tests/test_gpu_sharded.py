@@ -26,4 +26,4 @@ def test_two_rank_sharded_matches_unsharded():
                        timeout=600, cwd=ROOT)
     out = p.stdout + p.stderr
     assert p.returncode == 0, out[-3000:]
-    assert out.count("-> PASS") == 4 and "FAIL" not in out, out[-3000:]
+    assert out.count("-> PASS") == 5 and "FAIL" not in out, out[-3000:]

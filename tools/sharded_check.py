@@ -63,6 +63,29 @@ def main():
         if rank == 0:
             uid.copy_(torch.from_numpy(capi.nccl_unique_id()))
         dist.broadcast(uid, 0)
+    # pair-shared kernel with most-attracting tracking on unequal masses: candidate keys are max-reduced over the ranks
+    n = 8192 * world
+    w = synth.plummer(n, seed=23)
+    gf = w["gf"] * 10.0 ** np.random.default_rng(7).uniform(-2, 2, n)
+    dt = synth.default_dt(n)
+    ctx = capi.Context(local)
+    ctx.shard_attach(rank, world, uid.cpu().numpy())
+    ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], gf)
+    ctx.step(3, dt, kernel=capi.KERNEL_PAIRED, track_most_attracting=True)
+    got = ctx.download()
+    if rank == 0:
+        ref = capi.Context(local)
+        ref.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], gf)
+        ref.step(3, dt, kernel=capi.KERNEL_TILED, track_most_attracting=True)
+        exp = ref.download()
+        own = slice(0, n // world)  # most / max_attraction are kept for a rank's own targets
+        same = np.array_equal(got["most"][own], exp["most"][own])
+        rel = np.abs(got["max_attraction"][own] - exp["max_attraction"][own]).max() / np.abs(exp["max_attraction"][own]).max()
+        good = same and rel <= 1e-11 and (got["most"][own] >= 0).sum() >= n // world - 1
+        ok = ok and good
+        print("sharded_check pair-shared tracking n=%d ranks=%d links_equal=%s maxattr_rel=%.2e -> %s" % (n, world, same, rel, "PASS" if good else "FAIL"), flush=True)
+        ref.close()
+    ctx.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
