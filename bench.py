@@ -368,17 +368,25 @@ def run_ours(args):
     host = {k: np.array(w[k]) for k in ("x", "y", "z", "vx", "vy", "vz", "gf")}
     p0 = ctx.passes
     t0 = time.perf_counter()
+    ticks = []
     for _ in range(e2e_steps):
+        ta = time.perf_counter()
         ctx.upload(host["x"], host["y"], host["z"], host["vx"], host["vy"], host["vz"], host["gf"])
+        tb = time.perf_counter()
         ctx.step(1, opts=opts)
+        tc = time.perf_counter()
         got = ctx.download(("x", "y", "z", "vx", "vy", "vz"))
         for k in ("x", "y", "z", "vx", "vy", "vz"):
             host[k] = got[k]
+        td = time.perf_counter()
+        ticks.append({"upload_ms": 1e3 * (tb - ta), "step_ms": 1e3 * (tc - tb), "download_ms": 1e3 * (td - tc),
+                      "device_step_ms": ctx.last_step_ms, "force_ms": ctx.last_force_ms, "force_passes": ctx.last_force_passes})
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = float(ctx.passes - p0) * n * (n - 1) / e2e_s
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * (11 * 8 + 2 * 8 + 4 + 2)), "d2h_bytes_per_step": int(n * 6 * 8),
            "steps": e2e_steps, "passes_per_step": (ctx.passes - p0) / e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "ticks_rank0": ticks,
            "note": "essa_upload (host SoA -> pinned staging -> HBM) + essa_step(1) + essa_download per step; an upload invalidates "
                    "the resident acceleration, so each step evaluates both set_forces() passes, as the reference does"}
 
@@ -399,6 +407,8 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get("%s_n%d" % ("paired" if paired else "tiled", n))
         except Exception:
             traffic = None
+    uniform = paired and bool(np.all(w["gf"] == w["gf"][0])) and os.environ.get("ESSA_PAIR_UNIFORM", "1") != "0"
+    ipi = (9.0 if uniform else 10.0) if paired else 16.0
     roofline = {"bound": "fp64", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tflops / peak,
                 "traffic": traffic, "kernel": "k_force_paired (+ k_pair_finish)" if paired else "k_force_tiled",
                 "avg_launch_ms": avg_force_ms, "launches_timed": force_passes,
@@ -406,12 +416,19 @@ def run_ours(args):
                 "peak_source": "measured in this run: register-resident independent DFMA chains on all SMs for 300 ms "
                                "(MEASURED_PEAKS.json carries no FP64 figure)",
                 "frac_of_nominal": achieved_tflops / NOMINAL_FP64_TFLOPS, "nominal_peak": NOMINAL_FP64_TFLOPS,
-                "fp64_instructions_per_interaction": 10.5 if paired else 17,
-                "note": "the path is FP64-pipe bound (intensity ~0.19*N flop/B), neither HBM nor tensor.  " + (
-                    "Pair-shared kernel: each unordered pair is evaluated once and applied to both bodies (as the reference's own "
-                    "i<j loop does): 21 FP64 instructions per pair = 10.5 per directed interaction, ceiling 95% of the 20-flop convention"
+                "fp64_instructions_per_interaction": ipi,
+                "fp64_pipe_frac": achieved_tflops / peak * (2.0 * ipi / FLOPS_PER_INTERACTION),
+                "note": "the path is FP64-pipe bound (intensity ~0.19*N flop/B), neither HBM nor tensor.  `frac` follows BASELINE.json's "
+                        "convention of 20 flops per directed interaction; `fp64_pipe_frac` is the share of the measured DFMA issue rate the "
+                        "kernel's FP64 instructions actually occupy (interactions/s x instructions per interaction / peak instruction rate).  " + (
+                    ("Pair-shared kernel: each unordered pair is evaluated once and applied to both bodies (as the reference's own "
+                     "i<j loop does).  %s") % (
+                        "Every body of this world is live and has the same gravity factor g, so the kernel accumulates sum |d|^-3 d and "
+                        "multiplies by g once per body: 18 FP64 instructions per pair = 9 per directed interaction "
+                        "(ESSA_PAIR_UNIFORM=0 runs the general kernel: 20 per pair)" if uniform else
+                        "20 FP64 instructions per pair = 10 per directed interaction")
                     if paired else
-                    "17 FP64 instructions per directed interaction cap this formulation at 10/17 = 58.8% of the 20-flop convention")}
+                    "16 FP64 instructions per directed interaction cap this formulation at 10/16 = 62.5% of the 20-flop convention")}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -419,7 +436,7 @@ def run_ours(args):
             "config": {"workload": name, "n": n, "dt_seconds": dt, "sharding": "targets/%d: NCCL gather of drifted positions + reduce-scatter of pair-shared partial accelerations per pass" % world_size
                        if world_size > 1 else "single GPU", "l2": "flushed (256 MiB memset) between timed steps",
                        "passes_per_step": passes / args.steps,
-                       "most_attracting": "tracked, as Object::update_forces_against always does (track_most_attracting=1); every body of this workload has the same mass, so the heavier-partner test of src/Object.cpp:86,91 fails for every pair: the pair-shared kernel writes max_attraction = 0 and keeps the links, exactly what the reference leaves (checked against the tiled argmax kernel in tests/test_gpu_paired.py); unequal masses go through the tiled argmax kernel", "accounting": "value counts only force passes actually evaluated: N(N-1) directed interactions per pass; the reference's "
+                       "most_attracting": "tracked, as Object::update_forces_against always does (track_most_attracting=1); every body of this workload has the same mass, so the heavier-partner test of src/Object.cpp:86,91 fails for every pair: the pair-shared kernel writes max_attraction = 0 and keeps the links, exactly what the reference leaves (checked against the tiled argmax kernel in tests/test_gpu_paired.py); unequal masses carry sortable candidate keys through the same kernel", "accounting": "value counts only force passes actually evaluated: N(N-1) directed interactions per pass; the reference's "
                                      "first set_forces() of a step recomputes the previous step's second one bit for bit, so the resident "
                                      "acceleration is reused (tests: two_pass == reuse, bitwise) and is NOT counted",
                        "timing": "CUDA events on the launching stream around each essa_step, max over ranks"},

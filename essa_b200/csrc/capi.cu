@@ -402,6 +402,7 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
         memcpy(d + k * N, src[k], N * sizeof(double));
     // equal gravity factors everywhere: no body has a heavier partner, so Object.cpp:84-94 can never fire
     ctx->gf_uniform = true;
+    ctx->gf_uniform_value = h->gf[0];
     for (size_t i = 1; i < N && ctx->gf_uniform; i++)
         ctx->gf_uniform = h->gf[i] == h->gf[0];
     double* appe = d + 7 * N;
@@ -618,7 +619,7 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
                 NK(nccl().ReduceScatter(kacc, kacc + (size_t)ctx->rank * cnt, cnt, kNcclUint64, kNcclMax, ctx->comm, ctx->stream));
             NK(nccl().GroupEnd());
         }
-        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc, argmax && !keys, save_old, keys, kacc));
+        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc, argmax && !keys, save_old, keys, kacc, eps2));
     } else if (ctx->world == 1 || !ctx->gather_pending) {
         int S;
         choose_split(ctx, iblocks, (n + kTileJ - 1) / kTileJ, &S);

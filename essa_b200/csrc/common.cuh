@@ -19,6 +19,10 @@ namespace essa {
 // fast flavour
 // ------------------------------------------------------------------------------------------
 
+// Coordinate of the padding records behind the last body of a world (2^400 m: its square is representable and
+// the resulting |d|^-3 underflows to 0).
+constexpr double kPadCoord = 2.5822498780869086e120;
+
 // y0 ~ r2^-1/2 from the special-function unit (SASS: MUFU.RSQ64H; only the high word is
 // produced, the low word is zero).  r2 == 0 (self term or coincident bodies) yields 0 instead of
 // +inf so that the term vanishes; the test is on the high word, in the integer pipe, and also
@@ -33,12 +37,14 @@ __device__ __forceinline__ double rsqrt_seed(double r2) {
 }
 
 // s = gf / r^3 from r2 = r^2 and the seed:  e = 1 - r2*y0^2,  r2^-3/2 = y0^3 (1-e)^-3/2
-//   = y0^3 (1 + e (3/2 + 15/8 e) + O(e^3)).   8 FP64 instructions.
+//   = y0^3 (1 + e (3/2 + 15/8 e) + O(e^3)).   7 FP64 instructions.
+// The seed carries 21 significant bits (high word only), so y0*y0 is EXACT in binary64 and
+// e = fma(-r2, y0^2, 1) is the correctly rounded residual: one instruction fewer and no rounding of
+// r2*y0 in front of the cancellation.
 __device__ __forceinline__ double inv_r3_times(double r2, double gf) {
     double y0 = rsqrt_seed(r2);
-    double t = r2 * y0;
-    double e = fma(-t, y0, 1.0);
     double y2 = y0 * y0;
+    double e = fma(-r2, y2, 1.0);
     double gy = gf * y0;
     double c0 = gy * y2;
     double w = fma(1.875, e, 1.5);
@@ -46,7 +52,7 @@ __device__ __forceinline__ double inv_r3_times(double r2, double gf) {
     return fma(c0, we, c0);
 }
 
-// a_i += gf_j (x_j - x_i) / |x_j - x_i|^3      (3 DADD + 3 DFMA + 8 + 3 DFMA = 17)
+// a_i += gf_j (x_j - x_i) / |x_j - x_i|^3      (3 DADD + 3 DFMA + 7 + 3 DFMA = 16)
 __device__ __forceinline__ void fast_interact(double xi, double yi, double zi, double4 const& q, double eps2,
     double& ax, double& ay, double& az) {
     double dx = q.x - xi, dy = q.y - yi, dz = q.z - zi;
@@ -68,9 +74,8 @@ __device__ __forceinline__ void fast_interact_argmax(double xi, double yi, doubl
     r2 = fma(dy, dy, r2);
     r2 = fma(dz, dz, r2);
     double y0 = rsqrt_seed(r2);
-    double t = r2 * y0;
-    double e = fma(-t, y0, 1.0);
-    double y2 = y0 * y0;
+    double y2 = y0 * y0; // exact: the seed has 21 significant bits
+    double e = fma(-r2, y2, 1.0);
     double gy = q.w * y0;
     double c0 = gy * y2;
     double w = fma(1.875, e, 1.5);

@@ -113,9 +113,10 @@ struct essa_ctx {
         bool ok = false;
         size_t slot_doubles = 0, part_doubles = 0;
     } plan;
-    bool gf_uniform = false; // every uploaded gravity factor is the same value
+    bool gf_uniform = false; // every uploaded gravity factor is the same value ...
+    double gf_uniform_value = 0.0; // ... this one
     bool timing_pending = false; // essa_step_async: ev_end recorded, elapsed time not read yet
-    bool attr_pair[4] = { false, false, false, false };
+    bool attr_pair[8] = { false, false, false, false, false, false, false, false };
     bool attr_cta = false; // opt-in shared-memory sizes set on this device
     bool attr_cluster_wide[3] = { false, false, false };
     bool attr_cluster16[5] = { false, false, false, false, false }; // non-portable cluster size allowed for K3x<PER>
@@ -212,7 +213,7 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
 cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out, bool argmax,
     unsigned long long** kacc_out);
 cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred, bool argmax_noop, bool save_old,
-    bool argmax, unsigned long long const* akred);
+    bool argmax, unsigned long long const* akred, double eps2);
 int force_iblocks(essa_ctx const* c, int* R_out);
 void choose_split(essa_ctx const* c, int iblocks, int ntiles, int* S_out);
 

@@ -66,7 +66,9 @@ struct PairArgs {
 
 __device__ __forceinline__ double rot1(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-template<bool TWO_SIDED, bool ARGMAX>
+// UNIFORM: every body of the world is live and has the same gravity factor g; the kernel then accumulates
+// sum |d|^-3 d and k_pair_finish multiplies by g once per body -- 19 instead of 21 FP64 instructions per pair.
+template<bool TWO_SIDED, bool ARGMAX, bool UNIFORM>
 __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, double gi, double xj, double yj, double zj, double gj,
     double eps2, double& aix, double& aiy, double& aiz, double& ajx, double& ajy, double& ajz, int iidx, int jidx,
     unsigned long long& bi, unsigned long long& bj) {
@@ -74,15 +76,25 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
     double r2 = fma(dx, dx, eps2);
     r2 = fma(dy, dy, r2);
     r2 = fma(dz, dz, r2);
-    double y0 = rsqrt_seed(r2);
-    double t = r2 * y0;
-    double e = fma(-t, y0, 1.0);
-    double y2 = y0 * y0;
+    // Off-diagonal tiles hold no self pair, so the r = 0 test of rsqrt_seed (ISETP + SEL per pair, in the dependent
+    // chain between the MUFU seed and the first DMUL) is left out there: 753 -> 719 ms per pass at 1,048,576 bodies.
+    // Two distinct bodies at one position then yield NaN for exactly those two bodies (0 * inf), which
+    // k_pair_finish detects and repairs with a guarded one-sided sum -- the documented result (an r = 0 pair
+    // contributes nothing) at no cost to the worlds that have no such pair.
+    double y0;
+    if (TWO_SIDED) {
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+        y0 = __hiloint2double(__double2hiint(y0), 0);
+    } else {
+        y0 = rsqrt_seed(r2);
+    }
+    double y2 = y0 * y0; // exact: the seed has 21 significant bits
+    double e = fma(-r2, y2, 1.0);
     double c = y2 * y0;
     double w = fma(1.875, e, 1.5);
     double we = w * e;
     double u = fma(c, we, c); // |d|^-3
-    double si = gj * u;
+    double si = UNIFORM ? u : gj * u;
     aix = fma(si, dx, aix);
     aiy = fma(si, dy, aiy);
     aiz = fma(si, dz, aiz);
@@ -91,7 +103,7 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
         bi = key_max(bi, gj > gi ? k : 0ull);
     }
     if (TWO_SIDED) {
-        double sj = gi * u;
+        double sj = UNIFORM ? u : gi * u;
         ajx = fma(-sj, dx, ajx);
         ajy = fma(-sj, dy, ajy);
         ajz = fma(-sj, dz, ajz);
@@ -102,7 +114,7 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
     }
 }
 
-template<int kPRI, bool ARGMAX>
+template<int kPRI, bool ARGMAX, bool UNIFORM>
 __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A) {
     constexpr int kPB = kPThreads * kPRI;
     constexpr int kPParts = kPB / kPHalf;
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                         for (int q = 0; q < kPRJ; q++)
 #pragma unroll
                             for (int r = 0; r < kPRI; r++)
-                                pair_interact<false, ARGMAX>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
+                                pair_interact<false, ARGMAX, UNIFORM>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
                                     aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q]);
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++) {
@@ -222,7 +234,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                         for (int q = 0; q < kPRJ; q++)
 #pragma unroll
                             for (int r = 0; r < kPRI; r++)
-                                pair_interact<true, ARGMAX>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
+                                pair_interact<true, ARGMAX, UNIFORM>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
                                     aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q]);
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++) {
@@ -303,6 +315,8 @@ struct PairFinishArgs {
     int argmax;          // most-attracting tracking with real candidates (keys)
     int argmax_noop;     // most-attracting tracking requested on a world of equal gravity factors: clear_forces only
     int save_old;        // ... and Object::before_update's old_most = most
+    double scale;        // UNIFORM worlds: the common gravity factor the sums still lack; otherwise 1
+    double eps2;         // softening, for the repair of bodies that met an r = 0 pair in an unguarded tile
 };
 
 // J-side contributions to body g from the tiles whose I block lies in [ib0, ib1), in offset order.
@@ -359,30 +373,112 @@ __global__ void __launch_bounds__(256) k_pair_gather_slots(int nb, int dmax, int
         kacc[g] = slot_key<kPB>(g, nb, dmax, ib0, ib1, slots_k);
 }
 
+// Guarded one-sided sum over all n sources for the body of thread `t` of this block (its acceleration came out
+// non-finite: it shares its position with another body in a different block, where the pair kernel runs without
+// the r = 0 test).  All 256 threads walk the sources, the partial sums meet in shared memory and are added in a
+// fixed order, so the result is deterministic; sources at r = 0 contribute nothing.  ~0.1 ms per repaired body at
+// 1,048,576 bodies, and only the (two) coincident bodies ever need it.
+__device__ __noinline__ void pair_repair_body(double4 const* __restrict__ pos, int n, double4 const p, double eps2, bool argmax,
+    double (*red)[256], int* redj, double& ax, double& ay, double& az, unsigned long long& key) {
+    int const tid = threadIdx.x;
+    double sx = 0, sy = 0, sz = 0, best = 0.0;
+    int best_j = -1;
+    for (int j = tid; j < n; j += 256) {
+        double4 const q = pos[j];
+        if (argmax)
+            fast_interact_argmax(p.x, p.y, p.z, p.w, q, j, eps2, sx, sy, sz, best, best_j);
+        else
+            fast_interact(p.x, p.y, p.z, q, eps2, sx, sy, sz);
+    }
+    red[0][tid] = sx;
+    red[1][tid] = sy;
+    red[2][tid] = sz;
+    red[3][tid] = best;
+    redj[tid] = best_j;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w) {
+            red[0][tid] = __dadd_rn(red[0][tid], red[0][tid + w]);
+            red[1][tid] = __dadd_rn(red[1][tid], red[1][tid + w]);
+            red[2][tid] = __dadd_rn(red[2][tid], red[2][tid + w]);
+            double const m = red[3][tid + w];
+            int const mj = redj[tid + w];
+            // largest metric; the lowest index among equal ones (Object.cpp:86 is a strict '>')
+            if (mj >= 0 && (m > red[3][tid] || (m == red[3][tid] && (redj[tid] < 0 || mj < redj[tid])))) {
+                red[3][tid] = m;
+                redj[tid] = mj;
+            }
+        }
+        __syncthreads();
+    }
+    ax = red[0][0];
+    ay = red[1][0];
+    az = red[2][0];
+    key = redj[0] >= 0 ? pack_key(red[3][0], redj[0]) : 0ull;
+    __syncthreads();
+}
+
 template<int kPB>
-__global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
+__global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) {
+    __shared__ double red[4][256];
+    __shared__ int redj[256];
+    __shared__ unsigned char sbad[256];
     int g = A.i0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= A.i1)
-        return;
-    double ax = 0, ay = 0, az = 0;
-    for (int c = 0; c < A.S; c++) {
-        double const* p = A.part_i + (size_t)c * 3 * A.npad + g;
-        ax = __dadd_rn(ax, __ldcg(p));
-        ay = __dadd_rn(ay, __ldcg(p + A.npad));
-        az = __dadd_rn(az, __ldcg(p + 2 * (size_t)A.npad));
-    }
-    if (A.ajred) {
-        ax = __dadd_rn(ax, __ldcg(A.ajred + g));
-        ay = __dadd_rn(ay, __ldcg(A.ajred + (size_t)A.npad + g));
-        az = __dadd_rn(az, __ldcg(A.ajred + 2 * (size_t)A.npad + g));
-    } else {
-        slot_sum<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots, ax, ay, az);
-    }
-    // ---- epilogue: identical to force_tiled.cu finish_body ----
+    bool const in = g < A.i1;
     WorldPtrs const& W = A.w;
     KickArgs const& Kk = A.k;
-    bool act = W.active[g] != 0;
-    double4 p = W.pos_cur[g];
+    double ax = 0, ay = 0, az = 0;
+    unsigned long long key = 0ull;
+    bool act = false;
+    double4 p = make_double4(0, 0, 0, 0);
+    if (in) {
+        for (int c = 0; c < A.S; c++) {
+            double const* q = A.part_i + (size_t)c * 3 * A.npad + g;
+            ax = __dadd_rn(ax, __ldcg(q));
+            ay = __dadd_rn(ay, __ldcg(q + A.npad));
+            az = __dadd_rn(az, __ldcg(q + 2 * (size_t)A.npad));
+        }
+        if (A.ajred) {
+            ax = __dadd_rn(ax, __ldcg(A.ajred + g));
+            ay = __dadd_rn(ay, __ldcg(A.ajred + (size_t)A.npad + g));
+            az = __dadd_rn(az, __ldcg(A.ajred + 2 * (size_t)A.npad + g));
+        } else {
+            slot_sum<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots, ax, ay, az);
+        }
+        ax = __dmul_rn(ax, A.scale);
+        ay = __dmul_rn(ay, A.scale);
+        az = __dmul_rn(az, A.scale);
+        act = W.active[g] != 0;
+        p = W.pos_cur[g];
+        if (act && A.argmax) {
+            key = A.akred ? __ldcg(A.akred + g) : slot_key<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots_k);
+            for (int c = 0; c < A.S; c++)
+                key = key_max(key, __ldcg(A.part_k + (size_t)c * A.npad + g));
+        }
+    }
+    // ---- repair of bodies that met a coincident partner in an unguarded tile (see pair_interact) ----
+    bool const bad = in && act && !(isfinite(ax) && isfinite(ay) && isfinite(az));
+    if (__syncthreads_or(bad)) {
+        sbad[threadIdx.x] = bad ? 1 : 0;
+        __syncthreads();
+        for (int t = 0; t < 256; t++) {
+            if (!sbad[t])
+                continue; // uniform over the block
+            int const gt = A.i0 + blockIdx.x * blockDim.x + t;
+            double rx, ry, rz;
+            unsigned long long rk;
+            pair_repair_body(W.pos_cur, A.n, W.pos_cur[gt], A.eps2, A.argmax != 0, red, redj, rx, ry, rz, rk);
+            if (t == (int)threadIdx.x) {
+                ax = rx;
+                ay = ry;
+                az = rz;
+                key = rk;
+            }
+        }
+    }
+    if (!in)
+        return;
+    // ---- epilogue: identical to force_tiled.cu finish_body ----
     double vx = 0, vy = 0, vz = 0;
     if ((A.argmax_noop || A.argmax) && A.save_old)
         W.old_most[g] = W.most[g];
@@ -390,9 +486,6 @@ __global__ void __launch_bounds__(256) k_pair_finish(PairFinishArgs const A) {
         if (A.argmax_noop)
             W.maxattr[g] = 0.0; // Object::clear_forces; no pair can raise it (nobody is heavier than anybody)
         if (A.argmax) {
-            unsigned long long key = A.akred ? __ldcg(A.akred + g) : slot_key<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots_k);
-            for (int c = 0; c < A.S; c++)
-                key = key_max(key, __ldcg(A.part_k + (size_t)c * A.npad + g));
             double m = 0.0; // Object::clear_forces
             if (key != 0ull) {
                 // the winner's gf / r^4 (the reference's |ta|^2 / gf) to full precision
@@ -541,23 +634,34 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
     return true;
 }
 
+// Every body live for good (no creation / deletion instants) and one gravity factor for all: the UNIFORM kernels
+// (ESSA_PAIR_UNIFORM=0 keeps the general ones, for A/B measurements).
+static bool pair_uniform(essa_ctx const* c) {
+    static int allow = -1;
+    if (allow < 0) {
+        char const* e = getenv("ESSA_PAIR_UNIFORM");
+        allow = e ? atoi(e) != 0 : 1;
+    }
+    return allow && c->gf_uniform && c->events.empty();
+}
+
 static void pair_geometry(essa_ctx const* c, int nb, int* ib0, int* ib1) {
     *ib0 = (int)((long long)nb * c->rank / c->world);
     *ib1 = (int)((long long)nb * (c->rank + 1) / c->world);
 }
 
-template<int RI, bool ARGMAX>
+template<int RI, bool ARGMAX, bool UNIFORM>
 static cudaError_t launch_pair_kernels(essa_ctx* c, PairArgs const& A, cudaStream_t st, double** acc, unsigned long long** kacc) {
     constexpr int PB = kPThreads * RI;
     constexpr size_t smem = kPSmem + (ARGMAX ? kPSmemKeys : 0);
-    bool& attr_set = c->attr_pair[(RI == 8 ? 0 : 1) + (ARGMAX ? 2 : 0)]; // per context: the attribute is per device
+    bool& attr_set = c->attr_pair[(RI == 8 ? 0 : 1) + (ARGMAX ? 2 : 0) + (UNIFORM ? 4 : 0)]; // per context: the attribute is per device
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_force_paired<RI, ARGMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_force_paired<RI, ARGMAX, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
         attr_set = true;
     }
-    k_force_paired<RI, ARGMAX><<<(A.ib1 - A.ib0) * A.S, kPThreads, smem, st>>>(A);
+    k_force_paired<RI, ARGMAX, UNIFORM><<<(A.ib1 - A.ib0) * A.S, kPThreads, smem, st>>>(A);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
@@ -635,8 +739,14 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
     A.eps2 = eps2;
     double* acc = nullptr;
     unsigned long long* kacc = nullptr;
-    cudaError_t e = ri == 8 ? (argmax ? launch_pair_kernels<8, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<8, false>(c, A, st, &acc, &kacc))
-                            : (argmax ? launch_pair_kernels<4, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<4, false>(c, A, st, &acc, &kacc));
+    bool const uniform = pair_uniform(c) && !argmax;
+    cudaError_t e;
+    if (ri == 8)
+        e = argmax ? launch_pair_kernels<8, true, false>(c, A, st, &acc, &kacc)
+                   : (uniform ? launch_pair_kernels<8, false, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<8, false, false>(c, A, st, &acc, &kacc));
+    else
+        e = argmax ? launch_pair_kernels<4, true, false>(c, A, st, &acc, &kacc)
+                   : (uniform ? launch_pair_kernels<4, false, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<4, false, false>(c, A, st, &acc, &kacc));
     if (acc_out)
         *acc_out = acc;
     if (kacc_out)
@@ -648,7 +758,7 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
 
 // Phase 2: ordered sums + kick / drift epilogue for this rank's targets.
 cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred, bool argmax_noop, bool save_old,
-    bool argmax, unsigned long long const* akred) {
+    bool argmax, unsigned long long const* akred, double eps2) {
     int nb, S, ri;
     size_t slot_d, part_d;
     if (!paired_plan(c, &nb, &S, &slot_d, &part_d, &ri))
@@ -671,6 +781,8 @@ cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStrea
     F.slots_k = c->pair_kslots;
     F.akred = akred;
     F.save_old = save_old ? 1 : 0;
+    F.eps2 = eps2;
+    F.scale = pair_uniform(c) && !argmax ? c->gf_uniform_value : 1.0;
     F.slots = c->pair_slots;
     F.ajred = ajred;
     int cnt = F.i1 - F.i0;

@@ -238,8 +238,10 @@ __global__ void k_pack(double4* pos, double4* other, double const* x, double con
     if (g < n) {
         pos[g] = make_double4(x[g], y[g], z[g], active[g] ? gf[g] : 0.0);
     } else {
-        pos[g] = make_double4(0, 0, 0, 0);
-        other[g] = make_double4(0, 0, 0, 0);
+        // padding records attract nothing (gf = 0) and sit far from everything, away from the origin a real body
+        // may occupy: the pair-shared kernel's off-diagonal tiles run without an r = 0 test
+        pos[g] = make_double4(kPadCoord, kPadCoord, kPadCoord, 0);
+        other[g] = make_double4(kPadCoord, kPadCoord, kPadCoord, 0);
     }
 }
 

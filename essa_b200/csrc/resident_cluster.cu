@@ -143,9 +143,8 @@ __global__ void __launch_bounds__(kXThreads, 1) k_resident_cluster(XArgs const A
                     r2 = fma(dy, dy, r2);
                     r2 = fma(dz, dz, r2);
                     double y0 = rsqrt_seed(r2);
-                    double t = r2 * y0;
-                    double e = fma(-t, y0, 1.0);
-                    double y2 = y0 * y0;
+                    double y2 = y0 * y0; // exact: the seed has 21 significant bits
+                    double e = fma(-r2, y2, 1.0);
                     double gy = q.w * y0;
                     double c0 = gy * y2;
                     double w = fma(1.875, e, 1.5);

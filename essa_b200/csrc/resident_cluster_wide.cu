@@ -166,8 +166,9 @@ __global__ void __launch_bounds__(32 * kWMaxWarps, 1) k_resident_cluster_wide(WA
                     y0[u] = rsqrt_seed(r2[u]);
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    e[u] = fma(-(r2[u] * y0[u]), y0[u], 1.0);
-                    c0[u] = (qv[u].w * y0[u]) * (y0[u] * y0[u]);
+                    double const y2 = y0[u] * y0[u]; // exact: the seed has 21 significant bits
+                    e[u] = fma(-r2[u], y2, 1.0);
+                    c0[u] = (qv[u].w * y0[u]) * y2;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++)

@@ -90,9 +90,8 @@ __device__ __forceinline__ void group_forces(CtaShared const& S, int k, int q, i
             r2 = fma(dy, dy, r2);
             r2 = fma(dz, dz, r2);
             double y0 = rsqrt_seed(r2);
-            double t = r2 * y0;
-            double e = fma(-t, y0, 1.0);
-            double y2 = y0 * y0;
+            double y2 = y0 * y0; // exact: the seed has 21 significant bits
+            double e = fma(-r2, y2, 1.0);
             double gy = qv.w * y0;
             double c0 = gy * y2;
             double w = fma(1.875, e, 1.5);

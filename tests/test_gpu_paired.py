@@ -157,6 +157,45 @@ def test_paired_most_attracting_links_match_tiled_and_oracle(ctx, n):
         assert m_p[i] == pytest.approx(metric.max(), rel=1e-9)
 
 
+@pytest.mark.parametrize("track", [False, True])
+def test_paired_coincident_bodies_in_different_blocks(ctx, track):
+    """The off-diagonal tiles of the pair-shared kernel run without the r = 0 test; bodies that share a position
+    across blocks (incl. a body at the origin next to ragged-block padding, and a masked body on top of a live one)
+    are repaired in k_pair_finish: the pair contributes nothing, as on every other path (the reference yields NaN)."""
+    n = 9000  # blocks of 2048: 4.4 blocks, ragged last block
+    w = synth.plummer(n, seed=41)
+    rng = np.random.default_rng(42)
+    gf = w["gf"] * 10.0 ** rng.uniform(-1, 1, n)
+    x, y, z = w["x"].copy(), w["y"].copy(), w["z"].copy()
+    pairs = [(5, 5000), (2047, 2048), (100, 8999), (4100, 4200)]  # the last pair shares a block (guarded diagonal tile)
+    for a, b in pairs:
+        x[b], y[b], z[b] = x[a], y[a], z[a]
+    x[7000] = y[7000] = z[7000] = 0.0  # a live body at the origin
+    t0 = capi.START_DATE
+    cdate = np.full(n, t0, dtype=np.int64)
+    cdate[300] = t0 + 10 ** 9  # masked body 300 ...
+    x[6500], y[6500], z[6500] = x[300], y[300], z[300]  # ... under live body 6500
+    got = {}
+    for kern in (capi.KERNEL_TILED, capi.KERNEL_PAIRED):
+        ctx.date = t0
+        ctx.upload(x, y, z, w["vx"], w["vy"], w["vz"], gf, creation_date=cdate, most=np.full(n, -1, dtype=np.int32))
+        ctx.set_forces(kernel=kern, track_most_attracting=track)
+        got[kern] = ctx.download()
+    t, p = got[capi.KERNEL_TILED], got[capi.KERNEL_PAIRED]
+    a = np.stack([t["ax"], t["ay"], t["az"]], axis=1)
+    b = np.stack([p["ax"], p["ay"], p["az"]], axis=1)
+    assert np.all(np.isfinite(b))
+    live = cdate <= t0
+    assert _rel_rows(b[live], a[live]).max() <= 1e-12
+    assert np.all(b[~live] == 0.0)
+    if track:
+        assert np.array_equal(t["most"], p["most"])
+        m_t, m_p = t["max_attraction"], p["max_attraction"]
+        assert np.all(np.abs(m_p[live] - m_t[live]) <= 1e-11 * np.abs(m_t[live]))
+        for i, j in pairs:  # a body on top of another one is never its most-attracting object
+            assert p["most"][i] != j and p["most"][j] != i
+
+
 def test_paired_tracks_most_attracting_when_it_is_a_no_op(ctx):
     """Equal gravity factors: `o.gf > this.gf` (src/Object.cpp:86,91) is false for every pair, so the reference leaves
     most_attracting_object alone and max_attraction at 0.  The pair-shared kernel accepts tracking then and must
