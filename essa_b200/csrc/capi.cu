@@ -60,7 +60,7 @@ struct NcclApi {
     char const* (*GetErrorString)(int) = nullptr;
     std::string why;
 };
-constexpr int kNcclFloat64 = 8, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2; // ncclDataType_t / ncclRedOp_t values (nccl.h)
+constexpr int kNcclFloat64 = 8, kNcclUint64 = 5, kNcclUint32 = 3, kNcclSum = 0, kNcclMax = 2; // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
 NcclApi& nccl() {
     static NcclApi api;
@@ -279,6 +279,7 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     cudaFree(c->pair_part);
     cudaFree(c->pair_kslots);
     cudaFree(c->pair_kpart);
+    cudaFree(c->pair_prior);
     cudaFree(c->part);
     cudaFree(c->part_m);
     cudaFree(c->part_j);
@@ -367,6 +368,7 @@ extern "C" int essa_set_date(essa_ctx* ctx, int64_t date) {
     ctx->date = date;
     if (changed && ctx->n > 0) {
         CK(launch_refresh_active(ctx, ctx->stream));
+        ctx->pair_prior_valid = false;
         ctx->acc_valid = false;
     }
     return ESSA_OK;
@@ -387,6 +389,7 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
     ctx->n = n;
     ctx->acc_valid = false;
     ctx->acc_has_most = false;
+    ctx->pair_prior_valid = false;
     ctx->events.clear();
     if (n == 0)
         return ESSA_OK;
@@ -606,6 +609,14 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
         int npad = 0;
         // most-attracting tracking: real candidate keys, unless every gravity factor is equal (then it is a no-op)
         bool const keys = argmax && !ctx->gf_uniform;
+        if (keys && ctx->world > 1 && ctx->pair_prior_valid) {
+            // every rank's k_pair_finish rewrote the filter thresholds of its own targets: all ranks need all of them
+            size_t cnt = (size_t)n / ctx->world;
+            NK(nccl().GroupStart());
+            for (int r = 0; r < ctx->world; r++)
+                NK(nccl().Broadcast(ctx->pair_prior + r * cnt, ctx->pair_prior + r * cnt, cnt, kNcclUint32, r, ctx->comm, ctx->stream));
+            NK(nccl().GroupEnd());
+        }
         CK(launch_force_paired_compute(ctx, eps2, ctx->stream, &acc, &npad, keys, &kacc));
         if (ctx->world > 1) {
             // every rank holds J-side sums (and candidate keys) for every body: reduce-scatter them onto the owners (in place)
@@ -700,6 +711,7 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
             ctx->date = nd;
             if (flip) {
                 CK(launch_refresh_active(ctx, ctx->stream));
+                ctx->pair_prior_valid = false;
                 ctx->acc_valid = false;
             }
         }

@@ -144,6 +144,10 @@ struct essa_ctx {
     unsigned long long* pair_kslots = nullptr; // most-attracting candidate keys (pair-shared kernel with tracking)
     size_t pair_kslots_bytes = 0;
     unsigned long long* pair_kpart = nullptr;
+    unsigned* pair_prior = nullptr; // candidate-filter thresholds carried from pass to pass (force_paired.cu)
+    size_t pair_prior_n = 0;
+    int pair_prior_npad = 0;
+    bool pair_prior_valid = false;
     size_t pair_kpart_bytes = 0;
 
     // recording

@@ -36,7 +36,7 @@ constexpr int kPHalf = 512;     // records per staged part of a J block
 // of 1024) when 2048-body blocks would leave SMs idle.  Bodies per block = 256 * RI.
 constexpr int kPSub = 32 * kPRJ;
 constexpr size_t kPSmem = 2 * kPHalf * sizeof(double4) + 8 * 3 * kPHalf * sizeof(double) + 64;
-constexpr size_t kPSmemKeys = 8 * kPHalf * sizeof(unsigned long long); // + per-warp J-side candidate keys (ARGMAX)
+constexpr size_t kPSmemKeys = 8 * kPHalf * sizeof(unsigned long long) + 2 * kPHalf * sizeof(unsigned); // + per-warp J-side candidate keys and the staged prior thresholds of the visitors (ARGMAX)
 
 // Most-attracting candidates (src/Object.cpp:84-94) travel as sortable 64-bit keys: the bit pattern of the ranking
 // metric gf_p |d|^-3 y0 ~ gf_p / r^4 (positive doubles order like unsigned integers; y0 = rsqrt seed, relative
@@ -50,6 +50,33 @@ __device__ __forceinline__ unsigned long long pack_key(double m, int idx) {
 }
 __device__ __forceinline__ unsigned long long key_max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
+// Candidate filter in the integer pipe.  For a positive double v = 2^e (1 + f), its high word is
+//     L(v) = 2^20 (e + 1023 + f) = 2^20 (log2 v + 1023 + delta),   delta = f - log2(1 + f)  in  [-0.0861, 0]
+// (the mantissa is a piecewise-linear logarithm).  The metric of a pair is gf_p y0^4 up to 3e-6, so
+//     L(gf_p) / 4 + L(y0) - L(best) / 4 - 1023 * 2^20  >=  2^20 [(log2 metric - log2 best) / 4 - 0.0861 (1/4 + 1)] - 3
+// and a partner that beats the best candidate so far ALWAYS passes  lg(gf_p) + L(y0) > thr(best)  with the margin
+// below (as does one whose truncated gf is not smaller: a superset of "strictly heavier").  The pairs that pass --
+// a few dozen per body and pass, the running maxima of a random sequence and their near misses within a factor
+// 1.4 -- run the exact test (heavier partner, full key compare) in a cold block.  The hot path pays integer adds
+// and compares per side instead of DMUL + DSETP + 64-bit select chains.
+// Measured alternatives (N = 262,144, masses spread over a factor 4; untracked 1.56e12 interactions/s): the exact
+// test for every pair (DMUL + DSETP + 64-bit selects) 1.01e12; this filter with thresholds that start from scratch
+// in every CTA and visit 7.2e11 (the first rotations of each visit all pass); with priors 1.15e12; one test per
+// rotation against the lane's weakest threshold 8.0e11 (thresholds differ by orders of magnitude between core and
+// halo bodies, so the weakest of eight passes nearly everything).
+constexpr unsigned kKeyMargin = 114688u; // > 0.0861 * 1.25 * 2^20 = 112,853, + slack for the truncations
+// Thresholds survive from one force pass to the next ("priors"): k_pair_finish leaves, for every body, the threshold
+// of its winning key lowered by kPriorSlack (a factor 2 in the metric: bodies move little in a step), and the next
+// pass starts every filter there instead of at "anything goes" -- otherwise each CTA (I side) and each visit of a
+// 32-body subset (J side) would spend its first rotations in the cold block re-discovering the running maximum.
+// k_pair_finish accepts a winner only if  key_thr(winner) > prior  (then every better partner was above the prior
+// too and has been seen); otherwise that body is re-ranked from scratch by the repair path.
+constexpr unsigned kPriorSlack = 1u << 18;
+constexpr unsigned kPriorNone = 0x3FF00000u - kKeyMargin; // = key_thr(0): every real candidate passes
+constexpr unsigned kPriorNever = 0xFFFFFFFFu;              // padding and masked bodies: nothing passes
+__device__ __forceinline__ unsigned key_lg(double gf) { return (unsigned)__double2hiint(gf) >> 2; }
+__device__ __forceinline__ unsigned key_thr(unsigned long long key) { return ((unsigned)(key >> 32) >> 2) + (0x3FF00000u - kKeyMargin); }
+
 struct PairArgs {
     double4 const* pos; // padded to a multiple of kPB with {0,0,0,0}
     int nb;             // blocks in the world
@@ -61,6 +88,7 @@ struct PairArgs {
     double* slots;      // [ib1-ib0][dmax][3][kPB]  J-side partials of tile (I, d), d = 1 .. dmax
     unsigned long long* part_k;  // [S][npad]              I-side candidate keys (ARGMAX)
     unsigned long long* slots_k; // [ib1-ib0][dmax][kPB]   J-side candidate keys of tile (I, d)
+    unsigned const* prior;       // [npad] filter thresholds left by the previous pass (ARGMAX)
     double eps2;
 };
 
@@ -71,7 +99,7 @@ __device__ __forceinline__ double rot1(double v, int src) { return __shfl_sync(0
 template<bool TWO_SIDED, bool ARGMAX, bool UNIFORM>
 __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, double gi, double xj, double yj, double zj, double gj,
     double eps2, double& aix, double& aiy, double& aiz, double& ajx, double& ajy, double& ajz, int iidx, int jidx,
-    unsigned long long& bi, unsigned long long& bj) {
+    unsigned long long& bi, unsigned long long& bj, unsigned lgi, unsigned lgj, unsigned thi, unsigned thj, bool& anyp) {
     double dx = xj - xi, dy = yj - yi, dz = zj - zi;
     double r2 = fma(dx, dx, eps2);
     r2 = fma(dy, dy, r2);
@@ -98,18 +126,66 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
     aix = fma(si, dx, aix);
     aiy = fma(si, dy, aiy);
     aiz = fma(si, dz, aiz);
-    if (ARGMAX) {
-        unsigned long long k = pack_key(si * y0, jidx);
-        bi = key_max(bi, gj > gi ? k : 0ull);
-    }
+    double sj = 0.0;
     if (TWO_SIDED) {
-        double sj = UNIFORM ? u : gi * u;
+        sj = UNIFORM ? u : gi * u;
         ajx = fma(-sj, dx, ajx);
         ajy = fma(-sj, dy, ajy);
         ajz = fma(-sj, dz, ajz);
-        if (ARGMAX) {
-            unsigned long long k = pack_key(sj * y0, iidx);
-            bj = key_max(bj, gi > gj ? k : 0ull);
+    }
+    if (ARGMAX) {
+        // candidate filter; the exact test runs once per rotation, for all targets of the lane, behind ONE
+        // warp-uniform branch (pair_exact below): a branch per pair would make every pair its own basic block and
+        // serialise the eight independent chains of a rotation
+        unsigned const ly = (unsigned)__double2hiint(y0);
+        bool const pi = lgj + ly > thi && lgj >= lgi;
+        bool const pj = TWO_SIDED && lgi + ly > thj && lgi >= lgj;
+        anyp = anyp || pi || pj;
+    }
+}
+
+// Cold path: some lane saw a pair pass the filter during this rotation.  Re-evaluates the pair with
+// the very same operations (so the seed, and with it the key, are the ones the hot path saw) and applies
+// Object.cpp:84-94 -- strictly heavier partner, larger key -- to both bodies.
+template<bool TWO_SIDED>
+__device__ __forceinline__ void pair_exact(double xi, double yi, double zi, double gi, double xj, double yj, double zj, double gj,
+    double eps2, int iidx, int jidx, unsigned long long& bi, unsigned long long& bj, unsigned lgi, unsigned lgj, unsigned& thi,
+    unsigned& thj) {
+    double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    double r2 = fma(dx, dx, eps2);
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    double y0;
+    if (TWO_SIDED) {
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+        y0 = __hiloint2double(__double2hiint(y0), 0);
+    } else {
+        y0 = rsqrt_seed(r2);
+    }
+    unsigned const ly = (unsigned)__double2hiint(y0);
+    bool const pi = lgj + ly > thi && gj > gi;
+    bool const pj = TWO_SIDED && lgi + ly > thj && gi > gj;
+    if (pi || pj) {
+        double y2 = y0 * y0;
+        double e = fma(-r2, y2, 1.0);
+        double c = y2 * y0;
+        double w = fma(1.875, e, 1.5);
+        double we = w * e;
+        double u = fma(c, we, c);
+        if (pi) {
+            double si = gj * u;
+            unsigned long long const k = pack_key(si * y0, jidx);
+            if (k > bi) {
+                bi = k;
+                thi = max(thi, key_thr(k));
+            }
+        } else {
+            double sj = gi * u;
+            unsigned long long const k = pack_key(sj * y0, iidx);
+            if (k > bj) {
+                bj = k;
+                thj = max(thj, key_thr(k));
+            }
         }
     }
 }
@@ -123,6 +199,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
     double* accj = reinterpret_cast<double*>(smem_raw + 2 * kPHalf * sizeof(double4)); // [8][3][kPHalf]
     unsigned long long* full = reinterpret_cast<unsigned long long*>(accj + 8 * 3 * kPHalf); // [2]
     unsigned long long* acck = full + 8;                                                        // [8][kPHalf] (ARGMAX)
+    unsigned* tprior = reinterpret_cast<unsigned*>(acck + 8 * kPHalf);                          // [2][kPHalf] (ARGMAX)
 
     int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int const ibl = blockIdx.x / A.S, chunk = blockIdx.x - ibl * A.S;
@@ -142,9 +219,13 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
         aix[r] = aiy[r] = aiz[r] = 0.0;
     }
     unsigned long long bi[kPRI]; // best candidate key per target
+    unsigned lgi[kPRI], thi[kPRI]; // ... with the filter's view of the target's gf and of its best key
 #pragma unroll
-    for (int r = 0; r < kPRI; r++)
+    for (int r = 0; r < kPRI; r++) {
         bi[r] = 0ull;
+        lgi[r] = key_lg(gi[r]);
+        thi[r] = ARGMAX ? A.prior[(size_t)I * kPB + warp * (32 * kPRI) + r * 32 + lane] : 0u;
+    }
     int const ibase = I * kPB + warp * (32 * kPRI) + lane; // + r * 32
 
     if (tid == 0) {
@@ -161,8 +242,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
         if (J >= A.nb)
             J -= A.nb;
         unsigned bytes = kPHalf * (unsigned)sizeof(double4);
-        mbar_expect_tx(&full[buf], bytes);
+        mbar_expect_tx(&full[buf], bytes + (ARGMAX ? kPHalf * (unsigned)sizeof(unsigned) : 0u));
         bulk_g2s(tile + (size_t)buf * kPHalf, A.pos + (size_t)J * kPB + half * kPHalf, bytes, &full[buf]);
+        if (ARGMAX)
+            bulk_g2s(tprior + (size_t)buf * kPHalf, A.prior + (size_t)J * kPB + half * kPHalf, kPHalf * (unsigned)sizeof(unsigned), &full[buf]);
     };
 
     int seq = 0; // tiles consumed so far (parity bookkeeping)
@@ -207,11 +290,16 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                     ajx[q] = ajy[q] = ajz[q] = 0.0;
                 }
                 unsigned long long bjk[kPRJ]; // the visitors' own candidate keys travel with them
+                unsigned lgj[kPRJ], thj[kPRJ];
 #pragma unroll
-                for (int q = 0; q < kPRJ; q++)
+                for (int q = 0; q < kPRJ; q++) {
                     bjk[q] = 0ull;
+                    lgj[q] = key_lg(gj[q]);
+                    thj[q] = ARGMAX ? tprior[(size_t)buf * kPHalf + sub * kPSub + q * 32 + lane] : 0u;
+                }
                 int const jbase = J * kPB + half * kPHalf + sub * kPSub; // + q * 32 + home lane of the visitor
                 int const src = (lane + 31) & 31; // take from the previous lane = pass to the next
+                bool anyp = false;                // some pair of this rotation passed the candidate filter
                 if (d == 0) {
                     for (int rot = 0; rot < 32; rot++) {
 #pragma unroll
@@ -219,13 +307,27 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
 #pragma unroll
                             for (int r = 0; r < kPRI; r++)
                                 pair_interact<false, ARGMAX, UNIFORM>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
-                                    aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q]);
+                                    aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q],
+                                    thi[r], thj[q], anyp);
+                        if (ARGMAX) {
+                            if (__any_sync(0xffffffffu, anyp)) {
+#pragma unroll
+                                for (int q = 0; q < kPRJ; q++)
+#pragma unroll
+                                    for (int r = 0; r < kPRI; r++)
+                                        pair_exact<false>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
+                                            jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q], thi[r], thj[q]);
+                            }
+                            anyp = false;
+                        }
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++) {
                             xj[q] = rot1(xj[q], src);
                             yj[q] = rot1(yj[q], src);
                             zj[q] = rot1(zj[q], src);
                             gj[q] = rot1(gj[q], src);
+                            if (ARGMAX)
+                                lgj[q] = __shfl_sync(0xffffffffu, lgj[q], src);
                         }
                     }
                 } else {
@@ -235,7 +337,19 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
 #pragma unroll
                             for (int r = 0; r < kPRI; r++)
                                 pair_interact<true, ARGMAX, UNIFORM>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
-                                    aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q]);
+                                    aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q],
+                                    thi[r], thj[q], anyp);
+                        if (ARGMAX) {
+                            if (__any_sync(0xffffffffu, anyp)) {
+#pragma unroll
+                                for (int q = 0; q < kPRJ; q++)
+#pragma unroll
+                                    for (int r = 0; r < kPRI; r++)
+                                        pair_exact<true>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
+                                            jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q], thi[r], thj[q]);
+                            }
+                            anyp = false;
+                        }
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++) {
                             xj[q] = rot1(xj[q], src);
@@ -245,8 +359,11 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                             ajx[q] = rot1(ajx[q], src);
                             ajy[q] = rot1(ajy[q], src);
                             ajz[q] = rot1(ajz[q], src);
-                            if (ARGMAX)
+                            if (ARGMAX) {
                                 bjk[q] = __shfl_sync(0xffffffffu, bjk[q], src);
+                                lgj[q] = __shfl_sync(0xffffffffu, lgj[q], src);
+                                thj[q] = __shfl_sync(0xffffffffu, thj[q], src);
+                            }
                         }
                     }
                     // 32 rotations: every visitor is back in its home lane
@@ -315,6 +432,7 @@ struct PairFinishArgs {
     int argmax;          // most-attracting tracking with real candidates (keys)
     int argmax_noop;     // most-attracting tracking requested on a world of equal gravity factors: clear_forces only
     int save_old;        // ... and Object::before_update's old_most = most
+    unsigned* prior;     // ARGMAX: [npad] filter thresholds, read (what the pass used) and rewritten (for the next pass)
     double scale;        // UNIFORM worlds: the common gravity factor the sums still lack; otherwise 1
     double eps2;         // softening, for the repair of bodies that met an r = 0 pair in an unguarded tile
 };
@@ -456,8 +574,15 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
                 key = key_max(key, __ldcg(A.part_k + (size_t)c * A.npad + g));
         }
     }
-    // ---- repair of bodies that met a coincident partner in an unguarded tile (see pair_interact) ----
-    bool const bad = in && act && !(isfinite(ax) && isfinite(ay) && isfinite(az));
+    // ---- repair: bodies that met a coincident partner in an unguarded tile (see pair_interact), and bodies whose
+    // winning candidate does not clear the prior threshold the pass filtered with (a better partner may have been
+    // skipped: its most-attracting body weakened by more than kPriorSlack since the last pass) ----
+    bool const bad_acc = in && act && !(isfinite(ax) && isfinite(ay) && isfinite(az));
+    bool bad = bad_acc;
+    if (in && act && A.argmax) {
+        unsigned const P = A.prior[g];
+        bad = bad || !(P == kPriorNone || (key != 0ull && key_thr(key) > P));
+    }
     if (__syncthreads_or(bad)) {
         sbad[threadIdx.x] = bad ? 1 : 0;
         __syncthreads();
@@ -469,15 +594,19 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
             unsigned long long rk;
             pair_repair_body(W.pos_cur, A.n, W.pos_cur[gt], A.eps2, A.argmax != 0, red, redj, rx, ry, rz, rk);
             if (t == (int)threadIdx.x) {
-                ax = rx;
-                ay = ry;
-                az = rz;
+                if (bad_acc) {
+                    ax = rx;
+                    ay = ry;
+                    az = rz;
+                }
                 key = rk;
             }
         }
     }
     if (!in)
         return;
+    if (A.argmax) // where the next pass starts its filters
+        A.prior[g] = !act ? kPriorNever : (key != 0ull ? key_thr(key) - kPriorSlack : kPriorNone);
     // ---- epilogue: identical to force_tiled.cu finish_body ----
     double vx = 0, vy = 0, vz = 0;
     if ((A.argmax_noop || A.argmax) && A.save_old)
@@ -533,6 +662,13 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
         }
         W.pos_next[g] = p;
     }
+}
+
+// First tracked pass after an upload or a change of the active mask: no priors yet.
+__global__ void __launch_bounds__(256) k_pair_prior_reset(unsigned* prior, uint8_t const* active, int n, int npad) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < npad)
+        prior[g] = g < n && active[g] ? kPriorNone : kPriorNever;
 }
 
 // Can this world go through the pair-shared kernel, and with which block size?  Whole blocks per
@@ -725,7 +861,27 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
         if (e != cudaSuccess)
             return e;
     }
+    if (argmax) {
+        size_t const want = (size_t)nb * kPThreads * ri;
+        if (want > c->pair_prior_n) {
+            cudaFree(c->pair_prior);
+            c->pair_prior = nullptr;
+            c->pair_prior_n = 0;
+            c->pair_prior_valid = false;
+            cudaError_t e = cudaMalloc(&c->pair_prior, want * sizeof(unsigned));
+            if (e != cudaSuccess)
+                return e;
+            c->pair_prior_n = want;
+        }
+        if (!c->pair_prior_valid || c->pair_prior_npad != (int)want) {
+            k_pair_prior_reset<<<(unsigned)((want + 255) / 256), 256, 0, st>>>(c->pair_prior, c->active, c->n, (int)want);
+            c->launches++;
+            c->pair_prior_valid = true;
+            c->pair_prior_npad = (int)want;
+        }
+    }
     PairArgs A;
+    A.prior = c->pair_prior;
     A.pos = c->pos[c->cur];
     A.nb = nb;
     A.dmax = nb / 2;
@@ -779,6 +935,7 @@ cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStrea
     F.argmax = argmax ? 1 : 0;
     F.part_k = c->pair_kpart;
     F.slots_k = c->pair_kslots;
+    F.prior = c->pair_prior;
     F.akred = akred;
     F.save_old = save_old ? 1 : 0;
     F.eps2 = eps2;

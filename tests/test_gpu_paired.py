@@ -196,6 +196,36 @@ def test_paired_coincident_bodies_in_different_blocks(ctx, track):
             assert p["most"][i] != j and p["most"][j] != i
 
 
+@pytest.mark.parametrize("dt_scale", [1, 40])
+def test_paired_link_thresholds_survive_passes_and_large_moves(ctx, dt_scale):
+    """The pair-shared kernel filters candidates against thresholds left by the previous pass; a body whose
+    most-attracting partner weakened by more than the slack (here: steps 40x too long, bodies move a lot) is
+    re-ranked from scratch in k_pair_finish.  Links and max_attraction must stay those of the tiled kernel."""
+    n = 8192
+    w = synth.plummer(n, seed=51)
+    rng = np.random.default_rng(52)
+    gf = w["gf"] * rng.uniform(0.5, 2.0, n)
+    dt = synth.default_dt(n) * dt_scale
+    got = {}
+    for kern in (capi.KERNEL_TILED, capi.KERNEL_PAIRED):
+        ctx.date = capi.START_DATE
+        ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], gf, most=np.full(n, -1, dtype=np.int32))
+        hist = []
+        for _ in range(5):
+            ctx.step(1, dt, kernel=kern, track_most_attracting=True)
+            d = ctx.download()
+            hist.append((d["most"].copy(), d["max_attraction"].copy()))
+        got[kern] = hist
+    changed = 0
+    for (mt, at), (mp, ap_) in zip(got[capi.KERNEL_TILED], got[capi.KERNEL_PAIRED]):
+        assert np.array_equal(mt, mp)
+        assert np.all(np.abs(ap_ - at) <= 1e-9 * np.abs(at))
+    first, last = got[capi.KERNEL_PAIRED][0][0], got[capi.KERNEL_PAIRED][-1][0]
+    changed = int((first != last).sum())
+    if dt_scale > 1:
+        assert changed > 50  # the long steps did reshuffle the links
+
+
 def test_paired_tracks_most_attracting_when_it_is_a_no_op(ctx):
     """Equal gravity factors: `o.gf > this.gf` (src/Object.cpp:86,91) is false for every pair, so the reference leaves
     most_attracting_object alone and max_attraction at 0.  The pair-shared kernel accepts tracking then and must
