@@ -134,9 +134,9 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
         ajz = fma(-sj, dz, ajz);
     }
     if (ARGMAX) {
-        // candidate filter; the exact test runs once per rotation, for all targets of the lane, behind ONE
-        // warp-uniform branch (pair_exact below): a branch per pair would make every pair its own basic block and
-        // serialise the eight independent chains of a rotation
+        // candidate filter; the exact tests run after the 32 rotations of a visit, behind ONE warp-uniform branch
+        // (pair_exact below): a branch per pair would make every pair its own basic block and serialise the
+        // eight independent chains of a rotation, a branch per rotation still drains the pipeline every 8 pairs
         unsigned const ly = (unsigned)__double2hiint(y0);
         bool const pi = lgj + ly > thi && lgj >= lgi;
         bool const pj = TWO_SIDED && lgi + ly > thj && lgi >= lgj;
@@ -144,8 +144,8 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
     }
 }
 
-// Cold path: some lane saw a pair pass the filter during this rotation.  Re-evaluates the pair with
-// the very same operations (so the seed, and with it the key, are the ones the hot path saw) and applies
+// Cold path: some lane saw a pair pass the filter during this visit of a 32-body subset.  Re-evaluates the pair
+// with the very same operations (so the seed, and with it the key, are the ones the hot path saw) and applies
 // Object.cpp:84-94 -- strictly heavier partner, larger key -- to both bodies.
 template<bool TWO_SIDED>
 __device__ __forceinline__ void pair_exact(double xi, double yi, double zi, double gi, double xj, double yj, double zj, double gj,
@@ -309,17 +309,6 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                                 pair_interact<false, ARGMAX, UNIFORM>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
                                     aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q],
                                     thi[r], thj[q], anyp);
-                        if (ARGMAX) {
-                            if (__any_sync(0xffffffffu, anyp)) {
-#pragma unroll
-                                for (int q = 0; q < kPRJ; q++)
-#pragma unroll
-                                    for (int r = 0; r < kPRI; r++)
-                                        pair_exact<false>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
-                                            jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q], thi[r], thj[q]);
-                            }
-                            anyp = false;
-                        }
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++) {
                             xj[q] = rot1(xj[q], src);
@@ -328,6 +317,26 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                             gj[q] = rot1(gj[q], src);
                             if (ARGMAX)
                                 lgj[q] = __shfl_sync(0xffffffffu, lgj[q], src);
+                        }
+                    }
+                    // 32 rotations: every visitor is back in its home lane.  Did any pair pass the candidate filter?
+                    // Then walk the subset once more, exact tests only (see pair_exact).
+                    if (ARGMAX && __any_sync(0xffffffffu, anyp)) {
+                        for (int rot = 0; rot < 32; rot++) {
+#pragma unroll
+                            for (int q = 0; q < kPRJ; q++)
+#pragma unroll
+                                for (int r = 0; r < kPRI; r++)
+                                    pair_exact<false>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
+                                        jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q], thi[r], thj[q]);
+#pragma unroll
+                            for (int q = 0; q < kPRJ; q++) {
+                                xj[q] = rot1(xj[q], src);
+                                yj[q] = rot1(yj[q], src);
+                                zj[q] = rot1(zj[q], src);
+                                gj[q] = rot1(gj[q], src);
+                                lgj[q] = __shfl_sync(0xffffffffu, lgj[q], src);
+                            }
                         }
                     }
                 } else {
@@ -339,17 +348,6 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                                 pair_interact<true, ARGMAX, UNIFORM>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
                                     aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q],
                                     thi[r], thj[q], anyp);
-                        if (ARGMAX) {
-                            if (__any_sync(0xffffffffu, anyp)) {
-#pragma unroll
-                                for (int q = 0; q < kPRJ; q++)
-#pragma unroll
-                                    for (int r = 0; r < kPRI; r++)
-                                        pair_exact<true>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
-                                            jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q], thi[r], thj[q]);
-                            }
-                            anyp = false;
-                        }
 #pragma unroll
                         for (int q = 0; q < kPRJ; q++) {
                             xj[q] = rot1(xj[q], src);
@@ -359,14 +357,36 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                             ajx[q] = rot1(ajx[q], src);
                             ajy[q] = rot1(ajy[q], src);
                             ajz[q] = rot1(ajz[q], src);
-                            if (ARGMAX) {
+                            if (ARGMAX) { // what the filter needs of the visitor; its key stays at home
+                                lgj[q] = __shfl_sync(0xffffffffu, lgj[q], src);
+                                thj[q] = __shfl_sync(0xffffffffu, thj[q], src);
+                            }
+                        }
+                    }
+                    // 32 rotations: every visitor is back in its home lane.  Did any pair pass the candidate filter?
+                    // Then walk the subset once more, exact tests only (see pair_exact); the branch sits here and not
+                    // in the rotation loop, where it would drain the pipeline eight pairs at a time (ncu: FP64 pipe
+                    // 64 % busy, "wait" stalls 1.5 per issue with the vote per rotation).
+                    if (ARGMAX && __any_sync(0xffffffffu, anyp)) {
+                        for (int rot = 0; rot < 32; rot++) {
+#pragma unroll
+                            for (int q = 0; q < kPRJ; q++)
+#pragma unroll
+                                for (int r = 0; r < kPRI; r++)
+                                    pair_exact<true>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
+                                        jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q], thi[r], thj[q]);
+#pragma unroll
+                            for (int q = 0; q < kPRJ; q++) {
+                                xj[q] = rot1(xj[q], src);
+                                yj[q] = rot1(yj[q], src);
+                                zj[q] = rot1(zj[q], src);
+                                gj[q] = rot1(gj[q], src);
                                 bjk[q] = __shfl_sync(0xffffffffu, bjk[q], src);
                                 lgj[q] = __shfl_sync(0xffffffffu, lgj[q], src);
                                 thj[q] = __shfl_sync(0xffffffffu, thj[q], src);
                             }
                         }
                     }
-                    // 32 rotations: every visitor is back in its home lane
 #pragma unroll
                     for (int q = 0; q < kPRJ; q++) {
                         int j = sub * kPSub + q * 32 + lane;
