@@ -4,8 +4,9 @@
 //
 //   d = x_j - x_i ;  u = |d|^-3 ;  a_i += gf_j u d ;  a_j -= gf_i u d
 //
-// 21 FP64-pipe instructions per pair = 10.5 per directed interaction (K1 needs 17), which lifts the
-// ceiling of the 20-flop-per-interaction roofline from 58.8 % to 95 %.
+// 20 FP64-pipe instructions per pair = 10 per directed interaction (18 = 9 when every body has the same
+// gravity factor; K1 needs 16), so the 20-flop-per-interaction convention of BASELINE.json tops out at
+// 100 % (111 %) of the DFMA peak instead of K1's 62.5 %.
 //
 // Decomposition.  Bodies are cut into blocks of 2048.  Unordered block pairs are enumerated as
 // (I, J = I + d mod nb), d = 0 .. nb/2, so that every block does the same amount of work.  One CTA
@@ -14,7 +15,7 @@
 // four 512-record parts; each warp walks a part in 32-body subsets, 1 body per lane, and ROTATES the
 // subset -- positions, gf and the subset's own accumulators -- around the warp with shuffles, so
 // that after 32 rotations all 256 x 32 pairs of (targets, subset) have been visited with nothing
-// but registers (14 shuffles per 8 pairs).  Measured on B200 at N = 1,048,576: 8 x 1 blocking 755 ms,
+// but registers (14 shuffles per 8 pairs).  Measured on B200 at N = 1,048,576 (then 21 instructions per pair): 8 x 1 blocking 755 ms,
 // 4 x 2 blocking 804 ms, 4 x 2 at two CTAs per SM 824 ms per pass.  The subset's accumulated a_j goes to a per-warp shared-memory array; after a
 // part, the 8 warps' arrays are summed in warp order and written to the slot (I, d) of the J block.
 // No floating-point atomics anywhere: k_pair_finish adds, per body, the I-side partials and the
@@ -54,7 +55,7 @@ __device__ __forceinline__ unsigned long long key_max(unsigned long long a, unsi
 //     L(v) = 2^20 (e + 1023 + f) = 2^20 (log2 v + 1023 + delta),   delta = f - log2(1 + f)  in  [-0.0861, 0]
 // (the mantissa is a piecewise-linear logarithm).  The metric of a pair is gf_p y0^4 up to 3e-6, so
 //     L(gf_p) / 4 + L(y0) - L(best) / 4 - 1023 * 2^20  >=  2^20 [(log2 metric - log2 best) / 4 - 0.0861 (1/4 + 1)] - 3
-// and a partner that beats the best candidate so far ALWAYS passes  lg(gf_p) + L(y0) > thr(best)  with the margin
+// and a partner that beats the best candidate so far ALWAYS passes  lg(gf_p) + L(y0) >= thr(best)  with the margin
 // below (as does one whose truncated gf is not smaller: a superset of "strictly heavier").  The pairs that pass --
 // a few dozen per body and pass, the running maxima of a random sequence and their near misses within a factor
 // 1.4 -- run the exact test (heavier partner, full key compare) in a cold block.  The hot path pays integer adds
@@ -72,10 +73,11 @@ constexpr unsigned kKeyMargin = 114688u; // > 0.0861 * 1.25 * 2^20 = 112,853, + 
 // k_pair_finish accepts a winner only if  key_thr(winner) > prior  (then every better partner was above the prior
 // too and has been seen); otherwise that body is re-ranked from scratch by the repair path.
 constexpr unsigned kPriorSlack = 1u << 18;
-constexpr unsigned kPriorNone = 0x3FF00000u - kKeyMargin; // = key_thr(0): every real candidate passes
+constexpr unsigned kPriorNone = 0x3FF00000u - kKeyMargin + 1u; // = key_thr(0): every real candidate passes
 constexpr unsigned kPriorNever = 0xFFFFFFFFu;              // padding and masked bodies: nothing passes
 __device__ __forceinline__ unsigned key_lg(double gf) { return (unsigned)__double2hiint(gf) >> 2; }
-__device__ __forceinline__ unsigned key_thr(unsigned long long key) { return ((unsigned)(key >> 32) >> 2) + (0x3FF00000u - kKeyMargin); }
+// a partner passes when  lg(gf_p) + L(y0) >= key_thr(best)
+__device__ __forceinline__ unsigned key_thr(unsigned long long key) { return ((unsigned)(key >> 32) >> 2) + (0x3FF00000u - kKeyMargin + 1u); }
 
 struct PairArgs {
     double4 const* pos; // padded to a multiple of kPB with {0,0,0,0}
@@ -95,7 +97,7 @@ struct PairArgs {
 __device__ __forceinline__ double rot1(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // UNIFORM: every body of the world is live and has the same gravity factor g; the kernel then accumulates
-// sum |d|^-3 d and k_pair_finish multiplies by g once per body -- 19 instead of 21 FP64 instructions per pair.
+// sum |d|^-3 d and k_pair_finish multiplies by g once per body -- 18 instead of 20 FP64 instructions per pair.
 template<bool TWO_SIDED, bool ARGMAX, bool UNIFORM>
 __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, double gi, double xj, double yj, double zj, double gj,
     double eps2, double& aix, double& aiy, double& aiz, double& ajx, double& ajy, double& ajz, int iidx, int jidx,
@@ -137,9 +139,12 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
         // candidate filter; the exact tests run after the 32 rotations of a visit, behind ONE warp-uniform branch
         // (pair_exact below): a branch per pair would make every pair its own basic block and serialise the
         // eight independent chains of a rotation, a branch per rotation still drains the pipeline every 8 pairs
+        // With A = lg_j + L(y0) and B = lg_i + L(y0):  "A >= thr_i and lg_j >= lg_i"  is  A >= max(thr_i, B)
+        // (integer add-max, add, compare: six instructions per pair for both sides).
         unsigned const ly = (unsigned)__double2hiint(y0);
-        bool const pi = lgj + ly > thi && lgj >= lgi;
-        bool const pj = TWO_SIDED && lgi + ly > thj && lgi >= lgj;
+        unsigned const a = lgj + ly, b = lgi + ly;
+        bool const pi = a >= max(b, thi);
+        bool const pj = TWO_SIDED && b >= max(a, thj);
         anyp = anyp || pi || pj;
     }
 }
@@ -163,8 +168,8 @@ __device__ __forceinline__ void pair_exact(double xi, double yi, double zi, doub
         y0 = rsqrt_seed(r2);
     }
     unsigned const ly = (unsigned)__double2hiint(y0);
-    bool const pi = lgj + ly > thi && gj > gi;
-    bool const pj = TWO_SIDED && lgi + ly > thj && gi > gj;
+    bool const pi = lgj + ly >= thi && gj > gi;
+    bool const pj = TWO_SIDED && lgi + ly >= thj && gi > gj;
     if (pi || pj) {
         double y2 = y0 * y0;
         double e = fma(-r2, y2, 1.0);
