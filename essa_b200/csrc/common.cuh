@@ -4,7 +4,7 @@
 // (reference src/Object.cpp:64-95):
 //   * exact_*  -- the reference's operation order with IEEE-754 round-to-nearest add/mul/div/sqrt
 //                 and no FMA contraction: bit-identical to an x86-64 SSE2 build of the reference.
-//   * fast_*   -- 17 FP64-pipe instructions per directed interaction: MUFU.RSQ64H seed, one
+//   * fast_*   -- 16 FP64-pipe instructions per directed interaction: MUFU.RSQ64H seed, one
 //                 third-order correction fused with the cube, FMA accumulation.
 #pragma once
 

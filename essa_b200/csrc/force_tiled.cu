@@ -15,8 +15,8 @@
 // completes an i-block last (atomic ticket) sums the S partials in slot order -- deterministic,
 // no floating-point atomics -- and runs the kick / drift epilogue.
 //
-// Roofline: FP64 pipe.  17 FP64 instructions per directed interaction (common.cuh), i.e.
-// 10/17 = 58.8 % of the 20-flop-per-interaction convention is the ceiling of this formulation.
+// Roofline: FP64 pipe.  16 FP64 instructions per directed interaction (common.cuh), i.e.
+// 10/16 = 62.5 % of the 20-flop-per-interaction convention is the ceiling of this formulation.
 #include "common.cuh"
 #include "ctx.hpp"
 

@@ -1,7 +1,7 @@
 // K3x -- resident kernel for worlds of 33 .. 128 bodies (jupiter_system.essa: Jupiter + 76 moons) in fast
 // arithmetic, spread over a THREAD-BLOCK CLUSTER of 16 SMs that exchange positions through distributed
 // shared memory.  Same World::update loop (src/World.cpp:86-139) in one launch as K3 / K3c, but a step of a
-// single trajectory is a dependent chain, and on one SM that chain is n (n - 1) x 17 FP64 instructions deep
+// single trajectory is a dependent chain, and on one SM that chain is n (n - 1) x 16 FP64 instructions deep
 // for the 64 FP64 lanes of the SM (K3c: 3,600 cycles per step at 77 bodies).  Here:
 //
 //   * every CTA of the cluster owns up to 8 bodies; ONE WARP PER BODY evaluates that body's partners
