@@ -196,6 +196,27 @@ def test_paired_coincident_bodies_in_different_blocks(ctx, track):
             assert p["most"][i] != j and p["most"][j] != i
 
 
+def test_paired_coincident_bodies_uniform_masses(ctx):
+    """Same for the UNIFORM instantiation (every body live, one gravity factor: sums scaled once per body)."""
+    n = 9000
+    w = synth.plummer(n, seed=43)
+    x, y, z = w["x"].copy(), w["y"].copy(), w["z"].copy()
+    for a, b in [(5, 5000), (2047, 2048), (100, 8999)]:
+        x[b], y[b], z[b] = x[a], y[a], z[a]
+    x[7000] = y[7000] = z[7000] = 0.0
+    assert np.all(w["gf"] == w["gf"][0])
+    got = {}
+    for kern in (capi.KERNEL_TILED, capi.KERNEL_PAIRED):
+        ctx.date = capi.START_DATE
+        ctx.upload(x, y, z, w["vx"], w["vy"], w["vz"], w["gf"])
+        ctx.set_forces(kernel=kern)
+        got[kern] = ctx.download(("ax", "ay", "az"))
+    a = np.stack([got[capi.KERNEL_TILED][k] for k in ("ax", "ay", "az")], axis=1)
+    b = np.stack([got[capi.KERNEL_PAIRED][k] for k in ("ax", "ay", "az")], axis=1)
+    assert np.all(np.isfinite(b))
+    assert _rel_rows(b, a).max() <= 1e-12
+
+
 @pytest.mark.parametrize("dt_scale", [1, 40])
 def test_paired_link_thresholds_survive_passes_and_large_moves(ctx, dt_scale):
     """The pair-shared kernel filters candidates against thresholds left by the previous pass; a body whose
