@@ -80,6 +80,8 @@ SYMBOLS = [
     ("essa_step", C.c_int, [_P, C.c_int, C.POINTER(StepOpts)]),
     ("essa_step_async", C.c_int, [_P, C.c_int, C.POINTER(StepOpts)]),
     ("essa_set_forces", C.c_int, [_P, C.POINTER(StepOpts)]),
+    ("essa_persist_configure", C.c_int, [_P, C.c_int, C.c_int]),
+    ("essa_persist_stats", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("essa_record_configure", C.c_int, [_P, C.c_int, _i32p, C.c_int]),
     ("essa_tracked_count", C.c_int, [_P]),
     ("essa_record_reset", C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
@@ -247,9 +249,21 @@ class Context:
         o = opts if opts is not None else self.opts(dt, **kw)
         self._ck(self._L.essa_step(self._h, int(steps), C.byref(o)))
 
+    def step_async(self, steps, dt=None, opts=None, **kw):
+        o = opts if opts is not None else self.opts(dt, **kw)
+        self._ck(self._L.essa_step_async(self._h, int(steps), C.byref(o)))
+
     def set_forces(self, dt=1, opts=None, **kw):
         o = opts if opts is not None else self.opts(dt, **kw)
         self._ck(self._L.essa_set_forces(self._h, C.byref(o)))
+
+    def persist_configure(self, enable=True, idle_timeout_us=0):
+        self._ck(self._L.essa_persist_configure(self._h, int(enable), int(idle_timeout_us)))
+
+    def persist_stats(self):
+        out = (C.c_int64 * 4)()
+        self._ck(self._L.essa_persist_stats(self._h, out))
+        return dict(zip(("live", "ticks", "launches", "idle_exits"), (int(v) for v in out)))
 
     def sync(self):
         self._ck(self._L.essa_sync(self._h))

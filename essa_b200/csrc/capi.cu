@@ -109,6 +109,172 @@ NcclApi& nccl() {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// persistent resident kernel (resident_warp.cu, K3q): the kernel that served the previous
+// World::update(steps) stays on its two SMs and takes the next tick from a mailbox in mapped pinned
+// memory -- no launch, no stream synchronisation and no packing kernel per tick.  What the GUI's
+// cadence needs (SimulationView::update calls World::update(iterations) once per tick and reads the
+// objects back, src/SimulationView.cpp:374-397).  Every other entry point parks the kernel first
+// (PARK): it stores its state to HBM exactly as a one-shot launch does at its end, so nothing else in
+// this file knows about it.  A kernel nobody rings for `idle_us` retires by itself.
+// ---------------------------------------------------------------------------------------------
+#include <chrono>
+
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+}
+
+static int persist_launch(essa_ctx* ctx, int steps, essa_step_opts const& o);
+
+// The tick in flight has been published (ack == seq).  A kernel found retired (idle timeout raced with the doorbell)
+// never saw the tick: it is started again with that tick as its first.
+static int persist_wait_ack(essa_ctx* ctx) {
+    auto& p = ctx->persist;
+    if (!p.live || !p.pending)
+        return ESSA_OK;
+    PersistMailbox* mb = p.mailbox;
+    auto const t0 = std::chrono::steady_clock::now();
+    double const limit_s = 10.0 + 5e-6 * (double)p.pending_steps;
+    int const n = ctx->n, words = 29 * n + 2;
+    auto landed = [&]() { // every word of the result carries this tick's number (checked back to front: the tail lands last)
+        for (int w = words - 1; w >= 0; w--)
+            if ((unsigned)(__atomic_load_n(&mb->ll[w], __ATOMIC_RELAXED) >> 32) != p.seq)
+                return false;
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        return true;
+    };
+    for (unsigned spin = 0;; spin++) {
+        if (landed())
+            break;
+        if (__atomic_load_n(&mb->ack[1], __ATOMIC_ACQUIRE) != 0) {
+            // retired without seeing the doorbell
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (landed())
+                break;
+            p.live = false;
+            p.idle_exits++;
+            p.ticks--; // the doorbell was not answered: this tick is the new kernel's first
+            int rc = persist_launch(ctx, p.pending_steps, p.opts);
+            if (rc != ESSA_OK)
+                return rc;
+            continue;
+        }
+        if ((spin & 0xfff) == 0xfff) {
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s) {
+                ctx->err = "persistent resident kernel does not answer";
+                return ESSA_ERR_CUDA;
+            }
+            cudaError_t e = cudaStreamQuery(ctx->stream); // a kernel that died shows up here
+            if (e != cudaSuccess && e != cudaErrorNotReady) {
+                p.live = false;
+                ctx->err = std::string("persistent resident kernel: ") + cudaGetErrorString(e);
+                return ESSA_ERR_CUDA;
+            }
+        }
+        cpu_relax();
+    }
+    p.pending = false;
+    p.result_valid = true;
+    // unpack into essa_download's staging layout: 15 n doubles (field 9, gf, is not carried) ... links at double offset 17 n
+    {
+        size_t const N = (size_t)n;
+        for (int f = 0; f < 14; f++) {
+            double* dst = p.staged + (size_t)(f < 9 ? f : f + 1) * N;
+            unsigned long long const* src = mb->ll + (size_t)f * 2 * N;
+            for (size_t k = 0; k < N; k++) {
+                unsigned long long const bits = (src[2 * k] & 0xffffffffull) | (src[2 * k + 1] << 32);
+                memcpy(dst + k, &bits, sizeof(double));
+            }
+        }
+        int32_t* most = reinterpret_cast<int32_t*>(p.staged + 17 * N);
+        for (size_t k = 0; k < N; k++)
+            most[k] = (int32_t)(unsigned)mb->ll[28 * N + k];
+        unsigned long long const ns = (mb->ll[29 * N] & 0xffffffffull) | (mb->ll[29 * N + 1] << 32);
+        ctx->last_step_ms = (double)ns * 1e-6;
+    }
+    return ESSA_OK;
+}
+
+// Retire the kernel (its epilogue stores the world and the recording cursors to HBM) and wait for it.
+static int persist_park(essa_ctx* ctx) {
+    auto& p = ctx->persist;
+    if (!p.live)
+        return ESSA_OK;
+    int rc = persist_wait_ack(ctx);
+    if (p.live) {
+        p.seq++;
+        __atomic_store_n(&p.mailbox->cmd, (unsigned long long)p.seq << 32, __ATOMIC_RELEASE);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    p.live = false;
+    p.pending = false;
+    p.result_valid = false;
+    if (rc != ESSA_OK)
+        return rc;
+    CK(e);
+    return ESSA_OK;
+}
+
+#define PARK()                                                                                           \
+    do {                                                                                                 \
+        if (ctx->persist.live) {                                                                         \
+            int prc__ = persist_park(ctx);                                                               \
+            if (prc__ != ESSA_OK)                                                                        \
+                return prc__;                                                                            \
+        }                                                                                                \
+    } while (0)
+
+// Start a persistent kernel whose first tick is `steps`.
+static int persist_launch(essa_ctx* ctx, int steps, essa_step_opts const& o) {
+    auto& p = ctx->persist;
+    if (!p.mailbox) {
+        void* m = nullptr;
+        CK(cudaHostAlloc(&m, sizeof(PersistMailbox), cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(m, 0, sizeof(PersistMailbox));
+        p.mailbox = static_cast<PersistMailbox*>(m);
+    }
+    p.seq++;
+    int const k = steps < 0 ? -steps : steps;
+    p.mailbox->ack[1] = 0;
+    __atomic_store_n(&p.mailbox->cmd, ((unsigned long long)p.seq << 32) | (unsigned)k, __ATOMIC_RELEASE);
+    CK(launch_resident_warp(ctx, steps, o, false, ctx->stream, true));
+    p.live = true;
+    p.pending = true;
+    p.pending_steps = steps;
+    p.result_valid = false;
+    p.opts = o;
+    p.sign = steps >= 0 ? 1 : -1;
+    p.granted = k;
+    p.launches++;
+    return ESSA_OK;
+}
+
+// Can the live kernel take this call as its next tick?
+static bool persist_takes(essa_ctx const* ctx, int steps, essa_step_opts const& o) {
+    auto const& p = ctx->persist;
+    long long const k = steps < 0 ? -(long long)steps : steps;
+    return p.live && p.enabled && (steps >= 0 ? 1 : -1) == p.sign && o.dt_seconds == p.opts.dt_seconds
+        && o.forward_simulated == p.opts.forward_simulated && o.offset_trails == p.opts.offset_trails && o.record == p.opts.record
+        && o.track_most_attracting == p.opts.track_most_attracting && o.exact_order == p.opts.exact_order && o.two_pass == p.opts.two_pass
+        && o.eps2 == p.opts.eps2 && (o.kernel == ESSA_KERNEL_AUTO || o.kernel == ESSA_KERNEL_RESIDENT)
+        && p.granted + k < (1ll << 30); // the kernel counts steps in 32-bit integers
+}
+
+// Ring the doorbell.
+static void persist_post(essa_ctx* ctx, int steps) {
+    auto& p = ctx->persist;
+    unsigned const k = (unsigned)(steps < 0 ? -steps : steps);
+    p.seq++;
+    __atomic_store_n(&p.mailbox->cmd, ((unsigned long long)p.seq << 32) | k, __ATOMIC_RELEASE);
+    p.pending = true;
+    p.pending_steps = steps;
+    p.result_valid = false;
+    p.granted += k;
+    p.ticks++;
+}
+
+// ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
 static void free_world(essa_ctx* c) {
@@ -212,6 +378,10 @@ extern "C" int essa_ctx_create(int device, int capacity, essa_ctx** out) {
     }
     essa_ctx* ctx = new essa_ctx();
     ctx->device = device;
+    if (char const* e = getenv("ESSA_PERSIST"))
+        ctx->persist.enabled = atoi(e) != 0;
+    if (char const* e = getenv("ESSA_PERSIST_IDLE_US"))
+        ctx->persist.idle_us = std::max(1, std::min(1000000, atoi(e)));
     ctx->sm_count = prop.multiProcessorCount;
     auto fail = [&](char const* what, cudaError_t ce) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
@@ -269,6 +439,9 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     if (!c)
         return;
     cudaSetDevice(c->device);
+    (void)persist_park(c);
+    if (c->persist.mailbox)
+        cudaFreeHost(c->persist.mailbox);
     if (c->stream)
         cudaStreamSynchronize(c->stream);
     if (c->comm && nccl().CommDestroy)
@@ -344,6 +517,7 @@ extern "C" int essa_shard_world(const essa_ctx* c) { return c ? c->world : 1; }
 extern "C" int essa_sync(essa_ctx* ctx) {
     ARG(ctx, "ctx is null");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->comm_stream));
     return ESSA_OK;
@@ -364,6 +538,7 @@ static bool mask_changes(essa_ctx const* c, int64_t d_from, int64_t d_to) {
 extern "C" int essa_set_date(essa_ctx* ctx, int64_t date) {
     ARG(ctx, "ctx is null");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     bool changed = mask_changes(ctx, ctx->date, date);
     ctx->date = date;
     if (changed && ctx->n > 0) {
@@ -382,6 +557,7 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
     ARG(h && n >= 0, "bad arguments");
     ARG(n == 0 || (h->x && h->y && h->z && h->vx && h->vy && h->vz && h->gf), "x,y,z,vx,vy,vz,gf are required");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     int rc = reserve_world(ctx, n);
     if (rc != ESSA_OK)
@@ -481,6 +657,25 @@ extern "C" int essa_download(essa_ctx* ctx, essa_bodies* h) {
     ARG(h, "host view is null");
     CK(cudaSetDevice(ctx->device));
     size_t N = (size_t)ctx->n, cap = (size_t)ctx->cap;
+    if (ctx->persist.live && (ctx->persist.pending || ctx->persist.result_valid) && !h->gf && !h->creation_date && !h->deletion_date
+        && !h->deleted) {
+        // the persistent kernel has published (or is about to publish) exactly this state in the mailbox
+        int prc = persist_wait_ack(ctx);
+        if (prc != ESSA_OK)
+            return prc;
+        if (ctx->persist.live && ctx->persist.result_valid) {
+            double const* d = ctx->persist.staged;
+            double* dst[15] = { h->x, h->y, h->z, h->vx, h->vy, h->vz, h->ax, h->ay, h->az, nullptr, h->max_attraction, h->ap, h->pe,
+                h->ap_vel, h->pe_vel };
+            for (int k = 0; k < 15; k++)
+                if (dst[k])
+                    memcpy(dst[k], d + k * N, N * sizeof(double));
+            if (h->most)
+                memcpy(h->most, d + 17 * N, N * sizeof(int32_t));
+            return ESSA_OK;
+        }
+    }
+    PARK();
     if (N == 0)
         return ESSA_OK;
     size_t bytes = 15 * N * sizeof(double) + 2 * N * sizeof(int64_t) + N * sizeof(int32_t) + N;
@@ -791,15 +986,35 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
     ARG(opts, "opts is null");
     ARG(forces_only || steps != 0, "steps must not be 0 (assert in src/World.cpp:87)");
     CK(cudaSetDevice(ctx->device));
+    essa_step_opts o = *opts;
+    if (o.record)
+        o.track_most_attracting = 1;
+    if (ctx->persist.live) {
+        // the kernel of the previous call is still resident: same kind of tick, no date at which Object::deleted() flips -> doorbell
+        if (!forces_only && persist_takes(ctx, steps, o)
+            && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds))) {
+            int prc = persist_wait_ack(ctx); // (a tick nobody has read back yet)
+            if (prc != ESSA_OK)
+                return prc;
+            if (ctx->persist.live) {
+                persist_post(ctx, steps);
+                int const k = steps < 0 ? -steps : steps;
+                ctx->passes += o.two_pass ? 2 * k : k;
+                ctx->interactions += (double)(o.two_pass ? 2 * k : k) * (double)ctx->n * (double)(ctx->n - 1);
+                ctx->last_force_passes = o.two_pass ? 2 * k : k;
+                if (!async && (prc = persist_wait_ack(ctx)) != ESSA_OK)
+                    return prc;
+                return resident_finish(ctx, steps, o, false);
+            }
+        }
+        PARK();
+    }
     settle_timing(ctx); // the events are about to be reused
     if (ctx->n == 0) {
         if (!forces_only && !opts->forward_simulated)
             ctx->date += (int64_t)steps * opts->dt_seconds;
         return ESSA_OK;
     }
-    essa_step_opts o = *opts;
-    if (o.record)
-        o.track_most_attracting = 1;
     // AUTO: one resident launch for all steps up to ESSA_RESIDENT_MAX bodies.  Plain fast-arithmetic calls run on a
     // 16-SM cluster (K3x / K3xw: 0.7 .. 20 us per step, always below the tiled path's ~24 us of launches per step);
     // what the cluster kernels do not take (a mask that flips during the call, two_pass) goes to the single-CTA K3
@@ -829,10 +1044,20 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
     if (resident) {
         // worlds of up to 32 bodies in fast arithmetic: one-warp kernel with a recorder warp (resident_warp.cu)
         bool const closest = o.forward_simulated && ctx->closest && ctx->closest_n == ctx->n;
-        if (ctx->n <= 32 && !closest && !forces_only)
-            CK(launch_resident_warp(ctx, steps, o,
-                !o.forward_simulated && mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds), ctx->stream));
-        else if (resident_cta_applicable(ctx, o, forces_only)
+        if (ctx->n <= 32 && !closest && !forces_only) {
+            bool const flips = !o.forward_simulated && mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds);
+            long long const k = steps < 0 ? -(long long)steps : steps;
+            if (ctx->persist.enabled && !flips && k < (1ll << 30) && resident_persist_applicable(ctx, o, forces_only)) {
+                // stays resident after this tick and takes the following ones from its mailbox
+                rc = persist_launch(ctx, steps, o);
+                if (rc != ESSA_OK)
+                    return rc;
+                if (!async && (rc = persist_wait_ack(ctx)) != ESSA_OK)
+                    return rc;
+                return resident_finish(ctx, steps, o, forces_only);
+            }
+            CK(launch_resident_warp(ctx, steps, o, flips, ctx->stream));
+        } else if (resident_cta_applicable(ctx, o, forces_only)
             && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds))) {
             // 33 .. 128 bodies: a cluster of 8 / 16 SMs (resident_cluster.cu); one SM if the cluster cannot be placed
             bool clustered = false;
@@ -874,6 +1099,27 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
     return ESSA_OK;
 }
 
+extern "C" int essa_persist_configure(essa_ctx* ctx, int enable, int idle_timeout_us) {
+    ARG(ctx, "ctx is null");
+    ARG(idle_timeout_us >= 0 && idle_timeout_us <= 1000000, "idle timeout must be in [0, 1e6] microseconds");
+    CK(cudaSetDevice(ctx->device));
+    PARK();
+    ctx->persist.enabled = enable != 0;
+    if (idle_timeout_us > 0)
+        ctx->persist.idle_us = idle_timeout_us;
+    return ESSA_OK;
+}
+
+extern "C" int essa_persist_stats(const essa_ctx* c, int64_t out[4]) {
+    if (!c || !out)
+        return ESSA_ERR_ARG;
+    out[0] = c->persist.live ? 1 : 0;
+    out[1] = c->persist.ticks;
+    out[2] = c->persist.launches;
+    out[3] = c->persist.idle_exits;
+    return ESSA_OK;
+}
+
 extern "C" int essa_step(essa_ctx* ctx, int steps, const essa_step_opts* opts) { return step_common(ctx, steps, opts, false); }
 extern "C" int essa_set_forces(essa_ctx* ctx, const essa_step_opts* opts) { return step_common(ctx, 1, opts, true); }
 extern "C" int essa_step_async(essa_ctx* ctx, int steps, const essa_step_opts* opts) { return step_common(ctx, steps, opts, false, true); }
@@ -887,6 +1133,7 @@ extern "C" int essa_record_configure(essa_ctx* ctx, int n_tracked, const int32_t
     ARG(n_tracked == 0 || trail_capacity, "trail_capacity is null");
     ARG(keep >= 0 && keep <= ctx->tracked && keep <= n_tracked, "keep out of range");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < keep; k++)
         ARG(trail_capacity[k] == ctx->trail_cap[k], "kept bodies must keep their trail capacity");
@@ -967,6 +1214,7 @@ extern "C" int essa_record_reset(essa_ctx* ctx, int body, int history, int trail
     ARG(ctx, "ctx is null");
     ARG(body >= 0 && body < ctx->tracked, "body is not tracked");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     if (history) { // History::reset(): the list becomes { m_first_entry } (src/History.cpp:55-59)
         int32_t one = 1, zero = 0;
@@ -987,6 +1235,7 @@ extern "C" int essa_history_read(essa_ctx* ctx, int body, double* out) {
     ARG(ctx, "ctx is null");
     ARG(body >= 0 && body < ctx->tracked, "body is not tracked");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     int32_t start = 0, len = 0;
     CK(cudaMemcpy(&start, ctx->hist_start + body, sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -1007,6 +1256,7 @@ extern "C" int essa_history_write(essa_ctx* ctx, int body, const double* entries
     ARG(body >= 0 && body < ctx->tracked, "body is not tracked");
     ARG(entries && count >= 1 && count <= ESSA_HISTORY_SEGMENTS, "count must be in [1, ESSA_HISTORY_SEGMENTS]");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     int32_t zero = 0;
     CK(cudaMemcpy(ctx->hist + (size_t)body * ESSA_HISTORY_SEGMENTS * 6, entries, (size_t)count * 6 * sizeof(double), cudaMemcpyHostToDevice));
@@ -1021,6 +1271,7 @@ extern "C" int essa_trail_read(essa_ctx* ctx, int body, float* verts, essa_trail
     ARG(ctx, "ctx is null");
     ARG(body >= 0 && body < ctx->tracked, "body is not tracked");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     if (meta) {
         meta->capacity = ctx->trail_cap[body];
@@ -1044,6 +1295,7 @@ extern "C" int essa_trail_write(essa_ctx* ctx, int body, const float* verts, con
     ARG(meta->append_offset >= 0 && meta->append_offset < meta->capacity && meta->length >= 1 && meta->length <= meta->capacity,
         "append_offset / length out of range");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(ctx->append_off + body, &meta->append_offset, sizeof(int32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->tlength + body, &meta->length, sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -1061,6 +1313,7 @@ extern "C" int essa_trail_write(essa_ctx* ctx, int body, const float* verts, con
 extern "C" int essa_energy(essa_ctx* ctx, double* kinetic, double* potential, double momentum[3]) {
     ARG(ctx, "ctx is null");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     double out[5] = { 0, 0, 0, 0, 0 };
     if (ctx->n > 0) {
         CK(launch_energy(ctx, ctx->stream));
@@ -1088,7 +1341,7 @@ extern "C" int essa_energy(essa_ctx* ctx, double* kinetic, double* potential, do
 extern "C" double essa_measure_fp64_peak(essa_ctx* ctx, double ms) {
     if (!ctx)
         return -1;
-    if (cudaSetDevice(ctx->device) != cudaSuccess)
+    if (cudaSetDevice(ctx->device) != cudaSuccess || persist_park(ctx) != ESSA_OK)
         return -1;
     return run_fp64_peak(ctx, ms);
 }
@@ -1096,6 +1349,7 @@ extern "C" double essa_measure_fp64_peak(essa_ctx* ctx, double ms) {
 extern "C" int essa_measure_rsqrt_error(essa_ctx* ctx, double* seed_rel_err, double* refined_rel_err) {
     ARG(ctx, "ctx is null");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     return run_rsqrt_error(ctx, seed_rel_err, refined_rel_err);
 }
 
@@ -1113,6 +1367,7 @@ extern "C" int essa_ensemble_init(essa_ctx* ctx, const essa_ensemble_opts* o) {
     ARG(ctx->n <= kEnsembleMaxBodies, "ensemble template must have at most ESSA_ENSEMBLE_MAX bodies");
     ARG(!o->closest_approaches || (o->approach_to >= 0 && o->approach_to < ctx->n), "approach_to out of range");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->ens_state);
     cudaFree(ctx->ens_gf);
@@ -1135,6 +1390,7 @@ extern "C" int essa_ensemble_step(essa_ctx* ctx, int steps) {
     ARG(steps != 0, "steps must not be 0");
     ARG(ctx->ens_copies > 0, "essa_ensemble_init first");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     CK(launch_ensemble_step(ctx, steps, ctx->stream));
     CK(cudaEventRecord(ctx->ev_end, ctx->stream));
@@ -1151,6 +1407,7 @@ extern "C" int essa_ensemble_read(essa_ctx* ctx, int first, int count, double* x
     ARG(ctx, "ctx is null");
     ARG(first >= 0 && count >= 0 && first + count <= ctx->ens_copies, "copy range out of bounds");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     size_t n = (size_t)ctx->ens_n;
     double* dst[6] = { x, y, z, vx, vy, vz };
@@ -1192,6 +1449,7 @@ extern "C" int essa_shard_attach(essa_ctx* ctx, int rank, int world, const uint8
     ARG(world >= 1 && rank >= 0 && rank < world && id, "bad rank / world / id");
     ARG(!ctx->comm, "already attached");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     if (world == 1)
         return ESSA_OK;
     NcclApi& api = nccl();
@@ -1214,6 +1472,7 @@ extern "C" int essa_shard_attach(essa_ctx* ctx, int rank, int world, const uint8
 extern "C" int essa_flush_l2(essa_ctx* ctx) {
     ARG(ctx, "ctx is null");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     size_t const bytes = 256u << 20;
     if (!ctx->l2_scratch)
         CK(cudaMalloc(&ctx->l2_scratch, bytes));
@@ -1229,6 +1488,7 @@ extern "C" int essa_flush_l2(essa_ctx* ctx) {
 extern "C" int essa_closest_enable(essa_ctx* ctx, int enable) {
     ARG(ctx, "ctx is null");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->closest);
     ctx->closest = nullptr;
@@ -1248,6 +1508,7 @@ extern "C" int essa_closest_read(essa_ctx* ctx, int body, int other, double out[
     ARG(out, "out is null");
     ARG(ctx->closest && body >= 0 && other >= 0 && body < ctx->closest_n && other < ctx->closest_n, "closest approaches not enabled / index");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(out, ctx->closest + ((size_t)body * ctx->closest_n + other) * 7, 7 * sizeof(double), cudaMemcpyDeviceToHost));
     return out[0] != 0.0 ? 1 : 0;
@@ -1269,5 +1530,6 @@ extern "C" int essa_measure_latency(essa_ctx* ctx, double out[8]) {
     ARG(ctx, "ctx is null");
     ARG(out, "out is null");
     CK(cudaSetDevice(ctx->device));
+    PARK();
     return run_latency(ctx, out);
 }

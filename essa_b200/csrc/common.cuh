@@ -193,6 +193,32 @@ __device__ __forceinline__ void st_async_u64(uint32_t remote_addr, unsigned long
 __device__ __forceinline__ void st_relaxed_cluster_u32(uint32_t remote_addr, unsigned v) {
     asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
 }
+// the same with release semantics (everything the caller and, through __syncwarp, its warp wrote before is visible to
+// a peer that acquires the counter): used where a peer reads DATA the caller stored remotely, once per tick
+__device__ __forceinline__ void st_release_cluster_u32(uint32_t remote_addr, unsigned v) {
+    asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
+}
+// plain stores into a peer CTA's shared memory (ordered by a later st_release_cluster_u32)
+__device__ __forceinline__ void st_cluster_f64(uint32_t remote_addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote_addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t remote_addr, unsigned v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
+}
+// ---- host <-> device mailbox in mapped pinned memory (persistent resident kernels) ----
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(unsigned long long const* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ unsigned ld_acquire_cluster_u32(void const* local) {
     unsigned v;
     asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(local)) : "memory");

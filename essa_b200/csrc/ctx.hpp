@@ -76,6 +76,20 @@ struct RecordPtrs {
     double* pe_vel;
 };
 
+// ---- persistent resident kernel (resident_quad.cu K3q): host <-> device mailbox in mapped pinned memory ----
+// The host rings the doorbell by writing `cmd`; the kernel answers by filling `ll` with self-validating words
+// {tick number (high half), 32 bits of payload (low half)}: the result is complete when every word carries the tick's number.
+constexpr int kPersistMaxBodies = 32;
+constexpr int kPersistWords = 28 * kPersistMaxBodies + kPersistMaxBodies + 2;
+struct PersistMailbox {
+    unsigned long long cmd;   // host -> device: (seq << 32) | steps;  steps == 0: retire
+    unsigned long long pad0[15];
+    unsigned ack[4];          // device -> host: [1] 1 = retired on request, 2 = retired after the idle timeout
+    unsigned pad1[28];
+    unsigned long long ll[kPersistWords]; // x y z vx vy vz ax ay az max_attraction ap pe ap_vel pe_vel as (low, high)
+                                          // halves per body, then the links, then the tick's device nanoseconds
+};
+
 } // namespace essa
 
 struct ncclComm;
@@ -187,6 +201,23 @@ struct essa_ctx {
     int rank = 0, world = 1;
     ncclComm* comm = nullptr;
 
+    // persistent resident kernel
+    struct {
+        bool enabled = true;
+        int idle_us = 1000;        // the kernel retires by itself after this long without a doorbell
+        essa::PersistMailbox* mailbox = nullptr;
+        bool live = false;         // a kernel was launched and has not been seen to retire
+        bool pending = false;      // a tick was posted and its acknowledgement not yet consumed
+        int pending_steps = 0;     // ... this one (signed)
+        bool result_valid = false; // `staged` holds the state as of the device's current state
+        double staged[18 * essa::kPersistMaxBodies]; // the last tick's result in essa_download's staging layout
+        unsigned seq = 0;
+        long long granted = 0;     // steps handed to the live kernel so far
+        essa_step_opts opts {};    // what the live kernel was launched with
+        int sign = 1;
+        int64_t ticks = 0, launches = 0, idle_exits = 0; // doorbell ticks served / kernels started / kernels found retired
+    } persist;
+
     // stats
     int64_t launches = 0;
     int64_t passes = 0;
@@ -222,7 +253,9 @@ int force_iblocks(essa_ctx const* c, int* R_out);
 void choose_split(essa_ctx const* c, int iblocks, int ntiles, int* S_out);
 
 cudaError_t launch_resident(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st);
-cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool mask_may_change, cudaStream_t st);
+cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool mask_may_change, cudaStream_t st,
+    bool persist = false);
+bool resident_persist_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
 bool resident_cta_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
 cudaError_t launch_resident_cta(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
 cudaError_t launch_download_small(essa_ctx* c, void* pinned_out, cudaStream_t st);

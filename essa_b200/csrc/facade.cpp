@@ -302,6 +302,14 @@ essa_ctx* World::context() {
 
 double World::last_step_ms() const { return m_ctx ? essa_last_step_ms(m_ctx) : 0.0; }
 
+void World::set_persistent(bool enable, int idle_timeout_us) {
+    check(essa_persist_configure(context(), enable ? 1 : 0, idle_timeout_us), "essa_persist_configure");
+}
+
+void World::persist_stats(int64_t out[4]) {
+    check(essa_persist_stats(context(), out), "essa_persist_stats");
+}
+
 void World::set_date(SimulationTime d) {
     m_date = d;
     m_state_dirty = true;
@@ -527,8 +535,13 @@ void World::sync_from_device() {
     size_t const n = m_object_list.size();
     if (n == 0)
         return;
-    std::vector<double> f(14 * n);
-    std::vector<int32_t> most(n);
+    // scratch kept across calls: this runs once per GUI tick
+    std::vector<double>& f = m_scratch_f;
+    std::vector<int32_t>& most = m_scratch_most;
+    std::vector<Object*>& by_slot = m_scratch_by_slot;
+    f.resize(14 * n);
+    most.resize(n);
+    by_slot.resize(n);
     essa_bodies b;
     std::memset(&b, 0, sizeof(b));
     double* p = f.data();
@@ -538,7 +551,6 @@ void World::sync_from_device() {
     b.ap = p + 10 * n; b.pe = p + 11 * n; b.ap_vel = p + 12 * n; b.pe_vel = p + 13 * n;
     b.most = most.data();
     check(essa_download(m_ctx, &b), "essa_download");
-    std::vector<Object*> by_slot(n);
     size_t k = 0;
     for (auto& o : m_object_list)
         by_slot[k++] = o.get();

@@ -241,6 +241,10 @@ public:
 
     essa_ctx* context(); // creates the context on first use; throws std::runtime_error without a GPU
     double last_step_ms() const;
+    // essa_persist_configure / essa_persist_stats of the world's context: whether the kernel that served one update()
+    // stays resident for the next (the GUI's cadence: one update(iterations) + read-back per tick); default on
+    void set_persistent(bool enable, int idle_timeout_us = 0);
+    void persist_stats(int64_t out[4]);
 
 private:
     friend class Object;
@@ -255,6 +259,9 @@ private:
 
     int m_device;
     essa_ctx* m_ctx = nullptr;
+    std::vector<double> m_scratch_f;
+    std::vector<int32_t> m_scratch_most;
+    std::vector<Object*> m_scratch_by_slot;
     bool m_state_dirty = true, m_list_dirty = true;
     bool m_closest_enabled = false;
 

@@ -139,6 +139,19 @@ int essa_world_set_forces(essa_world* w) {
 
 double essa_world_last_step_ms(const essa_world* w) { return w ? w->world.last_step_ms() : 0.0; }
 
+int essa_world_set_persistent(essa_world* w, int enable, int idle_timeout_us) {
+    WANT(w, "null world");
+    GUARD(w->world.set_persistent(enable != 0, idle_timeout_us);)
+    return ESSA_OK;
+}
+
+int essa_world_persist_stats(essa_world* w, int64_t out[4]) {
+    WANT(w, "null world");
+    WANT(out, "out is null");
+    GUARD(w->world.persist_stats(out);)
+    return ESSA_OK;
+}
+
 int essa_world_get_state(essa_world* w, double* pos, double* vel, double* acc, double* gf, int32_t* most, double* appe, int32_t* active,
     double* maxattr) {
     WANT(w, "null world");

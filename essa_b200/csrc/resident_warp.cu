@@ -26,35 +26,9 @@
 #include "common.cuh"
 #include "ctx.hpp"
 #include "record.cuh"
+#include "resident_small.cuh"
 
 namespace essa {
-
-constexpr int kRing = 16; // snapshots in flight
-
-struct WarpArgs {
-    WorldPtrs w;
-    RecordPtrs r;
-    long long const* cdate;
-    long long const* ddate;
-    uint8_t const* delflag;
-    uint8_t* active_out;
-    int n, steps, L, iters;
-    double hm, dtm; // (dt / 2) * mul, dt * mul
-    long long date, date_step;
-    double eps2;
-    int record, argmax, offset_trails, forward_sim, two_pass, acc_valid;
-};
-
-struct Snapshot {
-    double x[32], y[32], z[32], vx[32], vy[32], vz[32];
-    int most[32], old_most[32];
-    unsigned active_mask;
-    int pad;
-};
-
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // Partial force of lane (k, q) over its partners, then the ordered sum over the L lanes of body k.
 template<int P>
@@ -151,18 +125,6 @@ __device__ __forceinline__ void lane_forces_exact(int k, int q, int L, int iters
     maxattr = best;
     if (bp >= 0)
         most = bp;
-}
-
-// gf_p / r^4 of partner p as seen from body k (the reference's |ta|^2 / gf_p), to ~1e-15.
-__device__ __forceinline__ double attraction_metric(double xk, double yk, double zk, double xp, double yp, double zp, double gp) {
-    double dx = xp - xk, dy = yp - yk, dz = zp - zk;
-    double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-    double y0 = rsqrt_seed(r2);
-    double t = r2 * y0;
-    double e = fma(-t, y0, 1.0);
-    double y = fma(y0 * e, fma(0.375, e, 0.5), y0); // 1 / r
-    double y2 = y * y;
-    return gp * y2 * y2;
 }
 
 template<int P, bool EXACT>
@@ -443,448 +405,29 @@ __global__ void __launch_bounds__(128, 1) k_resident_warp(WarpArgs const A) {
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// K3q -- the fast flavour as a CLUSTER OF TWO CTAs (two SMs) talking through distributed shared memory.
-//
-// Every FP64 instruction of a warp occupies its SM sub-partition's FP64 pipe for two cycles (measured), and
-// one step of a 10-body world needs several hundred of them for the physics alone, so on a single SM the
-// attraction / recorder warps steal issue slots from the chain that limits the run.  Hence:
-//
-//   CTA 0  warps 0-3  physics.  Every warp carries the whole replicated state (positions, velocities,
-//                     accelerations: identical bits in all four) but evaluates only every fourth partner
-//                     slot; the four partial accelerations meet in shared memory behind ONE named barrier
-//                     per force pass and are added in a fixed order by every lane, so the replicas stay
-//                     identical and no position is ever broadcast.  Warps 1-3 publish the step's snapshot
-//                     (positions / velocities / mask) straight into CTA 1's ring with st.async: the store
-//                     itself completes the ring slot's mbarrier there (transaction bytes), so publishing
-//                     costs the physics warps seven stores and no handshake.
-//   CTA 1  warps 0-2  attraction: most-attracting links, steps dealt round-robin (a step's link depends
-//                     only on that step's final positions)
-//          warps 3, 5 Trail (even / odd bodies)
-//          warp 4     link bookkeeping + History
-//          warp 6     ap / pe
-//                     The consumers report progress with a release store into CTA 0's shared memory;
-//                     the physics warps look at it only when their cached copy says the ring could be full.
-// ------------------------------------------------------------------------------------------------
-constexpr int kQuadWarps = 4;
-constexpr int kAttrWarps = 3;
-constexpr int kHistWarp = 4, kConsumerEnd = 7; // CTA 1: warps 3 .. 6 consume
-constexpr int kQuadThreads = 32 * kConsumerEnd;
-
-template<int T, int LOG2L>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_resident_quad(WarpArgs const A) {
-    __shared__ double spos[kQuadWarps][4][32];            // CTA 0: per physics warp sx, sy, sz, sg (private copies)
-    __shared__ double part[2][kQuadWarps][3][32];         // CTA 0: partial accelerations, double-buffered
-    __shared__ double sgf[32];                            // CTA 1
-    __shared__ __align__(16) Snapshot ring[kRing];        // CTA 1
-    __shared__ __align__(8) unsigned long long full[kRing], ready[kRing]; // CTA 1
-    __shared__ unsigned done[4];                          // CTA 0: steps consumed by CTA 1's warps 3 .. 6
-
-    int const n = A.n, L = A.L; // attraction / recorder warps: L = 32 / n lanes per body, lane = k + q n
-    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned const cta = cluster_ctarank();
-    bool const rec_on = A.record != 0;
-    bool const argmax = A.argmax != 0;
-    bool const snap_on = rec_on || argmax;
-    unsigned const snap_bytes = (unsigned)n * 48u + 8u;
-
-    // full: st.async from CTA 0 (transaction bytes) -> the attraction warp that owns the step;
-    // ready: that warp -> warps 3, 4
-    if (threadIdx.x == 0) {
-        if (cta == 1) {
-            for (int i = 0; i < kRing; i++) {
-                mbar_init(&full[i], 1);
-                mbar_init(&ready[i], 1);
-            }
-            mbar_fence_init();
-            for (int i = 0; i < kRing; i++)
-                mbar_expect_tx(&full[i], snap_bytes);
-        } else {
-            done[0] = done[1] = done[2] = done[3] = 0;
-        }
-    }
-    __syncthreads();
-    cluster_sync_all();
-
-    if (cta == 1 && snap_on && warp < kAttrWarps) {
-        // ---------------- attraction warps ----------------
-        // Which heavier body pulls hardest on body k (src/Object.cpp:84-94) depends only on a step's final
-        // positions, so different steps are evaluated by different warps; the one sequential piece -- "keep
-        // the previous link when there is no candidate" -- is a register in the consumer warps.
-        // Candidates are ranked by gf_p y0^4 with y0 the rsqrt seed (relative error < 4e-6: enough unless two
-        // heavier bodies attract within 4 ppm of each other); max_attraction is formed for the final state only.
-        int const k = lane % n, q = lane / n;
-        bool const worker = lane < n * L;
-        bool const leader = lane < n;
-        double gfk = worker ? A.w.gf[k] : 0.0;
-        if (warp == 0 && leader)
-            sgf[k] = gfk;
-        asm volatile("bar.sync 2, %0;" ::"r"(32 * kAttrWarps) : "memory");
-        constexpr int kCand = 4;
-        int const per = (n + L - 1) / L;
-#ifdef ESSA_STAGE_CLOCKS
-        long long abusy = 0;
-#endif
-        for (int s = warp; s < A.steps; s += kAttrWarps) {
-            int const slot = s % kRing;
-            mbar_wait(&full[slot], (unsigned)(s / kRing) & 1u);
-            if (lane == 0)
-                mbar_expect_tx(&full[slot], snap_bytes); // armed for the slot's next use
-#ifdef ESSA_STAGE_CLOCKS
-            long long t0 = clock64();
-#endif
-            Snapshot& sn = ring[slot];
-            unsigned const amask = sn.active_mask;
-            double const xk = sn.x[k], yk = sn.y[k], zk = sn.z[k];
-            double best = 0;
-            int bp = -1;
-            for (int u0 = 0; u0 < per; u0 += kCand) {
-                double m[kCand];
-                int pi[kCand];
-#pragma unroll
-                for (int u = 0; u < kCand; u++) {
-                    int p = q + (u0 + u) * L;
-                    bool ok = (u0 + u) < per && p < n && p != k && ((amask >> p) & 1u);
-                    int pc = ok ? p : k;
-                    double gp = sgf[pc];
-                    ok = ok && gp > gfk;
-                    double dx = sn.x[pc] - xk, dy = sn.y[pc] - yk, dz = sn.z[pc] - zk;
-                    double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    double y0 = rsqrt_seed(r2);
-                    double y2 = y0 * y0;
-                    m[u] = ok ? gp * y2 * y2 : 0.0;
-                    pi[u] = ok ? p : -1;
-                }
-#pragma unroll
-                for (int u = 0; u < kCand; u++) // ascending p: strict '>' keeps the lowest index on ties
-                    if (m[u] > best) {
-                        best = m[u];
-                        bp = pi[u];
-                    }
-            }
-            double tb = 0;
-            int tp = -1;
-            for (int qq = 0; qq < L; qq++) {
-                int src = k + qq * n;
-                double mm = __shfl_sync(0xffffffffu, best, src);
-                int j = __shfl_sync(0xffffffffu, bp, src);
-                if (mm > tb || (mm == tb && j >= 0 && tp >= 0 && j < tp)) {
-                    tb = mm;
-                    tp = j;
-                }
-            }
-            if (leader)
-                sn.most[k] = ((amask >> k) & 1u) ? tp : -1; // the step's winner, -1: none (or body masked)
-            __syncwarp();
-#ifdef ESSA_STAGE_CLOCKS
-            abusy += clock64() - t0;
-#endif
-            if (lane == 0)
-                mbar_arrive(&ready[slot]);
-        }
-#ifdef ESSA_STAGE_CLOCKS
-        if (lane == 0)
-            printf("attraction warp %d: %lld busy clk per step of its own\n", warp, abusy / (A.steps / kAttrWarps + 1));
-#endif
-    } else if (cta == 1 && snap_on && warp < kConsumerEnd && (warp == kHistWarp || rec_on)) {
-        // ---------------- consumer warps ----------------
-        //   3, 5  Trail (bodies with even / odd index: an append is ~4x the cost of a decimated step and stalls
-        //         the whole warp, so two warps halve how often that happens to each)
-        //   4     link bookkeeping + History
-        //   6     ap / pe
-        // Every consumer follows the most-attracting links itself (a few integer instructions per step).
-        bool const body = lane < n;
-        bool const is_trail = warp == 3 || warp == 5;
-        bool const mine = rec_on && body && lane < A.r.tracked && (!is_trail || (lane & 1) == (warp == 5 ? 1 : 0));
-        uint32_t const done_remote = mapa_u32(&done[warp - 3], 0);
-        BodyRec b;
-        if (mine)
-            rec_load(A.r, lane, b);
-        int most = body ? A.w.most[lane] : -1, old_most = body ? A.w.old_most[lane] : -1;
-        bool const offset_trails = A.offset_trails != 0, forward_sim = A.forward_sim != 0;
-#ifdef ESSA_STAGE_CLOCKS
-        long long busy = 0;
-#endif
-        for (int s = 0; s < A.steps; s++) {
-            int const slot = s % kRing;
-            mbar_wait(&ready[slot], (unsigned)(s / kRing) & 1u);
-#ifdef ESSA_STAGE_CLOCKS
-            long long t0 = clock64();
-#endif
-            Snapshot const& sn = ring[slot];
-            bool const act = body && ((sn.active_mask >> lane) & 1u);
-            int const winner = body ? sn.most[lane] : -1;
-            old_most = most; // Object::before_update (every object)
-            if (act && winner >= 0)
-                most = winner;
-            if (mine && act) {
-                int const mi = most >= 0 ? most : 0;
-                double const mx = sn.x[mi], my = sn.y[mi], mz = sn.z[mi];
-                if (is_trail)
-                    record_trail(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], mx, my, mz, most,
-                        old_most, offset_trails, forward_sim, false);
-                else if (warp == kHistWarp) {
-                    if (!forward_sim)
-                        history_push(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane]);
-                } else
-                    record_appe(b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], mx, my, mz, most);
-            }
-            if (warp == kHistWarp && s == A.steps - 1 && act) {
-                // max_attraction as the last force pass left it: the winner's gf / r^4 to full precision, or 0
-                A.w.maxattr[lane] = winner >= 0 ? attraction_metric(sn.x[lane], sn.y[lane], sn.z[lane], sn.x[winner], sn.y[winner],
-                                                      sn.z[winner], A.w.gf[winner])
-                                                : 0.0;
-            }
-            __syncwarp();
-#ifdef ESSA_STAGE_CLOCKS
-            busy += clock64() - t0;
-#endif
-            if (lane == 0)
-                st_relaxed_cluster_u32(done_remote, (unsigned)(s + 1));
-        }
-#ifdef ESSA_STAGE_CLOCKS
-        if (lane == 0)
-            printf("consumer warp %d: %lld busy clk/step\n", warp, busy / A.steps);
-#endif
-        if (warp == kHistWarp && body) {
-            A.w.most[lane] = most;
-            A.w.old_most[lane] = old_most;
-        }
-        if (mine) {
-            if (is_trail) {
-                rec_store_trail(A.r, lane, b, false);
-            } else if (warp == kHistWarp) {
-                A.r.hist_start[lane] = b.hist_start;
-                A.r.hist_len[lane] = b.hist_len;
-            } else {
-                rec_store_appe(A.r, lane, b);
-            }
-        }
-    } else if (cta == 0 && warp < kQuadWarps) {
-        // ---------------- physics warps 0 .. 3 ----------------
-        // Lane layout here: PL = 2^LOG2L lanes per body in one contiguous group (lane = kb PL + qb), so that the
-        // group sum is a shuffle butterfly: every lane ends with the same bits (a + b == b + a exactly).
-        constexpr int PL = 1 << LOG2L;
-        int const kb = lane >> LOG2L, qb = lane & (PL - 1);
-        bool const pworker = kb < n;
-        bool const pleader = pworker && qb == 0;
-        int const kc = pworker ? kb : 0;
-        double* const sx = spos[warp][0];
-        double* const sy = spos[warp][1];
-        double* const sz = spos[warp][2];
-        double* const sg = spos[warp][3];
-        double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0;
-        bool active = false, delf = false;
-        long long cd = 0, dd = 0;
-        if (pworker) {
-            double4 p = A.w.pos_cur[kb];
-            x = p.x;
-            y = p.y;
-            z = p.z;
-            gfk = A.w.gf[kb];
-            vx = A.w.v[0][kb];
-            vy = A.w.v[1][kb];
-            vz = A.w.v[2][kb];
-            ax = A.w.a[0][kb];
-            ay = A.w.a[1][kb];
-            az = A.w.a[2][kb];
-            active = A.w.active[kb] != 0;
-            delf = A.delflag[kb] != 0;
-            cd = A.cdate[kb];
-            dd = A.ddate[kb];
-        }
-        if (pleader) {
-            sx[kb] = x;
-            sy[kb] = y;
-            sz[kb] = z;
-            sg[kb] = active ? gfk : 0.0;
-        }
-        __syncwarp();
-
-        // this warp's partner slots of this lane never change: indices and weights are loop invariants
-        int pidx[T];
-        double pgf[T];
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-            int p = qb + (warp + kQuadWarps * t) * PL;
-            bool in = p < n;
-            pidx[t] = in ? p : kc; // out of range -> the self term, which vanishes
-            pgf[t] = in ? sg[pidx[t]] : 0.0;
-        }
-        double* const my_part0 = &part[0][warp][0][kc];
-        double* const my_part1 = &part[1][warp][0][kc];
-        double const* const all_part0 = &part[0][0][0][kc];
-        double const* const all_part1 = &part[1][0][0][kc];
-
-        bool acc_valid = A.acc_valid != 0;
-        long long date = A.date;
-        double const hm = A.hm, dtm = A.dtm;
-        int par = 0;
-        // bit kb of the body mask <- bit (kb PL) of the leaders' ballot; it only changes with the date
-        auto body_mask = [&]() {
-            unsigned lead = __ballot_sync(0xffffffffu, pleader && active);
-            unsigned m = 0;
-            for (int b2 = 0; b2 < n; b2++)
-                m |= ((lead >> (b2 << LOG2L)) & 1u) << b2;
-            return m;
-        };
-        unsigned amask = body_mask();
-
-        // where this lane's part of a snapshot goes in CTA 1 (slot 0), and slot 0's mbarrier there
-        uint32_t const full_remote = mapa_u32(&full[0], 1);
-        uint32_t snap_remote = mapa_u32(&ring[0], 1);
-        if (warp == 1)
-            snap_remote += (uint32_t)offsetof(Snapshot, x) + 8u * kc;
-        else if (warp == 2)
-            snap_remote += (uint32_t)offsetof(Snapshot, vx) + 8u * kc;
-        else
-            snap_remote += (uint32_t)offsetof(Snapshot, active_mask);
-        int consumed = 0; // cached lower bound of the steps CTA 1 has finished with
-
-        auto forces = [&]() {
-            double fx[T], fy[T], fz[T];
-#pragma unroll
-            for (int t = 0; t < T; t++) {
-                fx[t] = fy[t] = fz[t] = 0.0;
-                int const pc = pidx[t];
-                double4 qv = make_double4(sx[pc], sy[pc], sz[pc], pgf[t]);
-                fast_interact(x, y, z, qv, A.eps2, fx[t], fy[t], fz[t]);
-            }
-            double px = fx[0], py = fy[0], pz = fz[0];
-#pragma unroll
-            for (int t = 1; t < T; t++) {
-                px += fx[t];
-                py += fy[t];
-                pz += fz[t];
-            }
-#pragma unroll
-            for (int off = PL >> 1; off > 0; off >>= 1) {
-                px += __shfl_xor_sync(0xffffffffu, px, off);
-                py += __shfl_xor_sync(0xffffffffu, py, off);
-                pz += __shfl_xor_sync(0xffffffffu, pz, off);
-            }
-            double* const mine = par ? my_part1 : my_part0;
-            double const* const all = par ? all_part1 : all_part0;
-            if (pleader) {
-                mine[0] = px;
-                mine[32] = py;
-                mine[64] = pz;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            // part[par][w][c][k]: w stride 96 doubles, c stride 32
-            double tx = (all[0] + all[96]) + (all[192] + all[288]);
-            double ty = (all[32] + all[128]) + (all[224] + all[320]);
-            double tz = (all[64] + all[160]) + (all[256] + all[352]);
-            par ^= 1;
-            if (active) {
-                ax = tx;
-                ay = ty;
-                az = tz;
-            }
-        };
-
-        for (int s = 0; s < A.steps; s++) {
-            if (A.date_step != 0) { // only when the active mask can flip during this call
-                date += A.date_step;
-                bool act = pworker && body_active(delf, dd, cd, date);
-                bool changed = act != active;
-                active = act;
-                if (__any_sync(0xffffffffu, changed)) { // every physics warp sees the same change
-                    if (pleader)
-                        sg[kb] = active ? gfk : 0.0;
-                    acc_valid = false;
-                    __syncwarp();
-#pragma unroll
-                    for (int t = 0; t < T; t++)
-                        pgf[t] = (qb + (warp + kQuadWarps * t) * PL) < n ? sg[pidx[t]] : 0.0;
-                    amask = body_mask();
-                }
-            }
-            if (!acc_valid || A.two_pass)
-                forces();
-            if (active) {
-                vx = __dadd_rn(vx, __dmul_rn(ax, hm));
-                vy = __dadd_rn(vy, __dmul_rn(ay, hm));
-                vz = __dadd_rn(vz, __dmul_rn(az, hm));
-                x = __dadd_rn(x, __dmul_rn(vx, dtm));
-                y = __dadd_rn(y, __dmul_rn(vy, dtm));
-                z = __dadd_rn(z, __dmul_rn(vz, dtm));
-            }
-            __syncwarp();
-            if (pleader) {
-                sx[kb] = x;
-                sy[kb] = y;
-                sz[kb] = z;
-            }
-            __syncwarp();
-            forces();
-            if (active) {
-                vx = __dadd_rn(vx, __dmul_rn(ax, hm));
-                vy = __dadd_rn(vy, __dmul_rn(ay, hm));
-                vz = __dadd_rn(vz, __dmul_rn(az, hm));
-            }
-            acc_valid = true;
-            if (snap_on && warp != 0) {
-                int const slot = s % kRing;
-                if (s - consumed >= kRing) { // the slot may still be in use: look at CTA 1's progress
-                    do {
-                        consumed = (int)ld_acquire_cluster_u32(&done[kHistWarp - 3]);
-                        if (rec_on) {
-                            int const d0 = (int)ld_acquire_cluster_u32(&done[0]), d2 = (int)ld_acquire_cluster_u32(&done[2]),
-                                      d3 = (int)ld_acquire_cluster_u32(&done[3]);
-                            consumed = min(min(consumed, d0), min(d2, d3));
-                        }
-                    } while (s - consumed >= kRing);
-                }
-                uint32_t const dst = snap_remote + (uint32_t)slot * (uint32_t)sizeof(Snapshot);
-                uint32_t const bar = full_remote + 8u * (uint32_t)slot;
-                if (warp == 1) {
-                    if (pleader) {
-                        st_async_f64(dst, x, bar);
-                        st_async_f64(dst + 256u, y, bar);
-                        st_async_f64(dst + 512u, z, bar);
-                    }
-                } else if (warp == 2) {
-                    if (pleader) {
-                        st_async_f64(dst, vx, bar);
-                        st_async_f64(dst + 256u, vy, bar);
-                        st_async_f64(dst + 512u, vz, bar);
-                    }
-                } else if (lane == 0) {
-                    st_async_u64(dst, (unsigned long long)amask, bar);
-                }
-            }
-        }
-
-        if (warp == 0 && pleader) {
-            A.w.pos_cur[kb] = make_double4(x, y, z, active ? gfk : 0.0);
-            A.w.v[0][kb] = vx;
-            A.w.v[1][kb] = vy;
-            A.w.v[2][kb] = vz;
-            A.w.a[0][kb] = ax;
-            A.w.a[1][kb] = ay;
-            A.w.a[2][kb] = az;
-            A.active_out[kb] = active ? 1 : 0;
-        }
-    }
-    // nobody leaves while a peer may still store into (or signal) its shared memory
-    cluster_sync_all();
-}
-
-template<int T, int LOG2L>
-static void launch_quad(WarpArgs const& A, cudaStream_t st) {
-    k_resident_quad<T, LOG2L><<<2, kQuadThreads, 0, st>>>(A); // one cluster of two CTAs
-}
-
 template<int P>
-static void launch_warp_P(bool exact, WarpArgs const& A, cudaStream_t st) {
-    if (exact)
-        k_resident_warp<P, true><<<1, 128, 0, st>>>(A);
-    else
-        k_resident_warp<P, false><<<1, 128, 0, st>>>(A);
+static void launch_warp_P(bool, WarpArgs const& A, cudaStream_t st) {
+    k_resident_warp<P, true><<<1, 128, 0, st>>>(A); // the fast flavour runs on the two-CTA cluster (resident_quad.cu)
 }
 
-cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool mask_may_change, cudaStream_t st) {
+// Worlds the persistent flavour of K3q serves (capi.cu decides per call whether a live kernel can take the tick).
+bool resident_persist_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only) {
+    return !forces_only && !o.exact_order && c->n >= 1 && c->n <= 32 && c->world == 1
+        && !(o.forward_simulated && c->closest && c->closest_n == c->n);
+}
+
+cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool mask_may_change, cudaStream_t st, bool persist) {
+    PersistArgs PA {};
+    PersistArgs const* pa = nullptr;
+    if (persist && !o.exact_order) {
+        PersistMailbox* mb = c->persist.mailbox;
+        PA.cmd = &mb->cmd;
+        PA.ack = mb->ack;
+        PA.out = mb->ll;
+        PA.seq0 = c->persist.seq;
+        PA.idle_clk = (long long)c->persist.idle_us * 2000; // ~ SM cycles (1.965 GHz at full clock)
+        pa = &PA;
+    }
     WarpArgs A;
     A.w = world_ptrs(c);
     A.r = record_ptrs(c);
@@ -915,32 +458,9 @@ cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o
     int P = per_lane <= 1 ? 1 : (per_lane <= 2 ? 2 : (per_lane <= 4 ? 4 : 8));
     A.iters = (per_lane + P - 1) / P;
     if (!exact) {
-        // fast flavour: four physics warps, each with ceil(per_lane / 4) partner slots per lane
-        // physics lanes per body: the largest power of two that fits 32 lanes
-        int log2l = 0;
-        while ((2 << log2l) * c->n <= 32)
-            log2l++;
-        int const pl = 1 << log2l;
-        int const slots = (c->n + pl - 1) / pl;               // partner slots per lane
-        int const T = (slots + kQuadWarps - 1) / kQuadWarps;   // ... per physics warp
-        if (log2l == 4)
-            launch_quad<1, 4>(A, st);
-        else if (log2l == 3)
-            launch_quad<1, 3>(A, st);
-        else if (log2l == 2)
-            launch_quad<1, 2>(A, st);
-        else if (log2l == 1 && T <= 1)
-            launch_quad<1, 1>(A, st);
-        else if (log2l == 1)
-            launch_quad<2, 1>(A, st);
-        else if (T <= 1)
-            launch_quad<1, 0>(A, st);
-        else if (T <= 2)
-            launch_quad<2, 0>(A, st);
-        else if (T <= 4)
-            launch_quad<4, 0>(A, st);
-        else
-            launch_quad<8, 0>(A, st);
+        cudaError_t e = launch_resident_quad(c, A, pa, st); // resident_quad.cu
+        if (e != cudaSuccess)
+            return e;
     } else if (P == 1)
         launch_warp_P<1>(exact, A, st);
     else if (P == 2)

@@ -48,6 +48,8 @@ WORLD_SYMBOLS = [
     ("essa_world_update", C.c_int, [_P, C.c_int]),
     ("essa_world_set_forces", C.c_int, [_P]),
     ("essa_world_last_step_ms", C.c_double, [_P]),
+    ("essa_world_set_persistent", C.c_int, [_P, C.c_int, C.c_int]),
+    ("essa_world_persist_stats", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("essa_world_get_state", C.c_int, [_P, _dp, _dp, _dp, _dp, _i32p, _dp, _i32p, _dp]),
     ("essa_world_set_object", C.c_int, [_P, C.c_int, _dp, _dp, C.c_double]),
     ("essa_world_object_name", C.c_char_p, [_P, C.c_int]),
@@ -317,6 +319,16 @@ class World:
 
     def set_forces(self):
         self._ck(self._L.essa_world_set_forces(self._h))
+
+    def set_persistent(self, enable=True, idle_timeout_us=0):
+        """Keep the small-world kernel resident between update() calls (essa_persist_configure); default on."""
+        self._ck(self._L.essa_world_set_persistent(self._h, int(enable), int(idle_timeout_us)))
+
+    def persist_stats(self):
+        """{live, ticks served through the mailbox, persistent kernels launched, idle retirements seen}."""
+        out = (C.c_int64 * 4)()
+        self._ck(self._L.essa_world_persist_stats(self._h, out))
+        return dict(zip(("live", "ticks", "launches", "idle_exits"), (int(v) for v in out)))
 
     def set_flags(self, offset_trails=True, exact_order=False, two_pass=False):
         self._ck(self._L.essa_world_set_flags(self._h, int(offset_trails), int(exact_order), int(two_pass)))

@@ -128,8 +128,6 @@ int essa_sync(essa_ctx* ctx);
 int essa_upload(essa_ctx* ctx, int n, const essa_bodies* host);
 /* Copy current state out (members that are null are skipped). */
 int essa_download(essa_ctx* ctx, essa_bodies* host);
-/* Pinned-host variants for repeated transfers: identical semantics, the copies run on the
- * context's stream from/to cudaHostAlloc'ed staging buffers owned by the context. */
 int essa_set_date(essa_ctx* ctx, int64_t date);
 int64_t essa_get_date(const essa_ctx* ctx);
 int essa_body_count(const essa_ctx* ctx);
@@ -142,6 +140,20 @@ int essa_step(essa_ctx* ctx, int steps, const essa_step_opts* opts);
 int essa_step_async(essa_ctx* ctx, int steps, const essa_step_opts* opts);
 /* World::set_forces() alone (src/World.cpp:42-57): refreshes acc / most / max_attraction. */
 int essa_set_forces(essa_ctx* ctx, const essa_step_opts* opts);
+
+/* Persistent resident kernel.  The reference's caller, SimulationView::update (src/SimulationView.cpp:374-397), runs
+ * World::update(iterations) once per GUI tick (10 iterations by default, src/essagui/EssaSettings.cpp:34-47) and reads the
+ * objects back.  For worlds of up to 32 bodies in fast arithmetic the kernel that served one essa_step therefore stays
+ * resident on its SMs: the next essa_step / essa_step_async with the same options is handed to it through a mailbox in
+ * mapped pinned host memory (no launch, no stream synchronisation) and the following essa_download reads the state the
+ * kernel published there.  Any other call on the context retires the kernel first (it stores its state to device memory
+ * as a one-shot launch does), and a kernel nobody rings for `idle_timeout_us` retires by itself -- so the mode is
+ * invisible apart from its speed.  enable: 0 = one launch per call; idle_timeout_us: 0 keeps the current value
+ * (default 1000; environment: ESSA_PERSIST=0 / ESSA_PERSIST_IDLE_US). */
+int essa_persist_configure(essa_ctx* ctx, int enable, int idle_timeout_us);
+/* out = {kernel resident now (0/1), ticks served through the mailbox, persistent kernels launched,
+ *        kernels found retired by their idle timeout when the next tick came}. */
+int essa_persist_stats(const essa_ctx* ctx, int64_t out[4]);
 
 /* ---- recording: Object::m_history / m_trail (src/History.cpp, src/Trail.cpp) ---------------- */
 /* Track bodies [0, n_tracked): allocate History rings (ESSA_HISTORY_SEGMENTS entries) and Trail

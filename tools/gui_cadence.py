@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""The GUI's cadence (SimulationView::update: `iterations` steps per tick, state read back every tick):
-microseconds per World::update(k) call through the facade, solar.essa, recording on."""
+"""The GUI's cadence (SimulationView::update: `iterations` steps per tick, state read back every tick,
+src/SimulationView.cpp:374-397): microseconds per World::update(k) call through the facade, recording on,
+with the persistent resident kernel (mailbox doorbell) and with one launch per call."""
 import os
 import sys
 import time
@@ -10,14 +11,19 @@ from essa_b200 import world  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 fname = sys.argv[1] if len(sys.argv) > 1 else "solar.essa"
-pw = world.World.load(os.path.join(ROOT, "tests", "golden", "worlds", fname))
-pw.simulation_seconds_per_tick = 600
-pw.set_flags(offset_trails=True)
-pw.update(1000)
-for k in (1, 10, 100, 1000):
-    t0 = time.perf_counter()
-    for _ in range(200):
-        pw.update(k)
-    dt = (time.perf_counter() - t0) / 200
-    print("%s update(%4d): %7.1f us per call  %9.0f it/s  (kernel %6.1f us)" % (fname, k, dt * 1e6, k / dt, pw.last_step_ms * 1e3), flush=True)
-pw.close()
+for persist in (True, False):
+    pw = world.World.load(os.path.join(ROOT, "tests", "golden", "worlds", fname))
+    pw.simulation_seconds_per_tick = 600
+    pw.set_flags(offset_trails=True)
+    pw.set_persistent(persist)
+    pw.update(1000)
+    for k in (1, 10, 100, 1000):
+        for _ in range(20):
+            pw.update(k)
+        t0 = time.perf_counter()
+        for _ in range(500):
+            pw.update(k)
+        dt = (time.perf_counter() - t0) / 500
+        print("%s persistent=%d update(%4d): %7.2f us per call  %9.0f it/s  (device %6.2f us)  %s"
+              % (fname, persist, k, dt * 1e6, k / dt, pw.last_step_ms * 1e3, pw.persist_stats()), flush=True)
+    pw.close()

@@ -14,8 +14,10 @@ pw = world.World.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspa
 st = pw.state()
 caps = [pw.props(i)["trail_capacity"] for i in range(len(pw))]
 n = len(pw)
+persist = int(sys.argv[3]) if len(sys.argv) > 3 else 0  # 1: the persistent flavour of K3q (same step loop, doorbell between calls)
 for label, kw in (("physics", {}), ("physics+attraction", dict(track_most_attracting=True)), ("all", dict(record=True))):
     c = capi.Context(0)
+    c.persist_configure(persist)
     c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"],
              creation_date=np.full(n, capi.START_DATE, dtype=np.int64))
     c.record_configure(caps)
