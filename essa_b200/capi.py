@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libessa_b200.so")
+LIB_PATH = os.environ.get("ESSA_B200_LIB") or os.path.join(_HERE, "lib", "libessa_b200.so")  # (override: kernel experiments)
 
 GRAVITY = 6.67408e-11
 AU = 149597870700.0
@@ -261,9 +261,9 @@ class Context:
         self._ck(self._L.essa_persist_configure(self._h, int(enable), int(idle_timeout_us)))
 
     def persist_stats(self):
-        out = (C.c_int64 * 4)()
+        out = (C.c_int64 * 6)()
         self._ck(self._L.essa_persist_stats(self._h, out))
-        return dict(zip(("live", "ticks", "launches", "idle_exits"), (int(v) for v in out)))
+        return dict(zip(("live", "ticks", "launches", "idle_exits", "wait_ns", "host_ns"), (int(v) for v in out)))
 
     def sync(self):
         self._ck(self._L.essa_sync(self._h))

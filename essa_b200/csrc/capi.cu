@@ -55,12 +55,14 @@ struct NcclApi {
     int (*Broadcast)(void const*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
     int (*AllReduce)(void const*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
     int (*ReduceScatter)(void const*, void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
+    int (*Send)(void const*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     char const* (*GetErrorString)(int) = nullptr;
     std::string why;
 };
-constexpr int kNcclFloat64 = 8, kNcclUint64 = 5, kNcclUint32 = 3, kNcclSum = 0, kNcclMax = 2; // ncclDataType_t / ncclRedOp_t values (nccl.h)
+constexpr int kNcclFloat64 = 8, kNcclUint64 = 5, kNcclUint32 = 3, kNcclSum = 0; // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
 NcclApi& nccl() {
     static NcclApi api;
@@ -86,11 +88,13 @@ NcclApi& nccl() {
     SYM(Broadcast, "ncclBroadcast");
     SYM(AllReduce, "ncclAllReduce");
     SYM(ReduceScatter, "ncclReduceScatter");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
-    if (!api.GetUniqueId || !api.CommInitRank || !api.Broadcast || !api.GroupStart || !api.GroupEnd || !api.AllReduce || !api.ReduceScatter) {
+    if (!api.GetUniqueId || !api.CommInitRank || !api.Broadcast || !api.GroupStart || !api.GroupEnd || !api.AllReduce || !api.ReduceScatter || !api.Send || !api.Recv) {
         api.why = "libnccl.so.2 lacks required symbols";
         dlclose(api.lib);
         api.lib = nullptr;
@@ -138,6 +142,9 @@ static int persist_wait_ack(essa_ctx* ctx) {
     double const limit_s = 10.0 + 5e-6 * (double)p.pending_steps;
     int const n = ctx->n, words = 29 * n + 2;
     auto landed = [&]() { // every word of the result carries this tick's number (checked back to front: the tail lands last)
+#if defined(ESSA_PUB_MODE) && ESSA_PUB_MODE == 2
+        return __atomic_load_n(&mb->ack[0], __ATOMIC_ACQUIRE) == p.seq;
+#endif
         for (int w = words - 1; w >= 0; w--)
             if ((unsigned)(__atomic_load_n(&mb->ll[w], __ATOMIC_RELAXED) >> 32) != p.seq)
                 return false;
@@ -176,7 +183,14 @@ static int persist_wait_ack(essa_ctx* ctx) {
     }
     p.pending = false;
     p.result_valid = true;
+    p.t_landed = std::chrono::steady_clock::now();
+    p.wait_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(p.t_landed - p.t_post).count();
     // unpack into essa_download's staging layout: 15 n doubles (field 9, gf, is not carried) ... links at double offset 17 n
+#if defined(ESSA_PUB_MODE) && ESSA_PUB_MODE == 2
+    memcpy(p.staged, mb->ll, (size_t)n * 18 * sizeof(double));
+    ctx->last_step_ms = (double)(((unsigned long long)mb->ack[3] << 32) | mb->ack[2]) * 1e-6;
+    if (false)
+#endif
     {
         size_t const N = (size_t)n;
         for (int f = 0; f < 14; f++) {
@@ -239,6 +253,7 @@ static int persist_launch(essa_ctx* ctx, int steps, essa_step_opts const& o) {
     p.mailbox->ack[1] = 0;
     __atomic_store_n(&p.mailbox->cmd, ((unsigned long long)p.seq << 32) | (unsigned)k, __ATOMIC_RELEASE);
     CK(launch_resident_warp(ctx, steps, o, false, ctx->stream, true));
+    p.t_post = std::chrono::steady_clock::now();
     p.live = true;
     p.pending = true;
     p.pending_steps = steps;
@@ -266,6 +281,9 @@ static void persist_post(essa_ctx* ctx, int steps) {
     auto& p = ctx->persist;
     unsigned const k = (unsigned)(steps < 0 ? -steps : steps);
     p.seq++;
+    p.t_post = std::chrono::steady_clock::now();
+    if (p.ticks > 0 || p.launches > 0)
+        p.host_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(p.t_post - p.t_landed).count();
     __atomic_store_n(&p.mailbox->cmd, ((unsigned long long)p.seq << 32) | k, __ATOMIC_RELEASE);
     p.pending = true;
     p.pending_steps = steps;
@@ -453,6 +471,7 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     cudaFree(c->pair_kslots);
     cudaFree(c->pair_kpart);
     cudaFree(c->pair_prior);
+    cudaFree(c->pair_kall);
     cudaFree(c->part);
     cudaFree(c->part_m);
     cudaFree(c->part_j);
@@ -685,16 +704,30 @@ extern "C" int essa_download(essa_ctx* ctx, essa_bodies* h) {
     cudaStream_t st = ctx->stream;
     double* d = static_cast<double*>(ctx->pinned);
     if (ctx->world > 1) {
-        // every rank holds all positions (gathered each pass) but only its own targets' v, a, most
+        // every rank holds all positions (gathered each pass) but only its own targets' v, a, most-attracting link,
+        // max_attraction and ap / pe (post-conditions of World::update that Object::most_attracting_object() / get_info()
+        // show, src/Object.hpp:99, src/Object.cpp:248-266): gather what the caller asked for
+        bool const want_v = h->vx || h->vy || h->vz, want_a = h->ax || h->ay || h->az;
+        bool const want_appe = h->ap || h->pe || h->ap_vel || h->pe_vel;
         NK(nccl().GroupStart());
         for (int r = 0; r < ctx->world; r++) {
             long long a = (long long)ctx->n * r / ctx->world, b = (long long)ctx->n * (r + 1) / ctx->world;
             if (b <= a)
                 continue;
+            size_t const cnt = (size_t)(b - a);
             for (int k = 0; k < 3; k++) {
-                NK(nccl().Broadcast(ctx->vel + k * cap + a, ctx->vel + k * cap + a, (size_t)(b - a), kNcclFloat64, r, ctx->comm, st));
-                NK(nccl().Broadcast(ctx->acc + k * cap + a, ctx->acc + k * cap + a, (size_t)(b - a), kNcclFloat64, r, ctx->comm, st));
+                if (want_v)
+                    NK(nccl().Broadcast(ctx->vel + k * cap + a, ctx->vel + k * cap + a, cnt, kNcclFloat64, r, ctx->comm, st));
+                if (want_a)
+                    NK(nccl().Broadcast(ctx->acc + k * cap + a, ctx->acc + k * cap + a, cnt, kNcclFloat64, r, ctx->comm, st));
             }
+            if (h->most)
+                NK(nccl().Broadcast(ctx->most + a, ctx->most + a, cnt, kNcclUint32, r, ctx->comm, st));
+            if (h->max_attraction)
+                NK(nccl().Broadcast(ctx->maxattr + a, ctx->maxattr + a, cnt, kNcclFloat64, r, ctx->comm, st));
+            if (want_appe)
+                for (int k = 0; k < 4; k++)
+                    NK(nccl().Broadcast(ctx->appe + k * cap + a, ctx->appe + k * cap + a, cnt, kNcclFloat64, r, ctx->comm, st));
         }
         NK(nccl().GroupEnd());
     }
@@ -816,16 +849,30 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
         if (ctx->world > 1) {
             // every rank holds J-side sums (and candidate keys) for every body: reduce-scatter them onto the owners (in place)
             size_t cnt = (size_t)n / ctx->world;
+            if (keys && ctx->pair_kall_n < (size_t)n) {
+                cudaFree(ctx->pair_kall);
+                ctx->pair_kall = nullptr;
+                ctx->pair_kall_n = 0;
+                CK(cudaMalloc(&ctx->pair_kall, (size_t)n * sizeof(unsigned long long)));
+                ctx->pair_kall_n = (size_t)n;
+            }
             NK(nccl().GroupStart());
             for (int c3 = 0; c3 < 3; c3++) {
                 double* base = acc + (size_t)c3 * npad;
                 NK(nccl().ReduceScatter(base, base + (size_t)ctx->rank * cnt, cnt, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream));
             }
-            if (keys)
-                NK(nccl().ReduceScatter(kacc, kacc + (size_t)ctx->rank * cnt, cnt, kNcclUint64, kNcclMax, ctx->comm, ctx->stream));
+            if (keys) {
+                // every rank's candidate for each of my bodies (not an ncclMax: two keys that differ in the index only are
+                // re-decided exactly by k_pair_finish, which therefore has to see both)
+                for (int r = 0; r < ctx->world; r++) {
+                    NK(nccl().Send(kacc + (size_t)r * cnt, cnt, kNcclUint64, r, ctx->comm, ctx->stream));
+                    NK(nccl().Recv(ctx->pair_kall + (size_t)r * cnt, cnt, kNcclUint64, r, ctx->comm, ctx->stream));
+                }
+            }
             NK(nccl().GroupEnd());
         }
-        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc, argmax && !keys, save_old, keys, kacc, eps2));
+        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc, argmax && !keys, save_old, keys, keys && ctx->world > 1 ? ctx->pair_kall : nullptr,
+            eps2));
     } else if (ctx->world == 1 || !ctx->gather_pending) {
         int S;
         choose_split(ctx, iblocks, (n + kTileJ - 1) / kTileJ, &S);
@@ -1010,6 +1057,11 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
         PARK();
     }
     settle_timing(ctx); // the events are about to be reused
+    if (o.eps2 != ctx->acc_eps2) { // accelerations (and filter thresholds) left by a call with another softening are not reusable
+        ctx->acc_valid = false;
+        ctx->pair_prior_valid = false;
+        ctx->acc_eps2 = o.eps2;
+    }
     if (ctx->n == 0) {
         if (!forces_only && !opts->forward_simulated)
             ctx->date += (int64_t)steps * opts->dt_seconds;
@@ -1110,13 +1162,15 @@ extern "C" int essa_persist_configure(essa_ctx* ctx, int enable, int idle_timeou
     return ESSA_OK;
 }
 
-extern "C" int essa_persist_stats(const essa_ctx* c, int64_t out[4]) {
+extern "C" int essa_persist_stats(const essa_ctx* c, int64_t out[6]) {
     if (!c || !out)
         return ESSA_ERR_ARG;
     out[0] = c->persist.live ? 1 : 0;
     out[1] = c->persist.ticks;
     out[2] = c->persist.launches;
     out[3] = c->persist.idle_exits;
+    out[4] = c->persist.wait_ns;
+    out[5] = c->persist.host_ns;
     return ESSA_OK;
 }
 

@@ -84,8 +84,8 @@ __device__ __forceinline__ void fast_interact_argmax(double xi, double yi, doubl
     ax = fma(s, dx, ax);
     ay = fma(s, dy, ay);
     az = fma(s, dz, az);
-    // |ta|^2 / gf_j = gf_j / r^4 = s * (1/r);  1/r ~ y0 (1 + e/2)
-    double yr = fma(y0 * 0.5, e, y0);
+    // |ta|^2 / gf_j = gf_j / r^4 = s * (1/r);  1/r = y0 (1 + e/2 + 3/8 e^2 + O(e^3)), relative error ~1e-17
+    double yr = fma(y0 * e, fma(0.375, e, 0.5), y0);
     double metric = s * yr;
     if (metric > best && q.w > gfi) {
         best = metric;
@@ -143,17 +143,22 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifndef ESSA_MBAR_HINT_NS
+#define ESSA_MBAR_HINT_NS 0x989680
+#endif
+// (the suspend-time hint lets the hardware park the warp until the phase completes instead of returning after a short
+// default interval: a warp that spins on try_wait takes issue slots from the warps of its SM sub-partition)
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(ESSA_MBAR_HINT_NS)
         : "memory");
 }
 // ---- thread-block cluster / distributed shared memory ----

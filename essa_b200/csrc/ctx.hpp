@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -120,6 +121,7 @@ struct essa_ctx {
     bool acc_valid = false;     // acc[] holds set_forces() of pos[cur] under the current active mask
     bool acc_has_most = false;  // ... and most / max_attraction were evaluated with it
     bool acc_exact = false;     // ... in exact_order arithmetic
+    double acc_eps2 = 0.0;      // ... with this softening
     bool gather_pending = false;
     // paired_plan's last answer (a pure function of n, the sharding and the SM count)
     mutable struct {
@@ -158,6 +160,8 @@ struct essa_ctx {
     unsigned long long* pair_kslots = nullptr; // most-attracting candidate keys (pair-shared kernel with tracking)
     size_t pair_kslots_bytes = 0;
     unsigned long long* pair_kpart = nullptr;
+    unsigned long long* pair_kall = nullptr; // sharded: every rank's candidate key for each of this rank's bodies [world][n / world]
+    size_t pair_kall_n = 0;
     unsigned* pair_prior = nullptr; // candidate-filter thresholds carried from pass to pass (force_paired.cu)
     size_t pair_prior_n = 0;
     int pair_prior_npad = 0;
@@ -216,6 +220,9 @@ struct essa_ctx {
         essa_step_opts opts {};    // what the live kernel was launched with
         int sign = 1;
         int64_t ticks = 0, launches = 0, idle_exits = 0; // doorbell ticks served / kernels started / kernels found retired
+        // host clock: nanoseconds between a doorbell (or launch) and its result / between a result and the next doorbell
+        int64_t wait_ns = 0, host_ns = 0;
+        std::chrono::steady_clock::time_point t_post, t_landed;
     } persist;
 
     // stats

@@ -306,7 +306,7 @@ void World::set_persistent(bool enable, int idle_timeout_us) {
     check(essa_persist_configure(context(), enable ? 1 : 0, idle_timeout_us), "essa_persist_configure");
 }
 
-void World::persist_stats(int64_t out[4]) {
+void World::persist_stats(int64_t out[6]) {
     check(essa_persist_stats(context(), out), "essa_persist_stats");
 }
 

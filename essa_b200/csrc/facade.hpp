@@ -244,7 +244,7 @@ public:
     // essa_persist_configure / essa_persist_stats of the world's context: whether the kernel that served one update()
     // stays resident for the next (the GUI's cadence: one update(iterations) + read-back per tick); default on
     void set_persistent(bool enable, int idle_timeout_us = 0);
-    void persist_stats(int64_t out[4]);
+    void persist_stats(int64_t out[6]);
 
 private:
     friend class Object;

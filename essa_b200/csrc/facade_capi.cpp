@@ -145,7 +145,7 @@ int essa_world_set_persistent(essa_world* w, int enable, int idle_timeout_us) {
     return ESSA_OK;
 }
 
-int essa_world_persist_stats(essa_world* w, int64_t out[4]) {
+int essa_world_persist_stats(essa_world* w, int64_t out[6]) {
     WANT(w, "null world");
     WANT(out, "out is null");
     GUARD(w->world.persist_stats(out);)

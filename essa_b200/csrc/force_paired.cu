@@ -50,6 +50,37 @@ __device__ __forceinline__ unsigned long long pack_key(double m, int idx) {
     return ((unsigned long long)__double_as_longlong(m) & ~kKeyIdxMask) | (kKeyIdxMask - (unsigned long long)idx);
 }
 __device__ __forceinline__ unsigned long long key_max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+__device__ __forceinline__ int key_index(unsigned long long k) { return (int)(kKeyIdxMask - (k & kKeyIdxMask)); }
+
+// Two candidates whose keys agree in every metric bit a key keeps (the upper 31 mantissa bits: they attract within
+// 5e-10 of each other) but name different bodies: the key cannot rank them, and "lowest index" would be a guess.
+// The reference decides such a case in full binary64 (src/Object.cpp:84-94): mag = |ta|^2 / gf_p with
+// ta = (d / (r2 sqrt r2)) gf_p, strict '>', partners in ascending index order.  Re-evaluated here with the same IEEE
+// operations (no contraction) for exactly these two partners, so the link that comes out is the reference's -- also at an
+// exact tie, where the lower index wins.  Cold: a few loads and divisions for the rare body that has such a pair.
+__device__ __forceinline__ double reference_metric(double4 const t, double4 const p, double eps2) {
+    double dx = __dsub_rn(p.x, t.x), dy = __dsub_rn(p.y, t.y), dz = __dsub_rn(p.z, t.z);
+    double den = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    den = __dadd_rn(den, eps2); // eps2 == 0: the reference's expression
+    den = __dmul_rn(den, __dsqrt_rn(den));
+    double tx = __dmul_rn(__ddiv_rn(dx, den), p.w), ty = __dmul_rn(__ddiv_rn(dy, den), p.w), tz = __dmul_rn(__ddiv_rn(dz, den), p.w);
+    return __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz)), p.w);
+}
+__device__ __noinline__ unsigned long long key_resolve(double4 const* __restrict__ pos, int target, unsigned long long a, unsigned long long b,
+    double eps2) {
+    int const ia = key_index(a), ib = key_index(b);
+    double4 const t = pos[target];
+    double const ma = reference_metric(t, pos[ia], eps2), mb = reference_metric(t, pos[ib], eps2);
+    bool const take_a = ma > mb || (ma == mb && ia < ib);
+    return take_a ? a : b;
+}
+// max of two candidate keys of body `target`, with the exact re-decision where the keys cannot tell
+__device__ __forceinline__ unsigned long long key_merge(double4 const* __restrict__ pos, int target, unsigned long long a, unsigned long long b,
+    double eps2) {
+    if (a != b && a != 0ull && b != 0ull && ((a ^ b) >> kKeyIdxBits) == 0ull)
+        return key_resolve(pos, target, a, b, eps2);
+    return a > b ? a : b;
+}
 
 // Candidate filter in the integer pipe.  For a positive double v = 2^e (1 + f), its high word is
 //     L(v) = 2^20 (e + 1023 + f) = 2^20 (log2 v + 1023 + delta),   delta = f - log2(1 + f)  in  [-0.0861, 0]
@@ -153,9 +184,9 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
 // with the very same operations (so the seed, and with it the key, are the ones the hot path saw) and applies
 // Object.cpp:84-94 -- strictly heavier partner, larger key -- to both bodies.
 template<bool TWO_SIDED>
-__device__ __forceinline__ void pair_exact(double xi, double yi, double zi, double gi, double xj, double yj, double zj, double gj,
-    double eps2, int iidx, int jidx, unsigned long long& bi, unsigned long long& bj, unsigned lgi, unsigned lgj, unsigned& thi,
-    unsigned& thj) {
+__device__ __forceinline__ void pair_exact(double4 const* __restrict__ pos, double xi, double yi, double zi, double gi, double xj, double yj,
+    double zj, double gj, double eps2, int iidx, int jidx, unsigned long long& bi, unsigned long long& bj, unsigned lgi, unsigned lgj,
+    unsigned& thi, unsigned& thj) {
     double dx = xj - xi, dy = yj - yi, dz = zj - zi;
     double r2 = fma(dx, dx, eps2);
     r2 = fma(dy, dy, r2);
@@ -177,19 +208,25 @@ __device__ __forceinline__ void pair_exact(double xi, double yi, double zi, doub
         double w = fma(1.875, e, 1.5);
         double we = w * e;
         double u = fma(c, we, c);
+        // ranked on gf_p |d|^-3 (1/r) with the REFINED reciprocal (relative error ~1e-15), not on the raw seed: two heavier
+        // partners within 1e-6 of each other must not swap (the filter's margin covers the seed's error: it only decides
+        // who gets here)
+        double const yr = fma(y0 * e, fma(0.375, e, 0.5), y0);
         if (pi) {
             double si = gj * u;
-            unsigned long long const k = pack_key(si * y0, jidx);
-            if (k > bi) {
-                bi = k;
-                thi = max(thi, key_thr(k));
+            unsigned long long const k = pack_key(si * yr, jidx);
+            unsigned long long const nb_ = key_merge(pos, iidx, bi, k, eps2);
+            if (nb_ != bi) {
+                bi = nb_;
+                thi = max(thi, key_thr(nb_));
             }
         } else {
             double sj = gi * u;
-            unsigned long long const k = pack_key(sj * y0, iidx);
-            if (k > bj) {
-                bj = k;
-                thj = max(thj, key_thr(k));
+            unsigned long long const k = pack_key(sj * yr, iidx);
+            unsigned long long const nb_ = key_merge(pos, jidx, bj, k, eps2);
+            if (nb_ != bj) {
+                bj = nb_;
+                thj = max(thj, key_thr(nb_));
             }
         }
     }
@@ -332,7 +369,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                             for (int q = 0; q < kPRJ; q++)
 #pragma unroll
                                 for (int r = 0; r < kPRI; r++)
-                                    pair_exact<false>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
+                                    pair_exact<false>(A.pos, xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
                                         jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q], thi[r], thj[q]);
 #pragma unroll
                             for (int q = 0; q < kPRJ; q++) {
@@ -378,7 +415,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                             for (int q = 0; q < kPRJ; q++)
 #pragma unroll
                                 for (int r = 0; r < kPRI; r++)
-                                    pair_exact<true>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
+                                    pair_exact<true>(A.pos, xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
                                         jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q], thi[r], thj[q]);
 #pragma unroll
                             for (int q = 0; q < kPRJ; q++) {
@@ -420,7 +457,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                         unsigned long long k = 0ull;
 #pragma unroll
                         for (int w = 0; w < 8; w++)
-                            k = key_max(k, acck[(size_t)w * kPHalf + j]);
+                            k = key_merge(A.pos, J * kPB + half * kPHalf + j, k, acck[(size_t)w * kPHalf + j], A.eps2);
                         __stcg(slotk + j, k);
                     }
                 }
@@ -453,7 +490,9 @@ struct PairFinishArgs {
     double const* ajred; // sharded: [3][npad] J-side sums already reduced over ranks (slots are skipped)
     unsigned long long const* part_k;  // ARGMAX: I-side candidate keys [S][npad]
     unsigned long long const* slots_k; // ARGMAX: J-side candidate keys per tile
-    unsigned long long const* akred;   // sharded ARGMAX: [npad] J-side keys already max-reduced over ranks
+    unsigned long long const* akred;   // sharded ARGMAX: [world][i1 - i0] every rank's J-side key for this rank's bodies (an
+                                       // ncclMax over the ranks could not re-decide two keys that differ in the index only)
+    int world;
     int argmax;          // most-attracting tracking with real candidates (keys)
     int argmax_noop;     // most-attracting tracking requested on a world of equal gravity factors: clear_forces only
     int save_old;        // ... and Object::before_update's old_most = most
@@ -484,7 +523,8 @@ __device__ __forceinline__ void slot_sum(int g, int nb, int dmax, int ib0, int i
 
 // J-side candidate keys of body g from the tiles whose I block lies in [ib0, ib1).
 template<int kPB>
-__device__ __forceinline__ unsigned long long slot_key(int g, int nb, int dmax, int ib0, int ib1, unsigned long long const* slots_k) {
+__device__ __forceinline__ unsigned long long slot_key(int g, int nb, int dmax, int ib0, int ib1, unsigned long long const* slots_k,
+    double4 const* __restrict__ pos, double eps2) {
     int const K = g / kPB, jl = g - K * kPB;
     unsigned long long k = 0ull;
     for (int d = 1; d <= dmax; d++) {
@@ -495,7 +535,7 @@ __device__ __forceinline__ unsigned long long slot_key(int g, int nb, int dmax, 
             continue;
         if ((nb & 1) == 0 && d == nb / 2 && I >= nb / 2)
             continue;
-        k = key_max(k, __ldcg(slots_k + ((size_t)(I - ib0) * dmax + (d - 1)) * kPB + jl));
+        k = key_merge(pos, g, k, __ldcg(slots_k + ((size_t)(I - ib0) * dmax + (d - 1)) * kPB + jl), eps2);
     }
     return k;
 }
@@ -503,7 +543,7 @@ __device__ __forceinline__ unsigned long long slot_key(int g, int nb, int dmax, 
 // Sharded worlds: this rank's J-side sums for EVERY body, to be reduce-scattered over the ranks.
 template<int kPB>
 __global__ void __launch_bounds__(256) k_pair_gather_slots(int nb, int dmax, int ib0, int ib1, int npad, double const* slots,
-    double* acc, unsigned long long const* slots_k, unsigned long long* kacc) {
+    double* acc, unsigned long long const* slots_k, unsigned long long* kacc, double4 const* __restrict__ pos, double eps2) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= npad)
         return;
@@ -513,7 +553,7 @@ __global__ void __launch_bounds__(256) k_pair_gather_slots(int nb, int dmax, int
     acc[(size_t)npad + g] = ay;
     acc[2 * (size_t)npad + g] = az;
     if (kacc)
-        kacc[g] = slot_key<kPB>(g, nb, dmax, ib0, ib1, slots_k);
+        kacc[g] = slot_key<kPB>(g, nb, dmax, ib0, ib1, slots_k, pos, eps2);
 }
 
 // Guarded one-sided sum over all n sources for the body of thread `t` of this block (its acceleration came out
@@ -594,9 +634,14 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
         act = W.active[g] != 0;
         p = W.pos_cur[g];
         if (act && A.argmax) {
-            key = A.akred ? __ldcg(A.akred + g) : slot_key<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots_k);
+            if (A.akred) {
+                for (int r = 0; r < A.world; r++)
+                    key = key_merge(W.pos_cur, g, key, __ldcg(A.akred + (size_t)r * (A.i1 - A.i0) + (g - A.i0)), A.eps2);
+            } else {
+                key = slot_key<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots_k, W.pos_cur, A.eps2);
+            }
             for (int c = 0; c < A.S; c++)
-                key = key_max(key, __ldcg(A.part_k + (size_t)c * A.npad + g));
+                key = key_merge(W.pos_cur, g, key, __ldcg(A.part_k + (size_t)c * A.npad + g), A.eps2);
         }
     }
     // ---- repair: bodies that met a coincident partner in an unguarded tile (see pair_interact), and bodies whose
@@ -834,7 +879,7 @@ static cudaError_t launch_pair_kernels(essa_ctx* c, PairArgs const& A, cudaStrea
         if (ARGMAX)
             *kacc = c->pair_kpart + (size_t)A.S * A.npad;
         k_pair_gather_slots<PB><<<(A.npad + 255) / 256, 256, 0, st>>>(A.nb, A.dmax, A.ib0, A.ib1, A.npad, c->pair_slots, *acc,
-            c->pair_kslots, *kacc);
+            c->pair_kslots, *kacc, A.pos, A.eps2);
         c->launches++;
         e = cudaGetLastError();
     }
@@ -962,6 +1007,7 @@ cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStrea
     F.slots_k = c->pair_kslots;
     F.prior = c->pair_prior;
     F.akred = akred;
+    F.world = c->world;
     F.save_old = save_old ? 1 : 0;
     F.eps2 = eps2;
     F.scale = pair_uniform(c) && !argmax ? c->gf_uniform_value : 1.0;

@@ -15,6 +15,8 @@
 //
 // K6 -- the same recording as a kernel of its own for the tiled path (one thread per tracked
 // body), plus the constructor-time pushes (src/Object.cpp:32-43).
+#include <algorithm>
+
 #include "common.cuh"
 #include "ctx.hpp"
 #include "record.cuh"
@@ -178,9 +180,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_resident(ResidentArgs const A) {
 }
 
 // ---- K6: recording for the tiled path ------------------------------------------------------------
-__global__ void k_record(WorldPtrs const W, RecordPtrs const R, int offset_trails, int forward_sim) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= R.tracked || !W.active[k])
+// Sharded contexts record the tracked bodies they OWN ([i0, i1), essa_shard_range): only their velocity, links and ap / pe are
+// current on this rank (positions of every body are: the most-attracting object may live anywhere).
+__global__ void k_record(WorldPtrs const W, RecordPtrs const R, int offset_trails, int forward_sim, int i0, int i1) {
+    int k = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= i1 || k >= R.tracked || !W.active[k])
         return;
     BodyRec b;
     rec_load(R, k, b);
@@ -240,9 +244,11 @@ RecordPtrs record_ptrs(essa_ctx* c) {
 }
 
 cudaError_t launch_record(essa_ctx* c, int offset_trails, int forward_simulated, cudaStream_t st) {
-    if (c->tracked <= 0)
+    int const i0 = (int)((long long)c->n * c->rank / c->world);
+    int const i1 = std::min(c->tracked, (int)((long long)c->n * (c->rank + 1) / c->world));
+    if (i1 <= i0)
         return cudaSuccess;
-    k_record<<<(c->tracked + 127) / 128, 128, 0, st>>>(world_ptrs(c), record_ptrs(c), offset_trails, forward_simulated);
+    k_record<<<(i1 - i0 + 127) / 128, 128, 0, st>>>(world_ptrs(c), record_ptrs(c), offset_trails, forward_simulated, i0, i1);
     c->launches++;
     return cudaGetLastError();
 }

@@ -31,6 +31,8 @@
 // consumers' last step, then writes the packed state to the host as self-validating 64-bit words {sequence number,
 // 32 bits of payload} (what NCCL's LL protocol does over PCIe): no system-wide fence, no separate
 // acknowledgement -- the host has a tick's result when every word carries the tick's number.
+#include <type_traits>
+
 #include "common.cuh"
 #include "ctx.hpp"
 #include "record.cuh"
@@ -38,9 +40,22 @@
 
 namespace essa {
 
+#ifndef ESSA_POLL_DEPTH
+#define ESSA_POLL_DEPTH 1 // reads of the host's command word in flight.  Measured on B200 (PCIe Gen5 host): ONE read at a time sees
+#endif                    // a doorbell ~1.2 us after it was rung; four staggered reads of the same word took ~5 us (they do not
+                          // pipeline: each waits for the one before it at the host bridge), so the deeper variant is a dead end kept
+                          // for the record
+#ifndef ESSA_PUB_MODE
+#define ESSA_PUB_MODE 0 // how a tick's result reaches the host: 0 = self-validating 64-bit words (sys-scope stores), 1 = the same with
+#endif                  // weak stores, 2 = plain stores + system fence + acknowledgement word (capi.cu reads the same macro)
+
 constexpr int kQuadWarps = 4;
-constexpr int kHistWarp = 2, kAppeWarp = 3, kPubWarp = 4; // CTA 1
-constexpr int kQuadThreads = 32 * 5;
+// CTA 0: warps 0-3 physics, 4 courier, 5 poller.  CTA 1: warps 0-2 attraction, 3-6 Trail, 7 links + History, 8 ap / pe, 9 publisher.
+constexpr int kCourierWarp = 4, kPollWarp = 5;
+constexpr int kAttrWarps = 3, kTrailWarp0 = 3, kTrailWarps = 4, kHistWarp = 7, kAppeWarp = 8, kPubWarp = 9;
+constexpr int kConsumers = kTrailWarps + 2;
+constexpr int kQuadThreads = 32 * 10;
+constexpr int kStage = 4; // physics -> courier staging buffers
 
 struct QSnap {
     double x[32], y[32], z[32], vx[32], vy[32], vz[32];
@@ -48,58 +63,121 @@ struct QSnap {
     unsigned long long mask; // active bodies
 };
 
-__device__ __forceinline__ void st_async_u32(uint32_t remote_addr, unsigned v, uint32_t remote_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v),
-                 "r"(remote_bar)
-                 : "memory");
-}
 __device__ __forceinline__ bool mbar_try(unsigned long long* bar, unsigned parity) {
     unsigned ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000) // parked for up to ~2 us per try
         : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned ld_acquire_cta_u32(unsigned const* p) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+// The same on 32-bit shared-window addresses formed ONCE outside the step loop: a generic pointer into the shared memory of a
+// cluster kernel is converted with a read of SR_CgaCtaId (tens of cycles) wherever it is used, and the step loop of the physics
+// warps is one dependent chain.
+// (... and the compiler re-materialises such an address inside the loop instead of keeping it in a register unless it cannot
+// see where the value comes from)
+__device__ __forceinline__ uint32_t keep_in_register(uint32_t a) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared::cta.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, unsigned v) { asm volatile("st.shared::cta.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned lds_acquire_u32(uint32_t a) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+
+struct Q0 { // CTA 0
+    double spos[kQuadWarps][4][32];            // per physics warp sx, sy, sz, sg (private copies)
+    double part[2][kQuadWarps][3][32];         // partial accelerations, double-buffered
+    double stage[kStage][9][32];               // x y z vx vy vz ax ay az of a step, for the courier
+    unsigned long long stagebar[kStage];       // physics warps 1-3 have written a staging buffer
+    unsigned long long cmdt0;                  // globaltimer at the doorbell
+    unsigned stage_mask[kStage];               // active bodies of that step
+    unsigned courier_done;                     // steps the courier has forwarded
+    unsigned fin_sent;                         // ticks whose final bundle has left
+    unsigned done[kConsumers];                 // steps consumed by CTA 1's warps 3 .. 8
+    unsigned cmdw[2];                          // poller -> physics / courier: steps granted so far, tick number
+};
+struct Q1 { // CTA 1
+    QSnap ring[kRing];
+    unsigned long long full[kRing], ready[kRing]; // snapshot arrived (transaction bytes) / winners known
+    unsigned long long finbar, outbar;         // bundle arrived / consumers finished the last step
+    unsigned long long fin_meta[2];            // globaltimer at the doorbell, tick number
+    double sgf[32];                            // gravity factors
+    double fin[9][32];                         // x y z vx vy vz ax ay az as the tick left them
+    double outd[5][32];                        // max_attraction, ap, pe, ap_vel, pe_vel at the tick's end
+    int outmost[32];                           // most-attracting links at the tick's end
+    unsigned ctl[2];                           // steps granted so far, retire flag
+};
 
 template<int T, int LOG2L, bool ARG, bool PERSIST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_resident_quad(WarpArgs const A, PersistArgs const P) {
-    __shared__ double spos[kQuadWarps][4][32];            // CTA 0: per physics warp sx, sy, sz, sg (private copies)
-    __shared__ double part[2][kQuadWarps][4][32];         // CTA 0: partial accelerations + candidate keys, double-buffered
-    __shared__ unsigned done[4];                          // CTA 0: steps consumed by CTA 1's warps 0 .. 3
-    __shared__ unsigned cmdw[2];                          // CTA 0: poller -> physics warps: steps granted so far, tick number
-    __shared__ unsigned long long cmdt0;                  // CTA 0: globaltimer at the doorbell
-    __shared__ __align__(16) QSnap ring[kRing];           // CTA 1
-    __shared__ __align__(8) unsigned long long full[kRing]; // CTA 1: a slot's snapshot has arrived (transaction bytes)
-    __shared__ double sgf[32];                            // CTA 1: gravity factors
-    __shared__ unsigned ctl[2];                           // CTA 1: steps granted so far, retire flag
-    __shared__ double fin[9][32];                         // CTA 1: x y z vx vy vz ax ay az as the tick left them
-    __shared__ unsigned long long fin_meta[2];            // CTA 1: globaltimer at the doorbell, tick number
-    __shared__ __align__(8) unsigned long long finbar, outbar; // CTA 1: bundle arrived / consumers finished the last step
-    __shared__ double outd[5][32];                        // CTA 1: max_attraction, ap, pe, ap_vel, pe_vel at the tick's end
-    __shared__ int outmost[32];                           // CTA 1: most-attracting links at the tick's end
+#ifdef ESSA_FORCE_STAGE
+    constexpr bool STAGE = true; // (diagnostics: what the staging costs the physics warps, in the flavour that needs none)
+#else
+    constexpr bool STAGE = ARG || PERSIST; // the physics warps hand every step's state to the courier
+#endif
+    // the two CTAs use disjoint sets of shared variables: one union, same offsets in both (mapa needs that)
+    __shared__ __align__(16) union QShared {
+        Q0 a;
+        Q1 b;
+    } S;
+    auto& spos = S.a.spos;
+    auto& part = S.a.part;
+    auto& stage = S.a.stage;
+    auto& stage_mask = S.a.stage_mask;
+    auto& stagebar = S.a.stagebar;
+    auto& courier_done = S.a.courier_done;
+    auto& fin_sent = S.a.fin_sent;
+    auto& done = S.a.done;
+    auto& cmdw = S.a.cmdw;
+    auto& cmdt0 = S.a.cmdt0;
+    auto& ring = S.b.ring;
+    auto& full = S.b.full;
+    auto& ready = S.b.ready;
+    auto& sgf = S.b.sgf;
+    auto& ctl = S.b.ctl;
+    auto& fin = S.b.fin;
+    auto& fin_meta = S.b.fin_meta;
+    auto& finbar = S.b.finbar;
+    auto& outbar = S.b.outbar;
+    auto& outd = S.b.outd;
+    auto& outmost = S.b.outmost;
 
     int const n = A.n;
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned const cta = cluster_ctarank();
     bool const rec_on = A.record != 0;
-    bool const snap_on = ARG; // recording implies tracking
-    unsigned const snap_bytes = (unsigned)n * 48u + 8u + (ARG ? (unsigned)n * 4u : 0u);
+    constexpr bool snap_on = ARG; // recording implies tracking
+    unsigned const snap_bytes = (unsigned)n * 48u + 8u;
     unsigned const fin_bytes = (unsigned)n * 72u + 16u;
     unsigned const nout = (snap_on ? 1u : 0u) + (rec_on ? 1u : 0u); // consumer warps that report a tick's end
 
     if (threadIdx.x == 0) {
         if (cta == 1) {
-            for (int i = 0; i < kRing; i++)
+            for (int i = 0; i < kRing; i++) {
                 mbar_init(&full[i], 1);
+                mbar_init(&ready[i], kAttrWarps);
+            }
             mbar_init(&finbar, 1);
             mbar_init(&outbar, nout ? nout : 1u);
             mbar_fence_init();
@@ -109,7 +187,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
             ctl[0] = (unsigned)A.steps;
             ctl[1] = 0;
         } else {
-            done[0] = done[1] = done[2] = done[3] = 0;
+            for (int i = 0; i < kStage; i++)
+                mbar_init(&stagebar[i], kQuadWarps);
+            mbar_fence_init();
+            for (int i = 0; i < kConsumers; i++)
+                done[i] = 0;
+            courier_done = 0;
+            fin_sent = 0;
         }
     }
     if (cta == 1 && threadIdx.x < 32) {
@@ -128,42 +212,110 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
     __syncthreads();
     cluster_sync_all();
 
-    if (cta == 1 && warp <= kAppeWarp) {
-        // ---------------- consumer warps: 0, 1 Trail; 2 links + History; 3 ap / pe ----------------
-        // Every consumer follows the most-attracting links itself (a few integer instructions per step).
-        if (snap_on && (warp == kHistWarp || rec_on)) {
+    // persistent mode, CTA 1: wait until steps beyond `end` are granted (the doorbell, forwarded by CTA 0); false: retire
+    auto more_steps = [&](int s, int& end) {
+        if constexpr (PERSIST) {
+            bool quit;
+            for (;;) {
+                end = (int)ld_acquire_cluster_u32(&ctl[0]);
+                quit = ld_acquire_cluster_u32(&ctl[1]) != 0;
+                if (s < end || quit)
+                    break;
+                __nanosleep(64); // (a spinning warp would take issue slots from the warps that still work)
+            }
+        }
+        return s < end;
+    };
+
+    if (cta == 1 && warp < kAttrWarps) {
+        // ---------------- attraction warps: the step's most-attracting candidates (src/Object.cpp:84-94) ----------------
+        // Which heavier body pulls hardest on body k depends only on the step's final positions and never feeds back into
+        // the trajectory.  The three warps share the bodies of ONE step (a third each; a lane is a partner, four bodies in
+        // flight at a time), so a step's winners are known a few hundred cycles after its snapshot landed; the one
+        // sequential piece -- "keep the previous link when there is no candidate" -- is a register in the consumer warps.
+        // Candidates are ranked by gf_p y0^4 (1 + 2 e) ~ gf_p / r^4 (y0: rsqrt seed, e = 1 - r^2 y0^2; relative error
+        // ~1e-11) as sortable keys -- bit pattern with the 5 lowest mantissa bits replaced by 31 - p -- and the winner of a
+        // body comes from two full-warp integer reductions (redux.sync; with a partial mask the intrinsic is a loop);
+        // max_attraction is formed to full precision for a tick's final state only.
+        if (snap_on) {
+            int const per_w = (n + kAttrWarps - 1) / kAttrWarps; // bodies per warp
+            int const k0 = warp * per_w, k1 = min(n, k0 + per_w);
+            int const p = lane;                                   // a lane is a partner
+            int const pc = p < n ? p : 0;
+            double const gp = sgf[pc];
+            int end = A.steps;
+            for (int s = 0;; s++) {
+                if (s >= end && !more_steps(s, end))
+                    break;
+                int const slot = s % kRing;
+                mbar_wait(&full[slot], (unsigned)(s / kRing) & 1u);
+                if (warp == 0 && lane == 0)
+                    mbar_expect_tx(&full[slot], snap_bytes); // armed for the slot's next use (16 steps from now)
+                QSnap& sn = ring[slot];
+                unsigned const amask = (unsigned)sn.mask;
+                bool const inp = p < n && ((amask >> p) & 1u);
+                double const xp = sn.x[pc], yp = sn.y[pc], zp = sn.z[pc];
+                for (int kb = k0; kb < k1; kb += 4) {
+                    unsigned hi[4], lo[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { // four bodies at a time: independent chains
+                        int const k = min(kb + u, n - 1);
+                        double const gfk = sgf[k];
+                        bool const ok = inp && p != k && gp > gfk;
+                        double const dx = xp - sn.x[k], dy = yp - sn.y[k], dz = zp - sn.z[k];
+                        double const r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                        double const y0 = rsqrt_seed(r2);
+                        double const y2 = y0 * y0;
+                        double const e = fma(-r2, y2, 1.0);
+                        double const t4 = gp * (y2 * y2);
+                        double const m = fma(t4, e + e, t4);
+                        unsigned const mh = (unsigned)__double2hiint(m), ml = (unsigned)__double2loint(m);
+                        bool const cand = ok && (mh | ml) != 0u;
+                        hi[u] = cand ? mh : 0u;
+                        lo[u] = cand ? ((ml & ~31u) | (unsigned)(31 - p)) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        unsigned const mh = __reduce_max_sync(0xffffffffu, hi[u]);
+                        unsigned const ml = __reduce_max_sync(0xffffffffu, hi[u] == mh ? lo[u] : 0u);
+                        int const k = kb + u;
+                        if (lane == 0 && k < k1)
+                            sn.win[k] = ((mh | ml) != 0u && ((amask >> k) & 1u)) ? 31 - (int)(ml & 31u) : -1;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&ready[slot]);
+            }
+        }
+    } else if (cta == 1 && warp <= kAppeWarp) {
+        // ---------------- consumer warps: 3 .. 6 Trail (bodies by index mod 4); 7 links + History; 8 ap / pe ----------------
+        // Every consumer follows the most-attracting links itself (a few integer instructions per step).  One copy of the loop
+        // per role (ROLE is a compile-time constant in each): a step costs a warp ~5 cycles per instruction and ~20 per taken
+        // branch, and only the links + ap / pe warps are waited for at a tick's end (the Trail warps may lag up to the depth of
+        // the ring and catch up while the host reads the tick).
+        auto consumer = [&](auto role) {
+            constexpr int ROLE = decltype(role)::value; // 0: Trail, 1: links + History, 2: ap / pe
             bool const body = lane < n;
-            bool const is_trail = warp < kHistWarp;
-            bool const mine = rec_on && body && lane < A.r.tracked && (!is_trail || (lane & 1) == warp);
-            uint32_t const done_remote = mapa_u32(&done[warp], 0);
+            bool const mine = rec_on && body && lane < A.r.tracked && (ROLE != 0 || (lane & (kTrailWarps - 1)) == (warp - kTrailWarp0));
+            uint32_t const done_remote = mapa_u32(&done[warp - kTrailWarp0], 0);
             BodyRec b;
             if (mine)
                 rec_load(A.r, lane, b);
             int most = body ? A.w.most[lane] : -1, old_most = body ? A.w.old_most[lane] : -1;
-            double maxattr = (warp == kHistWarp && body) ? A.w.maxattr[lane] : 0.0;
+            double maxattr = (ROLE == 1 && body) ? A.w.maxattr[lane] : 0.0;
             bool const offset_trails = A.offset_trails != 0, forward_sim = A.forward_sim != 0;
 #ifdef ESSA_STAGE_CLOCKS
             long long busy = 0;
 #endif
             int end = A.steps; // steps granted so far (persistent mode: grows with every doorbell)
             for (int s = 0;; s++) {
-                if (s >= end) {
-                    if constexpr (PERSIST) { // wait for the next doorbell (forwarded by CTA 0), or for the order to retire
-                        bool quit;
-                        do {
-                            end = (int)ld_acquire_cluster_u32(&ctl[0]);
-                            quit = ld_acquire_cluster_u32(&ctl[1]) != 0;
-                        } while (s >= end && !quit);
-                    }
-                    if (s >= end)
-                        break;
-                }
+                if (s >= end && !more_steps(s, end))
+                    break;
                 // the host extends `end` only after it has this tick's result, i.e. after this warp reported its last step
                 bool const last = s == end - 1;
                 int const slot = s % kRing;
-                mbar_wait(&full[slot], (unsigned)(s / kRing) & 1u);
-                if (warp == kHistWarp && lane == 0)
-                    mbar_expect_tx(&full[slot], snap_bytes); // armed for the slot's next use (16 steps from now)
+                mbar_wait(&ready[slot], (unsigned)(s / kRing) & 1u);
 #ifdef ESSA_STAGE_CLOCKS
                 long long t0 = clock64();
 #endif
@@ -175,28 +327,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                     most = winner;
                 if (mine && act) {
                     int const mi = most >= 0 ? most : 0;
-                    double const mx = sn.x[mi], my = sn.y[mi], mz = sn.z[mi];
-                    if (is_trail)
-                        record_trail(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], mx, my, mz, most,
-                            old_most, offset_trails, forward_sim, false);
-                    else if (warp == kHistWarp) {
+                    if (ROLE == 0)
+                        record_trail(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], sn.x[mi], sn.y[mi],
+                            sn.z[mi], most, old_most, offset_trails, forward_sim, false);
+                    else if (ROLE == 1) {
                         if (!forward_sim)
                             history_push(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane]);
                     } else
-                        record_appe(b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], mx, my, mz, most);
+                        record_appe(b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], sn.x[mi], sn.y[mi], sn.z[mi],
+                            most);
                 }
-                if (warp == kHistWarp && last && act) {
+                if (ROLE == 1 && last && act) {
                     // max_attraction as the last force pass left it: the winner's gf / r^4 to full precision, or 0
                     maxattr = winner >= 0 ? attraction_metric(sn.x[lane], sn.y[lane], sn.z[lane], sn.x[winner], sn.y[winner], sn.z[winner],
                                                 sgf[winner])
                                           : 0.0;
                 }
-                if (PERSIST && last) { // what the host reads back after the tick: handed to the publisher warp
-                    if (warp == kHistWarp && body) {
+                if (PERSIST && ROLE != 0 && last) { // what the host reads back after the tick: handed to the publisher warp
+                    if (ROLE == 1 && body) {
                         outd[0][lane] = maxattr;
                         outmost[lane] = most;
                     }
-                    if (warp == kAppeWarp && mine) {
+                    if (ROLE == 2 && mine) {
                         ap_flush(b);
                         pe_flush(b);
                         outd[1][lane] = b.ap;
@@ -210,7 +362,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                 busy += clock64() - t0;
 #endif
                 if (lane == 0) {
-                    if (PERSIST && last && warp >= kHistWarp)
+                    if (PERSIST && ROLE != 0 && last)
                         mbar_arrive(&outbar);
                     st_relaxed_cluster_u32(done_remote, (unsigned)(s + 1));
                 }
@@ -219,28 +371,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
             if (lane == 0)
                 printf("consumer warp %d: %lld busy clk/step\n", warp, busy / max(end, 1));
 #endif
-            if (warp == kHistWarp && body) {
+            if (ROLE == 1 && body) {
                 A.w.most[lane] = most;
                 A.w.old_most[lane] = old_most;
                 A.w.maxattr[lane] = maxattr;
             }
             if (mine) {
-                if (is_trail) {
+                if (ROLE == 0) {
                     rec_store_trail(A.r, lane, b, false);
-                } else if (warp == kHistWarp) {
+                } else if (ROLE == 1) {
                     A.r.hist_start[lane] = b.hist_start;
                     A.r.hist_len[lane] = b.hist_len;
                 } else {
                     rec_store_appe(A.r, lane, b);
                 }
             }
+        };
+        if (snap_on && (warp == kHistWarp || rec_on)) {
+            if (warp == kHistWarp)
+                consumer(std::integral_constant<int, 1> {});
+            else if (warp == kAppeWarp)
+                consumer(std::integral_constant<int, 2> {});
+            else
+                consumer(std::integral_constant<int, 0> {});
         }
     } else if (PERSIST && cta == 1 && warp == kPubWarp) {
         // ---------------- publisher ----------------
         // Word w of the host buffer carries 32 bits of payload under the tick's number: fields x y z vx vy vz ax ay az
         // max_attraction ap pe ap_vel pe_vel as (low, high) halves of body 0, 1, ..., then the links, then the device
         // nanoseconds between doorbell and publication.
-        int const words_d = 28 * n, words = words_d + n + 2;
+        int const words_d = 28 * n;
         for (unsigned tick = 0;; tick++) {
             bool quit = false;
             while (!mbar_try(&finbar, tick & 1u)) {
@@ -255,25 +415,230 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                 mbar_expect_tx(&finbar, fin_bytes); // armed for the next tick's bundle
             if (nout)
                 mbar_wait(&outbar, tick & 1u);
-            unsigned long long const tag = (unsigned long long)(unsigned)fin_meta[1] << 32;
+            unsigned const seq = (unsigned)fin_meta[1];
+            unsigned long long const tag = (unsigned long long)seq << 32;
             unsigned long long const t0 = fin_meta[0];
-            for (int w = lane; w < words; w += 32) {
-                unsigned v;
-                if (w < words_d) {
-                    int const f = w / (2 * n), r = w - f * 2 * n, k = r >> 1;
-                    double const d = f < 9 ? fin[f][k] : outd[f - 9][k];
-                    v = (r & 1) ? (unsigned)__double2hiint(d) : (unsigned)__double2loint(d);
-                } else if (w < words_d + n) {
-                    v = (unsigned)outmost[w - words_d];
-                } else {
-                    unsigned long long const dtn = globaltimer_ns() - t0;
-                    v = w == words_d + n ? (unsigned)dtn : (unsigned)(dtn >> 32);
+#if ESSA_PUB_MODE == 2
+            // plain coalesced stores of the packed state, one system-wide fence, then the acknowledgement
+            {
+                double* const od = reinterpret_cast<double*>(P.out);
+                size_t const N = (size_t)n;
+                if (lane < n) {
+#pragma unroll
+                    for (int f = 0; f < 14; f++)
+                        od[(size_t)(f < 9 ? f : f + 1) * N + lane] = f < 9 ? fin[f][lane] : outd[f - 9][lane];
+                    reinterpret_cast<int*>(od + 17 * N)[lane] = outmost[lane];
                 }
-                st_relaxed_sys_u64(P.out + w, tag | v);
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0) {
+                    unsigned long long const dtn = globaltimer_ns() - t0;
+                    st_relaxed_sys_u32(P.ack + 2, (unsigned)dtn);
+                    st_relaxed_sys_u32(P.ack + 3, (unsigned)(dtn >> 32));
+                    st_relaxed_sys_u32(P.ack, seq);
+                }
             }
+#else
+            // a lane is (body, half) of a field: no division, 14 coalesced stores of 2 n words
+            for (int h = 0; h < 2; h++) {
+                int const r = lane + 32 * h;
+                if (r < 2 * n) {
+                    int const k = r >> 1;
+#pragma unroll
+                    for (int f = 0; f < 14; f++) {
+                        double const d = f < 9 ? fin[f][k] : outd[f - 9][k];
+                        unsigned const v = (r & 1) ? (unsigned)__double2hiint(d) : (unsigned)__double2loint(d);
+#if ESSA_PUB_MODE == 1
+                        P.out[f * 2 * n + r] = tag | v;
+#else
+                        st_relaxed_sys_u64(P.out + f * 2 * n + r, tag | v);
+#endif
+                    }
+                }
+            }
+            if (lane < n)
+                st_relaxed_sys_u64(P.out + words_d + lane, tag | (unsigned)outmost[lane]);
+            if (lane == 0) {
+                unsigned long long const dtn = globaltimer_ns() - t0;
+                st_relaxed_sys_u64(P.out + words_d + n, tag | (unsigned)dtn);
+                st_relaxed_sys_u64(P.out + words_d + n + 1, tag | (unsigned)(dtn >> 32));
+            }
+#endif
+        }
+    } else if (STAGE && cta == 0 && warp == kCourierWarp) {
+        // ---------------- courier: forwards what the physics warps staged, so that they never issue a remote store ----------------
+        uint32_t const full_remote = mapa_u32(&full[0], 1);
+        uint32_t const ring_remote = mapa_u32(&ring[0], 1);
+        uint32_t const fr = mapa_u32(&fin[0][0], 1) + 8u * (uint32_t)lane, fb = mapa_u32(&finbar, 1), fm = mapa_u32(&fin_meta[0], 1);
+        int consumed = 0; // cached lower bound of the steps CTA 1 has finished with
+        int s = 0, end = A.steps;
+        unsigned seq = P.seq0;
+        unsigned long long tick_t0 = PERSIST ? globaltimer_ns() : 0ull;
+        for (;;) {
+            for (; s < end; s++) {
+                int const buf = s % kStage;
+                mbar_wait(&stagebar[buf], (unsigned)(s / kStage) & 1u);
+                bool const tick_end = PERSIST && s == end - 1;
+                double v[9];
+#pragma unroll
+                for (int c = 0; c < 6; c++)
+                    v[c] = stage[buf][c][lane];
+#pragma unroll
+                for (int c = 6; c < 9; c++)
+                    v[c] = tick_end ? stage[buf][c][lane] : 0.0;
+                unsigned const amask = stage_mask[buf];
+                __syncwarp();
+                if (lane == 0)
+                    st_release_cta_u32(&courier_done, (unsigned)(s + 1)); // the buffer may be rewritten
+                if (snap_on) {
+                    int const slot = s % kRing;
+                    if (s - consumed >= kRing) { // the slot may still be in use: look at CTA 1's progress
+                        do {
+                            consumed = (int)ld_acquire_cluster_u32(&done[kHistWarp - kTrailWarp0]);
+                            if (rec_on) {
+#pragma unroll
+                                for (int i = 0; i < kConsumers; i++)
+                                    if (i != kHistWarp - kTrailWarp0)
+                                        consumed = min(consumed, (int)ld_acquire_cluster_u32(&done[i]));
+                            }
+                        } while (s - consumed >= kRing);
+                    }
+                    uint32_t const dst = ring_remote + (uint32_t)slot * (uint32_t)sizeof(QSnap) + 8u * (uint32_t)lane;
+                    uint32_t const bar = full_remote + 8u * (uint32_t)slot;
+                    if (lane < n) {
+#pragma unroll
+                        for (int c = 0; c < 6; c++)
+                            st_async_f64(dst + 256u * c, v[c], bar);
+                    }
+                    if (lane == 0)
+                        st_async_u64(ring_remote + (uint32_t)slot * (uint32_t)sizeof(QSnap) + (uint32_t)offsetof(QSnap, mask),
+                            (unsigned long long)amask, bar);
+                }
+                if (tick_end) { // the tick's final state, for the publisher
+                    if (lane < n) {
+#pragma unroll
+                        for (int c = 0; c < 9; c++)
+                            st_async_f64(fr + 256u * c, v[c], fb);
+                    }
+                    if (lane == 0) {
+                        st_async_u64(fm, tick_t0, fb);
+                        st_async_u64(fm + 8u, (unsigned long long)seq, fb);
+                    }
+                }
+            }
+            if (!PERSIST)
+                break;
+            __syncwarp();
+            if (lane == 0)
+                st_release_cta_u32(&fin_sent, ld_acquire_cta_u32(&fin_sent) + 1u); // the poller's idle clock may start
+            asm volatile("bar.sync 3, 192;" ::: "memory");
+            if (cmdw[0] == (unsigned)end)
+                break; // retire
+            end = (int)cmdw[0];
+            seq = cmdw[1];
+            tick_t0 = cmdt0;
+        }
+    } else if (PERSIST && cta == 0 && warp == kPollWarp) {
+        // ---------------- poller: the host's doorbell ----------------
+        // One lane reads the command word over PCIe, one read in flight (see ESSA_POLL_DEPTH); on its own warp, so that the
+        // round trip never stalls a physics warp.
+        unsigned seq = P.seq0;
+        unsigned ticks = 1; // granted so far
+        int end = A.steps;
+        long long q = 0;
+        for (;;) {
+            unsigned long long c = 0ull;
+            bool idle = false;
+            if (lane == 0) { // one lane reads: 32 lanes reading the same word of system memory are 32 requests
+#if ESSA_POLL_DEPTH == 1
+                long long idle0 = 0;
+                for (;;) {
+                    c = ld_relaxed_sys_u64(P.cmd);
+                    if ((unsigned)(c >> 32) != seq)
+                        break;
+                    if (idle0 == 0) {
+                        if (ld_acquire_cta_u32(&fin_sent) == ticks)
+                            idle0 = clock64();
+                    } else if (clock64() - idle0 > P.idle_clk) {
+                        idle = true;
+                        break;
+                    }
+                }
+#else
+                unsigned long long c0, c1, c2, c3;
+                long long idle0 = 0;
+                long long t = clock64();
+                c0 = ld_relaxed_sys_u64(P.cmd);
+                if (q == 0 && (unsigned)(c0 >> 32) == seq) {
+                    q = (clock64() - t) >> 2; // (a returned value was consumed: this is one round trip)
+                    q = q < 700 ? q : 700;    // (the very first read of the page can take much longer than the rest)
+                    t = clock64();
+                    c0 = ld_relaxed_sys_u64(P.cmd);
+                }
+                while (clock64() - t < q) { }
+                c1 = ld_relaxed_sys_u64(P.cmd);
+                while (clock64() - t < 2 * q) { }
+                c2 = ld_relaxed_sys_u64(P.cmd);
+                while (clock64() - t < 3 * q) { }
+                c3 = ld_relaxed_sys_u64(P.cmd);
+                for (;;) {
+                    if ((unsigned)((c = c0) >> 32) != seq)
+                        break;
+                    c0 = ld_relaxed_sys_u64(P.cmd);
+                    if ((unsigned)((c = c1) >> 32) != seq)
+                        break;
+                    c1 = ld_relaxed_sys_u64(P.cmd);
+                    if ((unsigned)((c = c2) >> 32) != seq)
+                        break;
+                    c2 = ld_relaxed_sys_u64(P.cmd);
+                    if ((unsigned)((c = c3) >> 32) != seq)
+                        break;
+                    c3 = ld_relaxed_sys_u64(P.cmd);
+                    // the idle clock runs from the moment the tick in flight has left for the host
+                    if (idle0 == 0) {
+                        if (ld_acquire_cta_u32(&fin_sent) == ticks)
+                            idle0 = clock64();
+                    } else if (clock64() - idle0 > P.idle_clk) {
+                        idle = true;
+                        break;
+                    }
+                }
+#endif
+            }
+            c = __shfl_sync(0xffffffffu, c, 0);
+            idle = __shfl_sync(0xffffffffu, idle ? 1 : 0, 0) != 0;
+            unsigned const add = idle ? 0u : (unsigned)c; // steps of the new tick; 0: retire
+            if (lane == 0) {
+                cmdt0 = globaltimer_ns();
+                if (add == 0) { // (2: nobody rang for idle_clk cycles; the host starts another kernel when it comes back)
+                    st_relaxed_sys_u32(P.ack + 1, idle ? 2u : 1u);
+                    st_relaxed_cluster_u32(mapa_u32(&ctl[1], 1), 1u);
+                    cmdw[0] = (unsigned)end;
+                } else { // `add` more steps, for everybody
+                    cmdw[0] = (unsigned)end + add;
+                    cmdw[1] = (unsigned)(c >> 32);
+                    st_relaxed_cluster_u32(mapa_u32(&ctl[0], 1), (unsigned)end + add);
+                }
+            }
+            __syncwarp();
+            asm volatile("bar.arrive 3, 192;" ::: "memory");
+            if (add == 0)
+                break;
+            end += (int)add;
+            seq = (unsigned)(c >> 32);
+            ticks++;
+            // nothing to listen for until this tick has left for the host; asleep, this warp does not compete with physics
+            // warp 1 for their sub-partition's issue slots (measured: a spinning neighbour costs the chain ~300 cycles per step)
+            while (ld_acquire_cta_u32(&fin_sent) != ticks)
+                __nanosleep(200);
         }
     } else if (cta == 0 && warp < kQuadWarps) {
         // ---------------- physics warps 0 .. 3 ----------------
+        // One copy of the loop per warp (W is a compile-time constant in each): the step is one dependent chain issued by
+        // one warp, where a taken branch costs ~20 cycles -- selecting "what this warp stages" at run time cost 170 cycles
+        // per step (measured), three predicated stores in straight-line code cost ~20.
+        auto physics = [&](auto role) {
+        constexpr int W = decltype(role)::value;
         // Lane layout: PL = 2^LOG2L lanes per body in one contiguous group (lane = kb PL + qb), so that the group sum
         // is a shuffle butterfly: every lane ends with the same bits (a + b == b + a exactly).
         constexpr int PL = 1 << LOG2L;
@@ -281,10 +646,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
         bool const pworker = kb < n;
         bool const pleader = pworker && qb == 0;
         int const kc = pworker ? kb : 0;
-        double* const sx = spos[warp][0];
-        double* const sy = spos[warp][1];
-        double* const sz = spos[warp][2];
-        double* const sg = spos[warp][3];
+        double* const sx = spos[W][0];
+        double* const sy = spos[W][1];
+        double* const sz = spos[W][2];
+        double* const sg = spos[W][3];
         double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0;
         bool active = false, delf = false;
         long long cd = 0, dd = 0;
@@ -313,20 +678,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
         }
         __syncwarp();
 
-        // this warp's partner slots of this lane never change: indices, weights and who is heavier are loop invariants
+        // this warp's partner slots of this lane never change: indices and weights are loop invariants
         int pidx[T];
         double pgf[T];
-        bool heav[T];
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            int p = qb + (warp + kQuadWarps * t) * PL;
+            int p = qb + (W + kQuadWarps * t) * PL;
             bool in = p < n;
             pidx[t] = in ? p : kc; // out of range -> the self term, which vanishes
             pgf[t] = in ? sg[pidx[t]] : 0.0;
-            heav[t] = pgf[t] > gfk; // masked partners weigh 0: never heavier
         }
-        double* const my_part0 = &part[0][warp][0][kc];
-        double* const my_part1 = &part[1][warp][0][kc];
+        double* const my_part0 = &part[0][W][0][kc];
+        double* const my_part1 = &part[1][W][0][kc];
         double const* const all_part0 = &part[0][0][0][kc];
         double const* const all_part1 = &part[1][0][0][kc];
 
@@ -334,7 +697,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
         long long date = A.date;
         double const hm = A.hm, dtm = A.dtm;
         int par = 0;
-        int winner = -1; // the last force pass's most-attracting candidate of body kb
         // bit kb of the body mask <- bit (kb PL) of the leaders' ballot; it only changes with the date
         auto body_mask = [&]() {
             unsigned lead = __ballot_sync(0xffffffffu, pleader && active);
@@ -344,48 +706,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
             return m;
         };
         unsigned amask = body_mask();
-
-        // where this lane's part of a snapshot goes in CTA 1 (slot 0), and slot 0's mbarrier there
-        uint32_t const full_remote = mapa_u32(&full[0], 1);
-        uint32_t snap_remote = mapa_u32(&ring[0], 1);
-        if (warp == 1)
-            snap_remote += (uint32_t)offsetof(QSnap, x) + 8u * kc;
-        else if (warp == 2)
-            snap_remote += (uint32_t)offsetof(QSnap, vx) + 8u * kc;
-        else
-            snap_remote += (uint32_t)offsetof(QSnap, win) + 4u * kc;
-        uint32_t const mask_remote = mapa_u32(&ring[0].mask, 1);
-        int consumed = 0; // cached lower bound of the steps CTA 1 has finished with
+        int cdone = 0; // cached lower bound of the steps the courier has forwarded
+        // staging addresses of this lane (buffer 0): this warp's rows of stage[][9][32], column kb.  Warp 0 stages x y,
+        // warp 1 z vx, warp 2 vy vz, warp 3 the mask (and the accelerations at a tick's end)
+        uint32_t const stage_a = keep_in_register(smem_u32(&stage[0][W == 3 ? 6 : 2 * W][kc]));
+        uint32_t const mask_a = keep_in_register(smem_u32(&stage_mask[0])), sbar_a = keep_in_register(smem_u32(&stagebar[0])),
+                       cdone_a = keep_in_register(smem_u32(&courier_done));
 
         auto forces = [&]() {
             double fx[T], fy[T], fz[T];
-            unsigned long long key = 0ull;
 #pragma unroll
             for (int t = 0; t < T; t++) {
+                fx[t] = fy[t] = fz[t] = 0.0;
                 int const pc = pidx[t];
-                double const dx = sx[pc] - x, dy = sy[pc] - y, dz = sz[pc] - z;
-                double r2 = fma(dx, dx, A.eps2);
-                r2 = fma(dy, dy, r2);
-                r2 = fma(dz, dz, r2);
-                double const y0 = rsqrt_seed(r2);
-                double const y2 = y0 * y0; // exact: the seed has 21 significant bits
-                double const e = fma(-r2, y2, 1.0);
-                double const gy = pgf[t] * y0;
-                double const c0 = gy * y2;
-                double const w = fma(1.875, e, 1.5);
-                double const we = w * e;
-                double const sc = fma(c0, we, c0);
-                fx[t] = sc * dx;
-                fy[t] = sc * dy;
-                fz[t] = sc * dz;
-                if (ARG) {
-                    // |ta|^2 / gf_p = gf_p / r^4 = s (1/r), 1/r ~ y0 (1 + e/2); strictly heavier partners only; the
-                    // largest key is the largest metric and, among equal ones, the lowest index
-                    double const m = sc * fma(y0 * 0.5, e, y0);
-                    unsigned long long const mb = (unsigned long long)__double_as_longlong(m);
-                    unsigned long long const ku = (heav[t] && mb != 0ull) ? ((mb & ~31ull) | (unsigned long long)(31 - pc)) : 0ull;
-                    key = ku > key ? ku : key;
-                }
+                double4 qv = make_double4(sx[pc], sy[pc], sz[pc], pgf[t]);
+                fast_interact(x, y, z, qv, A.eps2, fx[t], fy[t], fz[t]);
             }
             double px = fx[0], py = fy[0], pz = fz[0];
 #pragma unroll
@@ -399,10 +734,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                 px += __shfl_xor_sync(0xffffffffu, px, off);
                 py += __shfl_xor_sync(0xffffffffu, py, off);
                 pz += __shfl_xor_sync(0xffffffffu, pz, off);
-                if (ARG) {
-                    unsigned long long const o = __shfl_xor_sync(0xffffffffu, key, off);
-                    key = o > key ? o : key;
-                }
             }
             double* const mine = par ? my_part1 : my_part0;
             double const* const all = par ? all_part1 : all_part0;
@@ -410,72 +741,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                 mine[0] = px;
                 mine[32] = py;
                 mine[64] = pz;
-                if (ARG)
-                    mine[96] = __longlong_as_double((long long)key);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            // part[par][w][c][k]: w stride 128 doubles, c stride 32
-            double tx = (all[0] + all[128]) + (all[256] + all[384]);
-            double ty = (all[32] + all[160]) + (all[288] + all[416]);
-            double tz = (all[64] + all[192]) + (all[320] + all[448]);
-            int win = -1;
-            if (ARG) {
-                unsigned long long k0 = (unsigned long long)__double_as_longlong(all[96]), k1 = (unsigned long long)__double_as_longlong(all[224]),
-                                   k2 = (unsigned long long)__double_as_longlong(all[352]), k3 = (unsigned long long)__double_as_longlong(all[480]);
-                k0 = k1 > k0 ? k1 : k0;
-                k2 = k3 > k2 ? k3 : k2;
-                k0 = k2 > k0 ? k2 : k0;
-                win = k0 != 0ull ? 31 - (int)(k0 & 31ull) : -1;
-            }
+            // part[par][w][c][k]: w stride 96 doubles, c stride 32
+            double tx = (all[0] + all[96]) + (all[192] + all[288]);
+            double ty = (all[32] + all[128]) + (all[224] + all[320]);
+            double tz = (all[64] + all[160]) + (all[256] + all[352]);
             par ^= 1;
             if (active) {
                 ax = tx;
                 ay = ty;
                 az = tz;
-                winner = win;
-            }
-        };
-
-        // four reads of the host's command word in flight, a quarter of the measured round trip apart: a doorbell is seen
-        // about half a one-way trip + an eighth of a round trip after it was rung
-        auto doorbell = [&](unsigned seq, bool& idle) -> unsigned long long {
-            long long t = clock64();
-            unsigned long long c0 = ld_relaxed_sys_u64(P.cmd);
-            if ((unsigned)(c0 >> 32) != seq)
-                return c0;
-            long long const q = (clock64() - t) >> 2; // (a returned value was consumed: this is one round trip)
-            unsigned long long c1, c2, c3;
-            t = clock64();
-            c0 = ld_relaxed_sys_u64(P.cmd);
-            while (clock64() - t < q) { }
-            c1 = ld_relaxed_sys_u64(P.cmd);
-            while (clock64() - t < 2 * q) { }
-            c2 = ld_relaxed_sys_u64(P.cmd);
-            while (clock64() - t < 3 * q) { }
-            c3 = ld_relaxed_sys_u64(P.cmd);
-            for (;;) {
-                if ((unsigned)(c0 >> 32) != seq)
-                    return c0;
-                c0 = ld_relaxed_sys_u64(P.cmd);
-                if ((unsigned)(c1 >> 32) != seq)
-                    return c1;
-                c1 = ld_relaxed_sys_u64(P.cmd);
-                if ((unsigned)(c2 >> 32) != seq)
-                    return c2;
-                c2 = ld_relaxed_sys_u64(P.cmd);
-                if ((unsigned)(c3 >> 32) != seq)
-                    return c3;
-                c3 = ld_relaxed_sys_u64(P.cmd);
-                if (clock64() - t > P.idle_clk) {
-                    idle = true;
-                    return 0ull;
-                }
             }
         };
 
         int s = 0, end = A.steps;
-        unsigned seq = P.seq0;
-        unsigned long long tick_t0 = PERSIST ? globaltimer_ns() : 0ull;
         for (;;) {
             for (; s < end; s++) {
                 if (A.date_step != 0) { // only when the active mask can flip during this call
@@ -489,10 +769,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                         acc_valid = false;
                         __syncwarp();
 #pragma unroll
-                        for (int t = 0; t < T; t++) {
-                            pgf[t] = (qb + (warp + kQuadWarps * t) * PL) < n ? sg[pidx[t]] : 0.0;
-                            heav[t] = pgf[t] > gfk;
-                        }
+                        for (int t = 0; t < T; t++)
+                            pgf[t] = (qb + (W + kQuadWarps * t) * PL) < n ? sg[pidx[t]] : 0.0;
                         amask = body_mask();
                     }
                 }
@@ -520,91 +798,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                     vz = __dadd_rn(vz, __dmul_rn(az, hm));
                 }
                 acc_valid = true;
-                if (snap_on && warp != 0) {
-                    int const slot = s % kRing;
-                    if (s - consumed >= kRing) { // the slot may still be in use: look at CTA 1's progress
-                        do {
-                            consumed = (int)ld_acquire_cluster_u32(&done[kHistWarp]);
-                            if (rec_on) {
-                                int const d0 = (int)ld_acquire_cluster_u32(&done[0]), d1 = (int)ld_acquire_cluster_u32(&done[1]),
-                                          d3 = (int)ld_acquire_cluster_u32(&done[3]);
-                                consumed = min(min(consumed, d0), min(d1, d3));
-                            }
-                        } while (s - consumed >= kRing);
+                if (STAGE) {
+                    // the step's state goes to a local staging buffer (two shared-memory stores per warp); the courier warp
+                    // forwards it to CTA 1
+                    unsigned const buf = (unsigned)s % kStage;
+                    if (s - cdone >= kStage) {
+                        do
+                            cdone = (int)lds_acquire_u32(cdone_a);
+                        while (s - cdone >= kStage);
                     }
-                    uint32_t const dst = snap_remote + (uint32_t)slot * (uint32_t)sizeof(QSnap);
-                    uint32_t const bar = full_remote + 8u * (uint32_t)slot;
-                    if (warp == 1) {
+                    uint32_t const a = stage_a + buf * (uint32_t)(9 * 32 * sizeof(double));
+                    if (W == 0) {
                         if (pleader) {
-                            st_async_f64(dst, x, bar);
-                            st_async_f64(dst + 256u, y, bar);
-                            st_async_f64(dst + 512u, z, bar);
+                            sts_f64(a, x);
+                            sts_f64(a + 256u, y);
                         }
-                    } else if (warp == 2) {
+                    } else if (W == 1) {
                         if (pleader) {
-                            st_async_f64(dst, vx, bar);
-                            st_async_f64(dst + 256u, vy, bar);
-                            st_async_f64(dst + 512u, vz, bar);
+                            sts_f64(a, z);
+                            sts_f64(a + 256u, vx);
+                        }
+                    } else if (W == 2) {
+                        if (pleader) {
+                            sts_f64(a, vy);
+                            sts_f64(a + 256u, vz);
                         }
                     } else {
-                        if (pleader)
-                            st_async_u32(dst, (unsigned)(active ? winner : -1), bar);
                         if (lane == 0)
-                            st_async_u64(mask_remote + (uint32_t)slot * (uint32_t)sizeof(QSnap), (unsigned long long)amask, bar);
+                            sts_u32(mask_a + 4u * buf, amask);
+                        if (PERSIST && s == end - 1 && pleader) { // the accelerations leave with a tick's final state only
+                            sts_f64(a, ax);
+                            sts_f64(a + 256u, ay);
+                            sts_f64(a + 512u, az);
+                        }
                     }
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive_a(sbar_a + 8u * buf);
                 }
             }
             if (!PERSIST)
                 break;
-            // ---------------- end of a tick: final state to the publisher, then wait for the next doorbell ----------------
-            {
-                uint32_t const fr = mapa_u32(&fin[0][0], 1) + 8u * (uint32_t)kc, fb = mapa_u32(&finbar, 1);
-                if (warp == 1 && pleader) {
-                    st_async_f64(fr, x, fb);
-                    st_async_f64(fr + 256u, y, fb);
-                    st_async_f64(fr + 512u, z, fb);
-                } else if (warp == 2 && pleader) {
-                    st_async_f64(fr + 768u, vx, fb);
-                    st_async_f64(fr + 1024u, vy, fb);
-                    st_async_f64(fr + 1280u, vz, fb);
-                } else if (warp == 3) {
-                    if (pleader) {
-                        st_async_f64(fr + 1536u, ax, fb);
-                        st_async_f64(fr + 1792u, ay, fb);
-                        st_async_f64(fr + 2048u, az, fb);
-                    }
-                    if (lane == 0) {
-                        uint32_t const fm = mapa_u32(&fin_meta[0], 1);
-                        st_async_u64(fm, tick_t0, fb);
-                        st_async_u64(fm + 8u, (unsigned long long)seq, fb);
-                    }
-                }
-            }
-            if (warp == 0 && lane == 0) {
-                bool idle = false;
-                unsigned long long const c = doorbell(seq, idle);
-                unsigned const add = (unsigned)c; // steps of the new tick; 0: retire
-                cmdt0 = globaltimer_ns();
-                if (add == 0) { // (2: nobody rang for idle_clk cycles; the host starts another kernel when it comes back)
-                    st_relaxed_sys_u32(P.ack + 1, idle ? 2u : 1u);
-                    st_relaxed_cluster_u32(mapa_u32(&ctl[1], 1), 1u);
-                    cmdw[0] = (unsigned)end;
-                } else { // `add` more steps, for everybody
-                    cmdw[0] = (unsigned)end + add;
-                    cmdw[1] = (unsigned)(c >> 32);
-                    st_relaxed_cluster_u32(mapa_u32(&ctl[0], 1), (unsigned)end + add);
-                }
-            }
+            // ---------------- end of a tick: wait for the next doorbell (poller warp) ----------------
             // (the next write to cmdw is a tick away: every step in between has a 128-thread barrier of its own)
-            asm volatile("bar.sync 3, 128;" ::: "memory");
+            asm volatile("bar.sync 3, 192;" ::: "memory");
             if (cmdw[0] == (unsigned)end)
                 break; // retire
             end = (int)cmdw[0];
-            seq = cmdw[1];
-            tick_t0 = cmdt0;
         }
 
-        if (warp == 0 && pleader) {
+        if (W == 0 && pleader) {
             A.w.pos_cur[kb] = make_double4(x, y, z, active ? gfk : 0.0);
             A.w.v[0][kb] = vx;
             A.w.v[1][kb] = vy;
@@ -613,6 +856,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
             A.w.a[1][kb] = ay;
             A.w.a[2][kb] = az;
             A.active_out[kb] = active ? 1 : 0;
+        }
+        };
+        switch (warp) {
+        case 0: physics(std::integral_constant<int, 0> {}); break;
+        case 1: physics(std::integral_constant<int, 1> {}); break;
+        case 2: physics(std::integral_constant<int, 2> {}); break;
+        default: physics(std::integral_constant<int, 3> {}); break;
         }
     }
     // nobody leaves while a peer may still store into (or signal) its shared memory

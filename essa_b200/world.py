@@ -326,9 +326,9 @@ class World:
 
     def persist_stats(self):
         """{live, ticks served through the mailbox, persistent kernels launched, idle retirements seen}."""
-        out = (C.c_int64 * 4)()
+        out = (C.c_int64 * 6)()
         self._ck(self._L.essa_world_persist_stats(self._h, out))
-        return dict(zip(("live", "ticks", "launches", "idle_exits"), (int(v) for v in out)))
+        return dict(zip(("live", "ticks", "launches", "idle_exits", "wait_ns", "host_ns"), (int(v) for v in out)))
 
     def set_flags(self, offset_trails=True, exact_order=False, two_pass=False):
         self._ck(self._L.essa_world_set_flags(self._h, int(offset_trails), int(exact_order), int(two_pass)))

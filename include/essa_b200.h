@@ -152,8 +152,9 @@ int essa_set_forces(essa_ctx* ctx, const essa_step_opts* opts);
  * (default 1000; environment: ESSA_PERSIST=0 / ESSA_PERSIST_IDLE_US). */
 int essa_persist_configure(essa_ctx* ctx, int enable, int idle_timeout_us);
 /* out = {kernel resident now (0/1), ticks served through the mailbox, persistent kernels launched,
- *        kernels found retired by their idle timeout when the next tick came}. */
-int essa_persist_stats(const essa_ctx* ctx, int64_t out[4]);
+ *        kernels found retired by their idle timeout when the next tick came,
+ *        host nanoseconds spent between a doorbell (or launch) and its result, ... between a result and the next doorbell}. */
+int essa_persist_stats(const essa_ctx* ctx, int64_t out[6]);
 
 /* ---- recording: Object::m_history / m_trail (src/History.cpp, src/Trail.cpp) ---------------- */
 /* Track bodies [0, n_tracked): allocate History rings (ESSA_HISTORY_SEGMENTS entries) and Trail
@@ -223,7 +224,10 @@ double essa_ensemble_factor(uint64_t seed, double rel_sigma, int64_t copy, int b
 int essa_nccl_unique_id(uint8_t id[ESSA_NCCL_ID_BYTES]);
 /* Join the communicator.  After this, essa_upload takes the FULL world on every rank and
  * essa_step integrates bodies [rank*N/world, (rank+1)*N/world) with one all-gather of the
- * drifted positions per force pass; essa_download returns the full, gathered world. */
+ * drifted positions per force pass.  essa_download is collective (every rank calls it with the same members set) and
+ * returns the full world on every rank: positions are current everywhere, velocities, accelerations, most-attracting
+ * links, max_attraction and ap / pe are gathered from their owners.  Recording (essa_step_opts.record) runs for the
+ * tracked bodies a rank owns: History / Trail rings of body k are read on the rank whose essa_shard_range holds k. */
 int essa_shard_attach(essa_ctx* ctx, int rank, int world, const uint8_t id[ESSA_NCCL_ID_BYTES]);
 /* The target range [*i0, *i1) of a rank (pure function; what every kernel of a sharded context uses). */
 int essa_shard_range(int n, int rank, int world, int* i0, int* i1);

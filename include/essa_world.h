@@ -55,7 +55,7 @@ double essa_world_last_step_ms(const essa_world* w);
 /* essa_persist_configure / essa_persist_stats of the world's context (essa_b200.h): keep the small-world kernel
  * resident between update() calls (default on). */
 int essa_world_set_persistent(essa_world* w, int enable, int idle_timeout_us);
-int essa_world_persist_stats(essa_world* w, int64_t out[4]);
+int essa_world_persist_stats(essa_world* w, int64_t out[6]);
 
 /* Bulk read of the object list: pos/vel/acc are 3N doubles (xyz interleaved), gf N, most N
  * (index or -1), appe 4N (ap, pe, ap_vel, pe_vel), active N, maxattr N.  Any pointer may be null. */

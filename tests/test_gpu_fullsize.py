@@ -15,7 +15,9 @@ def _rel_rows(a, b):
     return np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
 
 
-@pytest.mark.parametrize("name,n,kernel", [("plummer", 262144, capi.KERNEL_AUTO), ("plummer", 262144, capi.KERNEL_TILED),
+@pytest.mark.parametrize("name,n,kernel", [("plummer", 16384, capi.KERNEL_AUTO), ("plummer", 16384, capi.KERNEL_TILED),
+                                           ("plummer", 16383, capi.KERNEL_AUTO),  # one below AUTO's switch to the pair-shared kernel
+                                           ("plummer", 262144, capi.KERNEL_AUTO), ("plummer", 262144, capi.KERNEL_TILED),
                                            ("galaxy", 1048576, capi.KERNEL_AUTO)])
 def test_full_size_force_pass_and_reversibility(name, n, kernel):
     w = synth.plummer(n) if name == "plummer" else synth.galaxy_collision(n)

@@ -28,7 +28,7 @@ def _upload(ctx, w):
 
 
 # blocks of 2048 bodies: nb = 2 (even, d = nb/2 handled by half the ring), 3 (odd), 4, 5, ragged last blocks, many blocks
-@pytest.mark.parametrize("n", [2049, 4096, 6000, 8192, 10000, 20000, 65536])
+@pytest.mark.parametrize("n", [2049, 4096, 6000, 8192, 10000, 16384, 20000, 65536])  # 16,384: BASELINE config and AUTO's routing boundary
 def test_paired_force_pass_matches_extended_precision(ctx, n):
     w = synth.plummer(n, seed=n)
     _upload(ctx, w)
@@ -119,7 +119,7 @@ def test_paired_refuses_what_it_cannot_do(ctx):
         ctx.step(1, 1000, kernel=capi.KERNEL_PAIRED)
 
 
-@pytest.mark.parametrize("n", [4096, 6000, 20000])
+@pytest.mark.parametrize("n", [4096, 6000, 16384, 20000])
 def test_paired_most_attracting_links_match_tiled_and_oracle(ctx, n):
     """Unequal masses: the pair-shared kernel carries the most-attracting candidates as sortable keys
     (src/Object.cpp:84-94: the heavier partner with the largest gf / r^4, lowest index on ties)."""
@@ -266,3 +266,69 @@ def test_paired_tracks_most_attracting_when_it_is_a_no_op(ctx):
     pos_t = np.stack([t["x"], t["y"], t["z"]], axis=1)
     pos_p = np.stack([p["x"], p["y"], p["z"]], axis=1)
     assert _rel_rows(pos_p, pos_t).max() <= 1e-12
+
+
+def _near_tie_world(n, t, a, b, delta, seed=5):
+    """Light bodies of one common mass far away (x + 1e13 m), and near the origin a light target `t` with two heavy
+    partners `a`, `b` whose attraction metrics gf / r^4 differ by the relative amount `delta` (a is the stronger one;
+    delta == 0: mirrored positions, bit-identical metrics in the reference's arithmetic)."""
+    w = synth.plummer(n, seed=seed)
+    x, y, z = w["x"] + 1e13, w["y"].copy(), w["z"].copy()
+    mass = np.full(n, 1e20)
+    d = 1.0e9
+    x[t], y[t], z[t] = 0.0, 0.0, 0.0
+    x[a], y[a], z[a] = d, 0.0, 0.0
+    x[b], y[b], z[b] = 0.0, d * (1.0 + delta / 4.0), 0.0
+    mass[a] = mass[b] = 1e26
+    return x, y, z, mass
+
+
+@pytest.mark.parametrize("kernel", [capi.KERNEL_PAIRED, capi.KERNEL_TILED])
+@pytest.mark.parametrize("delta", [1e-7, 1e-9, 1e-12, 0.0])
+@pytest.mark.parametrize("order", ["stronger_first", "stronger_last"])
+def test_most_attracting_near_ties_are_decided_as_the_reference_does(ctx, kernel, delta, order):
+    """src/Object.cpp:84-94 decides in full binary64 with a strict '>' in ascending index order.  The pair-shared kernel
+    ranks candidates by sortable keys that keep 31 mantissa bits of the metric: two heavier partners within 5e-10 of each
+    other (or exactly tied) must be re-decided exactly, wherever in the reduction they meet -- here the three bodies sit
+    in three different 2048-body blocks, so the candidates meet in k_pair_finish / in the J-side slot merge."""
+    n = 6144
+    t, a, b = 100, 2500, 5000
+    if order == "stronger_last":
+        a, b = b, a  # the stronger partner has the HIGHER index: "lowest index wins" would be the wrong guess
+    x, y, z, mass = _near_tie_world(n, t, a, b, delta)
+    ow = oracle.World()
+    ow.add_bodies(x, y, z, np.zeros(n), np.zeros(n), np.zeros(n), mass)
+    ow.set_forces()
+    ost = ow.state()
+    want = int(ost["most"][t])
+    assert want == (a if delta > 0 else min(a, b))  # the oracle itself: the stronger one; at the exact tie the lower index
+    ctx.date = capi.START_DATE
+    ctx.upload(x, y, z, np.zeros(n), np.zeros(n), np.zeros(n), ost["gf"], most=np.full(n, -1, dtype=np.int32))
+    ctx.set_forces(kernel=kernel, track_most_attracting=True)
+    got = ctx.download(("most", "max_attraction"))
+    assert int(got["most"][t]) == want
+    assert got["most"][a] == -1 and got["most"][b] == -1  # nobody is heavier than the two heavy ones
+    # every link, not only the constructed one
+    assert np.array_equal(got["most"], ost["most"])
+    assert got["max_attraction"][t] == pytest.approx(ost["maxattr"][t], rel=1e-12)
+    # ... and again after a second pass (the filter thresholds of the first pass are in force now)
+    ctx.set_forces(kernel=kernel, track_most_attracting=True)
+    assert np.array_equal(ctx.download(("most",))["most"], ost["most"])
+
+
+def test_most_attracting_near_tie_inside_one_block_and_one_warp_visit(ctx):
+    """The same, with target and both partners inside one 32-body subset of one block (the candidates then meet in a
+    lane's own running maximum, pair_exact) and in neighbouring subsets."""
+    n = 4096
+    for t, a, b in ((5, 9, 17), (5, 17, 9), (40, 70, 1030), (40, 1030, 70)):
+        for delta in (1e-9, 1e-12, 0.0):
+            x, y, z, mass = _near_tie_world(n, t, a, b, delta)
+            ow = oracle.World()
+            ow.add_bodies(x, y, z, np.zeros(n), np.zeros(n), np.zeros(n), mass)
+            ow.set_forces()
+            ost = ow.state()
+            ctx.date = capi.START_DATE
+            ctx.upload(x, y, z, np.zeros(n), np.zeros(n), np.zeros(n), ost["gf"], most=np.full(n, -1, dtype=np.int32))
+            ctx.set_forces(kernel=capi.KERNEL_PAIRED, track_most_attracting=True)
+            got = ctx.download(("most",))
+            assert np.array_equal(got["most"], ost["most"]), (t, a, b, delta, got["most"][t], ost["most"][t])

@@ -197,7 +197,8 @@ def test_exact_order_and_masked_calls_do_not_use_the_mailbox(worlds_dir):
     pw.set_flags(offset_trails=True, exact_order=True)
     for _ in range(5):
         pw.update(10)
-    assert pw.persist_stats() == {"live": 0, "ticks": 0, "launches": 0, "idle_exits": 0}
+    st = pw.persist_stats()
+    assert (st["live"], st["ticks"], st["launches"], st["idle_exits"]) == (0, 0, 0, 0)
     pw.close()
     # an object whose deletion date is crossed during a tick: that tick (and only that one) takes the one-shot kernel
     a, b = _two(worlds_dir)

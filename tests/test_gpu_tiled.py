@@ -33,7 +33,7 @@ def ctx():
     c.close()
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 255, 257, 1000, 4096])
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 257, 1000, 4096, 16384])  # 16,384: BASELINE.json's tiled-kernel config
 def test_force_pass_matches_extended_precision(ctx, n):
     w = synth.plummer(n, seed=n)
     _upload(ctx, w)

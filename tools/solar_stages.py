@@ -15,7 +15,10 @@ st = pw.state()
 caps = [pw.props(i)["trail_capacity"] for i in range(len(pw))]
 n = len(pw)
 persist = int(sys.argv[3]) if len(sys.argv) > 3 else 0  # 1: the persistent flavour of K3q (same step loop, doorbell between calls)
+only = sys.argv[4] if len(sys.argv) > 4 else None  # run one stage only
 for label, kw in (("physics", {}), ("physics+attraction", dict(track_most_attracting=True)), ("all", dict(record=True))):
+    if only and label != only:
+        continue
     c = capi.Context(0)
     c.persist_configure(persist)
     c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"],
