@@ -50,11 +50,12 @@ namespace essa {
 #endif                  // weak stores, 2 = plain stores + system fence + acknowledgement word (capi.cu reads the same macro)
 
 constexpr int kQuadWarps = 4;
-// CTA 0: warps 0-3 physics, 4 courier, 5 poller.  CTA 1: warps 0-2 attraction, 3-6 Trail, 7 links + History, 8 ap / pe, 9 publisher.
+// CTA 0: warps 0-3 physics, 4 courier, 5 poller.  CTA 1: warps 0-2 attraction, 3-6 Trail, 7 links + History, 8 apoapsis,
+// 9 periapsis, 10 publisher.
 constexpr int kCourierWarp = 4, kPollWarp = 5;
-constexpr int kAttrWarps = 3, kTrailWarp0 = 3, kTrailWarps = 4, kHistWarp = 7, kAppeWarp = 8, kPubWarp = 9;
-constexpr int kConsumers = kTrailWarps + 2;
-constexpr int kQuadThreads = 32 * 10;
+constexpr int kAttrWarps = 3, kTrailWarp0 = 3, kTrailWarps = 4, kHistWarp = 7, kApWarp = 8, kPeWarp = 9, kPubWarp = 10;
+constexpr int kConsumers = kTrailWarps + 3;
+constexpr int kQuadThreads = 32 * 11;
 constexpr int kStage = 4; // physics -> courier staging buffers
 
 struct QSnap {
@@ -114,7 +115,7 @@ struct Q0 { // CTA 0
     unsigned stage_mask[kStage];               // active bodies of that step
     unsigned courier_done;                     // steps the courier has forwarded
     unsigned fin_sent;                         // ticks whose final bundle has left
-    unsigned done[kConsumers];                 // steps consumed by CTA 1's warps 3 .. 8
+    unsigned done[kConsumers];                 // steps consumed by CTA 1's warps 3 .. 9
     unsigned cmdw[2];                          // poller -> physics / courier: steps granted so far, tick number
 };
 struct Q1 { // CTA 1
@@ -170,7 +171,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
     constexpr bool snap_on = ARG; // recording implies tracking
     unsigned const snap_bytes = (unsigned)n * 48u + 8u;
     unsigned const fin_bytes = (unsigned)n * 72u + 16u;
-    unsigned const nout = (snap_on ? 1u : 0u) + (rec_on ? 1u : 0u); // consumer warps that report a tick's end
+    unsigned const nout = (snap_on ? 1u : 0u) + (rec_on ? 2u : 0u); // consumer warps that report a tick's end
 
     if (threadIdx.x == 0) {
         if (cta == 1) {
@@ -288,14 +289,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                     mbar_arrive(&ready[slot]);
             }
         }
-    } else if (cta == 1 && warp <= kAppeWarp) {
-        // ---------------- consumer warps: 3 .. 6 Trail (bodies by index mod 4); 7 links + History; 8 ap / pe ----------------
+    } else if (cta == 1 && warp <= kPeWarp) {
+        // ---------------- consumer warps: 3 .. 6 Trail (bodies by index mod 4); 7 links + History; 8 apoapsis; 9 periapsis ----------------
         // Every consumer follows the most-attracting links itself (a few integer instructions per step).  One copy of the loop
         // per role (ROLE is a compile-time constant in each): a step costs a warp ~5 cycles per instruction and ~20 per taken
         // branch, and only the links + ap / pe warps are waited for at a tick's end (the Trail warps may lag up to the depth of
         // the ring and catch up while the host reads the tick).
         auto consumer = [&](auto role) {
-            constexpr int ROLE = decltype(role)::value; // 0: Trail, 1: links + History, 2: ap / pe
+            constexpr int ROLE = decltype(role)::value; // 0: Trail, 1: links + History, 2: apoapsis, 3: periapsis (the two halves of
+                                                        // Object.cpp:111-123 are independent chains of ~30 dependent instructions each)
             bool const body = lane < n;
             bool const mine = rec_on && body && lane < A.r.tracked && (ROLE != 0 || (lane & (kTrailWarps - 1)) == (warp - kTrailWarp0));
             uint32_t const done_remote = mapa_u32(&done[warp - kTrailWarp0], 0);
@@ -333,9 +335,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                     else if (ROLE == 1) {
                         if (!forward_sim)
                             history_push(A.r, lane, b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane]);
-                    } else
-                        record_appe(b, sn.x[lane], sn.y[lane], sn.z[lane], sn.vx[lane], sn.vy[lane], sn.vz[lane], sn.x[mi], sn.y[mi], sn.z[mi],
-                            most);
+                    } else if (most >= 0) {
+                        double const dx = __dsub_rn(sn.x[lane], sn.x[mi]), dy = __dsub_rn(sn.y[lane], sn.y[mi]), dz = __dsub_rn(sn.z[lane], sn.z[mi]);
+                        double const d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        if (ROLE == 2)
+                            apoapsis_step(b, d2, sn.vx[lane], sn.vy[lane], sn.vz[lane]);
+                        else
+                            periapsis_step(b, d2, sn.vx[lane], sn.vy[lane], sn.vz[lane]);
+                    }
                 }
                 if (ROLE == 1 && last && act) {
                     // max_attraction as the last force pass left it: the winner's gf / r^4 to full precision, or 0
@@ -350,10 +357,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                     }
                     if (ROLE == 2 && mine) {
                         ap_flush(b);
-                        pe_flush(b);
                         outd[1][lane] = b.ap;
-                        outd[2][lane] = b.pe;
                         outd[3][lane] = b.apv;
+                    }
+                    if (ROLE == 3 && mine) {
+                        pe_flush(b);
+                        outd[2][lane] = b.pe;
                         outd[4][lane] = b.pev;
                     }
                 }
@@ -382,16 +391,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                 } else if (ROLE == 1) {
                     A.r.hist_start[lane] = b.hist_start;
                     A.r.hist_len[lane] = b.hist_len;
+                } else if (ROLE == 2) {
+                    ap_flush(b);
+                    A.r.ap[lane] = b.ap;
+                    A.r.ap_vel[lane] = b.apv;
                 } else {
-                    rec_store_appe(A.r, lane, b);
+                    pe_flush(b);
+                    A.r.pe[lane] = b.pe;
+                    A.r.pe_vel[lane] = b.pev;
                 }
             }
         };
         if (snap_on && (warp == kHistWarp || rec_on)) {
             if (warp == kHistWarp)
                 consumer(std::integral_constant<int, 1> {});
-            else if (warp == kAppeWarp)
+            else if (warp == kApWarp)
                 consumer(std::integral_constant<int, 2> {});
+            else if (warp == kPeWarp)
+                consumer(std::integral_constant<int, 3> {});
             else
                 consumer(std::integral_constant<int, 0> {});
         }
@@ -545,7 +562,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
         unsigned seq = P.seq0;
         unsigned ticks = 1; // granted so far
         int end = A.steps;
+#if ESSA_POLL_DEPTH != 1
         long long q = 0;
+#endif
         for (;;) {
             unsigned long long c = 0ull;
             bool idle = false;
