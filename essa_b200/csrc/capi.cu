@@ -140,14 +140,23 @@ static int persist_wait_ack(essa_ctx* ctx) {
     PersistMailbox* mb = p.mailbox;
     auto const t0 = std::chrono::steady_clock::now();
     double const limit_s = 10.0 + 5e-6 * (double)p.pending_steps;
-    int const n = ctx->n, words = 29 * n + 2;
-    auto landed = [&]() { // every word of the result carries this tick's number (checked back to front: the tail lands last)
-#if defined(ESSA_PUB_MODE) && ESSA_PUB_MODE == 2
-        return __atomic_load_n(&mb->ack[0], __ATOMIC_ACQUIRE) == p.seq;
-#endif
-        for (int w = words - 1; w >= 0; w--)
+    int const n = ctx->n;
+    bool const field_major = n <= kPersistFieldMajorMax;
+    auto landed = [&]() { // every word of the result carries this tick's number (checked back to front)
+        if (field_major) {
+            for (int w = 29 * n + 1; w >= 0; w--)
+                if ((unsigned)(__atomic_load_n(&mb->ll[w], __ATOMIC_RELAXED) >> 32) != p.seq)
+                    return false;
+            __atomic_thread_fence(__ATOMIC_ACQUIRE);
+            return true;
+        }
+        for (int w = kPersistRecWords * n + 1; w >= kPersistRecWords * n; w--)
             if ((unsigned)(__atomic_load_n(&mb->ll[w], __ATOMIC_RELAXED) >> 32) != p.seq)
                 return false;
+        for (int k = n - 1; k >= 0; k--)
+            for (int w = kPersistRecUsed - 1; w >= 0; w--)
+                if ((unsigned)(__atomic_load_n(&mb->ll[kPersistRecWords * k + w], __ATOMIC_RELAXED) >> 32) != p.seq)
+                    return false;
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
         return true;
     };
@@ -186,12 +195,7 @@ static int persist_wait_ack(essa_ctx* ctx) {
     p.t_landed = std::chrono::steady_clock::now();
     p.wait_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(p.t_landed - p.t_post).count();
     // unpack into essa_download's staging layout: 15 n doubles (field 9, gf, is not carried) ... links at double offset 17 n
-#if defined(ESSA_PUB_MODE) && ESSA_PUB_MODE == 2
-    memcpy(p.staged, mb->ll, (size_t)n * 18 * sizeof(double));
-    ctx->last_step_ms = (double)(((unsigned long long)mb->ack[3] << 32) | mb->ack[2]) * 1e-6;
-    if (false)
-#endif
-    {
+    if (field_major) {
         size_t const N = (size_t)n;
         for (int f = 0; f < 14; f++) {
             double* dst = p.staged + (size_t)(f < 9 ? f : f + 1) * N;
@@ -204,8 +208,20 @@ static int persist_wait_ack(essa_ctx* ctx) {
         int32_t* most = reinterpret_cast<int32_t*>(p.staged + 17 * N);
         for (size_t k = 0; k < N; k++)
             most[k] = (int32_t)(unsigned)mb->ll[28 * N + k];
-        unsigned long long const ns = (mb->ll[29 * N] & 0xffffffffull) | (mb->ll[29 * N + 1] << 32);
-        ctx->last_step_ms = (double)ns * 1e-6;
+        ctx->last_step_ms = (double)((mb->ll[29 * N] & 0xffffffffull) | (mb->ll[29 * N + 1] << 32)) * 1e-6;
+    } else {
+        size_t const N = (size_t)n;
+        int32_t* most = reinterpret_cast<int32_t*>(p.staged + 17 * N);
+        for (size_t k = 0; k < N; k++) {
+            unsigned long long const* rec = mb->ll + kPersistRecWords * k;
+            for (int f = 0; f < 14; f++) {
+                unsigned long long const bits = (rec[2 * f] & 0xffffffffull) | (rec[2 * f + 1] << 32);
+                memcpy(p.staged + (size_t)(f < 9 ? f : f + 1) * N + k, &bits, sizeof(double));
+            }
+            most[k] = (int32_t)(unsigned)rec[28];
+        }
+        unsigned long long const* tw = mb->ll + kPersistRecWords * N;
+        ctx->last_step_ms = (double)((tw[0] & 0xffffffffull) | (tw[1] << 32)) * 1e-6;
     }
     return ESSA_OK;
 }
@@ -252,7 +268,10 @@ static int persist_launch(essa_ctx* ctx, int steps, essa_step_opts const& o) {
     int const k = steps < 0 ? -steps : steps;
     p.mailbox->ack[1] = 0;
     __atomic_store_n(&p.mailbox->cmd, ((unsigned long long)p.seq << 32) | (unsigned)k, __ATOMIC_RELEASE);
-    CK(launch_resident_warp(ctx, steps, o, false, ctx->stream, true));
+    if (ctx->n <= 32)
+        CK(launch_resident_warp(ctx, steps, o, false, ctx->stream, true)); // K3q
+    else
+        CK(launch_resident_cluster(ctx, steps, o, ctx->stream, true));     // K3x
     p.t_post = std::chrono::steady_clock::now();
     p.live = true;
     p.pending = true;
@@ -1113,6 +1132,18 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
             && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds))) {
             // 33 .. 128 bodies: a cluster of 8 / 16 SMs (resident_cluster.cu); one SM if the cluster cannot be placed
             bool clustered = false;
+            long long const k = steps < 0 ? -(long long)steps : steps;
+            if (ctx->persist.enabled && k < (1ll << 30) && resident_cluster_persist_applicable(ctx, o, forces_only)) {
+                // stays resident after this tick and takes the following ones from its mailbox (if the cluster can be placed)
+                rc = persist_launch(ctx, steps, o);
+                if (rc == ESSA_OK) {
+                    if (!async && (rc = persist_wait_ack(ctx)) != ESSA_OK)
+                        return rc;
+                    return resident_finish(ctx, steps, o, forces_only);
+                }
+                (void)cudaGetLastError();
+                ctx->persist.live = false;
+            }
             if (resident_cluster_applicable(ctx, o, forces_only)) {
                 clustered = launch_resident_cluster(ctx, steps, o, ctx->stream) == cudaSuccess;
                 if (!clustered)

@@ -216,6 +216,9 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(unsigned long l
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void st_relaxed_sys_u32(unsigned* p, unsigned v) {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

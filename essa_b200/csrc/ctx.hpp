@@ -80,15 +80,22 @@ struct RecordPtrs {
 // ---- persistent resident kernel (resident_quad.cu K3q): host <-> device mailbox in mapped pinned memory ----
 // The host rings the doorbell by writing `cmd`; the kernel answers by filling `ll` with self-validating words
 // {tick number (high half), 32 bits of payload (low half)}: the result is complete when every word carries the tick's number.
-constexpr int kPersistMaxBodies = 32;
-constexpr int kPersistWords = 28 * kPersistMaxBodies + kPersistMaxBodies + 2;
+constexpr int kPersistMaxBodies = 128; // K3q: up to 32 bodies, K3x: up to 128
+// Two layouts of the published words (32 bits of payload each, doubles as (low, high) halves):
+//  * worlds of up to 32 bodies (K3q, one publisher warp): field-major -- x y z vx vy vz ax ay az max_attraction ap pe ap_vel pe_vel
+//    as 2 n words each, then n links, then two words with the tick's device nanoseconds;
+//  * larger worlds (K3x, every warp publishes its own body): one 32-word record per body (256 bytes, so that a body's words leave
+//    the GPU as one or two contiguous stores) -- words 0 .. 17 x .. az, 18 .. 27 max_attraction ap pe ap_vel pe_vel, 28 the link,
+//    29 .. 31 unused -- then the two time words.
+constexpr int kPersistFieldMajorMax = 32;
+constexpr int kPersistRecWords = 32, kPersistRecUsed = 29;
+constexpr int kPersistWords = kPersistRecWords * kPersistMaxBodies + 2;
 struct PersistMailbox {
     unsigned long long cmd;   // host -> device: (seq << 32) | steps;  steps == 0: retire
     unsigned long long pad0[15];
     unsigned ack[4];          // device -> host: [1] 1 = retired on request, 2 = retired after the idle timeout
     unsigned pad1[28];
-    unsigned long long ll[kPersistWords]; // x y z vx vy vz ax ay az max_attraction ap pe ap_vel pe_vel as (low, high)
-                                          // halves per body, then the links, then the tick's device nanoseconds
+    unsigned long long ll[kPersistWords];
 };
 
 } // namespace essa
@@ -269,7 +276,8 @@ cudaError_t launch_download_small(essa_ctx* c, void* pinned_out, cudaStream_t st
 bool resident_cluster_wide_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
 cudaError_t launch_resident_cluster_wide(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
 bool resident_cluster_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
-cudaError_t launch_resident_cluster(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st);
+cudaError_t launch_resident_cluster(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st, bool persist = false);
+bool resident_cluster_persist_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st);
 cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st);
 cudaError_t launch_energy(essa_ctx* c, cudaStream_t st); // result in c->escratch[0..5)

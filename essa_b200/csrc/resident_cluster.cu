@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "ctx.hpp"
 #include "record.cuh"
+#include "resident_small.cuh"
 
 namespace essa {
 
@@ -40,7 +41,7 @@ constexpr int kXLocalMax = 8; // bodies per CTA
 constexpr int kXRing = 8;     // step slots
 constexpr int kXRoles = 4;    // consumer warps per CTA
 constexpr int kXCtas = 16;    // cluster size (non-portable: needs the opt-in attribute)
-constexpr int kXThreads = 32 * (kXLocalMax + kXRoles);
+constexpr int kXThreads = 32 * (kXLocalMax + kXRoles + 1); // + the poller warp of the persistent flavour
 
 struct XArgs {
     WorldPtrs w;
@@ -57,6 +58,9 @@ struct XShared {
     unsigned long long full[kXRing];   // all n records of the slot have arrived (transaction bytes)
     unsigned long long vready[kXRing]; // local velocities / winners written
     unsigned done[kXRoles * kXCtas];   // steps consumed by role r of CTA c, at [r * kXCtas + c]
+    unsigned long long grant;          // persistent flavour: (tick number << 32) | steps granted so far, written by the poller
+    unsigned long long tick_t0;        // ... globaltimer at the doorbell
+    unsigned quit;                     // ... the order to retire
 };
 
 __device__ __forceinline__ void x_arrive(unsigned long long* bar) {
@@ -79,11 +83,30 @@ __device__ __forceinline__ double x_metric(double4 const& pk, double4 const& pp,
     return gp * y2 * y2;
 }
 
+// persistent flavour: wait until steps beyond `s` are granted (the doorbell, forwarded by CTA 0's poller); false: retire
+__device__ __forceinline__ bool x_more_steps(unsigned long long const* grant, unsigned const* quit, int s, int& end, unsigned& seq) {
+    for (;;) {
+        unsigned long long g;
+        asm volatile("ld.acquire.cluster.shared::cta.u64 %0, [%1];" : "=l"(g) : "r"(smem_u32(grant)) : "memory");
+        end = (int)(unsigned)g;
+        seq = (unsigned)(g >> 32);
+        if (s < end)
+            return true;
+        if (ld_acquire_cluster_u32(quit) != 0)
+            return false;
+        __nanosleep(32);
+    }
+}
+
 // PER = partners per lane = ceil(n / 32): a compile-time bound keeps the partner loop one straight-line block, so
 // that the PER dependent chains interleave (with a run-time bound each partner was its own basic block: 760
 // instead of 440 cycles for three partners, measured)
-template<int PER, bool ARGMAX>
-__global__ void __launch_bounds__(kXThreads, 1) k_resident_cluster(XArgs const A) {
+// PERSIST (essa_persist_configure): the kernel outlives the call.  An extra warp of CTA 0 polls the host's command word in
+// mapped pinned memory and forwards every doorbell to the 16 CTAs; at a tick's end every physics warp writes its body's
+// x v a, and the link / ap-pe consumer warps their results, straight to the host as self-validating words {tick number,
+// 32 bits of payload} (resident_quad.cu has the protocol): the host has the tick when every word carries its number.
+template<int PER, bool ARGMAX, bool PERSIST>
+__global__ void __launch_bounds__(kXThreads, 1) k_resident_cluster(XArgs const A, PersistArgs const P) {
     __shared__ __align__(16) XShared S;
     int const n = A.n, nbl = A.nbl;
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,6 +127,11 @@ __global__ void __launch_bounds__(kXThreads, 1) k_resident_cluster(XArgs const A
     }
     for (int i = threadIdx.x; i < kXRoles * kXCtas; i += blockDim.x)
         S.done[i] = 0;
+    if (threadIdx.x == 0) {
+        S.grant = ((unsigned long long)P.seq0 << 32) | (unsigned)A.steps;
+        S.quit = 0;
+        S.tick_t0 = PERSIST ? globaltimer_ns() : 0ull;
+    }
     for (int i = threadIdx.x; i < kXRing * kXMaxBodies; i += blockDim.x) {
         // slot 0 = the state at launch; everywhere the padding behind body n - 1 is read with weight 0
         int const b = i % kXMaxBodies;
@@ -206,7 +234,10 @@ __global__ void __launch_bounds__(kXThreads, 1) k_resident_cluster(XArgs const A
             uint32_t const full_remote = mapa_u32(&S.full[0], sender ? lane : 0);
             int consumed = 0; // cached lower bound of the versions every consumer of the cluster has finished with
 
-            for (int s = 0; s < A.steps; s++) {
+            int s = 0, end = A.steps;
+            unsigned seq = P.seq0;
+            for (;;) {
+            for (; s < end; s++) {
                 int const v = s + 1, slot = v % kXRing;
                 if (active) { // first half kick + drift (src/World.cpp:112,115)
                     vx = __dadd_rn(vx, __dmul_rn(ax, hm));
@@ -252,6 +283,20 @@ __global__ void __launch_bounds__(kXThreads, 1) k_resident_cluster(XArgs const A
                     x_arrive(&S.vready[slot]);
                 }
             }
+            if (!PERSIST)
+                break;
+            // ---- end of a tick: this body's x v a to the host (words 0 .. 17 of its record, ctx.hpp: one coalesced store), then the next doorbell ----
+            {
+                unsigned long long const tag = (unsigned long long)seq << 32;
+                int const f = lane >> 1;
+                double const d = f == 0 ? x : f == 1 ? y : f == 2 ? z : f == 3 ? vx : f == 4 ? vy : f == 5 ? vz : f == 6 ? ax : f == 7 ? ay : az;
+                unsigned const w = (lane & 1) ? (unsigned)__double2hiint(d) : (unsigned)__double2loint(d);
+                if (lane < 18)
+                    st_relaxed_sys_u64(P.out + (size_t)kPersistRecWords * k + lane, tag | w);
+            }
+            if (!x_more_steps(&S.grant, &S.quit, s, end, seq))
+                break; // retire
+            }
             if (lane == 0) {
                 A.w.pos_cur[k] = make_double4(x, y, z, gfe);
                 A.w.v[0][k] = vx;
@@ -277,7 +322,15 @@ __global__ void __launch_bounds__(kXThreads, 1) k_resident_cluster(XArgs const A
             if (mine)
                 rec_load(A.r, k, b);
             int most = body ? A.w.most[k] : -1, old_most = body ? A.w.old_most[k] : -1;
-            for (int v = 1; v <= A.steps; v++) {
+            double maxattr = (role == 1 && body) ? A.w.maxattr[k] : 0.0;
+            int end = A.steps;
+            unsigned seq = P.seq0;
+            for (int v = 1;; v++) {
+                if (v > end) {
+                    if (!PERSIST || !x_more_steps(&S.grant, &S.quit, v - 1, end, seq))
+                        break;
+                }
+                bool const last = v == end; // (the host extends `end` only after it has this tick's result)
                 int const slot = v % kXRing;
                 unsigned const par = x_parity(v);
                 mbar_wait(&S.full[slot], par);
@@ -299,9 +352,34 @@ __global__ void __launch_bounds__(kXThreads, 1) k_resident_cluster(XArgs const A
                     } else
                         record_appe(b, pk.x, pk.y, pk.z, vx, vy, vz, pm.x, pm.y, pm.z, most);
                 }
-                if (role == 1 && v == A.steps && act) {
+                if (role == 1 && last && act) {
                     // max_attraction as the last force pass left it: the winner's gf / r^4 to full precision, or 0
-                    A.w.maxattr[k] = winner >= 0 ? x_metric(pp[k], pp[winner], A.w.gf[winner]) : 0.0;
+                    maxattr = winner >= 0 ? x_metric(pp[k], pp[winner], A.w.gf[winner]) : 0.0;
+                }
+                if (PERSIST && last && body) { // this warp's share of what the host reads back (fields 9 .. 13, then the links)
+                    unsigned long long const tag = (unsigned long long)seq << 32;
+                    auto put = [&](int f, double d) { // field f of body k: words 2 f, 2 f + 1 of its record
+                        st_relaxed_sys_u64(P.out + (size_t)kPersistRecWords * k + 2 * f, tag | (unsigned)__double2loint(d));
+                        st_relaxed_sys_u64(P.out + (size_t)kPersistRecWords * k + 2 * f + 1, tag | (unsigned)__double2hiint(d));
+                    };
+                    if (role == 1) {
+                        put(9, maxattr);
+                        st_relaxed_sys_u64(P.out + (size_t)kPersistRecWords * k + 28, tag | (unsigned)most);
+                        if (k == 0) {
+                            unsigned long long const dtn = globaltimer_ns() - S.tick_t0;
+                            st_relaxed_sys_u64(P.out + (size_t)kPersistRecWords * n, tag | (unsigned)dtn);
+                            st_relaxed_sys_u64(P.out + (size_t)kPersistRecWords * n + 1, tag | (unsigned)(dtn >> 32));
+                        }
+                    } else if (role == 3) {
+                        if (mine) {
+                            ap_flush(b);
+                            pe_flush(b);
+                        }
+                        put(10, mine ? b.ap : A.r.ap[k]);
+                        put(11, mine ? b.pe : A.r.pe[k]);
+                        put(12, mine ? b.apv : A.r.ap_vel[k]);
+                        put(13, mine ? b.pev : A.r.pe_vel[k]);
+                    }
                 }
                 __syncwarp();
                 if (lane < A.ctas)
@@ -310,6 +388,7 @@ __global__ void __launch_bounds__(kXThreads, 1) k_resident_cluster(XArgs const A
             if (role == 1 && body) {
                 A.w.most[k] = most;
                 A.w.old_most[k] = old_most;
+                A.w.maxattr[k] = maxattr;
             }
             if (mine) {
                 if (is_trail) {
@@ -320,6 +399,50 @@ __global__ void __launch_bounds__(kXThreads, 1) k_resident_cluster(XArgs const A
                 } else {
                     rec_store_appe(A.r, k, b);
                 }
+            }
+        }
+    }
+    else if (PERSIST && cta == 0 && warp == nbl + kXRoles) {
+        // ---------------- poller: the host's doorbell (one lane reads the command word over PCIe, one read in flight) ----------------
+        unsigned seq = P.seq0;
+        unsigned end = (unsigned)A.steps;
+        uint32_t const grant_remote = mapa_u32(&S.grant, lane < kXCtas ? lane : 0), quit_remote = mapa_u32(&S.quit, lane < kXCtas ? lane : 0),
+                       t0_remote = mapa_u32(&S.tick_t0, 0);
+        for (;;) {
+            unsigned long long c = 0ull;
+            bool idle = false;
+            if (lane == 0) {
+                long long const i0 = clock64(); // (a tick longer than the idle time retires the kernel after it: harmless)
+                for (;;) {
+                    c = ld_relaxed_sys_u64(P.cmd);
+                    if ((unsigned)(c >> 32) != seq)
+                        break;
+                    if (clock64() - i0 > P.idle_clk) {
+                        idle = true;
+                        break;
+                    }
+                }
+            }
+            c = __shfl_sync(0xffffffffu, c, 0);
+            idle = __shfl_sync(0xffffffffu, idle ? 1 : 0, 0) != 0;
+            unsigned const add = idle ? 0u : (unsigned)c; // steps of the new tick; 0: retire
+            if (add == 0) {
+                if (lane == 0)
+                    st_relaxed_sys_u32(P.ack + 1, idle ? 2u : 1u);
+                if (lane < kXCtas)
+                    st_relaxed_cluster_u32(quit_remote, 1u);
+                break;
+            }
+            end += add;
+            seq = (unsigned)(c >> 32);
+            if (lane == 0) {
+                unsigned long long const now = globaltimer_ns();
+                asm volatile("st.relaxed.cluster.shared::cluster.u64 [%0], %1;" ::"r"(t0_remote), "l"(now) : "memory");
+            }
+            __syncwarp();
+            if (lane < kXCtas) {
+                unsigned long long const g = ((unsigned long long)seq << 32) | end;
+                asm volatile("st.relaxed.cluster.shared::cluster.u64 [%0], %1;" ::"r"(grant_remote), "l"(g) : "memory");
             }
         }
     }
@@ -337,19 +460,41 @@ bool resident_cluster_applicable(essa_ctx const* c, essa_step_opts const& o, boo
 }
 
 template<int PER>
-static cudaError_t launch_x(essa_ctx* c, cudaLaunchConfig_t const& cfg, XArgs const& A) {
+static cudaError_t launch_x(essa_ctx* c, cudaLaunchConfig_t const& cfg, XArgs const& A, PersistArgs const* pa) {
     if (!c->attr_cluster16[PER]) {
-        cudaError_t e = cudaFuncSetAttribute(k_resident_cluster<PER, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaError_t e = cudaFuncSetAttribute(k_resident_cluster<PER, true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_resident_cluster<PER, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            e = cudaFuncSetAttribute(k_resident_cluster<PER, false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_resident_cluster<PER, true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess)
             return e;
         c->attr_cluster16[PER] = true;
     }
-    return A.argmax ? cudaLaunchKernelEx(&cfg, k_resident_cluster<PER, true>, A) : cudaLaunchKernelEx(&cfg, k_resident_cluster<PER, false>, A);
+    if (pa)
+        return cudaLaunchKernelEx(&cfg, k_resident_cluster<PER, true, true>, A, *pa);
+    PersistArgs const none {};
+    return A.argmax ? cudaLaunchKernelEx(&cfg, k_resident_cluster<PER, true, false>, A, none)
+                    : cudaLaunchKernelEx(&cfg, k_resident_cluster<PER, false, false>, A, none);
 }
 
-cudaError_t launch_resident_cluster(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st) {
+// Worlds the persistent flavour of K3x serves: recording on for every body (what the World facade runs).
+bool resident_cluster_persist_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only) {
+    return resident_cluster_applicable(c, o, forces_only) && o.record && c->tracked >= c->n && c->world == 1;
+}
+
+cudaError_t launch_resident_cluster(essa_ctx* c, int steps, essa_step_opts const& o, cudaStream_t st, bool persist) {
+    PersistArgs PA {};
+    PersistArgs const* pa = nullptr;
+    if (persist) {
+        PersistMailbox* mb = c->persist.mailbox;
+        PA.cmd = &mb->cmd;
+        PA.ack = mb->ack;
+        PA.out = mb->ll;
+        PA.seq0 = c->persist.seq;
+        PA.idle_clk = (long long)c->persist.idle_us * 2000; // ~ SM cycles (1.965 GHz at full clock)
+        pa = &PA;
+    }
     XArgs A;
     A.w = world_ptrs(c);
     A.r = record_ptrs(c);
@@ -369,7 +514,7 @@ cudaError_t launch_resident_cluster(essa_ctx* c, int steps, essa_step_opts const
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kXCtas, 1, 1);
-    cfg.blockDim = dim3(32 * (A.nbl + kXRoles), 1, 1);
+    cfg.blockDim = dim3(32 * (A.nbl + kXRoles + 1), 1, 1);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -380,7 +525,7 @@ cudaError_t launch_resident_cluster(essa_ctx* c, int steps, essa_step_opts const
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int const per = (c->n + 31) / 32; // 2 .. 4
-    cudaError_t e = per == 2 ? launch_x<2>(c, cfg, A) : per == 3 ? launch_x<3>(c, cfg, A) : launch_x<4>(c, cfg, A);
+    cudaError_t e = per == 2 ? launch_x<2>(c, cfg, A, pa) : per == 3 ? launch_x<3>(c, cfg, A, pa) : launch_x<4>(c, cfg, A, pa);
     if (e != cudaSuccess)
         return e;
     c->launches++;

@@ -45,9 +45,8 @@ namespace essa {
 #endif                    // a doorbell ~1.2 us after it was rung; four staggered reads of the same word took ~5 us (they do not
                           // pipeline: each waits for the one before it at the host bridge), so the deeper variant is a dead end kept
                           // for the record
-#ifndef ESSA_PUB_MODE
-#define ESSA_PUB_MODE 0 // how a tick's result reaches the host: 0 = self-validating 64-bit words (sys-scope stores), 1 = the same with
-#endif                  // weak stores, 2 = plain stores + system fence + acknowledgement word (capi.cu reads the same macro)
+// How a tick's result reaches the host: self-validating 64-bit words (below).  Measured alternative: plain stores of the packed
+// doubles + __threadfence_system() + an acknowledgement word cost 2 us more per tick (the system-scope fence).
 
 constexpr int kQuadWarps = 4;
 // CTA 0: warps 0-3 physics, 4 courier, 5 poller.  CTA 1: warps 0-2 attraction, 3-6 Trail, 7 links + History, 8 apoapsis,
@@ -76,9 +75,6 @@ __device__ __forceinline__ bool mbar_try(unsigned long long* bar, unsigned parit
         : "r"(smem_u32(bar)), "r"(parity), "r"(2000) // parked for up to ~2 us per try
         : "memory");
     return ok != 0;
-}
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_cta_u32(unsigned const* p) {
     unsigned v;
@@ -417,7 +413,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
         // Word w of the host buffer carries 32 bits of payload under the tick's number: fields x y z vx vy vz ax ay az
         // max_attraction ap pe ap_vel pe_vel as (low, high) halves of body 0, 1, ..., then the links, then the device
         // nanoseconds between doorbell and publication.
-        int const words_d = 28 * n;
         for (unsigned tick = 0;; tick++) {
             bool quit = false;
             while (!mbar_try(&finbar, tick & 1u)) {
@@ -435,28 +430,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
             unsigned const seq = (unsigned)fin_meta[1];
             unsigned long long const tag = (unsigned long long)seq << 32;
             unsigned long long const t0 = fin_meta[0];
-#if ESSA_PUB_MODE == 2
-            // plain coalesced stores of the packed state, one system-wide fence, then the acknowledgement
-            {
-                double* const od = reinterpret_cast<double*>(P.out);
-                size_t const N = (size_t)n;
-                if (lane < n) {
-#pragma unroll
-                    for (int f = 0; f < 14; f++)
-                        od[(size_t)(f < 9 ? f : f + 1) * N + lane] = f < 9 ? fin[f][lane] : outd[f - 9][lane];
-                    reinterpret_cast<int*>(od + 17 * N)[lane] = outmost[lane];
-                }
-                __threadfence_system();
-                __syncwarp();
-                if (lane == 0) {
-                    unsigned long long const dtn = globaltimer_ns() - t0;
-                    st_relaxed_sys_u32(P.ack + 2, (unsigned)dtn);
-                    st_relaxed_sys_u32(P.ack + 3, (unsigned)(dtn >> 32));
-                    st_relaxed_sys_u32(P.ack, seq);
-                }
-            }
-#else
-            // a lane is (body, half) of a field: no division, 14 coalesced stores of 2 n words
+            // field-major words (ctx.hpp): a lane is (body, half) of a field: no division, 14 coalesced stores of 2 n words
+            int const words_d = 28 * n;
             for (int h = 0; h < 2; h++) {
                 int const r = lane + 32 * h;
                 if (r < 2 * n) {
@@ -465,11 +440,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                     for (int f = 0; f < 14; f++) {
                         double const d = f < 9 ? fin[f][k] : outd[f - 9][k];
                         unsigned const v = (r & 1) ? (unsigned)__double2hiint(d) : (unsigned)__double2loint(d);
-#if ESSA_PUB_MODE == 1
-                        P.out[f * 2 * n + r] = tag | v;
-#else
                         st_relaxed_sys_u64(P.out + f * 2 * n + r, tag | v);
-#endif
                     }
                 }
             }
@@ -480,7 +451,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                 st_relaxed_sys_u64(P.out + words_d + n, tag | (unsigned)dtn);
                 st_relaxed_sys_u64(P.out + words_d + n + 1, tag | (unsigned)(dtn >> 32));
             }
-#endif
         }
     } else if (STAGE && cta == 0 && warp == kCourierWarp) {
         // ---------------- courier: forwards what the physics warps staged, so that they never issue a remote store ----------------

@@ -1,4 +1,5 @@
-"""The persistent resident kernel (essa_persist_configure; resident_warp.cu K3q with a mailbox in mapped pinned memory).
+"""The persistent resident kernels (essa_persist_configure; resident_quad.cu K3q for up to 32 bodies and resident_cluster.cu K3x
+for 33 .. 128, with a mailbox in mapped pinned memory).
 
 What the reference's caller does -- SimulationView::update runs World::update(iterations) once per GUI tick and
 reads the objects back (src/SimulationView.cpp:374-397, 10 iterations by default) -- is served by a kernel that
@@ -46,7 +47,7 @@ def _same(a, b, rings=False):
 
 
 @pytest.mark.parametrize("fname,dt", [("solar.essa", 600), ("8body.essa", 600), ("2body.essa", 600), ("trail_test.essa", 3600),
-                                      ("solar.essa", 43200)])
+                                      ("solar.essa", 43200), ("jupiter_system.essa", 600), ("jupiter_system.essa", 7200)])
 def test_gui_cadence_is_bit_identical_to_one_launch_per_call(worlds_dir, fname, dt):
     a, b = _two(worlds_dir, fname, dt)
     for tick in range(120):
