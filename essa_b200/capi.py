@@ -204,23 +204,28 @@ class Context:
         self._ck(self._L.essa_upload(self._h, n, C.byref(b)))
 
     def download(self, fields=("x", "y", "z", "vx", "vy", "vz", "ax", "ay", "az", "gf", "most", "max_attraction", "ap", "pe",
-                               "ap_vel", "pe_vel")):
+                               "ap_vel", "pe_vel"), out=None):
+        """`out`: a dict of arrays from an earlier call to write into (what a host program with its own SoA buffers does;
+        fresh arrays cost a page fault per 4 KiB on first touch)."""
         n = self.n
-        out = {}
+        out = {} if out is None else out
         b = Bodies()
+
+        def buf(f, dtype):
+            a = out.get(f)
+            if a is None or a.dtype != dtype or a.shape != (n,) or not a.flags.c_contiguous:
+                a = out[f] = np.zeros(n, dtype=dtype)
+            return a
+
         for f in fields:
             if f in self._DOUBLE_FIELDS:
-                out[f] = np.zeros(n, dtype=np.float64)
-                setattr(b, f, _ptr(out[f], _dp))
+                setattr(b, f, _ptr(buf(f, np.float64), _dp))
             elif f == "most":
-                out[f] = np.zeros(n, dtype=np.int32)
-                b.most = _ptr(out[f], _i32p)
+                b.most = _ptr(buf(f, np.int32), _i32p)
             elif f in ("creation_date", "deletion_date"):
-                out[f] = np.zeros(n, dtype=np.int64)
-                setattr(b, f, _ptr(out[f], _i64p))
+                setattr(b, f, _ptr(buf(f, np.int64), _i64p))
             elif f == "deleted":
-                out[f] = np.zeros(n, dtype=np.uint8)
-                b.deleted = _ptr(out[f], _u8p)
+                b.deleted = _ptr(buf(f, np.uint8), _u8p)
             else:
                 raise KeyError(f)
         self._ck(self._L.essa_download(self._h, C.byref(b)))

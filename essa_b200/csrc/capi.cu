@@ -3,7 +3,11 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
+#include <climits>
+#include <functional>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -590,6 +594,45 @@ extern "C" int essa_set_date(essa_ctx* ctx, int64_t date) {
 // ---------------------------------------------------------------------------------------------
 // upload / download
 // ---------------------------------------------------------------------------------------------
+// Host edge of large worlds: the caller's SoA arrays are ordinary pageable memory, the DMA engine wants pinned memory.
+// Copying 59 MB (N = 1,048,576: x y z vx vy vz gf) into the staging buffer with one thread ran at 7 GB/s and was the
+// longest part of an end-to-end tick's host side; a handful of threads bring it to memory bandwidth.
+static void parallel_chunks(size_t total, size_t chunk, int max_threads, std::function<void(size_t, size_t)> const& fn) {
+    size_t const nchunks = (total + chunk - 1) / chunk;
+    int threads = (int)std::min<size_t>(nchunks, (size_t)max_threads);
+    if (threads <= 1) {
+        if (total)
+            fn(0, total);
+        return;
+    }
+    std::atomic<size_t> next { 0 };
+    auto work = [&]() {
+        for (;;) {
+            size_t c = next.fetch_add(1);
+            if (c >= nchunks)
+                return;
+            size_t lo = c * chunk, hi = std::min(total, lo + chunk);
+            fn(lo, hi);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++)
+        pool.emplace_back(work);
+    work();
+    for (auto& th : pool)
+        th.join();
+}
+
+static int host_threads() {
+    static int const v = [] {
+        if (char const* e = getenv("ESSA_HOST_THREADS"))
+            return std::max(1, atoi(e));
+        unsigned hc = std::thread::hardware_concurrency();
+        return (int)std::max(1u, std::min(8u, hc ? hc / 2 : 4u));
+    }();
+    return v;
+}
+
 extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
     ARG(ctx, "ctx is null");
     ARG(h && n >= 0, "bad arguments");
@@ -608,6 +651,13 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
     if (n == 0)
         return ESSA_OK;
     size_t N = (size_t)n, cap = (size_t)ctx->cap;
+    if (h->most)
+        for (size_t i = 0; i < N; i++)
+            if (h->most[i] < -1 || h->most[i] >= n) {
+                ctx->err = "most[] must hold list indices in [0, n) or -1";
+                ctx->n = 0; // nothing was uploaded
+                return ESSA_ERR_ARG;
+            }
     // staging layout: 7 N doubles | 4 N doubles (ap pe apv pev) | 2 N int64 | N int32 | 2 N bytes
     size_t bytes = 11 * N * sizeof(double) + 2 * N * sizeof(int64_t) + N * sizeof(int32_t) + 2 * N;
     rc = reserve_pinned(ctx, bytes);
@@ -615,45 +665,21 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
         return rc;
     double* d = static_cast<double*>(ctx->pinned);
     double const* src[7] = { h->x, h->y, h->z, h->vx, h->vy, h->vz, h->gf };
-    for (int k = 0; k < 7; k++)
-        memcpy(d + k * N, src[k], N * sizeof(double));
-    // equal gravity factors everywhere: no body has a heavier partner, so Object.cpp:84-94 can never fire
-    ctx->gf_uniform = true;
-    ctx->gf_uniform_value = h->gf[0];
-    for (size_t i = 1; i < N && ctx->gf_uniform; i++)
-        ctx->gf_uniform = h->gf[i] == h->gf[0];
-    double* appe = d + 7 * N;
-    for (size_t i = 0; i < N; i++) {
-        appe[i] = h->ap ? h->ap[i] : 0.0;
-        appe[N + i] = h->pe ? h->pe[i] : DBL_MAX;
-        appe[2 * N + i] = h->ap_vel ? h->ap_vel[i] : 0.0;
-        appe[3 * N + i] = h->pe_vel ? h->pe_vel[i] : 0.0;
-    }
-    int64_t* dates = reinterpret_cast<int64_t*>(d + 11 * N);
-    int32_t* most = reinterpret_cast<int32_t*>(dates + 2 * N);
-    uint8_t* flags = reinterpret_cast<uint8_t*>(most + N);
-    for (size_t i = 0; i < N; i++) {
-        int64_t cd = h->creation_date ? h->creation_date[i] : INT64_MIN;
-        int64_t dd = h->deletion_date ? h->deletion_date[i] : 0;
-        uint8_t del = h->deleted ? (h->deleted[i] != 0) : 0;
-        dates[i] = cd;
-        dates[N + i] = dd;
-        flags[i] = del;
-        flags[N + i] = body_active_host(del, dd, cd, ctx->date) ? 1 : 0;
-        most[i] = h->most ? h->most[i] : -1;
-        if (most[i] < -1 || most[i] >= n) {
-            ctx->err = "most[] must hold list indices in [0, n) or -1";
-            ctx->n = 0; // nothing was uploaded
-            return ESSA_ERR_ARG;
-        }
-        if (cd != INT64_MIN)
-            ctx->events.push_back(cd);
-        if (del)
-            ctx->events.push_back(dd);
-    }
-    std::sort(ctx->events.begin(), ctx->events.end());
-    ctx->events.erase(std::unique(ctx->events.begin(), ctx->events.end()), ctx->events.end());
-
+    // required arrays: staged by several threads (chunks of 256 Ki elements of all seven arrays); the same pass finds out
+    // whether every gravity factor is the same value (then no body has a heavier partner: Object.cpp:84-94 can never fire)
+    std::atomic<bool> uniform { true };
+    double const g0 = h->gf[0];
+    parallel_chunks(N, (size_t)1 << 18, N >= ((size_t)1 << 17) ? host_threads() : 1, [&](size_t lo, size_t hi) {
+        for (int k = 0; k < 7; k++)
+            memcpy(d + k * N + lo, src[k] + lo, (hi - lo) * sizeof(double));
+        bool u = true;
+        for (size_t i = lo; i < hi && u; i++)
+            u = h->gf[i] == g0;
+        if (!u)
+            uniform.store(false, std::memory_order_relaxed);
+    });
+    ctx->gf_uniform = uniform.load();
+    ctx->gf_uniform_value = g0;
     cudaStream_t st = ctx->stream;
     // x y z go through velh (scratch between steps) and are packed into 32-byte j-records
     for (int k = 0; k < 3; k++) {
@@ -661,6 +687,55 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
         CK(cudaMemcpyAsync(ctx->vel + k * cap, d + (3 + k) * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
     }
     CK(cudaMemcpyAsync(ctx->gf, d + 6 * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    // ap / pe: members the caller left out get the Object constructor's values ON THE DEVICE (0, DBL_MAX, 0, 0: no host loop, no copy)
+    double const* appe_in[4] = { h->ap, h->pe, h->ap_vel, h->pe_vel };
+    double const appe_def[4] = { 0.0, DBL_MAX, 0.0, 0.0 };
+    for (int k = 0; k < 4; k++) {
+        if (appe_in[k]) {
+            memcpy(d + (7 + k) * N, appe_in[k], N * sizeof(double));
+            CK(cudaMemcpyAsync(ctx->appe + k * cap, d + (7 + k) * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
+        } else {
+            CK(launch_fill_f64(ctx, ctx->appe + k * cap, appe_def[k], N, st));
+        }
+    }
+    int64_t* dates = reinterpret_cast<int64_t*>(d + 11 * N);
+    int32_t* most = reinterpret_cast<int32_t*>(dates + 2 * N);
+    uint8_t* flags = reinterpret_cast<uint8_t*>(most + N);
+    if (h->creation_date || h->deletion_date || h->deleted) {
+        for (size_t i = 0; i < N; i++) {
+            int64_t cd = h->creation_date ? h->creation_date[i] : INT64_MIN;
+            int64_t dd = h->deletion_date ? h->deletion_date[i] : 0;
+            uint8_t del = h->deleted ? (h->deleted[i] != 0) : 0;
+            dates[i] = cd;
+            dates[N + i] = dd;
+            flags[i] = del;
+            flags[N + i] = body_active_host(del, dd, cd, ctx->date) ? 1 : 0;
+            if (cd != INT64_MIN)
+                ctx->events.push_back(cd);
+            if (del)
+                ctx->events.push_back(dd);
+        }
+        std::sort(ctx->events.begin(), ctx->events.end());
+        ctx->events.erase(std::unique(ctx->events.begin(), ctx->events.end()), ctx->events.end());
+        CK(cudaMemcpyAsync(ctx->cdate, dates, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->ddate, dates + N, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->delflag, flags, N, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->active, flags + N, N, cudaMemcpyHostToDevice, st));
+    } else {
+        // "always there": creation date in the infinite past, never deleted, active
+        CK(launch_fill_i64(ctx, ctx->cdate, INT64_MIN, N, st));
+        CK(cudaMemsetAsync(ctx->ddate, 0, N * sizeof(int64_t), st));
+        CK(cudaMemsetAsync(ctx->delflag, 0, N, st));
+        CK(cudaMemsetAsync(ctx->active, 1, N, st));
+    }
+    if (h->most) {
+        memcpy(most, h->most, N * sizeof(int32_t));
+        CK(cudaMemcpyAsync(ctx->most, most, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->old_most, most, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    } else { // -1: no most attracting object
+        CK(cudaMemsetAsync(ctx->most, 0xff, N * sizeof(int32_t), st));
+        CK(cudaMemsetAsync(ctx->old_most, 0xff, N * sizeof(int32_t), st));
+    }
     // m_attraction_factor / m_max_attraction are outputs of set_forces(), except for bodies that
     // Object::deleted() masks: those keep whatever they held (clear_forces skips them), so a caller
     // that re-uploads a world with masked bodies may pass them along.  Default 0.
@@ -675,14 +750,6 @@ extern "C" int essa_upload(essa_ctx* ctx, int n, const essa_bodies* h) {
         CK(cudaMemcpyAsync(ctx->maxattr, h->max_attraction, N * sizeof(double), cudaMemcpyHostToDevice, st));
     else
         CK(cudaMemsetAsync(ctx->maxattr, 0, N * sizeof(double), st));
-    for (int k = 0; k < 4; k++)
-        CK(cudaMemcpyAsync(ctx->appe + k * cap, appe + k * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->cdate, dates, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->ddate, dates + N, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->most, most, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->old_most, most, N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->delflag, flags, N, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->active, flags + N, N, cudaMemcpyHostToDevice, st));
     CK(launch_pack(ctx, ctx->velh, ctx->velh + cap, ctx->velh + 2 * cap, st));
     CK(cudaStreamSynchronize(st));
     return ESSA_OK;
@@ -786,9 +853,11 @@ extern "C" int essa_download(essa_ctx* ctx, essa_bodies* h) {
     CK(cudaStreamSynchronize(st));
     double* dst[15] = { h->x, h->y, h->z, h->vx, h->vy, h->vz, h->ax, h->ay, h->az, h->gf, h->max_attraction, h->ap, h->pe, h->ap_vel,
         h->pe_vel };
-    for (int k = 0; k < 15; k++)
-        if (dst[k])
-            memcpy(dst[k], d + k * N, N * sizeof(double));
+    parallel_chunks(N, (size_t)1 << 18, N >= ((size_t)1 << 17) ? host_threads() : 1, [&](size_t lo, size_t hi) {
+        for (int k = 0; k < 15; k++)
+            if (dst[k])
+                memcpy(dst[k] + lo, d + k * N + lo, (hi - lo) * sizeof(double));
+    });
     if (h->creation_date)
         memcpy(h->creation_date, dates, N * sizeof(int64_t));
     if (h->deletion_date)

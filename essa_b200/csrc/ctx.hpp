@@ -256,6 +256,8 @@ cudaError_t launch_kick_drift(essa_ctx* c, KickArgs const& k, cudaStream_t st);
 cudaError_t launch_refresh_active(essa_ctx* c, cudaStream_t st);
 cudaError_t launch_record(essa_ctx* c, int offset_trails, int forward_simulated, cudaStream_t st);
 cudaError_t launch_record_init(essa_ctx* c, int first, cudaStream_t st);
+cudaError_t launch_fill_f64(essa_ctx* c, double* dst, double v, size_t n, cudaStream_t st);
+cudaError_t launch_fill_i64(essa_ctx* c, int64_t* dst, int64_t v, size_t n, cudaStream_t st);
 cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double const* z, cudaStream_t st);
 cudaError_t launch_unpack(essa_ctx* c, double* x, double* y, double* z, cudaStream_t st);
 bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles, int* ri_out = nullptr);

@@ -401,6 +401,29 @@ cudaError_t launch_refresh_active(essa_ctx* c, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// Values the Object constructor gives to members an upload leaves out (ap = 0, pe = DBL_MAX, creation date "always"): written
+// here instead of being looped over on the host and copied.
+template<class T>
+__global__ void k_fill(T* dst, T v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = v;
+}
+cudaError_t launch_fill_f64(essa_ctx* c, double* dst, double v, size_t n, cudaStream_t st) {
+    if (n == 0)
+        return cudaSuccess;
+    k_fill<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, v, n);
+    c->launches++;
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_i64(essa_ctx* c, int64_t* dst, int64_t v, size_t n, cudaStream_t st) {
+    if (n == 0)
+        return cudaSuccess;
+    k_fill<long long><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<long long*>(dst), (long long)v, n);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double const* z, cudaStream_t st) {
     if (c->n <= 0)
         return cudaSuccess;

@@ -21,10 +21,8 @@ for it in range(4):
     t1 = time.perf_counter()
     c.step(1, opts=opts)
     t2 = time.perf_counter()
-    got = c.download(("x", "y", "z", "vx", "vy", "vz"))
+    c.download(("x", "y", "z", "vx", "vy", "vz"), out=host)
     t3 = time.perf_counter()
-    for k in ("x", "y", "z", "vx", "vy", "vz"):
-        host[k] = got[k]
     print("tick %d: upload %.1f ms, step %.1f ms (device %.1f, force %.1f in %d passes), download %.1f ms" % (
         it, 1e3 * (t1 - t0), 1e3 * (t2 - t1), c.last_step_ms, c.last_force_ms, c.last_force_passes, 1e3 * (t3 - t2)), flush=True)
 for it in range(2):
