@@ -388,19 +388,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world_size == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    from essa_b200 import dist as edist  # the rendezvous-level plumbing (tests/test_dist_cpu.py exercises it under gloo)
 
-    def fresh_uid():
-        uid = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.from_numpy(capi.nccl_unique_id()))
-        dist.broadcast(uid, 0)
-        return uid.cpu().numpy()
+    def max_over_ranks(x):
+        return x if world_size == 1 else edist.max_over_ranks(x)
+
+    fresh_uid = edist.broadcast_unique_id
 
     n = args.n
     w, dt, name = workload(n)

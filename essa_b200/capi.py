@@ -57,6 +57,11 @@ class EnsembleOpts(C.Structure):
                 ("approach_to", C.c_int)]
 
 
+class TrailView(C.Structure):
+    _fields_ = [("verts_device", C.c_void_p), ("capacity", C.c_int32), ("append_offset", C.c_int32), ("length", C.c_int32),
+                ("pad", C.c_int32), ("offset", C.c_double * 3)]
+
+
 # every symbol include/essa_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = [
@@ -89,6 +94,10 @@ SYMBOLS = [
     ("essa_history_write", C.c_int, [_P, C.c_int, _dp, C.c_int, C.c_int]),
     ("essa_trail_read", C.c_int, [_P, C.c_int, _fp, C.POINTER(TrailMeta)]),
     ("essa_trail_write", C.c_int, [_P, C.c_int, _fp, C.POINTER(TrailMeta)]),
+    ("essa_trail_device_view", C.c_int, [_P, C.c_int, C.POINTER(TrailView)]),
+    ("essa_snapshot_size", C.c_int64, [_P]),
+    ("essa_snapshot_write", C.c_int, [_P, C.c_void_p, C.c_int64]),
+    ("essa_snapshot_read", C.c_int, [_P, C.c_void_p, C.c_int64]),
     ("essa_closest_enable", C.c_int, [_P, C.c_int]),
     ("essa_closest_read", C.c_int, [_P, C.c_int, C.c_int, _dp]),
     ("essa_energy", C.c_int, [_P, _dp, _dp, _dp]),
@@ -308,6 +317,24 @@ class Context:
                          (C.c_double * 3)(*[float(v) for v in trail["offset"]]), float(trail["last_xy_angle"]))
         verts = _arr(trail["verts"], np.float32)
         self._ck(self._L.essa_trail_write(self._h, body, _ptr(verts, _fp), C.byref(meta)))
+
+    def trail_device_view(self, body):
+        """Zero-copy view of the Trail ring in device memory (what a renderer maps): dict with the device pointer."""
+        v = TrailView()
+        self._ck(self._L.essa_trail_device_view(self._h, body, C.byref(v)))
+        return dict(verts_device=v.verts_device, capacity=v.capacity, append_offset=v.append_offset, length=v.length,
+                    offset=np.array(list(v.offset)))
+
+    def snapshot(self):
+        """The whole context as one flat blob (bytes)."""
+        n = self._ck(self._L.essa_snapshot_size(self._h))
+        buf = np.zeros(n, dtype=np.uint8)
+        self._ck(self._L.essa_snapshot_write(self._h, buf.ctypes.data_as(C.c_void_p), n))
+        return buf.tobytes()
+
+    def restore(self, blob):
+        buf = np.frombuffer(blob, dtype=np.uint8).copy()
+        self._ck(self._L.essa_snapshot_read(self._h, buf.ctypes.data_as(C.c_void_p), len(buf)))
 
     def closest_enable(self, enable=True):
         self._ck(self._L.essa_closest_enable(self._h, int(enable)))

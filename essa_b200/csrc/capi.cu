@@ -1462,6 +1462,184 @@ extern "C" int essa_trail_write(essa_ctx* ctx, int body, const float* verts, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// consumers of the recording: zero-copy Trail view for a renderer, flat snapshot
+// ---------------------------------------------------------------------------------------------
+extern "C" int essa_trail_device_view(essa_ctx* ctx, int body, essa_trail_view* out) {
+    ARG(ctx, "ctx is null");
+    ARG(out, "out is null");
+    ARG(body >= 0 && body < ctx->tracked, "body is not tracked");
+    CK(cudaSetDevice(ctx->device));
+    PARK();
+    CK(cudaStreamSynchronize(ctx->stream));
+    out->verts_device = ctx->verts + (size_t)ctx->vert_off_h[body] * 3;
+    out->capacity = ctx->trail_cap[body];
+    out->pad = 0;
+    CK(cudaMemcpy(&out->append_offset, ctx->append_off + body, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&out->length, ctx->tlength + body, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out->offset, ctx->toff + (size_t)body * 3, 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return ESSA_OK;
+}
+
+// Snapshot layout (all little-endian, naturally aligned because every section is a multiple of 8 bytes):
+//   char[8] "ESSASNAP" | u32 version = 1 | u32 n | u32 tracked | u32 0 | i64 date
+//   f64[15][n]  x y z vx vy vz ax ay az gf max_attraction ap pe ap_vel pe_vel
+//   i64[2][n]   creation_date deletion_date | i32[n] most (+ pad to 8) | u8[n] deleted (+ pad to 8)
+//   per tracked body: i32 capacity, i32 append_offset, i32 length, i32 history_entries, f64 offset[3], f64 last_xy_angle,
+//                     f64[6] History::m_first_entry, f64[history_entries][6] (oldest first), f32[capacity][3] (+ pad to 8)
+namespace {
+constexpr char kSnapMagic[8] = { 'E', 'S', 'S', 'A', 'S', 'N', 'A', 'P' };
+inline size_t pad8(size_t b) { return (b + 7) & ~(size_t)7; }
+}
+
+extern "C" int64_t essa_snapshot_size(essa_ctx* ctx) {
+    if (!ctx)
+        return ESSA_ERR_ARG;
+    size_t const N = (size_t)ctx->n;
+    size_t bytes = 8 + 4 * 4 + 8 + 15 * N * 8 + 2 * N * 8 + pad8(N * 4) + pad8(N);
+    for (int k = 0; k < ctx->tracked; k++) {
+        int len = essa_history_read(ctx, k, nullptr);
+        if (len < 0)
+            return len;
+        bytes += 4 * 4 + 4 * 8 + 6 * 8 + (size_t)len * 48 + pad8((size_t)ctx->trail_cap[k] * 12);
+    }
+    return (int64_t)bytes;
+}
+
+extern "C" int essa_snapshot_write(essa_ctx* ctx, void* blob, int64_t bytes) {
+    ARG(ctx, "ctx is null");
+    ARG(blob, "blob is null");
+    int64_t const need = essa_snapshot_size(ctx);
+    if (need < 0)
+        return (int)need;
+    ARG(bytes >= need, "blob is smaller than essa_snapshot_size()");
+    size_t const N = (size_t)ctx->n;
+    unsigned char* p = static_cast<unsigned char*>(blob);
+    memset(p, 0, (size_t)need);
+    memcpy(p, kSnapMagic, 8);
+    uint32_t hdr[4] = { 1u, (uint32_t)ctx->n, (uint32_t)ctx->tracked, 0u };
+    memcpy(p + 8, hdr, sizeof(hdr));
+    int64_t const date = ctx->date;
+    memcpy(p + 24, &date, 8);
+    p += 32;
+    essa_bodies b;
+    memset(&b, 0, sizeof(b));
+    double* f = reinterpret_cast<double*>(p);
+    double** dm[15] = { &b.x, &b.y, &b.z, &b.vx, &b.vy, &b.vz, &b.ax, &b.ay, &b.az, &b.gf, &b.max_attraction, &b.ap, &b.pe, &b.ap_vel, &b.pe_vel };
+    for (int k = 0; k < 15; k++)
+        *dm[k] = f + (size_t)k * N;
+    p += 15 * N * 8;
+    b.creation_date = reinterpret_cast<int64_t*>(p);
+    b.deletion_date = b.creation_date + N;
+    p += 2 * N * 8;
+    b.most = reinterpret_cast<int32_t*>(p);
+    p += pad8(N * 4);
+    b.deleted = p;
+    p += pad8(N);
+    if (N) {
+        int rc = essa_download(ctx, &b);
+        if (rc != ESSA_OK)
+            return rc;
+    }
+    for (int k = 0; k < ctx->tracked; k++) {
+        essa_trail_meta meta;
+        int32_t* ih = reinterpret_cast<int32_t*>(p);
+        double* dh = reinterpret_cast<double*>(p + 16);
+        int len = essa_history_read(ctx, k, dh + 4 + 6);
+        if (len < 0)
+            return len;
+        CK(cudaMemcpy(dh + 4, ctx->hist_first + (size_t)k * 6, 6 * sizeof(double), cudaMemcpyDeviceToHost));
+        float* verts = reinterpret_cast<float*>(p + 16 + 4 * 8 + 6 * 8 + (size_t)len * 48);
+        int rc = essa_trail_read(ctx, k, verts, &meta);
+        if (rc != ESSA_OK)
+            return rc;
+        ih[0] = meta.capacity;
+        ih[1] = meta.append_offset;
+        ih[2] = meta.length;
+        ih[3] = len;
+        memcpy(dh, meta.offset, 3 * sizeof(double));
+        dh[3] = meta.last_xy_angle;
+        p += 16 + 4 * 8 + 6 * 8 + (size_t)len * 48 + pad8((size_t)meta.capacity * 12);
+    }
+    return ESSA_OK;
+}
+
+extern "C" int essa_snapshot_read(essa_ctx* ctx, const void* blob, int64_t bytes) {
+    ARG(ctx, "ctx is null");
+    ARG(blob && bytes >= 32, "blob is too short");
+    unsigned char const* p = static_cast<unsigned char const*>(blob);
+    unsigned char const* const end = p + bytes;
+    ARG(memcmp(p, kSnapMagic, 8) == 0, "not an ESSASNAP blob");
+    uint32_t hdr[4];
+    memcpy(hdr, p + 8, sizeof(hdr));
+    ARG(hdr[0] == 1u, "unknown snapshot version");
+    size_t const N = hdr[1];
+    int const tracked = (int)hdr[2];
+    int64_t date;
+    memcpy(&date, p + 24, 8);
+    p += 32;
+    ARG((size_t)(end - p) >= 15 * N * 8 + 2 * N * 8 + pad8(N * 4) + pad8(N) && (size_t)tracked <= N, "blob is truncated");
+    int rc = essa_set_date(ctx, date);
+    if (rc != ESSA_OK)
+        return rc;
+    essa_bodies b;
+    memset(&b, 0, sizeof(b));
+    double* f = const_cast<double*>(reinterpret_cast<double const*>(p));
+    double** dm[15] = { &b.x, &b.y, &b.z, &b.vx, &b.vy, &b.vz, &b.ax, &b.ay, &b.az, &b.gf, &b.max_attraction, &b.ap, &b.pe, &b.ap_vel, &b.pe_vel };
+    for (int k = 0; k < 15; k++)
+        *dm[k] = f + (size_t)k * N;
+    p += 15 * N * 8;
+    b.creation_date = const_cast<int64_t*>(reinterpret_cast<int64_t const*>(p));
+    b.deletion_date = b.creation_date + N;
+    p += 2 * N * 8;
+    b.most = const_cast<int32_t*>(reinterpret_cast<int32_t const*>(p));
+    p += pad8(N * 4);
+    b.deleted = const_cast<uint8_t*>(p);
+    p += pad8(N);
+    rc = essa_upload(ctx, (int)N, &b);
+    if (rc != ESSA_OK)
+        return rc;
+    if (tracked == 0)
+        return essa_record_configure(ctx, 0, nullptr, 0);
+    // first pass: capacities, then the rings
+    std::vector<int32_t> caps(tracked);
+    unsigned char const* q = p;
+    for (int k = 0; k < tracked; k++) {
+        ARG((size_t)(end - q) >= 16 + 4 * 8 + 6 * 8, "blob is truncated");
+        int32_t ih[4];
+        memcpy(ih, q, sizeof(ih));
+        ARG(ih[0] >= 3 && ih[3] >= 1 && ih[3] <= ESSA_HISTORY_SEGMENTS, "bad recording header");
+        caps[k] = ih[0];
+        size_t const sz = 16 + 4 * 8 + 6 * 8 + (size_t)ih[3] * 48 + pad8((size_t)ih[0] * 12);
+        ARG((size_t)(end - q) >= sz, "blob is truncated");
+        q += sz;
+    }
+    rc = essa_record_configure(ctx, tracked, caps.data(), 0);
+    if (rc != ESSA_OK)
+        return rc;
+    for (int k = 0; k < tracked; k++) {
+        int32_t ih[4];
+        memcpy(ih, p, sizeof(ih));
+        double const* dh = reinterpret_cast<double const*>(p + 16);
+        if ((rc = essa_history_write(ctx, k, dh + 4, 1, 1)) != ESSA_OK) // History::m_first_entry
+            return rc;
+        if ((rc = essa_history_write(ctx, k, dh + 4 + 6, ih[3], 0)) != ESSA_OK)
+            return rc;
+        essa_trail_meta meta;
+        meta.capacity = ih[0];
+        meta.append_offset = ih[1];
+        meta.length = ih[2];
+        meta.pad = 0;
+        memcpy(meta.offset, dh, 3 * sizeof(double));
+        meta.last_xy_angle = dh[3];
+        float const* verts = reinterpret_cast<float const*>(p + 16 + 4 * 8 + 6 * 8 + (size_t)ih[3] * 48);
+        if ((rc = essa_trail_write(ctx, k, verts, &meta)) != ESSA_OK)
+            return rc;
+        p += 16 + 4 * 8 + 6 * 8 + (size_t)ih[3] * 48 + pad8((size_t)ih[0] * 12);
+    }
+    return ESSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // diagnostics
 // ---------------------------------------------------------------------------------------------
 extern "C" int essa_energy(essa_ctx* ctx, double* kinetic, double* potential, double momentum[3]) {

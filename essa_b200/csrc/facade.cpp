@@ -566,6 +566,14 @@ void World::sync_from_device() {
     }
 }
 
+void World::debug_stash_last_object() {
+    if (m_object_list.empty())
+        return;
+    m_object_history.push_to_entry(std::move(m_object_list.back())); // reset_history() brings its rings home first
+    m_object_list.pop_back();
+    m_list_dirty = true;
+}
+
 void World::update_history_and_date(bool reverse) {
     if (m_is_forward_simulated)
         return;

@@ -239,6 +239,12 @@ public:
     // Evaluate both set_forces() calls of every step (the reference does; results are identical).
     bool two_pass = false;
 
+    // Seeds the ObjectHistory with the list's last object.  The reference's current revision never does (src/World.cpp:76-81
+    // pushes only when the history already holds an entry), so the date-driven push / pop of World.cpp:59-84 can only be
+    // exercised from outside: this is the hook the tests use.
+    void debug_stash_last_object();
+    unsigned object_history_size() const { return m_object_history.size(); }
+
     essa_ctx* context(); // creates the context on first use; throws std::runtime_error without a GPU
     double last_step_ms() const;
     // essa_persist_configure / essa_persist_stats of the world's context: whether the kernel that served one update()

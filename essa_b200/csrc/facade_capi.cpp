@@ -139,6 +139,14 @@ int essa_world_set_forces(essa_world* w) {
 
 double essa_world_last_step_ms(const essa_world* w) { return w ? w->world.last_step_ms() : 0.0; }
 
+int essa_world_debug_stash_last_object(essa_world* w) {
+    WANT(w, "null world");
+    GUARD(w->world.debug_stash_last_object();)
+    return ESSA_OK;
+}
+
+int essa_world_object_history_size(const essa_world* w) { return w ? (int)w->world.object_history_size() : 0; }
+
 int essa_world_set_persistent(essa_world* w, int enable, int idle_timeout_us) {
     WANT(w, "null world");
     GUARD(w->world.set_persistent(enable != 0, idle_timeout_us);)

@@ -48,6 +48,8 @@ WORLD_SYMBOLS = [
     ("essa_world_update", C.c_int, [_P, C.c_int]),
     ("essa_world_set_forces", C.c_int, [_P]),
     ("essa_world_last_step_ms", C.c_double, [_P]),
+    ("essa_world_debug_stash_last_object", C.c_int, [_P]),
+    ("essa_world_object_history_size", C.c_int, [_P]),
     ("essa_world_set_persistent", C.c_int, [_P, C.c_int, C.c_int]),
     ("essa_world_persist_stats", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("essa_world_get_state", C.c_int, [_P, _dp, _dp, _dp, _dp, _i32p, _dp, _i32p, _dp]),
@@ -316,9 +318,20 @@ class World:
     # ---- stepping (what SimulationView::update does per GUI tick, src/SimulationView.cpp:374-397) ----
     def update(self, steps):
         self._ck(self._L.essa_world_update(self._h, int(steps)))
+        if self._L.essa_world_object_history_size(self._h) and self._L.essa_world_count(self._h) != len(self._uids):
+            self._resync_uids()  # objects left / rejoined the list with the date (ObjectHistory)
 
     def set_forces(self):
         self._ck(self._L.essa_world_set_forces(self._h))
+
+    def debug_stash_last_object(self):
+        """Seeds the ObjectHistory with the list's last object (see include/essa_world.h)."""
+        self._ck(self._L.essa_world_debug_stash_last_object(self._h))
+        self._resync_uids()
+
+    @property
+    def object_history_size(self):
+        return self._L.essa_world_object_history_size(self._h)
 
     def set_persistent(self, enable=True, idle_timeout_us=0):
         """Keep the small-world kernel resident between update() calls (essa_persist_configure); default on."""

@@ -16,6 +16,7 @@
  *                                  src/Object.cpp:60-62
  *     Object::m_history            src/History.cpp:6-59    essa_history_read / _write
  *     Object::m_trail              src/Trail.cpp:19-110    essa_trail_read / _write
+ *     Trail::draw's vertex data    src/Trail.cpp:90-103    essa_trail_device_view (zero-copy), essa_snapshot_*
  *     clone_for_forward_simulation src/World.cpp:230-238,  essa_ensemble_init / _step / _read
  *       + update(ticks)            src/essagui/EssaCreateObject.cpp:166-189
  *     (none: new diagnostic required by the north star)    essa_energy
@@ -181,6 +182,27 @@ typedef struct essa_trail_meta {
 /* verts: 3 * capacity floats (x y z per vertex, already divided by AU); may be null. */
 int essa_trail_read(essa_ctx* ctx, int body, float* verts, essa_trail_meta* meta);
 int essa_trail_write(essa_ctx* ctx, int body, const float* verts, const essa_trail_meta* meta);
+
+/* ---- consumers of the recording: what src/Trail.cpp:90-103 (Trail::draw) and src/World.cpp:150-161 (World::draw) do next ------ */
+/* Zero-copy view of a tracked body's Trail ring IN DEVICE MEMORY, for a renderer that draws from a CUDA-mapped vertex buffer
+ * (cudaGraphicsGLRegisterBuffer / external memory) or copies device-to-device: `verts_device` = the ring's first vertex
+ * (3 floats each, already divided by AU, `capacity` of them), plus the cursor Trail::draw needs to split the ring into its one
+ * or two line strips (draw [1, append_offset) while length != capacity, else [0, append_offset) and [append_offset, length)) and
+ * the offset its model matrix translates by.  The pointer stays valid until the next essa_record_configure / essa_ctx_destroy;
+ * the contents change with every essa_step (retire the view's reader first: the call synchronises the context). */
+typedef struct essa_trail_view {
+    const float* verts_device;
+    int32_t capacity, append_offset, length, pad;
+    double offset[3];
+} essa_trail_view;
+int essa_trail_device_view(essa_ctx* ctx, int body, essa_trail_view* out);
+/* Flat snapshot of the whole context -- bodies, date, History and Trail rings of the tracked bodies -- as one self-describing
+ * little-endian blob (the reference has no on-disk or wire format for simulation state; this one is
+ * "ESSASNAP" | u32 version | u32 n | u32 tracked | i64 date | per-field arrays, see capi.cu).  essa_snapshot_size returns the
+ * bytes essa_snapshot_write needs; essa_snapshot_read restores a context from a blob (upload + recording state). */
+int64_t essa_snapshot_size(essa_ctx* ctx);
+int essa_snapshot_write(essa_ctx* ctx, void* blob, int64_t bytes);
+int essa_snapshot_read(essa_ctx* ctx, const void* blob, int64_t bytes);
 
 /* ---- closest approaches of a forward-simulated world (src/Object.cpp:405-417) ------------------ */
 /* Allocate (enable != 0) or drop the N x N table; essa_step with forward_simulated set then keeps,

@@ -52,6 +52,11 @@ int essa_world_set_flags(essa_world* w, int offset_trails, int exact_order, int 
 int essa_world_update(essa_world* w, int steps);
 int essa_world_set_forces(essa_world* w);
 double essa_world_last_step_ms(const essa_world* w);
+/* ObjectHistory (src/ObjectHistory.cpp, src/World.cpp:59-84): objects leave the list when the date moves below their creation
+ * date and come back when it moves forward again -- but only once the history holds an entry, which the reference's current
+ * revision never creates.  This seeds it with the list's last object (tests; a future revision's rewind). */
+int essa_world_debug_stash_last_object(essa_world* w);
+int essa_world_object_history_size(const essa_world* w);
 /* essa_persist_configure / essa_persist_stats of the world's context (essa_b200.h): keep the small-world kernel
  * resident between update() calls (default on). */
 int essa_world_set_persistent(essa_world* w, int enable, int idle_timeout_us);

@@ -56,6 +56,8 @@ def lib():
         L.ow_set_flags.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ow_update.argtypes = [C.c_void_p, C.c_int]
         L.ow_set_forces.argtypes = [C.c_void_p]
+        L.ow_debug_stash_last.argtypes = [C.c_void_p]
+        L.ow_object_history_size.argtypes = [C.c_void_p]
         L.ow_count.argtypes = [C.c_void_p]
         L.ow_date.argtypes = [C.c_void_p]
         L.ow_date.restype = C.c_longlong
@@ -179,6 +181,14 @@ class World:
     def remove_object(self, idx):
         """World::delete_object_by_ptr (src/World.cpp:208-219)."""
         self._L.ow_remove_object(self._h, idx)
+
+    def debug_stash_last(self):
+        """Moves the list's last object into the ObjectHistory (see ow_debug_stash_last)."""
+        self._L.ow_debug_stash_last(self._h)
+
+    @property
+    def object_history_size(self):
+        return self._L.ow_object_history_size(self._h)
 
     def reset_history(self, idx):
         self._L.ow_reset_history(self._h, idx)

@@ -202,6 +202,8 @@ std::string load_essa(std::string const& text, World& world, bool angle_as_float
 using oracle::Object;
 using oracle::Vec3;
 using oracle::World;
+using oracle::History;
+using oracle::Trail;
 
 extern "C" {
 
@@ -290,6 +292,15 @@ void ow_remove_object(void* w, int idx) {
             o->delete_most_attracting_object();
 }
 void ow_reset_history(void* w, int idx) { static_cast<World*>(w)->object_at(idx)->reset_history(); }
+// Seeds the ObjectHistory (src/ObjectHistory.cpp:20-23 on the list's last object): the reference's current revision never does
+// this itself (World.cpp:76-81 pushes only when the history already holds an entry), so its date-driven push / pop logic
+// (World.cpp:59-84) can only be exercised from outside.
+void ow_debug_stash_last(void* w) {
+    auto* world = static_cast<World*>(w);
+    world->m_object_history.push_to_entry(std::move(world->m_object_list.back()));
+    world->m_object_list.pop_back();
+}
+int ow_object_history_size(void* w) { return (int)static_cast<World*>(w)->m_object_history.size(); }
 char const* ow_name(void* w, int idx) { return static_cast<World*>(w)->object_at(idx)->m_name.c_str(); }
 double ow_radius(void* w, int idx) { return static_cast<World*>(w)->object_at(idx)->m_radius; }
 double ow_orbit_len(void* w, int idx) { return static_cast<World*>(w)->object_at(idx)->m_orbit_len; }
@@ -510,6 +521,64 @@ void ow_add_bodies(void* w, int n, double const* x, double const* y, double cons
         o->m_creation_date = world->m_date;
         world->m_object_list.push_back(std::move(o)); // add_object's remove_if is O(N) per call; same end state
     }
+}
+
+// ---- the oracle's own History / Trail classes behind the C ABI of ref_driver.cpp (same signatures, prefix o instead of ref):
+// tests drive both with identical inputs and demand identical bits (tests/test_oracle_ref.py) ----
+void* o_history_new(unsigned segments, double const* first) {
+    return new History(segments, { { first[0], first[1], first[2] }, { first[3], first[4], first[5] } });
+}
+void o_history_free(void* h) { delete static_cast<History*>(h); }
+static int o_give(std::optional<History::Entry> const& e, double* out) {
+    if (!e)
+        return 0;
+    double v[6] = { e->pos.x, e->pos.y, e->pos.z, e->vel.x, e->vel.y, e->vel.z };
+    std::memcpy(out, v, sizeof(v));
+    return 1;
+}
+int o_history_move_forward(void* h, double const* e, double* out) {
+    return o_give(static_cast<History*>(h)->move_forward({ { e[0], e[1], e[2] }, { e[3], e[4], e[5] } }), out);
+}
+int o_history_move_backward(void* h, double const* e, double* out) {
+    return o_give(static_cast<History*>(h)->move_backward({ { e[0], e[1], e[2] }, { e[3], e[4], e[5] } }), out);
+}
+void o_history_reset(void* h) { static_cast<History*>(h)->reset(); }
+int o_history_read(void* h, double* out, int max_entries, int* side) {
+    auto* H = static_cast<History*>(h);
+    int k = 0;
+    for (auto const& e : H->entries()) {
+        if (k < max_entries) {
+            double v[6] = { e.pos.x, e.pos.y, e.pos.z, e.vel.x, e.vel.y, e.vel.z };
+            std::memcpy(out + 6 * k, v, sizeof(v));
+        }
+        k++;
+    }
+    if (side)
+        *side = H->side() ? 1 : 0;
+    return k;
+}
+void* o_trail_new(size_t max_trail_size) { return new Trail(max_trail_size); }
+void o_trail_free(void* t) { delete static_cast<Trail*>(t); }
+void o_trail_push_back(void* t, double x, double y, double z) { static_cast<Trail*>(t)->push_back({ x, y, z }); }
+void o_trail_change_current(void* t, double x, double y, double z) { static_cast<Trail*>(t)->change_current({ x, y, z }); }
+void o_trail_set_offset(void* t, double x, double y, double z) { static_cast<Trail*>(t)->set_offset({ x, y, z }); }
+void o_trail_recalculate_with_offset(void* t, double x, double y, double z) { static_cast<Trail*>(t)->recalculate_with_offset({ x, y, z }); }
+void o_trail_reset(void* t) { static_cast<Trail*>(t)->reset(); }
+void o_trail_read(void* t, float* verts, int* meta, double* real) {
+    auto* T = static_cast<Trail*>(t);
+    if (verts)
+        for (size_t i = 0; i < T->vertexes().size(); i++) {
+            verts[3 * i] = T->vertexes()[i].x;
+            verts[3 * i + 1] = T->vertexes()[i].y;
+            verts[3 * i + 2] = T->vertexes()[i].z;
+        }
+    meta[0] = (int)T->vertexes().size();
+    meta[1] = T->append_offset();
+    meta[2] = T->length();
+    real[0] = T->offset().x;
+    real[1] = T->offset().y;
+    real[2] = T->offset().z;
+    real[3] = T->last_xy_angle();
 }
 
 } // extern "C"

@@ -230,6 +230,7 @@ public:
     }
 
     std::list<Entry> const& entries() const { return m_entry_list; }
+    bool side() const { return m_side; }
 
 private:
     std::list<Entry> m_entry_list;

@@ -272,3 +272,95 @@ def test_ensemble_closest_approach_to_body(worlds_dir):
             continue
         assert got["min_distance"][5][b] == fw.closest_approach(b, 3)["distance"]
     c.close()
+
+
+def test_object_history_moves_objects_out_and_in_with_the_date(worlds_dir):
+    """src/World.cpp:59-84 + src/ObjectHistory.cpp:4-29: once the ObjectHistory holds an entry, stepping the date below the
+    creation date of the list's last object moves that object into the history (with its History / Trail reset), and stepping
+    forward pops entries back, one per step.  The reference's current revision never seeds the history itself, so both
+    sides are seeded through their debug hook; after that every step must agree bit for bit (exact_order), object count and
+    date included."""
+    ow, pw = _pair(worlds_dir, "8body.essa", 600)
+    for w in (ow, pw):
+        w.update(5)
+    ow.add_object(3e24, 1e6, (4e11, 1e10, 0), (0, 17000.0, 0), "Late1", 300)
+    pw.add_object(mass=3e24, radius=1e6, pos=(4e11, 1e10, 0), vel=(0, 17000.0, 0), name="Late1", period=300)
+    for w in (ow, pw):
+        w.update(4)
+    ow.add_object(5e23, 1e6, (-3e11, 2e10, 1e9), (0, -19000.0, 0), "Late2", 200)
+    pw.add_object(mass=5e23, radius=1e6, pos=(-3e11, 2e10, 1e9), vel=(0, -19000.0, 0), name="Late2", period=200)
+    for w in (ow, pw):
+        w.update(3)
+    _assert_same_state(pw, ow)
+    n_full = len(ow)
+    ow.debug_stash_last()
+    pw.debug_stash_last_object()
+    assert len(ow) == len(pw) == n_full - 1 and ow.object_history_size == pw.object_history_size == 1
+    # backwards past Late1's creation date: it joins Late2 in the history
+    for _ in range(9):
+        ow.update(-1)
+        pw.update(-1)
+        assert len(pw) == len(ow) and pw.object_history_size == ow.object_history_size
+        _assert_same_state(pw, ow)
+    assert len(ow) == n_full - 2 and ow.object_history_size == 2
+    # forwards again: entries come back one per step (masked by Object::deleted() until their creation date), histories reset
+    for _ in range(14):
+        ow.update(1)
+        pw.update(1)
+        assert len(pw) == len(ow) and pw.object_history_size == ow.object_history_size
+        _assert_same_state(pw, ow)
+    assert len(ow) == n_full and ow.object_history_size == 0
+    _assert_same_rings(pw, ow)
+    # with the history empty again the world is back on the ordinary path (several steps per call)
+    ow.update(20)
+    pw.update(20)
+    _assert_same_state(pw, ow)
+    _assert_same_rings(pw, ow)
+
+
+def test_snapshot_round_trip_and_zero_copy_trail_view(worlds_dir):
+    """What comes after the path: the Trail ring as a zero-copy device view for a renderer (src/Trail.cpp:90-103
+    draws exactly these vertices in one or two line strips), and a flat snapshot of the whole context -- bodies, date, History
+    and Trail rings -- that restores into a fresh context which then continues bit for bit."""
+    pw = world.World.load(os.path.join(worlds_dir, "solar.essa"))
+    st = pw.state()
+    caps = [pw.props(i)["trail_capacity"] for i in range(len(pw))]
+    pw.close()
+    n = len(caps)
+    a = capi.Context(0)
+    a.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"],
+             creation_date=np.full(n, capi.START_DATE, dtype=np.int64))
+    a.record_configure(caps)
+    a.step(1500, 43200, record=True, exact_order=True)  # History rings wrapped (1000), short trails wrapped
+    blob = a.snapshot()
+    assert blob[:8] == b"ESSASNAP"
+    b = capi.Context(0)
+    b.restore(blob)
+    assert b.date == a.date and b.n == n and b.tracked == n
+    for c in (a, b):
+        c.step(40, 43200, record=True, exact_order=True)
+    fa, fb = a.download(), b.download()
+    for k in fa:
+        assert np.array_equal(fa[k], fb[k]), k
+    for i in range(n):
+        assert np.array_equal(a.history(i), b.history(i))
+        ta, tb = a.trail(i), b.trail(i)
+        assert (ta["append_offset"], ta["length"]) == (tb["append_offset"], tb["length"])
+        assert np.array_equal(ta["verts"], tb["verts"]) and np.array_equal(ta["offset"], tb["offset"])
+        assert ta["last_xy_angle"] == tb["last_xy_angle"]
+    # the device view: same cursor, and the very bytes essa_trail_read copies out
+    try:
+        from cuda import cudart
+    except ImportError:
+        cudart = None
+    for i in (0, 3, n - 1):
+        v = a.trail_device_view(i)
+        t = a.trail(i)
+        assert v["verts_device"] and (v["capacity"], v["append_offset"], v["length"]) == (t["capacity"], t["append_offset"], t["length"])
+        assert np.array_equal(v["offset"], t["offset"])
+        if cudart is not None:
+            host = np.zeros((v["capacity"], 3), dtype=np.float32)
+            err, = cudart.cudaMemcpy(host.ctypes.data, v["verts_device"], host.nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+            assert int(err) == 0 and np.array_equal(host, t["verts"])
+    a.close()
+    b.close()

@@ -20,14 +20,11 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle  # noqa: E402  (the checker)
 from essa_b200 import capi, synth  # noqa: E402
+from essa_b200 import dist as edist  # noqa: E402
 
 
 def fresh_uid(rank):
-    uid = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        uid.copy_(torch.from_numpy(capi.nccl_unique_id()))
-    dist.broadcast(uid, 0)
-    return uid.cpu().numpy()
+    return edist.broadcast_unique_id()
 
 
 def main():
@@ -35,10 +32,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    uid = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        uid.copy_(torch.from_numpy(capi.nccl_unique_id()))
-    dist.broadcast(uid, 0)
+    uid = torch.from_numpy(edist.broadcast_unique_id())
     ok = True
     for n, steps, kern in ((4099, 6, capi.KERNEL_TILED), (70001, 3, capi.KERNEL_TILED), (8192 * world, 4, capi.KERNEL_PAIRED),
                            (65536, 3, capi.KERNEL_AUTO)):
@@ -86,10 +80,7 @@ def main():
             ref.close()
         ctx.close()
         # a fresh communicator for the next world
-        uid = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.from_numpy(capi.nccl_unique_id()))
-        dist.broadcast(uid, 0)
+        uid = torch.from_numpy(edist.broadcast_unique_id())
     # pair-shared kernel with most-attracting tracking on unequal masses: candidate keys are max-reduced over the ranks
     n = 8192 * world
     w = synth.plummer(n, seed=23)
