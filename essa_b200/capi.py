@@ -54,7 +54,7 @@ class TrailMeta(C.Structure):
 class EnsembleOpts(C.Structure):
     _fields_ = [("copies", C.c_int), ("first_copy", C.c_int64), ("dt_seconds", C.c_int), ("seed", C.c_uint64),
                 ("rel_sigma", C.c_double), ("exact_order", C.c_int), ("closest_approaches", C.c_int),
-                ("approach_to", C.c_int)]
+                ("approach_to", C.c_int), ("trail_every", C.c_int), ("trail_capacity", C.c_int)]
 
 
 class TrailView(C.Structure):
@@ -104,6 +104,8 @@ SYMBOLS = [
     ("essa_ensemble_init", C.c_int, [_P, C.POINTER(EnsembleOpts)]),
     ("essa_ensemble_step", C.c_int, [_P, C.c_int]),
     ("essa_ensemble_read", C.c_int, [_P, C.c_int, C.c_int] + [_dp] * 7),
+    ("essa_ensemble_read_approaches", C.c_int, [_P, C.c_int, C.c_int, _dp, _dp]),
+    ("essa_ensemble_read_trail", C.c_int, [_P, C.c_int, C.c_int, _dp, _i32p]),
     ("essa_ensemble_factor", C.c_double, [C.c_uint64, C.c_double, C.c_int64, C.c_int, C.c_int]),
     ("essa_nccl_unique_id", C.c_int, [_u8p]),
     ("essa_shard_attach", C.c_int, [_P, C.c_int, C.c_int, _u8p]),
@@ -403,11 +405,25 @@ class Context:
 
     # ---- ensemble ----
     def ensemble_init(self, copies, dt, seed=7, rel_sigma=1e-6, first_copy=0, exact_order=False, closest_approaches=False,
-                      approach_to=0):
+                      approach_to=0, trail_every=0, trail_capacity=0):
         o = EnsembleOpts(int(copies), int(first_copy), int(dt), int(seed), float(rel_sigma), int(exact_order),
-                         int(closest_approaches), int(approach_to))
+                         int(closest_approaches), int(approach_to), int(trail_every), int(trail_capacity))
         self._ck(self._L.essa_ensemble_init(self._h, C.byref(o)))
-        self._ens = (int(copies), self.n)
+        self._ens = (int(copies), self.n, int(trail_capacity))
+
+    def ensemble_approaches(self, first, count):
+        """(this_pos, other_pos): [count][N][3] positions of body k and of the designated body at their closest approach."""
+        n = self._ens[1]
+        a, b = np.zeros((count, n, 3)), np.zeros((count, n, 3))
+        self._ck(self._L.essa_ensemble_read_approaches(self._h, first, count, _ptr(a, _dp), _ptr(b, _dp)))
+        return a, b
+
+    def ensemble_trail(self, first, count):
+        """(xyz [count][capacity][3], lengths [count]): the designated body's trail per copy."""
+        cap = self._ens[2]
+        xyz, ln = np.zeros((count, cap, 3)), np.zeros(count, dtype=np.int32)
+        self._ck(self._L.essa_ensemble_read_trail(self._h, first, count, _ptr(xyz, _dp), _ptr(ln, _i32p)))
+        return xyz, ln
 
     def ensemble_step(self, steps):
         self._ck(self._L.essa_ensemble_step(self._h, int(steps)))

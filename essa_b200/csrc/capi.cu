@@ -502,6 +502,10 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     cudaFree(c->ens_state);
     cudaFree(c->ens_gf);
     cudaFree(c->ens_mind);
+    cudaFree(c->ens_active);
+    cudaFree(c->ens_apos);
+    cudaFree(c->ens_trail);
+    cudaFree(c->ens_trail_len);
     cudaFree(c->escratch);
     cudaFree(c->closest);
     cudaFree(c->l2_scratch);
@@ -1701,10 +1705,19 @@ extern "C" int essa_ensemble_init(essa_ctx* ctx, const essa_ensemble_opts* o) {
     CK(cudaSetDevice(ctx->device));
     PARK();
     CK(cudaStreamSynchronize(ctx->stream));
+    ARG(o->trail_every >= 0 && o->trail_capacity >= 0 && (o->trail_every == 0 || (o->closest_approaches && o->trail_capacity > 0)),
+        "trail_every needs closest_approaches and a positive trail_capacity");
     cudaFree(ctx->ens_state);
     cudaFree(ctx->ens_gf);
     cudaFree(ctx->ens_mind);
-    ctx->ens_state = ctx->ens_gf = ctx->ens_mind = nullptr;
+    cudaFree(ctx->ens_active);
+    cudaFree(ctx->ens_apos);
+    cudaFree(ctx->ens_trail);
+    cudaFree(ctx->ens_trail_len);
+    ctx->ens_state = ctx->ens_gf = ctx->ens_mind = ctx->ens_apos = ctx->ens_trail = nullptr;
+    ctx->ens_active = nullptr;
+    ctx->ens_trail_len = nullptr;
+    ctx->ens_steps_done = 0;
     ctx->ens_copies = o->copies;
     ctx->ens_n = ctx->n;
     ctx->ens = *o;
@@ -1712,6 +1725,17 @@ extern "C" int essa_ensemble_init(essa_ctx* ctx, const essa_ensemble_opts* o) {
     CK(cudaMalloc(&ctx->ens_state, total * 6 * sizeof(double)));
     CK(cudaMalloc(&ctx->ens_gf, (size_t)ctx->n * sizeof(double)));
     CK(cudaMalloc(&ctx->ens_mind, total * sizeof(double)));
+    CK(cudaMalloc(&ctx->ens_active, (size_t)ctx->n));
+    if (o->closest_approaches) {
+        CK(cudaMalloc(&ctx->ens_apos, total * 6 * sizeof(double)));
+        CK(cudaMemsetAsync(ctx->ens_apos, 0, total * 6 * sizeof(double), ctx->stream));
+    }
+    if (o->trail_every > 0) {
+        CK(cudaMalloc(&ctx->ens_trail, (size_t)o->copies * o->trail_capacity * 3 * sizeof(double)));
+        CK(cudaMalloc(&ctx->ens_trail_len, (size_t)o->copies * sizeof(int)));
+        CK(cudaMemsetAsync(ctx->ens_trail, 0, (size_t)o->copies * o->trail_capacity * 3 * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->ens_trail_len, 0, (size_t)o->copies * sizeof(int), ctx->stream));
+    }
     CK(launch_ensemble_init(ctx, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return ESSA_OK;
@@ -1753,6 +1777,41 @@ extern "C" int essa_ensemble_read(essa_ctx* ctx, int first, int count, double* x
         CK(cudaMemcpyAsync(min_distance, ctx->ens_mind + (size_t)first * n, (size_t)count * n * sizeof(double), cudaMemcpyDeviceToHost,
             ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return ESSA_OK;
+}
+
+extern "C" int essa_ensemble_read_approaches(essa_ctx* ctx, int first, int count, double* this_pos, double* other_pos) {
+    ARG(ctx, "ctx is null");
+    ARG(first >= 0 && count >= 0 && first + count <= ctx->ens_copies, "copy range out of bounds");
+    ARG(ctx->ens_apos, "the ensemble was initialised without closest_approaches");
+    CK(cudaSetDevice(ctx->device));
+    PARK();
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t const n = (size_t)ctx->ens_n, rows = (size_t)count * n;
+    std::vector<double> tmp(rows * 6);
+    CK(cudaMemcpy(tmp.data(), ctx->ens_apos + (size_t)first * n * 6, rows * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < rows; r++)
+        for (int c = 0; c < 3; c++) {
+            if (this_pos)
+                this_pos[3 * r + c] = tmp[6 * r + c];
+            if (other_pos)
+                other_pos[3 * r + c] = tmp[6 * r + 3 + c];
+        }
+    return ESSA_OK;
+}
+
+extern "C" int essa_ensemble_read_trail(essa_ctx* ctx, int first, int count, double* xyz, int32_t* lengths) {
+    ARG(ctx, "ctx is null");
+    ARG(first >= 0 && count >= 0 && first + count <= ctx->ens_copies, "copy range out of bounds");
+    ARG(ctx->ens_trail, "the ensemble was initialised without trail_every");
+    CK(cudaSetDevice(ctx->device));
+    PARK();
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t const cap = (size_t)ctx->ens.trail_capacity;
+    if (xyz)
+        CK(cudaMemcpy(xyz, ctx->ens_trail + (size_t)first * cap * 3, (size_t)count * cap * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (lengths)
+        CK(cudaMemcpy(lengths, ctx->ens_trail_len + first, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return ESSA_OK;
 }
 

@@ -199,6 +199,11 @@ struct essa_ctx {
     double* ens_state = nullptr; // [copies][6][n]
     double* ens_gf = nullptr;    // [n]
     double* ens_mind = nullptr;  // [copies][n]
+    uint8_t* ens_active = nullptr; // [n]  Object::deleted() of the template
+    double* ens_apos = nullptr;  // [copies][n][6] positions at the closest approach (closest_approaches)
+    double* ens_trail = nullptr; // [copies][trail_capacity][3] the designated body's trail
+    int* ens_trail_len = nullptr; // [copies]
+    long long ens_steps_done = 0;
 
     // closest approaches of a forward-simulated world: [n][n][7]
     double* closest = nullptr;

@@ -7,8 +7,10 @@
 // clones are resident in shared memory, several per CTA, for all steps of a launch.
 //
 // Layout in HBM: state[copy][6][n] (x y z vx vy vz), copy-major, so a CTA's copies are contiguous.
-// Thread t of a CTA owns (copy = t / n, body = t % n); all copies of a CTA step in lock step
-// behind the same two __syncthreads per KDK iteration.
+// Fast arithmetic: two bodies per thread (k_ensemble_duo); exact_order: one thread per (copy, body) in the reference's
+// summation order (k_ensemble_exact).  Besides the final state every copy can return, for a designated body (the candidate
+// of EssaCreateObject), its closest approach to EVERY other body -- distance and both positions, as
+// Object::ClosestApproachEntry holds them -- and its trail (positions after every k-th step).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -20,11 +22,14 @@ namespace essa {
 constexpr int kEnsThreadsMax = kEnsembleMaxBodies;
 
 __global__ void k_ensemble_init(double const* __restrict__ tx, double const* __restrict__ tv, double const* __restrict__ tgf,
-    double4 const* __restrict__ tpos, int cap, int n, int copies, long long first_copy, unsigned long long seed, double rel_sigma,
-    double* state, double* gf_out, double* mind) {
+    double4 const* __restrict__ tpos, uint8_t const* __restrict__ tactive, int cap, int n, int copies, long long first_copy,
+    unsigned long long seed, double rel_sigma, double* state, double* gf_out, uint8_t* active_out, double* mind) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < n)
+    if (idx < n) {
         gf_out[idx] = tpos[idx].w; // gf_eff: bodies masked by Object::deleted() are not cloned -> weight 0
+        // ... and are neither attracted nor moved; a live body of mass 0 (a test particle) is both
+        active_out[idx] = tactive[idx];
+    }
     if (idx >= (long long)copies * n)
         return;
     int c = (int)(idx / n), k = (int)(idx - (long long)c * n);
@@ -40,59 +45,72 @@ __global__ void k_ensemble_init(double const* __restrict__ tx, double const* __r
 struct EnsembleArgs {
     double* state;
     double const* gf;
+    uint8_t const* active; // Object::deleted() of the template, per body
     double* mind;
+    double* apos;          // [copies][n][6] {this xyz, other xyz} where mind was reached (ClosestApproachEntry), or null
+    double* trail;         // [copies][trail_cap][3] positions of body `approach_to` after every trail_every-th step, or null
+    int* trail_len;        // [copies]
     int n, copies, per_cta, steps;
     double mul, dt, h;
     int approaches, approach_to;
+    int trail_every, trail_cap;
+    long long steps_done;  // steps of earlier launches (the sampling continues across launches)
 };
 
-// Fast-arithmetic row: the n - 1 partners of body k in ring order p = k + 1, k + 2, ... (mod n) -- no self
-// term, no padding.  Every copy's arrays are stored twice back to back (entries [0, n) and [n, 2n - 1)), so the
-// ring needs no wrap-around arithmetic: the pointers passed in are the arrays offset by k + 1, and the loop is
-// loads at immediate offsets plus FP64 work only (integer address arithmetic was costing a third of the issue
-// slots).  The per-copy stride is congruent to n modulo 16, which keeps a warp's consecutive (copy, body)
-// lanes on distinct 8-byte bank pairs, exactly as if the copies were packed.
-__device__ __forceinline__ int ring_stride(int n) {
-    int s = 2 * n - 1;
-    return s + ((n - s) % 16 + 16) % 16;
-}
-
-__device__ __forceinline__ void ring_forces(int n, double const* px, double const* py, double const* pz, double const* pg, double x,
-    double y, double z, double& ax, double& ay, double& az) {
-    double fx[4] = { 0, 0, 0, 0 }, fy[4] = { 0, 0, 0, 0 }, fz[4] = { 0, 0, 0, 0 };
-    int j = 0;
-    for (; j + 4 <= n - 1; j += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            double4 q = make_double4(px[j + u], py[j + u], pz[j + u], pg[j + u]);
-            fast_interact(x, y, z, q, 0.0, fx[u], fy[u], fz[u]);
+// Object::update_closest_approaches for one (body, designated body) pair at a step's start: the running minimum of d2 with the
+// two positions it was seen at (src/Object.cpp:405-417 stores {this position, other position, distance}).
+struct Approach {
+    double m2 = -1.0; // < 0: nothing seen since the last restart
+    double p[6];
+    __device__ __forceinline__ void see(double x, double y, double z, double ox, double oy, double oz, double& md) {
+        double dx = __dsub_rn(ox, x), dy = __dsub_rn(oy, y), dz = __dsub_rn(oz, z);
+        double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (d2 == 0.0) { // a distance of exactly zero stores 0 == "unset" in the reference: the search restarts
+            md = 0.0;
+            m2 = -1.0;
+        } else if (m2 < 0.0 || d2 < m2) {
+            m2 = d2;
+            p[0] = x; p[1] = y; p[2] = z; p[3] = ox; p[4] = oy; p[5] = oz;
         }
     }
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-        if (j + u < n - 1) {
-            double4 q = make_double4(px[j + u], py[j + u], pz[j + u], pg[j + u]);
-            fast_interact(x, y, z, q, 0.0, fx[u], fy[u], fz[u]);
+    // RN o sqrt is monotone, so the minimum of d2 is tracked and the root taken once, at the end of a launch
+    __device__ __forceinline__ void settle(double& md, double* apos) const {
+        if (m2 < 0.0)
+            return;
+        double d = __dsqrt_rn(m2);
+        if (md == 0.0 || d < md) {
+            md = d;
+            if (apos)
+                for (int c = 0; c < 6; c++)
+                    apos[c] = p[c];
         }
     }
-    ax = (fx[0] + fx[1]) + (fx[2] + fx[3]);
-    ay = (fy[0] + fy[1]) + (fy[2] + fy[3]);
-    az = (fz[0] + fz[1]) + (fz[2] + fz[3]);
+};
+
+// The designated body's trail: its position after every trail_every-th step (what EssaCreateObject draws for the candidate).
+__device__ __forceinline__ void ens_trail(EnsembleArgs const& A, long long copy, int st, double x, double y, double z) {
+    long long const g = A.steps_done + st + 1;
+    if (g % A.trail_every != 0)
+        return;
+    long long const idx = g / A.trail_every - 1;
+    if (idx >= A.trail_cap)
+        return;
+    double* t = A.trail + ((size_t)copy * A.trail_cap + (size_t)idx) * 3;
+    t[0] = x; t[1] = y; t[2] = z;
+    A.trail_len[copy] = (int)idx + 1;
 }
 
-// Shared memory: sx[per_cta S] sy[..] sz[..] sg[..], copy-major inside each array (copy lc owns [lc S, lc S + S),
-// S = ring_stride(n) for the fast flavour (doubled arrays), n for exact_order).
-template<bool EXACT>
-__global__ void __launch_bounds__(kEnsThreadsMax, 2) k_ensemble(EnsembleArgs const A) {
+// exact_order flavour: one thread per (copy, body), the reference's summation order (rows.cuh), positions in shared memory,
+// copy-major (copy lc owns [lc n, lc n + n) of sx / sy / sz / sg); all copies of a CTA step in lock step.
+__global__ void __launch_bounds__(kEnsThreadsMax, 2) k_ensemble_exact(EnsembleArgs const A) {
     extern __shared__ double smem[];
     int const n = A.n;
     int const t = threadIdx.x;
     int const lc = t / n, k = t - lc * n;
     int const copy = blockIdx.x * A.per_cta + lc;
     bool const live = lc < A.per_cta && copy < A.copies;
-    int const S = EXACT ? n : ring_stride(n);
-    size_t const plane = (size_t)A.per_cta * S;
-    double* sx = smem + (size_t)(lc < A.per_cta ? lc : 0) * S;
+    size_t const plane = (size_t)A.per_cta * n;
+    double* sx = smem + (size_t)(lc < A.per_cta ? lc : 0) * n;
     double* sy = sx + plane;
     double* sz = sy + plane;
     double* sg = sz + plane;
@@ -100,6 +118,7 @@ __global__ void __launch_bounds__(kEnsThreadsMax, 2) k_ensemble(EnsembleArgs con
     double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0, md = 0, dummy_m = 0;
     int dummy_most = -1;
     double* s = A.state + (size_t)(live ? copy : 0) * 6 * n;
+    bool on = false;
     if (live) {
         x = s[k];
         y = s[(size_t)n + k];
@@ -109,47 +128,24 @@ __global__ void __launch_bounds__(kEnsThreadsMax, 2) k_ensemble(EnsembleArgs con
         vz = s[5 * (size_t)n + k];
         gfk = A.gf[k];
         md = A.mind[(size_t)copy * n + k];
+        on = A.active[k] != 0; // a body that deleted() masks is neither attracted nor moved
         sx[k] = x;
         sy[k] = y;
         sz[k] = z;
         sg[k] = gfk;
-        if (!EXACT && k < n - 1) {
-            sx[n + k] = x;
-            sy[n + k] = y;
-            sz[n + k] = z;
-            sg[n + k] = gfk;
-        }
     }
     __syncthreads();
-    bool const on = live && gfk != 0.0; // a body that deleted() masks is neither attracted nor moved
-    auto forces = [&]() {
-        if (EXACT)
-            row_forces<true, false>(k, n, n, sx, sy, sz, sg, x, y, z, gfk, 0.0, ax, ay, az, dummy_m, dummy_most);
-        else
-            ring_forces(n, sx + k + 1, sy + k + 1, sz + k + 1, sg + k + 1, x, y, z, ax, ay, az);
-    };
     if (on)
-        forces();
+        row_forces<true, false>(k, n, n, sx, sy, sz, sg, x, y, z, gfk, 0.0, ax, ay, az, dummy_m, dummy_most);
     // (a h) mul == a (h mul) and (v dt) mul == v (dt mul) exactly: mul is +-1
     double const hm = A.h * A.mul, dtm = A.dt * A.mul;
-    // Object::update_closest_approaches (src/Object.cpp:405-417) keeps min over steps of RN(sqrt(d2)); RN o sqrt
-    // is monotone, so the minimum of d2 is tracked and the root taken once.  m2 < 0: nothing seen since the
-    // last restart; a distance of exactly zero stores 0 == "unset" in the reference, i.e. restarts the search.
-    double m2 = -1.0;
+    Approach ap;
     bool const approaches = A.approaches && live && k != A.approach_to;
     int const to = A.approach_to;
 
     for (int st = 0; st < A.steps; st++) {
-        if (approaches) { // at the step's start
-            double dx = __dsub_rn(sx[to], x), dy = __dsub_rn(sy[to], y), dz = __dsub_rn(sz[to], z);
-            double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            if (d2 == 0.0) {
-                md = 0.0;
-                m2 = -1.0;
-            } else if (m2 < 0.0 || d2 < m2) {
-                m2 = d2;
-            }
-        }
+        if (approaches) // at the step's start
+            ap.see(x, y, z, sx[to], sy[to], sz[to], md);
         if (on) {
             vx = __dadd_rn(vx, __dmul_rn(ax, hm));
             vy = __dadd_rn(vy, __dmul_rn(ay, hm));
@@ -163,131 +159,19 @@ __global__ void __launch_bounds__(kEnsThreadsMax, 2) k_ensemble(EnsembleArgs con
             sx[k] = x;
             sy[k] = y;
             sz[k] = z;
-            if (!EXACT && k < n - 1) {
-                sx[n + k] = x;
-                sy[n + k] = y;
-                sz[n + k] = z;
-            }
         }
         __syncthreads();
         if (on) {
-            forces();
+            row_forces<true, false>(k, n, n, sx, sy, sz, sg, x, y, z, gfk, 0.0, ax, ay, az, dummy_m, dummy_most);
             vx = __dadd_rn(vx, __dmul_rn(ax, hm));
             vy = __dadd_rn(vy, __dmul_rn(ay, hm));
             vz = __dadd_rn(vz, __dmul_rn(az, hm));
         }
+        if (A.trail && live && k == to)
+            ens_trail(A, copy, st, x, y, z);
     }
-    if (approaches && m2 >= 0.0) {
-        double d = __dsqrt_rn(m2);
-        if (md == 0.0 || d < md)
-            md = d;
-    }
-    if (live) {
-        s[k] = x;
-        s[(size_t)n + k] = y;
-        s[2 * (size_t)n + k] = z;
-        s[3 * (size_t)n + k] = vx;
-        s[4 * (size_t)n + k] = vy;
-        s[5 * (size_t)n + k] = vz;
-        A.mind[(size_t)copy * n + k] = md;
-    }
-}
-
-// Warp-synchronous flavour for templates of up to 32 bodies (fast arithmetic): a warp owns 32 / n whole
-// copies and steps them with __syncwarp only.  Warps never wait for each other, so the SM's schedulers
-// always find a warp whose dependent FP64 chain is ready -- with block-wide barriers every warp of a CTA
-// sits in the same phase of the step and the FP64 pipe idles nearly half of the time (measured).
-constexpr int kEnsWarpsPerCta = 4;
-
-__global__ void __launch_bounds__(32 * kEnsWarpsPerCta, 5) k_ensemble_warp(EnsembleArgs const A) {
-    extern __shared__ double smem[]; // per warp: sx[cw n] sy[..] sz[..] sg[..]
-    int const n = A.n, cw = 32 / n;
-    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int const lc = lane / n, k = lane - lc * n;
-    long long const gw = (long long)blockIdx.x * kEnsWarpsPerCta + warp;
-    long long const copy = gw * cw + lc;
-    bool const live = lc < cw && copy < A.copies;
-    int const S = ring_stride(n), plane = cw * S;
-    double* sx = smem + (size_t)warp * 4 * plane + (lc < cw ? lc : 0) * S;
-    double* sy = sx + plane;
-    double* sz = sy + plane;
-    double* sg = sz + plane;
-
-    double x = 0, y = 0, z = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, gfk = 0, md = 0;
-    double* s = A.state + (size_t)(live ? copy : 0) * 6 * n;
-    if (live) {
-        x = s[k];
-        y = s[(size_t)n + k];
-        z = s[2 * (size_t)n + k];
-        vx = s[3 * (size_t)n + k];
-        vy = s[4 * (size_t)n + k];
-        vz = s[5 * (size_t)n + k];
-        gfk = A.gf[k];
-        md = A.mind[(size_t)copy * n + k];
-        sx[k] = x;
-        sy[k] = y;
-        sz[k] = z;
-        sg[k] = gfk;
-        if (k < n - 1) {
-            sx[n + k] = x;
-            sy[n + k] = y;
-            sz[n + k] = z;
-            sg[n + k] = gfk;
-        }
-    }
-    __syncwarp();
-    bool const on = live && gfk != 0.0;
-    double const *const px = sx + k + 1, *const py = sy + k + 1, *const pz = sz + k + 1, *const pg = sg + k + 1;
-    if (on)
-        ring_forces(n, px, py, pz, pg, x, y, z, ax, ay, az);
-    double const hm = A.h * A.mul, dtm = A.dt * A.mul;
-    double m2 = -1.0; // see k_ensemble
-    bool const approaches = A.approaches && live && k != A.approach_to;
-    int const to = A.approach_to;
-
-    for (int st = 0; st < A.steps; st++) {
-        if (approaches) {
-            double dx = __dsub_rn(sx[to], x), dy = __dsub_rn(sy[to], y), dz = __dsub_rn(sz[to], z);
-            double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            if (d2 == 0.0) {
-                md = 0.0;
-                m2 = -1.0;
-            } else if (m2 < 0.0 || d2 < m2) {
-                m2 = d2;
-            }
-        }
-        if (on) {
-            vx = __dadd_rn(vx, __dmul_rn(ax, hm));
-            vy = __dadd_rn(vy, __dmul_rn(ay, hm));
-            vz = __dadd_rn(vz, __dmul_rn(az, hm));
-            x = __dadd_rn(x, __dmul_rn(vx, dtm));
-            y = __dadd_rn(y, __dmul_rn(vy, dtm));
-            z = __dadd_rn(z, __dmul_rn(vz, dtm));
-        }
-        __syncwarp();
-        if (live) {
-            sx[k] = x;
-            sy[k] = y;
-            sz[k] = z;
-            if (k < n - 1) {
-                sx[n + k] = x;
-                sy[n + k] = y;
-                sz[n + k] = z;
-            }
-        }
-        __syncwarp();
-        if (on) {
-            ring_forces(n, px, py, pz, pg, x, y, z, ax, ay, az);
-            vx = __dadd_rn(vx, __dmul_rn(ax, hm));
-            vy = __dadd_rn(vy, __dmul_rn(ay, hm));
-            vz = __dadd_rn(vz, __dmul_rn(az, hm));
-        }
-    }
-    if (approaches && m2 >= 0.0) {
-        double d = __dsqrt_rn(m2);
-        if (md == 0.0 || d < md)
-            md = d;
-    }
+    if (approaches)
+        ap.settle(md, A.apos ? A.apos + ((size_t)copy * n + k) * 6 : nullptr);
     if (live) {
         s[k] = x;
         s[(size_t)n + k] = y;
@@ -340,12 +224,13 @@ __global__ void __launch_bounds__(WARP ? 32 * kDuoWarps : kDuoCtaThreads, WARP ?
 
     int const kb[2] = { h, h + half };
     bool own[2] = { live, live && h + half < n };
-    double x[2], y[2], z[2], vx[2], vy[2], vz[2], ax[2], ay[2], az[2], gf[2], md[2], m2[2];
+    double x[2], y[2], z[2], vx[2], vy[2], vz[2], ax[2], ay[2], az[2], gf[2], md[2];
+    Approach ap[2];
+    bool on[2] = { false, false };
     double* s = A.state + (size_t)(live ? copy : 0) * 6 * n;
 #pragma unroll
     for (int b = 0; b < 2; b++) {
         x[b] = y[b] = z[b] = vx[b] = vy[b] = vz[b] = ax[b] = ay[b] = az[b] = gf[b] = md[b] = 0.0;
-        m2[b] = -1.0; // see k_ensemble: minimum of d2, the root is taken once
         if (own[b]) {
             int const k = kb[b];
             x[b] = s[k];
@@ -356,13 +241,13 @@ __global__ void __launch_bounds__(WARP ? 32 * kDuoWarps : kDuoCtaThreads, WARP ?
             vz[b] = s[5 * (size_t)n + k];
             gf[b] = A.gf[k];
             md[b] = A.mind[(size_t)copy * n + k];
+            on[b] = A.active[k] != 0; // deleted() bodies are neither attracted nor moved; a live test particle (mass 0) is both
             rec[k] = make_double4(x[b], y[b], z[b], gf[b]);
         }
     }
     if (live && h == 0)
         rec[n] = make_double4(0, 0, 0, 0);
     sync();
-    bool const on[2] = { own[0] && gf[0] != 0.0, own[1] && gf[1] != 0.0 }; // deleted() bodies are neither attracted nor moved
 
     auto forces = [&]() {
         double fx[2][2] = { { 0, 0 }, { 0, 0 } }, fy[2][2] = { { 0, 0 }, { 0, 0 } }, fz[2][2] = { { 0, 0 }, { 0, 0 } };
@@ -391,16 +276,8 @@ __global__ void __launch_bounds__(WARP ? 32 * kDuoWarps : kDuoCtaThreads, WARP ?
             double4 const t = rec[to];
 #pragma unroll
             for (int b = 0; b < 2; b++)
-                if (own[b] && kb[b] != to) {
-                    double dx = __dsub_rn(t.x, x[b]), dy = __dsub_rn(t.y, y[b]), dz = __dsub_rn(t.z, z[b]);
-                    double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                    if (d2 == 0.0) {
-                        md[b] = 0.0;
-                        m2[b] = -1.0;
-                    } else if (m2[b] < 0.0 || d2 < m2[b]) {
-                        m2[b] = d2;
-                    }
-                }
+                if (own[b] && kb[b] != to)
+                    ap[b].see(x[b], y[b], z[b], t.x, t.y, t.z, md[b]);
         }
 #pragma unroll
         for (int b = 0; b < 2; b++)
@@ -426,16 +303,19 @@ __global__ void __launch_bounds__(WARP ? 32 * kDuoWarps : kDuoCtaThreads, WARP ?
                 vy[b] = __dadd_rn(vy[b], __dmul_rn(ay[b], hm));
                 vz[b] = __dadd_rn(vz[b], __dmul_rn(az[b], hm));
             }
+        if (A.trail) {
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+                if (own[b] && kb[b] == to)
+                    ens_trail(A, copy, st, x[b], y[b], z[b]);
+        }
     }
 #pragma unroll
     for (int b = 0; b < 2; b++)
         if (own[b]) {
             int const k = kb[b];
-            if (A.approaches && k != to && m2[b] >= 0.0) {
-                double d = __dsqrt_rn(m2[b]);
-                if (md[b] == 0.0 || d < md[b])
-                    md[b] = d;
-            }
+            if (A.approaches && k != to)
+                ap[b].settle(md[b], A.apos ? A.apos + ((size_t)copy * n + k) * 6 : nullptr);
             s[k] = x[b];
             s[(size_t)n + k] = y[b];
             s[2 * (size_t)n + k] = z[b];
@@ -449,18 +329,10 @@ __global__ void __launch_bounds__(WARP ? 32 * kDuoWarps : kDuoCtaThreads, WARP ?
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st) {
     long long total = (long long)c->ens_copies * c->ens_n;
     int blocks = (int)((total + 255) / 256);
-    k_ensemble_init<<<blocks, 256, 0, st>>>(nullptr, c->vel, c->gf, c->pos[c->cur], c->cap, c->ens_n, c->ens_copies, (long long)c->ens.first_copy,
-        (unsigned long long)c->ens.seed, c->ens.rel_sigma, c->ens_state, c->ens_gf, c->ens_mind);
+    k_ensemble_init<<<blocks, 256, 0, st>>>(nullptr, c->vel, c->gf, c->pos[c->cur], c->active, c->cap, c->ens_n, c->ens_copies,
+        (long long)c->ens.first_copy, (unsigned long long)c->ens.seed, c->ens.rel_sigma, c->ens_state, c->ens_gf, c->ens_active, c->ens_mind);
     c->launches++;
     return cudaGetLastError();
-}
-
-static bool ens_duo_enabled() {
-    static int const v = [] {
-        char const* e = getenv("ESSA_ENSEMBLE_DUO"); // diagnostics: 0 = one body per thread (k_ensemble_warp / k_ensemble)
-        return e ? atoi(e) : 1;
-    }();
-    return v != 0;
 }
 
 cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
@@ -468,7 +340,14 @@ cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
     EnsembleArgs A;
     A.state = c->ens_state;
     A.gf = c->ens_gf;
+    A.active = c->ens_active;
     A.mind = c->ens_mind;
+    A.apos = c->ens_apos;
+    A.trail = c->ens_trail;
+    A.trail_len = c->ens_trail_len;
+    A.trail_every = c->ens.trail_every > 0 ? c->ens.trail_every : 1;
+    A.trail_cap = c->ens.trail_capacity;
+    A.steps_done = c->ens_steps_done;
     A.n = n;
     A.copies = c->ens_copies;
     A.steps = steps < 0 ? -steps : steps;
@@ -477,26 +356,25 @@ cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
     A.h = A.dt / 2.0;
     A.approaches = c->ens.closest_approaches;
     A.approach_to = c->ens.approach_to;
-    int per_cta = n <= kEnsThreadsMax ? kEnsThreadsMax / n : 1;
-    if (per_cta > c->ens_copies)
-        per_cta = c->ens_copies;
-    A.per_cta = per_cta;
-    int threads = (per_cta * n + 31) / 32 * 32;
-    int const ring_s = [&] { int s2 = 2 * n - 1; return s2 + ((n - s2) % 16 + 16) % 16; }(); // = ring_stride(n)
-    size_t smem = (size_t)per_cta * 4 * (c->ens.exact_order ? n : ring_s) * sizeof(double);
-    int blocks = (c->ens_copies + per_cta - 1) / per_cta;
     cudaError_t e;
     if (c->ens.exact_order) {
-        if (threads > kEnsThreadsMax) // a template wider than one ensemble CTA: one copy per CTA at full width
+        int per_cta = n <= kEnsThreadsMax ? kEnsThreadsMax / n : 1;
+        if (per_cta > c->ens_copies)
+            per_cta = c->ens_copies;
+        A.per_cta = per_cta;
+        int threads = (per_cta * n + 31) / 32 * 32;
+        if (threads > kEnsThreadsMax) // a template wider than one ensemble CTA
             return cudaErrorInvalidConfiguration;
-        k_ensemble<true><<<blocks, threads, smem, st>>>(A);
-    } else if (ens_duo_enabled()) {
+        int blocks = (c->ens_copies + per_cta - 1) / per_cta;
+        k_ensemble_exact<<<blocks, threads, (size_t)per_cta * 4 * n * sizeof(double), st>>>(A);
+    } else {
         int const half = (n + 1) / 2;
         size_t const rec_bytes = (size_t)(n + 1) * sizeof(double4);
         if (half <= 32) { // up to 64 bodies: whole copies per warp
             int const cw = 32 / half;
             long long const warps = ((long long)c->ens_copies + cw - 1) / cw;
             int const wblocks = (int)((warps + kDuoWarps - 1) / kDuoWarps);
+            A.per_cta = cw;
             k_ensemble_duo<true><<<wblocks, 32 * kDuoWarps, (size_t)kDuoWarps * cw * rec_bytes, st>>>(A);
         } else {
             A.per_cta = kDuoCtaThreads / half;
@@ -505,15 +383,6 @@ cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
             int const dblocks = (c->ens_copies + A.per_cta - 1) / A.per_cta;
             k_ensemble_duo<false><<<dblocks, kDuoCtaThreads, (size_t)A.per_cta * rec_bytes, st>>>(A);
         }
-    } else if (n <= 32) {
-        int cw = 32 / n;
-        long long warps = ((long long)c->ens_copies + cw - 1) / cw;
-        int wblocks = (int)((warps + kEnsWarpsPerCta - 1) / kEnsWarpsPerCta);
-        k_ensemble_warp<<<wblocks, 32 * kEnsWarpsPerCta, (size_t)kEnsWarpsPerCta * 4 * cw * ring_s * sizeof(double), st>>>(A);
-    } else {
-        if (threads > kEnsThreadsMax)
-            return cudaErrorInvalidConfiguration;
-        k_ensemble<false><<<blocks, threads, smem, st>>>(A);
     }
     e = cudaGetLastError();
     c->launches++;
@@ -521,6 +390,7 @@ cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
     c->passes += P;
     c->interactions += (double)P * (double)c->ens_copies * (double)n * (double)(n - 1);
     c->last_force_passes = P;
+    c->ens_steps_done += A.steps;
     return e;
 }
 

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define ESSA_ABI_VERSION 1
+#define ESSA_ABI_VERSION 2
 
 typedef struct essa_ctx essa_ctx;
 
@@ -225,9 +225,13 @@ typedef struct essa_ensemble_opts {
     double rel_sigma;      /* every pos/vel component *= 1 + rel_sigma * n,  n ~ Irwin-Hall(12)-6 from
                               Philox4x32-10 keyed (seed; copy, body, component); global copy 0 unperturbed */
     int exact_order;       /* as essa_step_opts.exact_order */
-    int closest_approaches;/* Object::update_closest_approaches (src/Object.cpp:405-417): keep the minimum
-                              distance of every body to body `approach_to` over the run */
+    int closest_approaches;/* Object::update_closest_approaches (src/Object.cpp:405-417) for the designated body
+                              `approach_to` (the candidate of src/essagui/EssaCreateObject.cpp:166-189) against EVERY other
+                              body of its copy: minimum distance over the run and both positions there */
     int approach_to;
+    int trail_every;       /* > 0 (with closest_approaches): also keep the designated body's position after every
+                              trail_every-th step -- the trail the GUI draws for the candidate ... */
+    int trail_capacity;    /* ... up to this many points per copy */
 } essa_ensemble_opts;
 /* Build the copies on the device from the uploaded template (positions, velocities, gf). */
 int essa_ensemble_init(essa_ctx* ctx, const essa_ensemble_opts* opts);
@@ -236,6 +240,12 @@ int essa_ensemble_step(essa_ctx* ctx, int steps);
 /* State of `count` copies starting at local copy `first`: arrays of count * N doubles, copy-major. */
 int essa_ensemble_read(essa_ctx* ctx, int first, int count, double* x, double* y, double* z,
                        double* vx, double* vy, double* vz, double* min_distance);
+/* Closest approaches of `count` copies: this_pos / other_pos are count * N * 3 doubles -- for body k of a copy, where body k
+ * (this) and the designated body (other) were when their distance was smallest (Object::ClosestApproachEntry,
+ * src/Object.hpp:184-188); the distances are essa_ensemble_read's min_distance.  Either pointer may be null. */
+int essa_ensemble_read_approaches(essa_ctx* ctx, int first, int count, double* this_pos, double* other_pos);
+/* The designated body's trail of `count` copies: xyz = count * trail_capacity * 3 doubles, lengths = count points filled. */
+int essa_ensemble_read_trail(essa_ctx* ctx, int first, int count, double* xyz, int32_t* lengths);
 /* The perturbation factor (1 + rel_sigma * n) for one (copy, body, component 0..5), on the host,
  * bit-identical to what the device applies: lets a checker rebuild any copy's initial state. */
 double essa_ensemble_factor(uint64_t seed, double rel_sigma, int64_t copy, int body, int component);

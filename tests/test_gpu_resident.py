@@ -274,6 +274,80 @@ def test_ensemble_closest_approach_to_body(worlds_dir):
     c.close()
 
 
+@pytest.mark.parametrize("exact", [True, False])
+def test_ensemble_candidate_service_approach_table_and_trail(worlds_dir, exact):
+    """SURVEY 8 f2 -- what src/essagui/EssaCreateObject.cpp:166-189 does for ONE candidate on the GUI thread (clone the world,
+    update(ticks), show the candidate's trail and its closest approaches, src/Object.cpp:405-417), for many perturbed copies in
+    one launch: per copy, the designated body's closest approach to EVERY other body (distance + both positions) and its trail.
+    exact_order: bit-identical to the oracle's forward-simulated clone; fast arithmetic: 1e-11."""
+    ow = oracle.World.load(os.path.join(worlds_dir, "solar.essa"))
+    st = ow.state()
+    n, to, steps, every = len(ow), 3, 120, 10
+    c = capi.Context(0)
+    c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"])
+    c.ensemble_init(70, 600, seed=1, rel_sigma=0.0, exact_order=exact, closest_approaches=True, approach_to=to, trail_every=every,
+                    trail_capacity=steps // every + 3)
+    c.ensemble_step(50)   # two launches: minima, positions and the trail's sampling carry over
+    c.ensemble_step(steps - 50)
+    got = c.ensemble_read(0, 70, min_distance=True)
+    this_pos, other_pos = c.ensemble_approaches(0, 70)
+    trail, tlen = c.ensemble_trail(0, 70)
+    fw = ow.clone_for_forward_simulation()
+    fw.dt = 600
+    want_trail = []
+    for s in range(steps):
+        fw.update(1)
+        if (s + 1) % every == 0:
+            want_trail.append(fw.state()["pos"][to].copy())
+    want_trail = np.array(want_trail)
+    for cp in (0, 33, 69):  # sigma = 0: every copy is the template
+        assert tlen[cp] == steps // every
+        for b in range(n):
+            if b == to:
+                continue
+            e = fw.closest_approach(b, to)
+            if exact:
+                assert got["min_distance"][cp][b] == e["distance"]
+                assert np.array_equal(this_pos[cp][b], e["this_position"]) and np.array_equal(other_pos[cp][b], e["other_object_position"])
+            else:
+                assert got["min_distance"][cp][b] == pytest.approx(e["distance"], rel=1e-11)
+                assert np.allclose(this_pos[cp][b], e["this_position"], rtol=1e-10, atol=1e-3)
+                assert np.allclose(other_pos[cp][b], e["other_object_position"], rtol=1e-10, atol=1e-3)
+        if exact:
+            assert np.array_equal(trail[cp][:tlen[cp]], want_trail)
+        else:
+            assert np.allclose(trail[cp][:tlen[cp]], want_trail, rtol=1e-11, atol=1e-3)
+    c.close()
+
+
+def test_ensemble_moves_a_massless_test_particle(worlds_dir):
+    """A live body of mass 0 attracts nothing but is attracted and moves (the reference integrates it); only bodies that
+    Object::deleted() masks stay put.  The ensemble used to infer the mask from gf == 0."""
+    ow = oracle.World.load(os.path.join(worlds_dir, "8body.essa"))
+    ow.add_object(0.0, 1.0, (2.5e11, 0.0, 0.0), (0.0, 2.3e4, 0.0), "probe", 100)
+    st = ow.state()
+    n = len(ow)
+    assert st["gf"][n - 1] == 0.0
+    for exact in (True, False):
+        c = capi.Context(0)
+        c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"],
+                 creation_date=np.full(n, capi.START_DATE, dtype=np.int64))
+        c.ensemble_init(4, 600, seed=1, rel_sigma=0.0, exact_order=exact)
+        c.ensemble_step(50)
+        got = c.ensemble_read(0, 4)
+        fw = ow.clone_for_forward_simulation()
+        fw.dt = 600
+        fw.update(50)
+        ref = fw.state()["pos"]
+        mine = np.stack([got["x"][2], got["y"][2], got["z"][2]], axis=1)
+        assert not np.array_equal(mine[n - 1], st["pos"][n - 1])  # it moved
+        if exact:
+            assert np.array_equal(mine, ref)
+        else:
+            assert np.allclose(mine, ref, rtol=1e-11, atol=1e-2)
+        c.close()
+
+
 def test_object_history_moves_objects_out_and_in_with_the_date(worlds_dir):
     """src/World.cpp:59-84 + src/ObjectHistory.cpp:4-29: once the ObjectHistory holds an entry, stepping the date below the
     creation date of the list's last object moves that object into the history (with its History / Trail reset), and stepping
