@@ -465,22 +465,32 @@ def run_ours(args):
     ticks = []
     for _ in range(e2e_steps):
         ta = time.perf_counter()
-        ctx.upload(host["x"], host["y"], host["z"], host["vx"], host["vy"], host["vz"], host["gf"])
+        if world_size > 1:  # a sharded host program keeps and moves only the bodies its rank integrates
+            ctx.upload_shard(host["x"], host["y"], host["z"], host["vx"], host["vy"], host["vz"])
+        else:
+            ctx.upload(host["x"], host["y"], host["z"], host["vx"], host["vy"], host["vz"], host["gf"])
         tb = time.perf_counter()
         ctx.step(1, opts=opts)
         tc = time.perf_counter()
-        ctx.download(("x", "y", "z", "vx", "vy", "vz"), out=host)  # into the host program's own arrays
+        if world_size > 1:
+            ctx.download_shard(("x", "y", "z", "vx", "vy", "vz"), host)
+        else:
+            ctx.download(("x", "y", "z", "vx", "vy", "vz"), out=host)  # into the host program's own arrays
         td = time.perf_counter()
         ticks.append({"upload_ms": 1e3 * (tb - ta), "step_ms": 1e3 * (tc - tb), "download_ms": 1e3 * (td - tc),
                       "device_step_ms": ctx.last_step_ms, "force_ms": ctx.last_force_ms, "force_passes": ctx.last_force_passes})
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = float(ctx.passes - p0) * n * (n - 1) / e2e_s
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * (11 * 8 + 2 * 8 + 4 + 2)), "d2h_bytes_per_step": int(n * 6 * 8),
+    e2e = {"value": e2e_value, "unit": UNIT,
+           "h2d_bytes_per_step": int(n * 7 * 8) if world_size == 1 else int(n // world_size * 6 * 8) * world_size,
+           "d2h_bytes_per_step": int(n * 6 * 8),
            "steps": e2e_steps, "passes_per_step": (ctx.passes - p0) / e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
            "ticks_rank0": ticks,
-           "note": "after one untimed tick: essa_upload (host SoA -> pinned staging -> HBM) + essa_step(1) + essa_download per step; an upload invalidates "
-                   "the resident acceleration, so each step evaluates both set_forces() passes, as the reference does"}
+           "note": "after one untimed tick: essa_upload (host SoA -> pinned staging -> HBM) + essa_step(1) + essa_download per step "
+                   "(N > 1: essa_upload_shard / essa_download_shard -- every rank moves the bodies it integrates over its own PCIe link, "
+                   "the other ranks' records arrive over NVLink; bytes are whole-job totals); an upload invalidates the resident "
+                   "acceleration, so each step evaluates both set_forces() passes, as the reference does"}
 
     ctx.close()
     # ---- the other large-N configurations of BASELINE.json, on the same ranks (collective: every rank takes part) ----

@@ -79,6 +79,8 @@ SYMBOLS = [
     ("essa_sync", C.c_int, [_P]),
     ("essa_upload", C.c_int, [_P, C.c_int, C.POINTER(Bodies)]),
     ("essa_download", C.c_int, [_P, C.POINTER(Bodies)]),
+    ("essa_upload_shard", C.c_int, [_P, C.POINTER(Bodies)]),
+    ("essa_download_shard", C.c_int, [_P, C.POINTER(Bodies)]),
     ("essa_set_date", C.c_int, [_P, C.c_int64]),
     ("essa_get_date", C.c_int64, [_P]),
     ("essa_body_count", C.c_int, [_P]),
@@ -240,6 +242,33 @@ class Context:
             else:
                 raise KeyError(f)
         self._ck(self._L.essa_download(self._h, C.byref(b)))
+        return out
+
+    def upload_shard(self, x, y, z, vx, vy, vz):
+        """Positions / velocities of this rank's own bodies from full-length arrays (only the slice is read)."""
+        b = Bodies()
+        keep = [_arr(a, np.float64) for a in (x, y, z, vx, vy, vz)]
+        for name, a in zip(("x", "y", "z", "vx", "vy", "vz"), keep):
+            assert len(a) == self.n, name
+            setattr(b, name, _ptr(a, _dp))
+        self._ck(self._L.essa_upload_shard(self._h, C.byref(b)))
+
+    def download_shard(self, fields, out):
+        """This rank's own bodies into the slice [i0, i1) of the full-length arrays of `out` (created if missing)."""
+        n = self.n
+        b = Bodies()
+        for f in fields:
+            if f in self._DOUBLE_FIELDS:
+                if f not in out:
+                    out[f] = np.zeros(n, dtype=np.float64)
+                setattr(b, f, _ptr(out[f], _dp))
+            elif f == "most":
+                if f not in out:
+                    out[f] = np.zeros(n, dtype=np.int32)
+                b.most = _ptr(out[f], _i32p)
+            else:
+                raise KeyError(f)
+        self._ck(self._L.essa_download_shard(self._h, C.byref(b)))
         return out
 
     @property

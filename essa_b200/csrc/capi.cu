@@ -318,6 +318,8 @@ static void persist_post(essa_ctx* ctx, int steps) {
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
+static void pair_peer_close(essa_ctx* ctx);
+
 static void free_world(essa_ctx* c) {
     cudaFree(c->pos[0]);
     cudaFree(c->pos[1]);
@@ -481,6 +483,13 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
         return;
     cudaSetDevice(c->device);
     (void)persist_park(c);
+    if (c->pair_peer_ok) { // let go of the peers' buffers, and give them the chance to let go of ours before it is freed
+        pair_peer_close(c);
+        if (c->comm && c->peer_xchg && nccl().AllReduce
+            && nccl().AllReduce(c->peer_xchg, c->peer_xchg, 1, kNcclUint32, kNcclSum, c->comm, c->stream) == 0)
+            cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(c->peer_xchg);
     if (c->persist.mailbox)
         cudaFreeHost(c->persist.mailbox);
     if (c->stream)
@@ -873,6 +882,94 @@ extern "C" int essa_download(essa_ctx* ctx, essa_bodies* h) {
     return ESSA_OK;
 }
 
+// Sharded host programs: every rank holds (and moves over its own PCIe link) only the bodies it integrates.
+//   essa_upload_shard    positions / velocities of bodies [i0, i1) from the host; the j-records of the other ranks' bodies
+//                        arrive over NVLink (one grouped broadcast-gather), gravity factors / dates / masks stay as the last
+//                        essa_upload left them
+//   essa_download_shard  members of bodies [i0, i1) only, no collective
+// (i0, i1) = essa_shard_range.  Host arrays are indexed by GLOBAL body index (length n); only the slice is touched.
+extern "C" int essa_upload_shard(essa_ctx* ctx, const essa_bodies* h) {
+    ARG(ctx, "ctx is null");
+    ARG(h && h->x && h->y && h->z && h->vx && h->vy && h->vz, "x,y,z,vx,vy,vz are required");
+    ARG(ctx->n > 0, "essa_upload the whole world once first");
+    CK(cudaSetDevice(ctx->device));
+    PARK();
+    size_t const cap = (size_t)ctx->cap;
+    int const i0 = (int)((long long)ctx->n * ctx->rank / ctx->world), i1 = (int)((long long)ctx->n * (ctx->rank + 1) / ctx->world);
+    size_t const M = (size_t)(i1 - i0);
+    cudaStream_t st = ctx->stream;
+    CK(cudaStreamSynchronize(st));
+    int rc = reserve_pinned(ctx, 6 * M * sizeof(double));
+    if (rc != ESSA_OK)
+        return rc;
+    double* d = static_cast<double*>(ctx->pinned);
+    double const* src[6] = { h->x, h->y, h->z, h->vx, h->vy, h->vz };
+    parallel_chunks(M, (size_t)1 << 18, M >= ((size_t)1 << 17) ? host_threads() : 1, [&](size_t lo, size_t hi) {
+        for (int k = 0; k < 6; k++)
+            memcpy(d + k * M + lo, src[k] + i0 + lo, (hi - lo) * sizeof(double));
+    });
+    for (int k = 0; k < 3; k++) {
+        CK(cudaMemcpyAsync(ctx->velh + k * cap + i0, d + k * M, M * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->vel + k * cap + i0, d + (3 + k) * M, M * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CK(launch_pack_range(ctx, ctx->velh, ctx->velh + cap, ctx->velh + 2 * cap, i0, i1, st));
+    if (ctx->world > 1) { // the other ranks' records
+        double4* buf = ctx->pos[ctx->cur];
+        NK(nccl().GroupStart());
+        for (int r = 0; r < ctx->world; r++) {
+            long long a = (long long)ctx->n * r / ctx->world, b = (long long)ctx->n * (r + 1) / ctx->world;
+            if (b > a)
+                NK(nccl().Broadcast(buf + a, buf + a, (size_t)(b - a) * 4, kNcclFloat64, r, ctx->comm, st));
+        }
+        NK(nccl().GroupEnd());
+    }
+    ctx->acc_valid = false;
+    ctx->acc_has_most = false;
+    CK(cudaStreamSynchronize(st));
+    return ESSA_OK;
+}
+
+extern "C" int essa_download_shard(essa_ctx* ctx, essa_bodies* h) {
+    ARG(ctx, "ctx is null");
+    ARG(h, "host view is null");
+    CK(cudaSetDevice(ctx->device));
+    PARK();
+    size_t const cap = (size_t)ctx->cap;
+    int const i0 = (int)((long long)ctx->n * ctx->rank / ctx->world), i1 = (int)((long long)ctx->n * (ctx->rank + 1) / ctx->world);
+    size_t const M = (size_t)(i1 - i0);
+    if (M == 0)
+        return ESSA_OK;
+    int rc = reserve_pinned(ctx, 15 * M * sizeof(double) + M * sizeof(int32_t));
+    if (rc != ESSA_OK)
+        return rc;
+    cudaStream_t st = ctx->stream;
+    double* d = static_cast<double*>(ctx->pinned);
+    int32_t* most = reinterpret_cast<int32_t*>(d + 15 * M);
+    if (h->x || h->y || h->z) {
+        CK(launch_unpack(ctx, ctx->velh, ctx->velh + cap, ctx->velh + 2 * cap, st));
+        for (int k = 0; k < 3; k++)
+            CK(cudaMemcpyAsync(d + k * M, ctx->velh + k * cap + i0, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    double const* dev[15] = { nullptr, nullptr, nullptr, ctx->vel, ctx->vel + cap, ctx->vel + 2 * cap, ctx->acc, ctx->acc + cap, ctx->acc + 2 * cap,
+        ctx->gf, ctx->maxattr, ctx->appe, ctx->appe + cap, ctx->appe + 2 * cap, ctx->appe + 3 * cap };
+    double* dst[15] = { h->x, h->y, h->z, h->vx, h->vy, h->vz, h->ax, h->ay, h->az, h->gf, h->max_attraction, h->ap, h->pe, h->ap_vel,
+        h->pe_vel };
+    for (int k = 3; k < 15; k++)
+        if (dst[k])
+            CK(cudaMemcpyAsync(d + k * M, dev[k] + i0, M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h->most)
+        CK(cudaMemcpyAsync(most, ctx->most + i0, M * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    parallel_chunks(M, (size_t)1 << 18, M >= ((size_t)1 << 17) ? host_threads() : 1, [&](size_t lo, size_t hi) {
+        for (int k = 0; k < 15; k++)
+            if (dst[k])
+                memcpy(dst[k] + i0 + lo, d + k * M + lo, (hi - lo) * sizeof(double));
+    });
+    if (h->most)
+        memcpy(h->most + i0, most, M * sizeof(int32_t));
+    return ESSA_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // stepping
 // ---------------------------------------------------------------------------------------------
@@ -884,6 +981,123 @@ static cudaEvent_t force_event(essa_ctx* c, size_t idx) {
         c->force_events.push_back(ev);
     }
     return c->force_events[idx];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded pair-shared pass: peer-mapped slot buffers.
+// Tile (I, d) of the pair kernel produces J-side partial accelerations for block J = I + d, which another rank may own.
+// Instead of folding them locally and reduce-scattering 3 x N doubles with NCCL after the kernel, every rank maps every other
+// rank's slot buffer into its address space once (cudaIpcGetMemHandle / cudaIpcOpenMemHandle, the handles travel through an
+// ncclAllGather on the context's own communicator) and the kernel stores each tile's J-side sums directly into the owner's
+// memory over NVLink while it computes.  What is left per pass is a one-word all-reduce as a barrier ("every rank's kernel
+// has finished, its stores have landed") before k_pair_finish reads the slots -- and the owner adds them in the same fixed
+// order as a single GPU does, so the result no longer depends on the number of ranks.
+// ---------------------------------------------------------------------------------------------
+static void pair_peer_close(essa_ctx* ctx) {
+    for (int r = 0; r < essa_ctx::kMaxPeers; r++) {
+        if (r != ctx->rank) {
+            if (ctx->pair_slot_peer[r])
+                cudaIpcCloseMemHandle(ctx->pair_slot_peer[r]);
+            if (ctx->pair_kslot_peer[r])
+                cudaIpcCloseMemHandle(ctx->pair_kslot_peer[r]);
+        }
+        ctx->pair_slot_peer[r] = nullptr;
+        ctx->pair_kslot_peer[r] = nullptr;
+    }
+    ctx->pair_peer_ok = false;
+}
+
+// every rank's kernels issued so far on the context's stream have finished (device-side: one word through NCCL)
+static int shard_barrier(essa_ctx* ctx) {
+    if (!ctx->peer_xchg)
+        CK(cudaMalloc(&ctx->peer_xchg, (size_t)essa_ctx::kMaxPeers * 32 * sizeof(unsigned long long)));
+    NK(nccl().AllReduce(ctx->peer_xchg, ctx->peer_xchg, 1, kNcclUint32, kNcclSum, ctx->comm, ctx->stream));
+    return ESSA_OK;
+}
+
+// Collective over the ranks of the context (all of them run the same plan, so all of them get here together).
+static int pair_peer_setup(essa_ctx* ctx, bool keys) {
+    if (ctx->world <= 1 || ctx->pair_peer_failed)
+        return ESSA_OK;
+    static bool const disabled = [] {
+        char const* e = getenv("ESSA_PAIR_PEER"); // diagnostics: 0 = NCCL reduce-scatter instead of peer stores
+        return e && atoi(e) == 0;
+    }();
+    if (disabled || ctx->world > essa_ctx::kMaxPeers || !nccl().AllGather) {
+        ctx->pair_peer_failed = true;
+        return ESSA_OK;
+    }
+    bool const will_change = pair_reserve_would_change(ctx, keys);
+    if (ctx->pair_peer_ok && !will_change)
+        return ESSA_OK;
+    if (ctx->pair_peer_ok) { // the buffers the peers have mapped are about to be freed: everybody lets go first
+        pair_peer_close(ctx);
+        int rc = shard_barrier(ctx);
+        if (rc != ESSA_OK)
+            return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(pair_reserve(ctx, keys, nullptr));
+    if (!ctx->peer_xchg)
+        CK(cudaMalloc(&ctx->peer_xchg, (size_t)essa_ctx::kMaxPeers * 32 * sizeof(unsigned long long)));
+    // 32 words per rank: [0] ok flag, [1] has keys, [8..16) handle of the slots, [16..24) handle of the key slots
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    unsigned long long mine[32] = {};
+    cudaIpcMemHandle_t hs, hk;
+    bool ok = cudaIpcGetMemHandle(&hs, ctx->pair_slots) == cudaSuccess;
+    bool const have_k = ctx->pair_kslots != nullptr;
+    if (ok && have_k)
+        ok = cudaIpcGetMemHandle(&hk, ctx->pair_kslots) == cudaSuccess;
+    (void)cudaGetLastError();
+    mine[0] = ok ? 1 : 0;
+    mine[1] = have_k ? 1 : 0;
+    if (ok) {
+        memcpy(&mine[8], &hs, 64);
+        if (have_k)
+            memcpy(&mine[16], &hk, 64);
+    }
+    CK(cudaMemcpyAsync(ctx->peer_xchg + (size_t)ctx->rank * 32, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+    NK(nccl().AllGather(ctx->peer_xchg + (size_t)ctx->rank * 32, ctx->peer_xchg, 32, kNcclUint64, ctx->comm, ctx->stream));
+    std::vector<unsigned long long> all((size_t)ctx->world * 32);
+    CK(cudaMemcpyAsync(all.data(), ctx->peer_xchg, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    bool all_ok = true;
+    for (int r = 0; r < ctx->world; r++)
+        all_ok = all_ok && all[(size_t)r * 32] == 1 && all[(size_t)r * 32 + 1] == (have_k ? 1u : 0u);
+    if (all_ok) {
+        for (int r = 0; r < ctx->world && all_ok; r++) {
+            if (r == ctx->rank) {
+                ctx->pair_slot_peer[r] = ctx->pair_slots;
+                ctx->pair_kslot_peer[r] = ctx->pair_kslots;
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            void* ptr = nullptr;
+            memcpy(&h, &all[(size_t)r * 32 + 8], 64);
+            all_ok = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            ctx->pair_slot_peer[r] = static_cast<double*>(ptr);
+            if (all_ok && have_k) {
+                memcpy(&h, &all[(size_t)r * 32 + 16], 64);
+                ptr = nullptr;
+                all_ok = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                ctx->pair_kslot_peer[r] = static_cast<unsigned long long*>(ptr);
+            }
+        }
+        (void)cudaGetLastError();
+    }
+    // the decision must be the same everywhere: one more word around
+    unsigned long long flag = all_ok ? 1 : 0;
+    CK(cudaMemcpyAsync(ctx->peer_xchg, &flag, sizeof(flag), cudaMemcpyHostToDevice, ctx->stream));
+    NK(nccl().AllReduce(ctx->peer_xchg, ctx->peer_xchg, 1, kNcclUint64, kNcclSum, ctx->comm, ctx->stream));
+    CK(cudaMemcpyAsync(&flag, ctx->peer_xchg, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flag == (unsigned long long)ctx->world) {
+        ctx->pair_peer_ok = true;
+    } else {
+        pair_peer_close(ctx);
+        ctx->pair_peer_failed = true;
+    }
+    return ESSA_OK;
 }
 
 // In a sharded context every rank has just written its own targets' records into the `next`
@@ -937,8 +1151,19 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
                 NK(nccl().Broadcast(ctx->pair_prior + r * cnt, ctx->pair_prior + r * cnt, cnt, kNcclUint32, r, ctx->comm, ctx->stream));
             NK(nccl().GroupEnd());
         }
-        CK(launch_force_paired_compute(ctx, eps2, ctx->stream, &acc, &npad, keys, &kacc));
         if (ctx->world > 1) {
+            int prc = pair_peer_setup(ctx, keys);
+            if (prc != ESSA_OK)
+                return prc;
+        }
+        CK(launch_force_paired_compute(ctx, eps2, ctx->stream, &acc, &npad, keys, &kacc));
+        if (ctx->world > 1 && ctx->pair_peer_ok) {
+            // the J-side partials went straight into their owners' slot buffers: wait until every rank's kernel is through
+            int brc = shard_barrier(ctx);
+            if (brc != ESSA_OK)
+                return brc;
+            acc = nullptr;
+        } else if (ctx->world > 1) {
             // every rank holds J-side sums (and candidate keys) for every body: reduce-scatter them onto the owners (in place)
             size_t cnt = (size_t)n / ctx->world;
             if (keys && ctx->pair_kall_n < (size_t)n) {
@@ -963,8 +1188,8 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
             }
             NK(nccl().GroupEnd());
         }
-        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc, argmax && !keys, save_old, keys, keys && ctx->world > 1 ? ctx->pair_kall : nullptr,
-            eps2));
+        CK(launch_force_paired_finish(ctx, k, ctx->stream, acc, argmax && !keys, save_old, keys,
+            keys && ctx->world > 1 && !ctx->pair_peer_ok ? ctx->pair_kall : nullptr, eps2));
     } else if (ctx->world == 1 || !ctx->gather_pending) {
         int S;
         choose_split(ctx, iblocks, (n + kTileJ - 1) / kTileJ, &S);

@@ -167,6 +167,14 @@ struct essa_ctx {
     unsigned long long* pair_kslots = nullptr; // most-attracting candidate keys (pair-shared kernel with tracking)
     size_t pair_kslots_bytes = 0;
     unsigned long long* pair_kpart = nullptr;
+    // sharded pair-shared pass: every rank's J-side slot buffers mapped into this address space (cudaIpc, same node), so that
+    // the force kernel stores J-side partials straight into the owning rank's memory over NVLink (capi.cu pair_peer_setup)
+    static constexpr int kMaxPeers = 8;
+    double* pair_slot_peer[kMaxPeers] = {};
+    unsigned long long* pair_kslot_peer[kMaxPeers] = {};
+    bool pair_peer_ok = false;      // the tables above are valid
+    bool pair_peer_failed = false;  // peer mapping is not available here: NCCL reduce-scatter fallback
+    unsigned long long* peer_xchg = nullptr; // device scratch for the handle exchange / the per-pass barrier
     unsigned long long* pair_kall = nullptr; // sharded: every rank's candidate key for each of this rank's bodies [world][n / world]
     size_t pair_kall_n = 0;
     unsigned* pair_prior = nullptr; // candidate-filter thresholds carried from pass to pass (force_paired.cu)
@@ -263,8 +271,11 @@ cudaError_t launch_record(essa_ctx* c, int offset_trails, int forward_simulated,
 cudaError_t launch_record_init(essa_ctx* c, int first, cudaStream_t st);
 cudaError_t launch_fill_f64(essa_ctx* c, double* dst, double v, size_t n, cudaStream_t st);
 cudaError_t launch_fill_i64(essa_ctx* c, int64_t* dst, int64_t v, size_t n, cudaStream_t st);
+cudaError_t launch_pack_range(essa_ctx* c, double const* x, double const* y, double const* z, int i0, int i1, cudaStream_t st);
 cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double const* z, cudaStream_t st);
 cudaError_t launch_unpack(essa_ctx* c, double* x, double* y, double* z, cudaStream_t st);
+cudaError_t pair_reserve(essa_ctx* c, bool argmax, bool* changed);
+bool pair_reserve_would_change(essa_ctx const* c, bool argmax);
 bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_doubles, size_t* part_doubles, int* ri_out = nullptr);
 cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out, bool argmax,
     unsigned long long** kacc_out);

@@ -36,6 +36,7 @@ constexpr int kPHalf = 512;     // records per staged part of a J block
 // Targets per lane RI is a template parameter: 8 (blocks of 2048 bodies) for large worlds, 4 (blocks
 // of 1024) when 2048-body blocks would leave SMs idle.  Bodies per block = 256 * RI.
 constexpr int kPSub = 32 * kPRJ;
+constexpr int kPairMaxPeers = 8; // ranks whose slot buffers a kernel can address (one node)
 constexpr size_t kPSmem = 2 * kPHalf * sizeof(double4) + 8 * 3 * kPHalf * sizeof(double) + 64;
 constexpr size_t kPSmemKeys = 8 * kPHalf * sizeof(unsigned long long) + 2 * kPHalf * sizeof(unsigned); // + per-warp J-side candidate keys and the staged prior thresholds of the visitors (ARGMAX)
 
@@ -118,9 +119,20 @@ struct PairArgs {
     int ib0, ib1;       // I blocks owned by this context
     int npad;           // nb * kPB
     double* part_i;     // [S][3][npad]       I-side partial accelerations
-    double* slots;      // [ib1-ib0][dmax][3][kPB]  J-side partials of tile (I, d), d = 1 .. dmax
+    // J-side partials of tile (I, d), d = 1 .. dmax, live with the OWNER of block J = I + d: slot (J, d) of
+    // [blocks of the owner][dmax][3][kPB].  On one GPU that is this context's own buffer; in a sharded world the kernel
+    // stores them straight into the owning rank's buffer over NVLink (peer-mapped with cudaIpc, capi.cu) -- the force pass
+    // and its "reduce-scatter" are ONE kernel, and k_pair_finish adds a body's slots in the same fixed order (ascending d)
+    // on any number of ranks, so the result does not depend on the rank count.  owner_major == 0: the fallback when peer
+    // access is not available: writer-major slots [ib1-ib0][dmax][3][kPB] in local memory, folded by k_pair_gather_slots
+    // and reduce-scattered with NCCL.
+    double* slot_peer[kPairMaxPeers];
+    unsigned long long* slotk_peer[kPairMaxPeers]; // the same for the candidate keys (ARGMAX): [blocks of the owner][dmax][kPB]
+    int bpr;            // blocks per rank
+    int owner_major;
+    double* slots;      // writer-major fallback
     unsigned long long* part_k;  // [S][npad]              I-side candidate keys (ARGMAX)
-    unsigned long long* slots_k; // [ib1-ib0][dmax][kPB]   J-side candidate keys of tile (I, d)
+    unsigned long long* slots_k; // writer-major fallback
     unsigned const* prior;       // [npad] filter thresholds left by the previous pass (ARGMAX)
     double eps2;
 };
@@ -442,7 +454,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
             }
             __syncthreads();
             if (d > 0) {
-                double* slot = A.slots + ((size_t)ibl * A.dmax + (d - 1)) * 3 * kPB;
+                int const owner = A.owner_major ? J / A.bpr : 0;
+                size_t const tile = A.owner_major ? (size_t)(J - owner * A.bpr) * A.dmax + (d - 1) : (size_t)ibl * A.dmax + (d - 1);
+                double* slot = (A.owner_major ? A.slot_peer[owner] : A.slots) + tile * 3 * kPB;
                 for (int e = tid; e < 3 * kPHalf; e += kPThreads) {
                     int c = e / kPHalf, j = e - c * kPHalf;
                     double sum = 0.0;
@@ -452,7 +466,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                     __stcg(slot + (size_t)c * kPB + half * kPHalf + j, sum);
                 }
                 if (ARGMAX) {
-                    unsigned long long* slotk = A.slots_k + ((size_t)ibl * A.dmax + (d - 1)) * kPB + half * kPHalf;
+                    unsigned long long* slotk = (A.owner_major ? A.slotk_peer[owner] : A.slots_k) + tile * kPB + half * kPHalf;
                     for (int j = tid; j < kPHalf; j += kPThreads) {
                         unsigned long long k = 0ull;
 #pragma unroll
@@ -501,7 +515,40 @@ struct PairFinishArgs {
     double eps2;         // softening, for the repair of bodies that met an r = 0 pair in an unguarded tile
 };
 
-// J-side contributions to body g from the tiles whose I block lies in [ib0, ib1), in offset order.
+// J-side contributions to body g (block K = g / kPB, owned by this context) from every tile (I = K - d, d), in offset
+// order, out of the owner-major slots of this context.
+template<int kPB>
+__device__ __forceinline__ void slot_sum_owner(int g, int nb, int dmax, int ib0, double const* slots, double& ax, double& ay, double& az) {
+    int const K = g / kPB, jl = g - K * kPB;
+    for (int d = 1; d <= dmax; d++) {
+        int I = K - d;
+        if (I < 0)
+            I += nb;
+        if ((nb & 1) == 0 && d == nb / 2 && I >= nb / 2)
+            continue; // that tile belongs to the other half of the ring
+        double const* s = slots + ((size_t)(K - ib0) * dmax + (d - 1)) * 3 * kPB + jl;
+        ax = __dadd_rn(ax, __ldcg(s));
+        ay = __dadd_rn(ay, __ldcg(s + kPB));
+        az = __dadd_rn(az, __ldcg(s + 2 * kPB));
+    }
+}
+template<int kPB>
+__device__ __forceinline__ unsigned long long slot_key_owner(int g, int nb, int dmax, int ib0, unsigned long long const* slots_k,
+    double4 const* __restrict__ pos, double eps2) {
+    int const K = g / kPB, jl = g - K * kPB;
+    unsigned long long k = 0ull;
+    for (int d = 1; d <= dmax; d++) {
+        int I = K - d;
+        if (I < 0)
+            I += nb;
+        if ((nb & 1) == 0 && d == nb / 2 && I >= nb / 2)
+            continue;
+        k = key_merge(pos, g, k, __ldcg(slots_k + ((size_t)(K - ib0) * dmax + (d - 1)) * kPB + jl), eps2);
+    }
+    return k;
+}
+
+// (writer-major fallback) J-side contributions to body g from the tiles whose I block lies in [ib0, ib1), in offset order.
 template<int kPB>
 __device__ __forceinline__ void slot_sum(int g, int nb, int dmax, int ib0, int ib1, double const* slots, double& ax, double& ay,
     double& az) {
@@ -626,7 +673,7 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
             ay = __dadd_rn(ay, __ldcg(A.ajred + (size_t)A.npad + g));
             az = __dadd_rn(az, __ldcg(A.ajred + 2 * (size_t)A.npad + g));
         } else {
-            slot_sum<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots, ax, ay, az);
+            slot_sum_owner<kPB>(g, A.nb, A.dmax, A.ib0, A.slots, ax, ay, az);
         }
         ax = __dmul_rn(ax, A.scale);
         ay = __dmul_rn(ay, A.scale);
@@ -638,7 +685,7 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
                 for (int r = 0; r < A.world; r++)
                     key = key_merge(W.pos_cur, g, key, __ldcg(A.akred + (size_t)r * (A.i1 - A.i0) + (g - A.i0)), A.eps2);
             } else {
-                key = slot_key<kPB>(g, A.nb, A.dmax, A.ib0, A.ib1, A.slots_k, W.pos_cur, A.eps2);
+                key = slot_key_owner<kPB>(g, A.nb, A.dmax, A.ib0, A.slots_k, W.pos_cur, A.eps2);
             }
             for (int c = 0; c < A.S; c++)
                 key = key_merge(W.pos_cur, g, key, __ldcg(A.part_k + (size_t)c * A.npad + g), A.eps2);
@@ -874,7 +921,7 @@ static cudaError_t launch_pair_kernels(essa_ctx* c, PairArgs const& A, cudaStrea
         return e;
     *acc = nullptr;
     *kacc = nullptr;
-    if (c->world > 1) {
+    if (c->world > 1 && !A.owner_major) {
         *acc = c->pair_part + (size_t)A.S * 3 * A.npad;
         if (ARGMAX)
             *kacc = c->pair_kpart + (size_t)A.S * A.npad;
@@ -885,6 +932,7 @@ static cudaError_t launch_pair_kernels(essa_ctx* c, PairArgs const& A, cudaStrea
     }
     return e;
 }
+
 
 static cudaError_t grow(void** p, size_t* have, size_t want_bytes) {
     if (want_bytes <= *have)
@@ -898,12 +946,13 @@ static cudaError_t grow(void** p, size_t* have, size_t want_bytes) {
     return e;
 }
 
-// Phase 1: the pair kernel over this rank's I blocks; sharded worlds also fold their slots into
-// acc[3][npad] (returned through *acc_out) for the caller to reduce-scatter over the ranks.
-cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out, bool argmax,
-    unsigned long long** kacc_out) {
+// Buffers of the pair-shared pass for the current plan.  *changed: the slot buffers (what sharded ranks map into each other's
+// address space) were (re)allocated.
+cudaError_t pair_reserve(essa_ctx* c, bool argmax, bool* changed) {
     int nb, S, ri;
     size_t slot_d, part_d;
+    if (changed)
+        *changed = false;
     if (!paired_plan(c, &nb, &S, &slot_d, &part_d, &ri))
         return cudaErrorInvalidConfiguration;
     if (slot_d > c->pair_slots_n) {
@@ -914,6 +963,8 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
         if (e != cudaSuccess)
             return e;
         c->pair_slots_n = slot_d;
+        if (changed)
+            *changed = true;
     }
     if (part_d > c->pair_part_n) {
         cudaFree(c->pair_part);
@@ -925,9 +976,37 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
         c->pair_part_n = part_d;
     }
     if (argmax) { // candidate keys: one per slot body / per partial body (a third of the acceleration buffers)
+        size_t const before = c->pair_kslots_bytes;
         cudaError_t e = grow((void**)&c->pair_kslots, &c->pair_kslots_bytes, slot_d / 3 * sizeof(unsigned long long));
         if (e == cudaSuccess)
             e = grow((void**)&c->pair_kpart, &c->pair_kpart_bytes, (part_d / 3 + 1) * sizeof(unsigned long long));
+        if (e != cudaSuccess)
+            return e;
+        if (changed && c->pair_kslots_bytes != before)
+            *changed = true;
+    }
+    return cudaSuccess;
+}
+
+// Would pair_reserve have to (re)allocate a slot buffer?  (Sharded ranks unmap each other's buffers first.)
+bool pair_reserve_would_change(essa_ctx const* c, bool argmax) {
+    int nb, S, ri;
+    size_t slot_d, part_d;
+    if (!paired_plan(c, &nb, &S, &slot_d, &part_d, &ri))
+        return false;
+    return slot_d > c->pair_slots_n || (argmax && slot_d / 3 * sizeof(unsigned long long) > c->pair_kslots_bytes);
+}
+
+// Phase 1: the pair kernel over this rank's I blocks; sharded worlds also fold their slots into
+// acc[3][npad] (returned through *acc_out) for the caller to reduce-scatter over the ranks.
+cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t st, double** acc_out, int* npad_out, bool argmax,
+    unsigned long long** kacc_out) {
+    int nb, S, ri;
+    size_t slot_d, part_d;
+    if (!paired_plan(c, &nb, &S, &slot_d, &part_d, &ri))
+        return cudaErrorInvalidConfiguration;
+    {
+        cudaError_t e = pair_reserve(c, argmax, nullptr);
         if (e != cudaSuccess)
             return e;
     }
@@ -963,6 +1042,14 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
     A.part_k = c->pair_kpart;
     A.slots_k = c->pair_kslots;
     A.eps2 = eps2;
+    // J-side slots live with the owner of the J block: own memory on one GPU, peer-mapped memory when sharded (capi.cu set the
+    // table up); without peer access the writer-major fallback + NCCL reduce-scatter
+    A.owner_major = c->world == 1 || c->pair_peer_ok;
+    A.bpr = nb / c->world;
+    for (int r = 0; r < kPairMaxPeers; r++) {
+        A.slot_peer[r] = c->world == 1 ? c->pair_slots : (r < c->world ? c->pair_slot_peer[r] : nullptr);
+        A.slotk_peer[r] = c->world == 1 ? c->pair_kslots : (r < c->world ? c->pair_kslot_peer[r] : nullptr);
+    }
     double* acc = nullptr;
     unsigned long long* kacc = nullptr;
     bool const uniform = pair_uniform(c) && !argmax;

@@ -424,6 +424,21 @@ cudaError_t launch_fill_i64(essa_ctx* c, int64_t* dst, int64_t v, size_t n, cuda
     return cudaGetLastError();
 }
 
+// essa_upload_shard: the j-records of bodies [i0, i1) of the current buffer from freshly uploaded coordinates.
+__global__ void k_pack_range(double4* pos, double const* x, double const* y, double const* z, double const* gf, uint8_t const* active,
+    int i0, int i1) {
+    int g = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < i1)
+        pos[g] = make_double4(x[g], y[g], z[g], active[g] ? gf[g] : 0.0);
+}
+cudaError_t launch_pack_range(essa_ctx* c, double const* x, double const* y, double const* z, int i0, int i1, cudaStream_t st) {
+    if (i1 <= i0)
+        return cudaSuccess;
+    k_pack_range<<<(i1 - i0 + 255) / 256, 256, 0, st>>>(c->pos[c->cur], x, y, z, c->gf, c->active, i0, i1);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack(essa_ctx* c, double const* x, double const* y, double const* z, cudaStream_t st) {
     if (c->n <= 0)
         return cudaSuccess;

@@ -261,6 +261,13 @@ int essa_nccl_unique_id(uint8_t id[ESSA_NCCL_ID_BYTES]);
  * links, max_attraction and ap / pe are gathered from their owners.  Recording (essa_step_opts.record) runs for the
  * tracked bodies a rank owns: History / Trail rings of body k are read on the rank whose essa_shard_range holds k. */
 int essa_shard_attach(essa_ctx* ctx, int rank, int world, const uint8_t id[ESSA_NCCL_ID_BYTES]);
+/* A sharded host program keeps only its own bodies current on the host.  essa_upload_shard: positions / velocities of bodies
+ * [i0, i1) (essa_shard_range) from host arrays indexed by GLOBAL body index -- only that slice is read; the records of the
+ * other ranks' bodies arrive over NVLink (collective); gravity factors, dates and masks stay as the last essa_upload left
+ * them.  essa_download_shard: the requested members of bodies [i0, i1) only (same indexing, only the slice is written), no
+ * collective.  Per tick a rank then moves 1 / world of the state over its PCIe link instead of all of it. */
+int essa_upload_shard(essa_ctx* ctx, const essa_bodies* host);
+int essa_download_shard(essa_ctx* ctx, essa_bodies* host);
 /* The target range [*i0, *i1) of a rank (pure function; what every kernel of a sharded context uses). */
 int essa_shard_range(int n, int rank, int world, int* i0, int* i1);
 int essa_shard_rank(const essa_ctx* ctx);

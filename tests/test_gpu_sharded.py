@@ -27,4 +27,4 @@ def test_two_rank_sharded_matches_unsharded():
                        timeout=900, cwd=ROOT)
     out = p.stdout + p.stderr
     assert p.returncode == 0, out[-3000:]
-    assert out.count("-> PASS") == 17 and "FAIL" not in out, out[-3000:]
+    assert out.count("-> PASS") == 18 and "FAIL" not in out, out[-3000:]

@@ -35,7 +35,7 @@ def test_python_binding_covers_the_header():
     bound = {s[0] for s in capi.SYMBOLS} | {s[0] for s in world.WORLD_SYMBOLS}
     declared = set(_declared_functions("essa_b200.h")) | set(_declared_functions("essa_world.h"))
     assert declared <= bound, sorted(declared - bound)
-    assert capi.lib().essa_abi_version() == 1
+    assert capi.lib().essa_abi_version() == 2
 
 
 def test_no_cpu_fallback():
