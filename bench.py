@@ -291,6 +291,13 @@ def solar_leg():
         out["%s_ensemble_copy_iters_per_s" % tag] = copies * esteps / (ms * 1e-3)
         out["%s_ensemble_interactions_per_s" % tag] = copies * (esteps + 1) * n * (n - 1) / (ms * 1e-3)
         out["%s_ensemble_aggregate_vs_cpu_oracle" % tag] = out["%s_ensemble_copy_iters_per_s" % tag] / out["%s_iters_per_s_cpu_oracle" % tag]
+        if tag == "solar":
+            # 2,048 warps of one-copy-per-thread work leave a sixth of the 592 schedulers a warp short; 1,048,576 copies fill them
+            big = 1 << 20
+            c.ensemble_init(big, 600, seed=7, rel_sigma=1e-6)
+            c.ensemble_step(2)
+            c.ensemble_step(esteps)
+            out["solar_ensemble_1m_copies_copy_iters_per_s"] = big * esteps / (c.last_step_ms * 1e-3)
         c.close()
     out["note"] = ("dt=600 s, History + Trail + ap/pe recording on, offset trails, through the World facade (update(k) + read-back of every "
                    "object per call); *_iters_per_s_<mode> = one call of many steps, *_10_per_call = the GUI's cadence (10 iterations per "

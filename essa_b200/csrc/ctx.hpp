@@ -16,6 +16,7 @@ constexpr int kTileJ = 256;       // j-records per shared-memory tile (8 KiB)
 constexpr int kStages = 4;        // bulk-copy pipeline depth
 constexpr int kForceThreads = 256;
 constexpr int kEnsembleMaxBodies = 320; // widest template one ensemble CTA takes
+constexpr int kEnsembleSoloMax = 16;    // templates up to this size run one thread per copy (ensemble.cu k_ensemble_solo)
 
 // Arguments of the fused kick / drift epilogue (src/World.cpp:106-116,121-127).
 struct KickArgs {
@@ -212,6 +213,9 @@ struct essa_ctx {
     double* ens_trail = nullptr; // [copies][trail_capacity][3] the designated body's trail
     int* ens_trail_len = nullptr; // [copies]
     long long ens_steps_done = 0;
+    double ens_gf_host[essa::kEnsembleSoloMax] = {}; // the template's weights / live mask on the host (kernel parameters of k_ensemble_solo)
+    unsigned ens_on_mask = 0;
+    bool ens_solo = true;                      // ESSA_ENSEMBLE_SOLO=0: measurement switch, small templates take the duo kernel
 
     // closest approaches of a forward-simulated world: [n][n][7]
     double* closest = nullptr;

@@ -12,6 +12,7 @@
 // of EssaCreateObject), its closest approach to EVERY other body -- distance and both positions, as
 // Object::ClosestApproachEntry holds them -- and its trail (positions after every k-th step).
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "ctx.hpp"
@@ -326,6 +327,257 @@ __global__ void __launch_bounds__(WARP ? 32 * kDuoWarps : kDuoCtaThreads, WARP ?
         }
 }
 
+// Fast-arithmetic ensembles of SMALL templates (up to kEnsembleSoloMax bodies; the Solar System has 10): ONE THREAD PER COPY.
+// A thread holds the positions and accelerations of its whole copy in registers (N is a compile-time constant, every loop is
+// unrolled), so a force pass evaluates each PAIR once -- Newton's third law, as the pair-shared kernel K1p does for large worlds:
+// 3 DADD + 3 (r^2) + 6 (r^-3 from the MUFU seed) + 2 (the two weights) + 6 DFMA = 20 FP64 instructions per pair, 10 per
+// directed interaction, where the two-bodies-per-thread kernel below spends 16 -- and no shared-memory traffic, no barrier, no
+// shuffle in the loop at all: the N (N - 1) / 2 pairs of a step are independent chains for the FP64 pipe.  Weights gf_j are the
+// same in every copy and arrive as kernel parameters (constant-bank operands of the multiplies).  Velocities are touched twice
+// per step only and live in shared memory (component c of thread t at [c][t]: conflict free), as do the closest-approach
+// records of the candidate service (running minimum of d^2 and the six coordinates it was seen at, per body).
+constexpr int kSoloThreads = 32; // per CTA: small CTAs spread an ensemble of 65,536 copies evenly over 148 SMs in ONE wave
+
+// Every pair (i, j) of N bodies once, expanded at compile time, in round-robin tournament order (circle method): the pairs of a
+// round share no body, so neighbouring pairs in program order are independent chains (measured on B200, Solar System, 1 M copies:
+// 1.42e10 copy-iterations/s against 1.34e10 in row-major order).  M = N rounded up to even; index M - 1 is the bye of an odd N.
+template<int N, int R, int K, class F>
+__device__ __forceinline__ void for_each_pair_rr(F&& f) {
+    constexpr int M = N + (N & 1);
+    if constexpr (R < M - 1) {
+        constexpr int a = K == 0 ? M - 1 : (R + K) % (M - 1);
+        constexpr int b = (R + M - 1 - K) % (M - 1);
+        constexpr int lo = a < b ? a : b, hi = a < b ? b : a;
+        if constexpr (hi < N)
+            f(std::integral_constant<int, lo> {}, std::integral_constant<int, hi> {});
+        if constexpr (K + 1 < M / 2)
+            for_each_pair_rr<N, R, K + 1>(f);
+        else
+            for_each_pair_rr<N, R + 1, 0>(f);
+    }
+}
+
+template<int N>
+struct SoloConst {
+    double gf[N];
+    unsigned on; // bit k: body k is live (Object::deleted() masks the others: neither attracted nor moved)
+};
+
+template<int N, int MINB>
+__global__ void __launch_bounds__(kSoloThreads, MINB) k_ensemble_solo(EnsembleArgs const A, SoloConst<N> const G) {
+    extern __shared__ double solo_smem[];
+    constexpr int T = kSoloThreads;
+    int const tid = threadIdx.x;
+    long long const mine = (long long)blockIdx.x * T + tid;
+    bool const live = mine < A.copies;
+    long long const copy = live ? mine : 0; // a surplus lane repeats copy 0 and stores nothing
+    double* const sv = solo_smem + tid;     // velocity component c of body k at sv[(3 k + c) T]
+    double* const sm2 = sv + 3 * N * T;     // closest approaches: minimum of d^2 of body k in this launch (< 0: none) at sm2[k T]
+    double* const sp = sm2 + N * T;         // ... and the coordinates it was seen at, sp[(6 k + q) T]
+    double* const s = A.state + (size_t)copy * 6 * N;
+    double x[N], y[N], z[N], ax[N], ay[N], az[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        x[k] = s[k];
+        y[k] = s[N + k];
+        z[k] = s[2 * N + k];
+        sv[(3 * k) * T] = s[3 * N + k];
+        sv[(3 * k + 1) * T] = s[4 * N + k];
+        sv[(3 * k + 2) * T] = s[5 * N + k];
+    }
+    bool const approaches = A.approaches != 0;
+    bool const keep_pos = approaches && A.apos != nullptr;
+    int const to = A.approach_to;
+    if (approaches) {
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            sm2[k * T] = -1.0;
+    }
+
+    auto forces = [&]() {
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            ax[k] = ay[k] = az[k] = 0.0;
+        // (template recursion, not `#pragma unroll`: a nest of this size is left partly rolled, and the state it indexes then
+        // lives in local memory -- measured: 3.5e9 copy-iterations/s instead of 1.1e10)
+        for_each_pair_rr<N, 0, 0>([&](auto I, auto J) {
+            constexpr int i = decltype(I)::value, j = decltype(J)::value;
+            double const dx = x[j] - x[i], dy = y[j] - y[i], dz = z[j] - z[i];
+            double r2 = dx * dx;
+            r2 = fma(dy, dy, r2);
+            r2 = fma(dz, dz, r2);
+            // |d|^-3 = y0^3 (1 + e (3/2 + 15/8 e)),  e = 1 - r2 y0^2  (common.cuh inv_r3_times); 0 for coincident bodies
+            double const y0 = rsqrt_seed(r2);
+            double const y2 = y0 * y0;
+            double const e = fma(-r2, y2, 1.0);
+            double const y3 = y0 * y2;
+            double const we = fma(1.875, e, 1.5) * e;
+            double const c = fma(y3, we, y3);
+            double const si = G.gf[j] * c, sj = G.gf[i] * c;
+            ax[i] = fma(si, dx, ax[i]);
+            ay[i] = fma(si, dy, ay[i]);
+            az[i] = fma(si, dz, az[i]);
+            ax[j] = fma(-sj, dx, ax[j]);
+            ay[j] = fma(-sj, dy, ay[j]);
+            az[j] = fma(-sj, dz, az[j]);
+        });
+    };
+    // (a h) mul == a (h mul) and (v dt) mul == v (dt mul) exactly: mul is +-1
+    double const hm = A.h * A.mul, dtm = A.dt * A.mul;
+    int until = (int)(A.trail_every - A.steps_done % A.trail_every); // steps until the designated body's next trail sample
+    long long tidx = A.steps_done / A.trail_every;                   // ... which is sample number tidx
+
+    // st == -1 is the force pass in front of the first step.  (ONE call site for the force pass: a second one makes the
+    // compiler keep it out of line, and the state it works on would live in local memory instead of registers.)
+    for (int st = -1; st < A.steps; st++) {
+        if (st < 0)
+            goto pass;
+        if (approaches) { // Object::update_closest_approaches (src/Object.cpp:405-417), at the step's start
+            double tx = 0, ty = 0, tz = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                tx = k == to ? x[k] : tx;
+                ty = k == to ? y[k] : ty;
+                tz = k == to ? z[k] : tz;
+            }
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                if (k == to)
+                    continue;
+                double const dx = __dsub_rn(tx, x[k]), dy = __dsub_rn(ty, y[k]), dz = __dsub_rn(tz, z[k]);
+                double const d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                double const m2 = sm2[k * T];
+                // a distance of exactly zero stores 0 == "unset" in the reference: the search restarts
+                bool const zero = d2 == 0.0;
+                bool const better = !zero && (m2 < 0.0 || d2 < m2);
+                sm2[k * T] = zero ? -1.0 : (better ? d2 : m2); // unconditional: the copies of a warp take one path
+                if (zero && live)
+                    A.mind[(size_t)copy * N + k] = 0.0;
+                if (better && keep_pos) {
+                    sp[(6 * k) * T] = x[k];
+                    sp[(6 * k + 1) * T] = y[k];
+                    sp[(6 * k + 2) * T] = z[k];
+                    sp[(6 * k + 3) * T] = tx;
+                    sp[(6 * k + 4) * T] = ty;
+                    sp[(6 * k + 5) * T] = tz;
+                }
+            }
+        }
+        // the second kick of the previous step and the first of this one use the same acceleration: one pass over the velocities
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            if (!((G.on >> k) & 1u))
+                continue;
+            double const kx = __dmul_rn(ax[k], hm), ky = __dmul_rn(ay[k], hm), kz = __dmul_rn(az[k], hm);
+            double vx = sv[(3 * k) * T], vy = sv[(3 * k + 1) * T], vz = sv[(3 * k + 2) * T];
+            if (st > 0) {
+                vx = __dadd_rn(vx, kx);
+                vy = __dadd_rn(vy, ky);
+                vz = __dadd_rn(vz, kz);
+            }
+            vx = __dadd_rn(vx, kx);
+            vy = __dadd_rn(vy, ky);
+            vz = __dadd_rn(vz, kz);
+            x[k] = __dadd_rn(x[k], __dmul_rn(vx, dtm));
+            y[k] = __dadd_rn(y[k], __dmul_rn(vy, dtm));
+            z[k] = __dadd_rn(z[k], __dmul_rn(vz, dtm));
+            sv[(3 * k) * T] = vx;
+            sv[(3 * k + 1) * T] = vy;
+            sv[(3 * k + 2) * T] = vz;
+        }
+    pass:
+        forces();
+        if (st >= 0 && A.trail && --until == 0) { // the designated body's position after every trail_every-th step
+            until = A.trail_every;
+            if (live && tidx < A.trail_cap) {
+                double tx = 0, ty = 0, tz = 0;
+#pragma unroll
+                for (int k = 0; k < N; k++) {
+                    tx = k == to ? x[k] : tx;
+                    ty = k == to ? y[k] : ty;
+                    tz = k == to ? z[k] : tz;
+                }
+                double* t = A.trail + ((size_t)copy * A.trail_cap + (size_t)tidx) * 3;
+                t[0] = tx;
+                t[1] = ty;
+                t[2] = tz;
+                A.trail_len[copy] = (int)tidx + 1;
+            }
+            tidx++;
+        }
+    }
+    if (!live)
+        return;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        double vx = sv[(3 * k) * T], vy = sv[(3 * k + 1) * T], vz = sv[(3 * k + 2) * T];
+        if (A.steps > 0 && ((G.on >> k) & 1u)) { // the last step's second kick
+            vx = __dadd_rn(vx, __dmul_rn(ax[k], hm));
+            vy = __dadd_rn(vy, __dmul_rn(ay[k], hm));
+            vz = __dadd_rn(vz, __dmul_rn(az[k], hm));
+        }
+        s[k] = x[k];
+        s[N + k] = y[k];
+        s[2 * N + k] = z[k];
+        s[3 * N + k] = vx;
+        s[4 * N + k] = vy;
+        s[5 * N + k] = vz;
+        if (approaches && k != to) { // RN o sqrt is monotone: the root of the launch's minimum, taken once (Approach::settle)
+            double const m2 = sm2[k * T];
+            if (m2 >= 0.0) {
+                double const d = __dsqrt_rn(m2);
+                double const md = A.mind[(size_t)copy * N + k];
+                if (md == 0.0 || d < md) {
+                    A.mind[(size_t)copy * N + k] = d;
+                    if (keep_pos)
+                        for (int q = 0; q < 6; q++)
+                            A.apos[((size_t)copy * N + k) * 6 + q] = sp[(6 * k + q) * T];
+                }
+            }
+        }
+    }
+}
+
+template<int N>
+static cudaError_t launch_solo(essa_ctx* c, EnsembleArgs const& A, cudaStream_t st) {
+    SoloConst<N> G;
+    for (int k = 0; k < N; k++)
+        G.gf[k] = c->ens_gf_host[k];
+    G.on = c->ens_on_mask;
+    bool const approaches = A.approaches != 0;
+    size_t const smem = (size_t)kSoloThreads * sizeof(double) * (3 * N + (approaches ? N + (A.apos ? 6 * N : 0) : 0));
+    int const blocks = (int)(((long long)A.copies + kSoloThreads - 1) / kSoloThreads);
+    // Registers: 6 N doubles of state + the pairs in flight: 8 warps per SM, two per scheduler, whose unrolled pairs keep the
+    // FP64 pipe fed.  (A 65,536-copy ensemble is 2,048 warps on 592 schedulers: 3.46 each, so 4 on the busiest whichever way
+    // they are packed -- two waves of 8 warps per SM cost what one wave of 14 would, without its register spills.)
+#ifndef SOLO_MINB
+#define SOLO_MINB 8
+#endif
+    constexpr int MINB = SOLO_MINB;
+    auto kern = k_ensemble_solo<N, MINB>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+    }
+    kern<<<blocks, kSoloThreads, smem, st>>>(A, G);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_solo_n(essa_ctx* c, EnsembleArgs const& A, cudaStream_t st) {
+    switch (A.n) {
+#define ESSA_SOLO_CASE(N) \
+    case N: \
+        return launch_solo<N>(c, A, st);
+        ESSA_SOLO_CASE(2) ESSA_SOLO_CASE(3) ESSA_SOLO_CASE(4) ESSA_SOLO_CASE(5) ESSA_SOLO_CASE(6) ESSA_SOLO_CASE(7) ESSA_SOLO_CASE(8)
+        ESSA_SOLO_CASE(9) ESSA_SOLO_CASE(10) ESSA_SOLO_CASE(11) ESSA_SOLO_CASE(12) ESSA_SOLO_CASE(13) ESSA_SOLO_CASE(14)
+        ESSA_SOLO_CASE(15) ESSA_SOLO_CASE(16)
+#undef ESSA_SOLO_CASE
+    default:
+        return cudaErrorInvalidConfiguration;
+    }
+}
+
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st) {
     long long total = (long long)c->ens_copies * c->ens_n;
     int blocks = (int)((total + 255) / 256);
@@ -367,6 +619,11 @@ cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
             return cudaErrorInvalidConfiguration;
         int blocks = (c->ens_copies + per_cta - 1) / per_cta;
         k_ensemble_exact<<<blocks, threads, (size_t)per_cta * 4 * n * sizeof(double), st>>>(A);
+    } else if (n >= 2 && n <= kEnsembleSoloMax && c->ens_solo) {
+        A.per_cta = kSoloThreads;
+        e = launch_solo_n(c, A, st);
+        if (e != cudaSuccess)
+            return e;
     } else {
         int const half = (n + 1) / 2;
         size_t const rec_bytes = (size_t)(n + 1) * sizeof(double4);

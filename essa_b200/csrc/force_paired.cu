@@ -123,7 +123,7 @@ struct PairArgs {
     // [blocks of the owner][dmax][3][kPB].  On one GPU that is this context's own buffer; in a sharded world the kernel
     // stores them straight into the owning rank's buffer over NVLink (peer-mapped with cudaIpc, capi.cu) -- the force pass
     // and its "reduce-scatter" are ONE kernel, and k_pair_finish adds a body's slots in the same fixed order (ascending d)
-    // on any number of ranks, so the result does not depend on the rank count.  owner_major == 0: the fallback when peer
+    // on any number of ranks (the I-side chunking S still follows the plan, so rank counts agree to rounding only).  owner_major == 0: the fallback when peer
     // access is not available: writer-major slots [ib1-ib0][dmax][3][kPB] in local memory, folded by k_pair_gather_slots
     // and reduce-scattered with NCCL.
     double* slot_peer[kPairMaxPeers];

@@ -11,26 +11,33 @@
 //                     (identical bits in all four) but evaluates only every fourth partner slot; the four partial
 //                     accelerations meet in shared memory behind ONE named barrier per force pass and are added in
 //                     a fixed order by every lane, so the replicas stay identical and no position is ever
-//                     broadcast.  The most-attracting candidate (src/Object.cpp:84-94) rides along: a sortable
-//                     64-bit key per partner -- bit pattern of gf_p / r^4 (to ~1e-12: the refined reciprocal) with
-//                     the 5 lowest mantissa bits replaced by 31 - p -- maximised with integer instructions next to
-//                     the floating-point sums (round 1 ran this on three more warps of CTA 1: 800 cycles of latency
-//                     per step that every World::update call paid at its end).  Warps 1-3 publish the step's
-//                     snapshot (positions / velocities / mask + winners) into CTA 1's ring with st.async: the store
-//                     itself completes the ring slot's mbarrier there (transaction bytes).
-//   CTA 1  warps 0, 1 Trail (even / odd bodies: an append stalls the whole warp)
-//          warp 2     link bookkeeping + History
-//          warp 3     ap / pe
-//          warp 4     publisher (persistent mode)
-//                     The consumers report progress with a relaxed store into CTA 0's shared memory; the physics
-//                     warps look at it only when their cached copy says the ring could be full.
+//                     broadcast.  After a step each warp stores two components of the state into a LOCAL staging
+//                     buffer (two predicated STS + one mbarrier arrive; remote stores from these warps cost more).
+//          warp 4     courier: forwards a staged step to CTA 1's ring with st.async -- the store itself completes
+//                     the ring slot's mbarrier there (transaction bytes) -- and, at a tick's end, the final x v a.
+//          warp 5     poller (persistent flavour): reads the host's command word, grants ticks to both CTAs.
+//   CTA 1  warps 0-2  attraction: the most-attracting candidate of every body of ONE step (src/Object.cpp:84-94): a lane
+//                     is a partner, four bodies in flight, the winner from two full-warp redux.sync over sortable keys
+//                     (gf_p / r^4 with the refined reciprocal, the 5 lowest mantissa bits replaced by 31 - p).  Ranking
+//                     inside the physics warps was measured at +170 cycles per step; dealing whole steps round-robin to
+//                     these warps (round 1) at 800 cycles of latency that every World::update call paid at its end.
+//          warps 3-6  Trail (bodies by index mod 4: an append stalls the whole warp)
+//          warp 7     link bookkeeping + History
+//          warps 8, 9 apoapsis / periapsis (the two halves of src/Object.cpp:111-123 are independent chains)
+//          warp 10    publisher (persistent flavour)
+//                     The consumers report progress with a relaxed store into CTA 0's shared memory; the courier looks
+//                     at it only when its cached copy says the ring could be full.
 //
-// Persistent mode (essa_persist_configure, capi.cu): after the steps of a call the physics warps send their final
-// state to CTA 1 (st.async again), and warp 0 starts polling the host's command word in mapped pinned memory, four
-// reads in flight a quarter of a PCIe round trip apart.  CTA 1's publisher waits for that bundle and for the
-// consumers' last step, then writes the packed state to the host as self-validating 64-bit words {sequence number,
-// 32 bits of payload} (what NCCL's LL protocol does over PCIe): no system-wide fence, no separate
-// acknowledgement -- the host has a tick's result when every word carries the tick's number.
+// Every warp has ONE role and its own copy of the step loop (generic lambdas over std::integral_constant): in these
+// single-warp dependent chains a taken branch costs ~20 cycles and a divergent `if (lane == 0) asm...` region ~90.
+//
+// Persistent flavour (essa_persist_configure, capi.cu): the poller reads the host's command word in mapped pinned
+// memory (ONE read in flight, see ESSA_POLL_DEPTH), forwards each grant to CTA 1 and releases the physics warps from
+// a named barrier.  At a tick's end the courier sends the final state to CTA 1; the publisher waits for it and for the
+// links / ap / pe warps' last step, then writes the packed state to the host as self-validating 64-bit words
+// {tick number, 32 bits of payload} (what NCCL's LL protocol does over PCIe): no system-wide fence, no separate
+// acknowledgement -- the host has a tick's result when every word carries the tick's number.  Trail and History may
+// lag by up to the ring's depth; their rings are only read after the kernel has retired.
 #include <type_traits>
 
 #include "common.cuh"

@@ -256,6 +256,91 @@ def test_ensemble_copies_match_oracle(worlds_dir, exact):
     c.close()
 
 
+def _oracle_world_from(comp, gf):
+    w = oracle.World()
+    w.add_bodies(*comp, gf / oracle.GRAVITY)
+    for b in range(len(gf)):
+        w.set_object_state(b, gf=gf[b])
+    return w
+
+
+@pytest.mark.parametrize("case", ["2body.essa", "8body.essa", "solar.essa", "synthetic5", "synthetic13", "synthetic16"])
+def test_ensemble_small_templates_one_thread_per_copy(worlds_dir, case):
+    """Templates of up to 16 bodies in fast arithmetic run k_ensemble_solo (ensemble.cu): one thread holds a whole copy in
+    registers and evaluates each PAIR once.  Perturbed copies against oracle runs of the rebuilt initial state (1e-11, the bar
+    of the other fast-arithmetic kernels), several launches, a copy count that is no multiple of the CTA, time reversed."""
+    if case.endswith(".essa"):
+        st = oracle.World.load(os.path.join(worlds_dir, case)).state()
+    else:
+        n = int(case[len("synthetic"):])
+        rng = np.random.default_rng(n)
+        ang = rng.uniform(0, 2 * np.pi, n)
+        rad = 1e11 * (1 + np.arange(n))
+        m = np.concatenate([[2e30], 10 ** rng.uniform(22, 27, n - 1)])
+        v = np.sqrt(oracle.GRAVITY * 2e30 / rad)
+        pos = np.stack([rad * np.cos(ang), rad * np.sin(ang), 1e9 * rng.standard_normal(n)], axis=1)
+        vel = np.stack([-v * np.sin(ang), v * np.cos(ang), 10 * rng.standard_normal(n)], axis=1)
+        pos[0] = vel[0] = 0
+        st = {"pos": pos, "vel": vel, "gf": m * oracle.GRAVITY}
+    copies, dt, seed, sigma = 333, 600, 11, 1e-6
+    c = capi.Context(0)
+    c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"])
+    c.ensemble_init(copies, dt, seed=seed, rel_sigma=sigma)
+    for k in (1, 7, 32):
+        c.ensemble_step(k)
+    sample = [0, 1, 31, 32, 33, 319, 320, 332]
+    refs = {}
+    for cp in sample:
+        got = c.ensemble_read(cp, 1)
+        refs[cp] = ref = _ensemble_reference(st, cp, 40, dt, seed, sigma)
+        pos = np.stack([got["x"][0], got["y"][0], got["z"][0]], axis=1)
+        vel = np.stack([got["vx"][0], got["vy"][0], got["vz"][0]], axis=1)
+        assert np.abs(pos - ref["pos"]).max() <= 1e-11 * np.abs(ref["pos"]).max(), cp
+        assert np.abs(vel - ref["vel"]).max() <= 1e-10 * np.abs(ref["vel"]).max(), cp
+    # Leapfrog is time reversible: 40 steps back land on the perturbed initial state to rounding
+    c.ensemble_step(-40)
+    comp = [st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2]]
+    for cp in (1, 332):
+        got = c.ensemble_read(cp, 1)
+        for q, name in enumerate("xyz"):
+            want = np.array([comp[q][b] * capi.ensemble_factor(seed, sigma, cp, b, q) for b in range(len(st["gf"]))])
+            assert np.abs(got[name][0] - want).max() <= 1e-9 * np.abs(st["pos"]).max(), (cp, name)
+    c.close()
+
+
+def test_ensemble_solo_skips_a_deleted_body(worlds_dir):
+    """A body that Object::deleted() masks (src/Object.hpp deleted()) is neither attracted nor moved and attracts nobody:
+    the other bodies move as the oracle world WITHOUT it does, and it stays where it was -- in the one-thread-per-copy kernel
+    (fast arithmetic) and in the exact-order kernel alike."""
+    st = oracle.World.load(os.path.join(worlds_dir, "8body.essa")).state()
+    n, gone = len(st["gf"]), 2
+    keep = [b for b in range(n) if b != gone]
+    comp = [st["pos"][keep, 0], st["pos"][keep, 1], st["pos"][keep, 2], st["vel"][keep, 0], st["vel"][keep, 1], st["vel"][keep, 2]]
+    ow = _oracle_world_from(comp, st["gf"][keep])
+    ow.dt = 600
+    ow.update(30)
+    ref = ow.state()
+    deleted = np.zeros(n, dtype=np.uint8)
+    deleted[gone] = 1
+    for exact in (False, True):
+        c = capi.Context(0)
+        c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"],
+                 creation_date=np.full(n, capi.START_DATE, dtype=np.int64), deleted=deleted)
+        c.ensemble_init(40, 600, seed=3, rel_sigma=0.0, exact_order=exact)
+        c.ensemble_step(10)
+        c.ensemble_step(20)
+        got = c.ensemble_read(37, 1)
+        pos = np.stack([got["x"][0], got["y"][0], got["z"][0]], axis=1)
+        vel = np.stack([got["vx"][0], got["vy"][0], got["vz"][0]], axis=1)
+        assert np.array_equal(pos[gone], st["pos"][gone]) and np.array_equal(vel[gone], st["vel"][gone])
+        if exact:
+            assert np.array_equal(pos[keep], ref["pos"]) and np.array_equal(vel[keep], ref["vel"])
+        else:
+            assert np.abs(pos[keep] - ref["pos"]).max() <= 1e-11 * np.abs(ref["pos"]).max()
+            assert np.abs(vel[keep] - ref["vel"]).max() <= 1e-10 * np.abs(ref["vel"]).max()
+        c.close()
+
+
 def test_ensemble_closest_approach_to_body(worlds_dir):
     ow = oracle.World.load(os.path.join(worlds_dir, "solar.essa"))
     st = ow.state()

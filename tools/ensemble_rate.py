@@ -12,7 +12,10 @@ copies = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 c = capi.Context(0)
 peak = c.measure_fp64_peak()
 print("fp64 peak measured: %.2f TFLOP/s" % peak)
+only = sys.argv[2] if len(sys.argv) > 2 else ""
 for fname, steps in (("solar.essa", 2000), ("jupiter_system.essa", 100)):
+    if only and not fname.startswith(only):
+        continue
     pw = world.World.load(os.path.join(ROOT, "tests", "golden", "worlds", fname))
     st = pw.state()
     n = len(pw)
