@@ -578,6 +578,280 @@ static cudaError_t launch_solo_n(essa_ctx* c, EnsembleArgs const& A, cudaStream_
     }
 }
 
+// Fast-arithmetic ensembles of templates of 17 .. 160 bodies (jupiter_system.essa has 77): a copy lives on P = 2 .. 32 lanes of
+// ONE warp (P a power of two: 32 / P whole copies per warp, every lane busy), each lane the HOME of HB = ceil(n / P) <= 5 bodies
+// whose positions, weights and accelerations stay in its registers.  Pairs are shared as in K1p: lane k evaluates its home
+// bodies among themselves, then receives the home of lane k + d (d = 1 .. P / 2, the ring of a copy's lanes) as VISITORS from
+// shared memory, evaluates all HB x HB pairs once -- both accelerations -- and adds the visitors' share to a reaction array in
+// shared memory: in round d every lane's reaction slots have exactly one writer, so there is no atomic and no conflict, only a
+// __syncwarp per round.  (Round P / 2 pairs lane k with lane k + P / 2 both ways round; the lower half of the ring does it.)
+// 20 FP64 instructions per PAIR where the two-bodies-per-thread kernel spends 16 per directed interaction; padding costs
+// (P HB / n)^2 -- 80 slots for 77 bodies -- and the half-idle last round 1 / (P - 1) of the visits.  Shared memory holds one
+// double per (component, home slot, lane): consecutive lanes touch consecutive words, home and visitor accesses alike.
+constexpr int kRingWarps = 4;
+constexpr int kRingMaxHB = 5;
+constexpr int kRingComp = 10;          // x y z gf | reaction x y z | vx vy vz
+constexpr int kRingCompApproach = 7;   // + minimum d^2 of the launch and the six coordinates it was seen at
+
+template<int HB>
+__global__ void __launch_bounds__(32 * kRingWarps, 3) k_ensemble_ring(EnsembleArgs const A, int const P) {
+    extern __shared__ double ring_smem[];
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int const k = lane & (P - 1), cbase = lane - k; // place in the copy's ring; first lane of the copy
+    int const per_warp = 32 / P;
+    long long const mine = ((long long)blockIdx.x * kRingWarps + warp) * per_warp + (lane / P);
+    bool const live = mine < A.copies;
+    long long const copy = live ? mine : 0; // a surplus ring repeats copy 0 and stores nothing
+    int const n = A.n;
+    bool const approaches = A.approaches != 0;
+    bool const keep_pos = approaches && A.apos != nullptr;
+    int const comps = kRingComp + (approaches ? kRingCompApproach : 0);
+    double* const W = ring_smem + (size_t)warp * comps * HB * 32;
+    auto at = [&](int comp, int b, int l) -> double& { return W[(comp * HB + b) * 32 + l]; };
+
+    double hx[HB], hy[HB], hz[HB], hg[HB], ax[HB], ay[HB], az[HB];
+    bool real[HB], on[HB];
+    double* const s = A.state + (size_t)copy * 6 * n;
+#pragma unroll
+    for (int b = 0; b < HB; b++) {
+        int const idx = k * HB + b;
+        real[b] = idx < n;
+        on[b] = real[b] && A.active[idx] != 0; // a body that deleted() masks is neither attracted nor moved
+        // padding: weight 0, parked far away and apart from each other (no r = 0 among the dummies)
+        hx[b] = real[b] ? s[idx] : 1e30 * (double)(idx + 1);
+        hy[b] = real[b] ? s[(size_t)n + idx] : 0.0;
+        hz[b] = real[b] ? s[2 * (size_t)n + idx] : 0.0;
+        hg[b] = real[b] ? A.gf[idx] : 0.0;
+        at(3, b, lane) = hg[b];
+        at(7, b, lane) = real[b] ? s[3 * (size_t)n + idx] : 0.0;
+        at(8, b, lane) = real[b] ? s[4 * (size_t)n + idx] : 0.0;
+        at(9, b, lane) = real[b] ? s[5 * (size_t)n + idx] : 0.0;
+        if (approaches)
+            at(kRingComp, b, lane) = -1.0;
+        ax[b] = ay[b] = az[b] = 0.0;
+    }
+    // one pair, both accelerations (the r = 0 guard of rsqrt_seed stays: two bodies of a template may coincide)
+    auto pair = [&](double xi, double yi, double zi, double gi, double xj, double yj, double zj, double gj, double& aix, double& aiy,
+                    double& aiz, double& ajx, double& ajy, double& ajz) {
+        double const dx = xj - xi, dy = yj - yi, dz = zj - zi;
+        double r2 = dx * dx;
+        r2 = fma(dy, dy, r2);
+        r2 = fma(dz, dz, r2);
+        double const y0 = rsqrt_seed(r2);
+        double const y2 = y0 * y0;
+        double const e = fma(-r2, y2, 1.0);
+        double const y3 = y0 * y2;
+        double const we = fma(1.875, e, 1.5) * e;
+        double const u = fma(y3, we, y3);
+        double const si = gj * u, sj = gi * u;
+        aix = fma(si, dx, aix);
+        aiy = fma(si, dy, aiy);
+        aiz = fma(si, dz, aiz);
+        ajx = fma(-sj, dx, ajx);
+        ajy = fma(-sj, dy, ajy);
+        ajz = fma(-sj, dz, ajz);
+    };
+    int const half_ring = P >> 1;
+    auto forces = [&]() {
+#pragma unroll
+        for (int b = 0; b < HB; b++) {
+            at(0, b, lane) = hx[b];
+            at(1, b, lane) = hy[b];
+            at(2, b, lane) = hz[b];
+            at(4, b, lane) = 0.0;
+            at(5, b, lane) = 0.0;
+            at(6, b, lane) = 0.0;
+            ax[b] = ay[b] = az[b] = 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < HB; b++)
+#pragma unroll
+            for (int c = b + 1; c < HB; c++)
+                pair(hx[b], hy[b], hz[b], hg[b], hx[c], hy[c], hz[c], hg[c], ax[b], ay[b], az[b], ax[c], ay[c], az[c]);
+        for (int d = 1; d <= half_ring; d++) {
+            int const m = cbase + ((k + d) & (P - 1));
+            bool const act = d < half_ring || k < half_ring;
+            if (act) {
+                double vx[HB], vy[HB], vz[HB], vg[HB], rx[HB], ry[HB], rz[HB];
+#pragma unroll
+                for (int b = 0; b < HB; b++) {
+                    vx[b] = at(0, b, m);
+                    vy[b] = at(1, b, m);
+                    vz[b] = at(2, b, m);
+                    vg[b] = at(3, b, m);
+                    rx[b] = ry[b] = rz[b] = 0.0;
+                }
+#pragma unroll
+                for (int b = 0; b < HB; b++)
+#pragma unroll
+                    for (int c = 0; c < HB; c++)
+                        pair(hx[b], hy[b], hz[b], hg[b], vx[c], vy[c], vz[c], vg[c], ax[b], ay[b], az[b], rx[c], ry[c], rz[c]);
+#pragma unroll
+                for (int b = 0; b < HB; b++) {
+                    at(4, b, m) += rx[b];
+                    at(5, b, m) += ry[b];
+                    at(6, b, m) += rz[b];
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int b = 0; b < HB; b++) {
+            ax[b] += at(4, b, lane);
+            ay[b] += at(5, b, lane);
+            az[b] += at(6, b, lane);
+        }
+    };
+    double const hm = A.h * A.mul, dtm = A.dt * A.mul;
+    int const to = A.approach_to;
+    int const to_lane = cbase + to / HB, to_slot = to - (to / HB) * HB;
+    int until = (int)(A.trail_every - A.steps_done % A.trail_every);
+    long long tidx = A.steps_done / A.trail_every;
+
+    // st == -1 is the force pass in front of the first step (one call site, as in k_ensemble_solo)
+    for (int st = -1; st < A.steps; st++) {
+        if (st < 0)
+            goto pass;
+        if (approaches) { // Object::update_closest_approaches, at the step's start: shared memory holds the current positions
+            double tx = 0, ty = 0, tz = 0;
+#pragma unroll
+            for (int b = 0; b < HB; b++) {
+                tx = b == to_slot ? at(0, b, to_lane) : tx;
+                ty = b == to_slot ? at(1, b, to_lane) : ty;
+                tz = b == to_slot ? at(2, b, to_lane) : tz;
+            }
+#pragma unroll
+            for (int b = 0; b < HB; b++) {
+                int const idx = k * HB + b;
+                if (!real[b] || idx == to)
+                    continue;
+                double const dx = __dsub_rn(tx, hx[b]), dy = __dsub_rn(ty, hy[b]), dz = __dsub_rn(tz, hz[b]);
+                double const d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                double const m2 = at(kRingComp, b, lane);
+                bool const zero = d2 == 0.0; // stores 0 == "unset" in the reference: the search restarts
+                bool const better = !zero && (m2 < 0.0 || d2 < m2);
+                at(kRingComp, b, lane) = zero ? -1.0 : (better ? d2 : m2);
+                if (zero && live)
+                    A.mind[(size_t)copy * n + idx] = 0.0;
+                if (better && keep_pos) {
+                    at(kRingComp + 1, b, lane) = hx[b];
+                    at(kRingComp + 2, b, lane) = hy[b];
+                    at(kRingComp + 3, b, lane) = hz[b];
+                    at(kRingComp + 4, b, lane) = tx;
+                    at(kRingComp + 5, b, lane) = ty;
+                    at(kRingComp + 6, b, lane) = tz;
+                }
+            }
+            __syncwarp(); // the drift below must not overtake a neighbour's read of the designated body
+        }
+        // the second kick of the previous step and the first of this one use the same acceleration
+#pragma unroll
+        for (int b = 0; b < HB; b++) {
+            if (!on[b])
+                continue;
+            double const kx = __dmul_rn(ax[b], hm), ky = __dmul_rn(ay[b], hm), kz = __dmul_rn(az[b], hm);
+            double vx = at(7, b, lane), vy = at(8, b, lane), vz = at(9, b, lane);
+            if (st > 0) {
+                vx = __dadd_rn(vx, kx);
+                vy = __dadd_rn(vy, ky);
+                vz = __dadd_rn(vz, kz);
+            }
+            vx = __dadd_rn(vx, kx);
+            vy = __dadd_rn(vy, ky);
+            vz = __dadd_rn(vz, kz);
+            hx[b] = __dadd_rn(hx[b], __dmul_rn(vx, dtm));
+            hy[b] = __dadd_rn(hy[b], __dmul_rn(vy, dtm));
+            hz[b] = __dadd_rn(hz[b], __dmul_rn(vz, dtm));
+            at(7, b, lane) = vx;
+            at(8, b, lane) = vy;
+            at(9, b, lane) = vz;
+        }
+    pass:
+        forces();
+        if (st >= 0 && A.trail && --until == 0) {
+            until = A.trail_every;
+            if (live && lane == to_lane && tidx < A.trail_cap) {
+                double tx = 0, ty = 0, tz = 0;
+#pragma unroll
+                for (int b = 0; b < HB; b++) {
+                    tx = b == to_slot ? hx[b] : tx;
+                    ty = b == to_slot ? hy[b] : ty;
+                    tz = b == to_slot ? hz[b] : tz;
+                }
+                double* t = A.trail + ((size_t)copy * A.trail_cap + (size_t)tidx) * 3;
+                t[0] = tx;
+                t[1] = ty;
+                t[2] = tz;
+                A.trail_len[copy] = (int)tidx + 1;
+            }
+            tidx++;
+        }
+    }
+    if (!live)
+        return;
+#pragma unroll
+    for (int b = 0; b < HB; b++) {
+        int const idx = k * HB + b;
+        if (!real[b])
+            continue;
+        double vx = at(7, b, lane), vy = at(8, b, lane), vz = at(9, b, lane);
+        if (A.steps > 0 && on[b]) { // the last step's second kick
+            vx = __dadd_rn(vx, __dmul_rn(ax[b], hm));
+            vy = __dadd_rn(vy, __dmul_rn(ay[b], hm));
+            vz = __dadd_rn(vz, __dmul_rn(az[b], hm));
+        }
+        s[idx] = hx[b];
+        s[(size_t)n + idx] = hy[b];
+        s[2 * (size_t)n + idx] = hz[b];
+        s[3 * (size_t)n + idx] = vx;
+        s[4 * (size_t)n + idx] = vy;
+        s[5 * (size_t)n + idx] = vz;
+        if (approaches && idx != to) {
+            double const m2 = at(kRingComp, b, lane);
+            if (m2 >= 0.0) {
+                double const d = __dsqrt_rn(m2);
+                double const md = A.mind[(size_t)copy * n + idx];
+                if (md == 0.0 || d < md) {
+                    A.mind[(size_t)copy * n + idx] = d;
+                    if (keep_pos)
+                        for (int q = 0; q < 6; q++)
+                            A.apos[((size_t)copy * n + idx) * 6 + q] = at(kRingComp + 1 + q, b, lane);
+                }
+            }
+        }
+    }
+}
+
+// lanes per copy and home bodies per lane for a template of n bodies: the smallest ring whose homes hold at most kRingMaxHB
+static bool ring_shape(int n, int& P, int& HB) {
+    for (P = 2; P <= 32; P <<= 1) {
+        HB = (n + P - 1) / P;
+        if (HB <= kRingMaxHB) {
+            HB = HB < 3 ? 3 : HB;
+            return true;
+        }
+    }
+    return false;
+}
+
+template<int HB>
+static cudaError_t launch_ring(EnsembleArgs const& A, int P, cudaStream_t st) {
+    int const per_warp = 32 / P;
+    long long const warps = ((long long)A.copies + per_warp - 1) / per_warp;
+    int const blocks = (int)((warps + kRingWarps - 1) / kRingWarps);
+    int const comps = kRingComp + (A.approaches ? kRingCompApproach : 0);
+    size_t const smem = (size_t)kRingWarps * comps * HB * 32 * sizeof(double);
+    auto kern = k_ensemble_ring<HB>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+    }
+    kern<<<blocks, 32 * kRingWarps, smem, st>>>(A, P);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ensemble_init(essa_ctx* c, cudaStream_t st) {
     long long total = (long long)c->ens_copies * c->ens_n;
     int blocks = (int)((total + 255) / 256);
@@ -622,6 +896,11 @@ cudaError_t launch_ensemble_step(essa_ctx* c, int steps, cudaStream_t st) {
     } else if (n >= 2 && n <= kEnsembleSoloMax && c->ens_solo) {
         A.per_cta = kSoloThreads;
         e = launch_solo_n(c, A, st);
+        if (e != cudaSuccess)
+            return e;
+    } else if (int P = 0, HB = 0; c->ens_solo && n > kEnsembleSoloMax && ring_shape(n, P, HB)) {
+        A.per_cta = kRingWarps * (32 / P);
+        e = HB == 3 ? launch_ring<3>(A, P, st) : HB == 4 ? launch_ring<4>(A, P, st) : launch_ring<5>(A, P, st);
         if (e != cudaSuccess)
             return e;
     } else {

@@ -264,11 +264,15 @@ def _oracle_world_from(comp, gf):
     return w
 
 
-@pytest.mark.parametrize("case", ["2body.essa", "8body.essa", "solar.essa", "synthetic5", "synthetic13", "synthetic16"])
-def test_ensemble_small_templates_one_thread_per_copy(worlds_dir, case):
-    """Templates of up to 16 bodies in fast arithmetic run k_ensemble_solo (ensemble.cu): one thread holds a whole copy in
-    registers and evaluates each PAIR once.  Perturbed copies against oracle runs of the rebuilt initial state (1e-11, the bar
-    of the other fast-arithmetic kernels), several launches, a copy count that is no multiple of the CTA, time reversed."""
+@pytest.mark.parametrize("case", ["2body.essa", "8body.essa", "solar.essa", "synthetic5", "synthetic13", "synthetic16", "synthetic17",
+                                  "synthetic20", "synthetic33", "synthetic40", "synthetic64", "jupiter_system.essa", "synthetic100",
+                                  "synthetic160", "synthetic161"])
+def test_ensemble_pair_shared_kernels(worlds_dir, case):
+    """Fast-arithmetic ensembles evaluate each PAIR once (ensemble.cu): templates of up to 16 bodies on one thread per copy
+    (k_ensemble_solo), 17 .. 160 bodies on a ring of 2 .. 32 lanes per copy (k_ensemble_ring: every shape of the ring, full and
+    padded homes), larger ones on the two-bodies-per-thread kernel.  Perturbed copies against oracle runs of the rebuilt initial
+    state (1e-11, the bar of the other fast-arithmetic kernels), several launches, a copy count that is no multiple of the
+    CTA, time reversed."""
     if case.endswith(".essa"):
         st = oracle.World.load(os.path.join(worlds_dir, case)).state()
     else:
@@ -308,11 +312,12 @@ def test_ensemble_small_templates_one_thread_per_copy(worlds_dir, case):
     c.close()
 
 
-def test_ensemble_solo_skips_a_deleted_body(worlds_dir):
+@pytest.mark.parametrize("fname", ["8body.essa", "jupiter_system.essa"])
+def test_ensemble_skips_a_deleted_body(worlds_dir, fname):
     """A body that Object::deleted() masks (src/Object.hpp deleted()) is neither attracted nor moved and attracts nobody:
-    the other bodies move as the oracle world WITHOUT it does, and it stays where it was -- in the one-thread-per-copy kernel
-    (fast arithmetic) and in the exact-order kernel alike."""
-    st = oracle.World.load(os.path.join(worlds_dir, "8body.essa")).state()
+    the other bodies move as the oracle world WITHOUT it does, and it stays where it was -- in the pair-shared kernels
+    (fast arithmetic: one thread per copy / ring of lanes) and in the exact-order kernel alike."""
+    st = oracle.World.load(os.path.join(worlds_dir, fname)).state()
     n, gone = len(st["gf"]), 2
     keep = [b for b in range(n) if b != gone]
     comp = [st["pos"][keep, 0], st["pos"][keep, 1], st["pos"][keep, 2], st["vel"][keep, 0], st["vel"][keep, 1], st["vel"][keep, 2]]
@@ -359,15 +364,16 @@ def test_ensemble_closest_approach_to_body(worlds_dir):
     c.close()
 
 
-@pytest.mark.parametrize("exact", [True, False])
-def test_ensemble_candidate_service_approach_table_and_trail(worlds_dir, exact):
+@pytest.mark.parametrize("exact,fname,to", [(True, "solar.essa", 3), (False, "solar.essa", 3), (False, "jupiter_system.essa", 0),
+                                            (False, "jupiter_system.essa", 41), (True, "jupiter_system.essa", 76)])
+def test_ensemble_candidate_service_approach_table_and_trail(worlds_dir, exact, fname, to):
     """SURVEY 8 f2 -- what src/essagui/EssaCreateObject.cpp:166-189 does for ONE candidate on the GUI thread (clone the world,
     update(ticks), show the candidate's trail and its closest approaches, src/Object.cpp:405-417), for many perturbed copies in
     one launch: per copy, the designated body's closest approach to EVERY other body (distance + both positions) and its trail.
     exact_order: bit-identical to the oracle's forward-simulated clone; fast arithmetic: 1e-11."""
-    ow = oracle.World.load(os.path.join(worlds_dir, "solar.essa"))
+    ow = oracle.World.load(os.path.join(worlds_dir, fname))
     st = ow.state()
-    n, to, steps, every = len(ow), 3, 120, 10
+    n, steps, every = len(ow), 120, 10
     c = capi.Context(0)
     c.upload(st["pos"][:, 0], st["pos"][:, 1], st["pos"][:, 2], st["vel"][:, 0], st["vel"][:, 1], st["vel"][:, 2], st["gf"])
     c.ensemble_init(70, 600, seed=1, rel_sigma=0.0, exact_order=exact, closest_approaches=True, approach_to=to, trail_every=every,
