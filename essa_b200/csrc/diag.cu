@@ -34,31 +34,53 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     return r;
 }
 
-// grid = (i-blocks, S j-chunks); CTA (ib, sj) writes 5 partial sums:
-//   sum_i gf_i * sum_{j in chunk, j != i} gf_j / r_ij ,   and for sj == 0:  sum gf v^2, sum gf v.
+// Potential energy with every unordered pair evaluated ONCE (the pair-shared enumeration of K1p, force_paired.cu): bodies
+// are cut into tiles of 256; the CTA of target tile T meets source tiles T + d (mod ntiles), d = 0 .. ntiles / 2 -- the tile
+// against itself with j > i only, and for an even tile count the opposite tile from the lower half only -- so that every tile
+// does the same amount of work and no pair is seen twice: 12 FP64 instructions per PAIR (the energy needs no reaction term:
+// sum_pairs gf_i gf_j / r = sum_i gf_i sum_{j met by i} gf_j / r) where the one-sided version spent 13 per directed interaction.
+// grid = (tiles of this rank, S chunks of the offsets); CTA (T, sj) writes 5 partial sums:
+//   sum_i gf_i * sum_{j met in chunk} gf_j / r_ij ,   and for sj == 0:  sum gf v^2, sum gf v.
 __global__ void __launch_bounds__(kEThreads) k_energy(double4 const* pos, double const* vx, double const* vy, double const* vz, int n,
-    int i0, int i1, int S, double* partial) {
+    int tile0, int S, double* partial) {
     __shared__ double4 tile[kEThreads];
     __shared__ double red[kEThreads];
     int tid = threadIdx.x;
     int ib = blockIdx.x / S, sj = blockIdx.x - ib * S;
-    int i = i0 + ib * kEThreads + tid;
-    bool live = i < i1;
-    double4 pi = pos[live ? i : i1 - 1];
+    int const T = tile0 + ib;
+    int i = T * kEThreads + tid;
+    bool live = i < n;
+    double4 pi = pos[live ? i : n - 1];
     int ntiles = (n + kEThreads - 1) / kEThreads;
-    int t0 = (int)((long long)ntiles * sj / S), t1 = (int)((long long)ntiles * (sj + 1) / S);
+    int const nd = ntiles / 2 + 1; // offsets 0 .. ntiles / 2
+    int d0 = (int)((long long)nd * sj / S), d1 = (int)((long long)nd * (sj + 1) / S);
     double phi = 0;
-    for (int t = t0; t < t1; t++) {
+    for (int d = d0; d < d1; d++) {
+        if (d > 0 && 2 * d == ntiles && T >= d)
+            continue; // the opposite tile of an even ring: met from the lower half
+        int t = T + d;
+        t = t >= ntiles ? t - ntiles : t;
+        if (d > 0 && t == T)
+            continue; // a ring of one tile
         int j = t * kEThreads + tid;
         tile[tid] = j < n ? pos[j] : make_double4(0, 0, 0, 0);
         __syncthreads();
         int cnt = min(kEThreads, n - t * kEThreads);
+        if (d == 0) {
+            for (int jj = 0; jj < cnt; jj++) {
+                double4 q = tile[jj];
+                double dx = q.x - pi.x, dy = q.y - pi.y, dz = q.z - pi.z;
+                double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                phi = fma(jj > tid ? q.w : 0.0, inv_r(r2), phi);
+            }
+        } else {
 #pragma unroll 4
-        for (int jj = 0; jj < cnt; jj++) {
-            double4 q = tile[jj];
-            double dx = q.x - pi.x, dy = q.y - pi.y, dz = q.z - pi.z;
-            double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            phi = fma(q.w, inv_r(r2), phi);
+            for (int jj = 0; jj < cnt; jj++) {
+                double4 q = tile[jj];
+                double dx = q.x - pi.x, dy = q.y - pi.y, dz = q.z - pi.z;
+                double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                phi = fma(q.w, inv_r(r2), phi);
+            }
         }
         __syncthreads();
     }
@@ -95,7 +117,7 @@ __global__ void k_energy_final(double const* partial, int blocks, double* out) {
     if (threadIdx.x == 0) {
         double const invG = 1.0 / ESSA_GRAVITY;
         out[0] = 0.5 * r[0] * invG;          // sum 1/2 m v^2
-        out[1] = -0.5 * r[1] * invG;         // - sum_{i<j} G m_i m_j / r  (every pair was counted twice)
+        out[1] = -r[1] * invG;               // - sum_{i<j} G m_i m_j / r  (every pair was met once)
         out[2] = r[2] * invG;
         out[3] = r[3] * invG;
         out[4] = r[4] * invG;
@@ -104,11 +126,13 @@ __global__ void k_energy_final(double const* partial, int blocks, double* out) {
 
 cudaError_t launch_energy(essa_ctx* c, cudaStream_t st) {
     int n = c->n;
-    int i0 = (int)((long long)n * c->rank / c->world), i1 = (int)((long long)n * (c->rank + 1) / c->world);
-    int iblocks = (i1 - i0 + kEThreads - 1) / kEThreads;
     int ntiles = (n + kEThreads - 1) / kEThreads;
+    // whole tiles per rank (the sum over ranks is an all-reduce: which rank owns a body does not matter here)
+    int tile0 = (int)((long long)ntiles * c->rank / c->world), tile1 = (int)((long long)ntiles * (c->rank + 1) / c->world);
+    int iblocks = tile1 - tile0;
+    int const nd = ntiles / 2 + 1;
     int S = 1;
-    while ((long long)iblocks * S < 4LL * c->sm_count && S * 2 <= ntiles)
+    while ((long long)iblocks * S < 4LL * c->sm_count && S * 2 <= nd)
         S *= 2;
     int blocks = iblocks * S;
     size_t need = 8 + (size_t)blocks * 5;
@@ -124,7 +148,7 @@ cudaError_t launch_energy(essa_ctx* c, cudaStream_t st) {
     if (iblocks == 0)
         return cudaMemsetAsync(c->escratch, 0, 8 * sizeof(double), st);
     double* partial = c->escratch + 8;
-    k_energy<<<blocks, kEThreads, 0, st>>>(c->pos[c->cur], c->vel, c->vel + c->cap, c->vel + 2 * (size_t)c->cap, n, i0, i1, S, partial);
+    k_energy<<<blocks, kEThreads, 0, st>>>(c->pos[c->cur], c->vel, c->vel + c->cap, c->vel + 2 * (size_t)c->cap, n, tile0, S, partial);
     k_energy_final<<<1, kEThreads, 0, st>>>(partial, blocks, c->escratch);
     c->launches += 2;
     return cudaGetLastError();

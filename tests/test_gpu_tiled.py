@@ -165,6 +165,18 @@ def test_energy_matches_oracle_and_is_conserved(ctx):
     assert np.abs(mom2 - mom).max() <= 1e-9 * scale
 
 
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 512, 513, 769, 1000, 1025, 1537])
+def test_energy_pair_enumeration_edges(ctx, n):
+    """K5 meets every unordered pair once (tile T against tiles T + d, d = 0 .. ntiles / 2): one tile, two tiles (the opposite
+    tile met from the lower half only), odd and even rings, ragged last tiles -- each against the oracle's long-double sum."""
+    w = synth.plummer(n, seed=100 + n)
+    _upload(ctx, w)
+    ke, pe, mom = ctx.energy()
+    oke, ope, omom = oracle.energy(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
+    assert ke == pytest.approx(oke, rel=1e-12)
+    assert pe == pytest.approx(ope, rel=1e-12, abs=0.0)
+
+
 def test_most_attracting_tiled_matches_oracle(ctx, worlds_dir):
     """Argmax variant of K1 on a world with a mass hierarchy (jupiter_system.essa, 77 bodies)."""
     import os
