@@ -1233,6 +1233,8 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
         int nb, S;
         size_t slot_d = 0, part_d = 0;
         bool can = (!argmax || ctx->gf_uniform || ctx->n <= (1 << 21)) && paired_plan(ctx, &nb, &S, &slot_d, &part_d);
+        if (can && ctx->plan.batches > 1 && argmax && !ctx->gf_uniform)
+            can = false; // candidate keys are not batched (with the default budget only worlds beyond 2^21 bodies batch at all)
         if (can && (slot_d > ctx->pair_slots_n || part_d > ctx->pair_part_n)) { // first use at this size: will it fit?
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);

@@ -134,6 +134,7 @@ struct essa_ctx {
     // paired_plan's last answer (a pure function of n, the sharding and the SM count)
     mutable struct {
         int n = -1, world = 0, rank = 0, cap = 0, nb = 0, S = 0, ri = 0;
+        int db = 0, batches = 1; // offsets per launch / launches per pass (slot budget, force_paired.cu)
         bool ok = false;
         size_t slot_doubles = 0, part_doubles = 0;
     } plan;

@@ -115,6 +115,10 @@ struct PairArgs {
     double4 const* pos; // padded to a multiple of kPB with {0,0,0,0}
     int nb;             // blocks in the world
     int dmax;           // largest block offset evaluated: nb / 2
+    // Offsets of THIS launch: d0 .. d0 + dn - 1.  One launch covers 0 .. dmax unless the J-side slots of all offsets would not
+    // fit the slot budget (paired_plan): then the offsets go in batches of `dslots`, each batch folded into a running sum
+    // (k_pair_fold) before the next one reuses the slot planes.  Offset d owns plane d - dslot0 of a block's dslots planes.
+    int d0, dn, dslots, dslot0;
     int S;              // chunks of the offset range per I block (gridDim.x = owned blocks * S)
     int ib0, ib1;       // I blocks owned by this context
     int npad;           // nb * kPB
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
     int const ibl = blockIdx.x / A.S, chunk = blockIdx.x - ibl * A.S;
     int const I = A.ib0 + ibl;
     // work units of block I: (offset d = 0 .. dmax) x (kPParts parts of the J block), split into S chunks
-    int const nunits = (A.dmax + 1) * kPParts;
+    int const nunits = A.dn * kPParts;
     int const ulo = (int)((long long)nunits * chunk / A.S), uhi = (int)((long long)nunits * (chunk + 1) / A.S);
 
     double xi[kPRI], yi[kPRI], zi[kPRI], gi[kPRI], aix[kPRI], aiy[kPRI], aiz[kPRI];
@@ -305,13 +309,13 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
     int seq = 0; // tiles consumed so far (parity bookkeeping)
     // prime the pipeline with the first valid tile
     int nu = ulo;
-    while (nu < uhi && !valid(nu / kPParts))
+    while (nu < uhi && !valid(A.d0 + nu / kPParts))
         nu++;
     if (tid == 0 && nu < uhi)
-        issue(nu / kPParts, nu % kPParts, 0);
+        issue(A.d0 + nu / kPParts, nu % kPParts, 0);
 
     for (int u = ulo; u < uhi; u++) {
-        int const d = u / kPParts, half = u - d * kPParts;
+        int const d = A.d0 + u / kPParts, half = u % kPParts;
         if (!valid(d))
             continue;
         int J = I + d;
@@ -322,10 +326,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
             // prefetch the tile after this one into the other buffer
             {
                 int pu = u + 1;
-                while (pu < uhi && !valid(pu / kPParts))
+                while (pu < uhi && !valid(A.d0 + pu / kPParts))
                     pu++;
                 if (tid == 0 && pu < uhi)
-                    issue(pu / kPParts, pu % kPParts, buf ^ 1);
+                    issue(A.d0 + pu / kPParts, pu % kPParts, buf ^ 1);
             }
             mbar_wait(&full[buf], (unsigned)(seq >> 1) & 1u);
             double4 const* tp = tile + (size_t)buf * kPHalf;
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
             __syncthreads();
             if (d > 0) {
                 int const owner = A.owner_major ? J / A.bpr : 0;
-                size_t const tile = A.owner_major ? (size_t)(J - owner * A.bpr) * A.dmax + (d - 1) : (size_t)ibl * A.dmax + (d - 1);
+                size_t const tile = A.owner_major ? (size_t)(J - owner * A.bpr) * A.dslots + (d - A.dslot0) : (size_t)ibl * A.dslots + (d - A.dslot0);
                 double* slot = (A.owner_major ? A.slot_peer[owner] : A.slots) + tile * 3 * kPB;
                 for (int e = tid; e < 3 * kPHalf; e += kPThreads) {
                     int c = e / kPHalf, j = e - c * kPHalf;
@@ -585,6 +589,38 @@ __device__ __forceinline__ unsigned long long slot_key(int g, int nb, int dmax, 
         k = key_merge(pos, g, k, __ldcg(slots_k + ((size_t)(I - ib0) * dmax + (d - 1)) * kPB + jl), eps2);
     }
     return k;
+}
+
+// Batched offsets (single GPU, slots over budget): the running sum of a body's I-side partials and J-side slots, batch after
+// batch, every addition in a fixed order (chunks ascending, then offsets ascending); k_pair_finish then takes the sum as it is.
+template<int kPB>
+__global__ void __launch_bounds__(256) k_pair_fold(int nb, int npad, int S, int d_first, int d_last, int dslots, int dslot0, int first_batch,
+    double const* part_i, double const* slots, double* jacc) {
+    int const g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= npad)
+        return;
+    double ax = first_batch ? 0.0 : jacc[g], ay = first_batch ? 0.0 : jacc[(size_t)npad + g], az = first_batch ? 0.0 : jacc[2 * (size_t)npad + g];
+    for (int c = 0; c < S; c++) {
+        double const* q = part_i + (size_t)c * 3 * npad + g;
+        ax = __dadd_rn(ax, __ldcg(q));
+        ay = __dadd_rn(ay, __ldcg(q + npad));
+        az = __dadd_rn(az, __ldcg(q + 2 * (size_t)npad));
+    }
+    int const K = g / kPB, jl = g - K * kPB;
+    for (int d = d_first < 1 ? 1 : d_first; d <= d_last; d++) {
+        int I = K - d;
+        if (I < 0)
+            I += nb;
+        if ((nb & 1) == 0 && d == nb / 2 && I >= nb / 2)
+            continue; // that tile belongs to the other half of the ring
+        double const* s = slots + ((size_t)K * dslots + (d - dslot0)) * 3 * kPB + jl;
+        ax = __dadd_rn(ax, __ldcg(s));
+        ay = __dadd_rn(ay, __ldcg(s + kPB));
+        az = __dadd_rn(az, __ldcg(s + 2 * kPB));
+    }
+    jacc[g] = ax;
+    jacc[(size_t)npad + g] = ay;
+    jacc[2 * (size_t)npad + g] = az;
 }
 
 // Sharded worlds: this rank's J-side sums for EVERY body, to be reduce-scattered over the ranks.
@@ -790,6 +826,18 @@ __global__ void __launch_bounds__(256) k_pair_prior_reset(unsigned* prior, uint8
 
 // Can this world go through the pair-shared kernel, and with which block size?  Whole blocks per
 // rank, no argmax, slots must fit.  Sharded: rank g owns I blocks [nb g / G, nb (g+1) / G) = its own targets.
+// J-side slots of all offsets cost N * (nb / 2) * 24 bytes (6.4 GB at 1 M bodies, 26 GB at 2 M, 103 GB at 4 M).  Above this
+// budget a single GPU runs the offsets in batches.  A constant, not a function of the free memory: the batching decides the
+// order of the additions, and a world must give the same bits on every run.  (ESSA_PAIR_SLOT_BUDGET_MB: tests.)
+static size_t pair_slot_budget() {
+    static size_t v = 0;
+    if (v == 0) {
+        char const* e = getenv("ESSA_PAIR_SLOT_BUDGET_MB");
+        v = e && atoll(e) > 0 ? (size_t)atoll(e) << 20 : (size_t)32 << 30;
+    }
+    return v;
+}
+
 static int pair_ri_override() {
     static int v = -1;
     if (v < 0) {
@@ -826,7 +874,7 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
     c->plan.ok = false;
     long long const slots = c->sm_count; // 1 CTA per SM
     double best = -1;
-    int best_ri = 0, best_S = 1, best_nb = 0;
+    int best_ri = 0, best_S = 1, best_nb = 0, best_db = 0, best_batches = 1;
     for (int ri = 8; ri >= 4; ri -= 4) {
         if ((pair_ri_override() == 4 || pair_ri_override() == 8) && ri != pair_ri_override())
             continue;
@@ -839,8 +887,18 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
         int const own = c->world == 1 ? nb : nb / c->world;
         int const ib0 = (int)((long long)nb * c->rank / c->world);
         int const dmax = nb / 2;
-        int const U = (dmax + 1) * parts;
-        double const unit_time = ri == 8 ? 2.0 : 1.2;
+        // offsets per launch: all of them, or batches that keep the slot planes within the budget (single GPU only: a rank
+        // of a sharded world holds 1 / world of the slots)
+        int batches = 1, db = dmax;
+        size_t const slot_bytes = (size_t)own * dmax * 3 * pb * sizeof(double);
+        if (c->world == 1 && slot_bytes > pair_slot_budget() && dmax > 1) {
+            batches = (int)((slot_bytes + pair_slot_budget() - 1) / pair_slot_budget());
+            batches = batches > dmax ? dmax : batches;
+            db = (dmax + batches - 1) / batches;
+            batches = (dmax + db - 1) / db;
+        }
+        int const U = ((batches > 1 ? db : dmax) + 1) * parts; // units of (the largest) launch
+        double const unit_time = (ri == 8 ? 2.0 : 1.2) * batches;
         int const smax = U < 64 ? U : 64;
         for (int S = 1; S <= smax; S++) {
             // working CTAs and the longest chunk, counting only valid units (for an even block count the
@@ -869,6 +927,8 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
                 best_ri = ri;
                 best_S = S;
                 best_nb = nb;
+                best_db = db;
+                best_batches = batches;
             }
         }
     }
@@ -879,8 +939,11 @@ bool paired_plan(essa_ctx const* c, int* nb_out, int* S_out, size_t* slot_double
     c->plan.ok = true;
     c->plan.nb = *nb_out = best_nb;
     c->plan.S = *S_out = best_S;
-    c->plan.slot_doubles = *slot_doubles = (size_t)own * (best_nb / 2) * 3 * pb;
-    c->plan.part_doubles = *part_doubles = (size_t)best_S * 3 * best_nb * pb + (c->world > 1 ? (size_t)3 * best_nb * pb : 0);
+    c->plan.db = best_db;
+    c->plan.batches = best_batches;
+    c->plan.slot_doubles = *slot_doubles = (size_t)own * best_db * 3 * pb;
+    // + [3][npad] behind the partials: the sharded fallback's folded slots, or the running sum of a batched pass
+    c->plan.part_doubles = *part_doubles = (size_t)best_S * 3 * best_nb * pb + (c->world > 1 || best_batches > 1 ? (size_t)3 * best_nb * pb : 0);
     c->plan.ri = best_ri;
     if (ri_out)
         *ri_out = best_ri;
@@ -1053,13 +1116,34 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
     double* acc = nullptr;
     unsigned long long* kacc = nullptr;
     bool const uniform = pair_uniform(c) && !argmax;
-    cudaError_t e;
-    if (ri == 8)
-        e = argmax ? launch_pair_kernels<8, true, false>(c, A, st, &acc, &kacc)
-                   : (uniform ? launch_pair_kernels<8, false, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<8, false, false>(c, A, st, &acc, &kacc));
-    else
-        e = argmax ? launch_pair_kernels<4, true, false>(c, A, st, &acc, &kacc)
-                   : (uniform ? launch_pair_kernels<4, false, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<4, false, false>(c, A, st, &acc, &kacc));
+    int const batches = c->plan.batches, db = c->plan.db;
+    if (batches > 1 && (argmax || c->world > 1))
+        return cudaErrorInvalidConfiguration; // candidate keys and peer slots are not batched (the routing never asks for it)
+    A.dslots = batches > 1 ? db : A.dmax;
+    cudaError_t e = cudaSuccess;
+    for (int b = 0; b < batches && e == cudaSuccess; b++) {
+        int const last = (b + 1) * db < A.dmax ? (b + 1) * db : A.dmax;
+        A.d0 = b == 0 ? 0 : b * db + 1; // the diagonal tile (d = 0, no slot) rides with the first batch
+        A.dn = last - A.d0 + 1;
+        A.dslot0 = b * db + 1;
+        if (ri == 8)
+            e = argmax ? launch_pair_kernels<8, true, false>(c, A, st, &acc, &kacc)
+                       : (uniform ? launch_pair_kernels<8, false, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<8, false, false>(c, A, st, &acc, &kacc));
+        else
+            e = argmax ? launch_pair_kernels<4, true, false>(c, A, st, &acc, &kacc)
+                       : (uniform ? launch_pair_kernels<4, false, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<4, false, false>(c, A, st, &acc, &kacc));
+        if (e == cudaSuccess && batches > 1) {
+            double* const jacc = c->pair_part + (size_t)A.S * 3 * A.npad;
+            if (ri == 8)
+                k_pair_fold<kPThreads * 8><<<(A.npad + 255) / 256, 256, 0, st>>>(nb, A.npad, A.S, A.d0, last, A.dslots, A.dslot0, b == 0, c->pair_part,
+                    c->pair_slots, jacc);
+            else
+                k_pair_fold<kPThreads * 4><<<(A.npad + 255) / 256, 256, 0, st>>>(nb, A.npad, A.S, A.d0, last, A.dslots, A.dslot0, b == 0, c->pair_part,
+                    c->pair_slots, jacc);
+            c->launches++;
+            e = cudaGetLastError();
+        }
+    }
     if (acc_out)
         *acc_out = acc;
     if (kacc_out)
@@ -1100,6 +1184,10 @@ cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStrea
     F.scale = pair_uniform(c) && !argmax ? c->gf_uniform_value : 1.0;
     F.slots = c->pair_slots;
     F.ajred = ajred;
+    if (c->plan.batches > 1) { // the batches left their running sum behind the partials: nothing else to add
+        F.ajred = c->pair_part + (size_t)S * 3 * F.npad;
+        F.S = 0;
+    }
     int cnt = F.i1 - F.i0;
     if (cnt <= 0)
         return cudaSuccess;

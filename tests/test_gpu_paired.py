@@ -332,3 +332,22 @@ def test_most_attracting_near_tie_inside_one_block_and_one_warp_visit(ctx):
             ctx.set_forces(kernel=capi.KERNEL_PAIRED, track_most_attracting=True)
             got = ctx.download(("most",))
             assert np.array_equal(got["most"], ost["most"]), (t, a, b, delta, got["most"][t], ost["most"][t])
+
+
+@pytest.mark.parametrize("budget_mb", ["1", "4", None])
+def test_paired_offsets_in_batches_when_the_slots_exceed_the_budget(budget_mb):
+    """The J-side slots of all offsets cost N * (nb / 2) * 24 bytes: 103 GB at 4 M bodies.  Above the slot budget (32 GiB) a
+    single GPU walks the offsets in batches and folds each batch into a running sum (k_pair_fold).  A small budget pushes
+    10,000 .. 65,536-body worlds through 2 .. 16 batches: same bar against the oracle as the unbatched pass, momentum
+    conserved, deterministic, trajectories equal to the tiled kernel's.  (Subprocess: the budget is read once per process.)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env.pop("ESSA_PAIR_SLOT_BUDGET_MB", None)
+    if budget_mb:
+        env["ESSA_PAIR_SLOT_BUDGET_MB"] = budget_mb
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "batched_check.py")], env=env, capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("batched_check")]
+    assert p.returncode == 0 and len(lines) == 7 and all(ln.endswith("PASS") for ln in lines), p.stdout + p.stderr
