@@ -1129,12 +1129,18 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
     int n = ctx->n;
     int R;
     int iblocks = force_iblocks(ctx, &R);
-    cudaEvent_t e0 = force_event(ctx, (*ev_idx)++), e1 = force_event(ctx, (*ev_idx)++);
-    if (!e0 || !e1) {
-        ctx->err = "cudaEventCreate failed";
-        return ESSA_ERR_CUDA;
+    // ev_idx == nullptr: a call of many steps brackets ALL its passes with one pair of events (step_tiled) -- two timestamp
+    // records around every pass keep back-to-back launches from overlapping their ramp-up, microseconds that matter at mid sizes
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ev_idx) {
+        e0 = force_event(ctx, (*ev_idx)++);
+        e1 = force_event(ctx, (*ev_idx)++);
+        if (!e0 || !e1) {
+            ctx->err = "cudaEventCreate failed";
+            return ESSA_ERR_CUDA;
+        }
+        CK(cudaEventRecord(e0, ctx->stream));
     }
-    CK(cudaEventRecord(e0, ctx->stream));
     if (ctx->use_paired) {
         if (ctx->gather_pending) { // the pair kernel walks the whole ring of blocks: all positions must be in
             CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
@@ -1194,16 +1200,16 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
             keys && ctx->world > 1 && !ctx->pair_peer_ok ? ctx->pair_kall : nullptr, eps2));
     } else if (ctx->world == 1 || !ctx->gather_pending) {
         int S;
-        choose_split(ctx, iblocks, (n + kTileJ - 1) / kTileJ, &S);
+        choose_split(ctx, iblocks, (n + kChunkQ - 1) / kChunkQ, &S);
         CK(launch_force_pass(ctx, 0, n, S, 0, S, argmax, save_old, k, eps2, ctx->stream));
     } else {
         int i0 = (int)((long long)n * ctx->rank / ctx->world), i1 = (int)((long long)n * (ctx->rank + 1) / ctx->world);
         int SA, SB0 = 0, SB1 = 0;
-        choose_split(ctx, iblocks, (i1 - i0 + kTileJ - 1) / kTileJ, &SA);
+        choose_split(ctx, iblocks, (i1 - i0 + kChunkQ - 1) / kChunkQ, &SA);
         if (i0 > 0)
-            choose_split(ctx, iblocks, (i0 + kTileJ - 1) / kTileJ, &SB0);
+            choose_split(ctx, iblocks, (i0 + kChunkQ - 1) / kChunkQ, &SB0);
         if (i1 < n)
-            choose_split(ctx, iblocks, (n - i1 + kTileJ - 1) / kTileJ, &SB1);
+            choose_split(ctx, iblocks, (n - i1 + kChunkQ - 1) / kChunkQ, &SB1);
         int total = SA + SB0 + SB1;
         // slot order follows source index so that the ordered reduction is the same on every rank count
         CK(launch_force_pass(ctx, i0, i1, SA, SB0, total, argmax, save_old, k, eps2, ctx->stream));
@@ -1214,12 +1220,15 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
         if (SB1)
             CK(launch_force_pass(ctx, i1, n, SB1, SB0 + SA, total, argmax, save_old, k, eps2, ctx->stream));
     }
-    CK(cudaEventRecord(e1, ctx->stream));
+    if (e1)
+        CK(cudaEventRecord(e1, ctx->stream));
     int i0 = (int)((long long)n * ctx->rank / ctx->world), i1 = (int)((long long)n * (ctx->rank + 1) / ctx->world);
     ctx->passes++;
     ctx->interactions += (double)(i1 - i0) * (double)(n - 1);
     return ESSA_OK;
 }
+
+constexpr int kPairedAutoMin = 12288; // AUTO takes the pair-shared kernel above this many bodies
 
 static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool forces_only) {
     int const K = forces_only ? 0 : std::abs(steps);
@@ -1244,7 +1253,9 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
             ctx->err = "pair-shared kernel needs >= 1025 bodies (whole 1024- or 2048-body blocks per rank when sharded), at most 2^21 bodies when the most-attracting links are tracked, and room for its slots";
             return ESSA_ERR_ARG;
         }
-        ctx->use_paired = can && (o.kernel == ESSA_KERNEL_PAIRED || (o.kernel == ESSA_KERNEL_AUTO && ctx->n >= 16384));
+        // AUTO: measured crossover on B200 (tools/crossover.py): 12,288 bodies 185 (tiled) vs 190 us per step (pair-shared),
+        // 16,383 bodies 313 vs 192
+        ctx->use_paired = can && (o.kernel == ESSA_KERNEL_PAIRED || (o.kernel == ESSA_KERNEL_AUTO && ctx->n > kPairedAutoMin));
     }
     KickArgs base;
     base.dt = (double)o.dt_seconds;
@@ -1253,6 +1264,18 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
     base.second_kick = 0;
     base.advance = 0;
     size_t ev = 0;
+    // calls of more than two steps time their passes as one span (see force_pass)
+    bool const span = K > 2;
+    size_t* const evp = span ? nullptr : &ev;
+    int span_passes = 0;
+    if (span) {
+        cudaEvent_t e0 = force_event(ctx, 0), e1 = force_event(ctx, 1);
+        if (!e0 || !e1) {
+            ctx->err = "cudaEventCreate failed";
+            return ESSA_ERR_CUDA;
+        }
+        CK(cudaEventRecord(e0, ctx->stream));
+    }
     if (ctx->gather_pending) { // never left pending between calls, defensive
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
         ctx->gather_pending = false;
@@ -1282,7 +1305,8 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
         if (!fused_prev) {
             if (!ctx->acc_valid || o.two_pass || (argmax && !ctx->acc_has_most)) {
                 KickArgs ka = base; // first set_forces() of the step: store only
-                int rc = force_pass(ctx, argmax, need_save_old, ka, o.eps2, &ev);
+                int rc = force_pass(ctx, argmax, need_save_old, ka, o.eps2, evp);
+                span_passes++;
                 if (rc != ESSA_OK)
                     return rc;
                 need_save_old = false;
@@ -1303,7 +1327,8 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
         KickArgs ks = base;
         ks.second_kick = 1;
         ks.advance = advance ? 1 : 0;
-        int rc = force_pass(ctx, argmax, need_save_old, ks, o.eps2, &ev);
+        int rc = force_pass(ctx, argmax, need_save_old, ks, o.eps2, evp);
+        span_passes++;
         if (rc != ESSA_OK)
             return rc;
         ctx->acc_valid = true;
@@ -1318,6 +1343,10 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
         if (o.record && ctx->tracked > 0)
             CK(launch_record(ctx, o.offset_trails, o.forward_simulated, ctx->stream));
     }
+    if (span) {
+        CK(cudaEventRecord(force_event(ctx, 1), ctx->stream));
+        ev = 2;
+    }
     CK(cudaEventRecord(ctx->ev_end, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0, total = 0;
@@ -1326,7 +1355,7 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
         total += ms;
     }
     ctx->last_force_ms = total;
-    ctx->last_force_passes = (int)(ev / 2);
+    ctx->last_force_passes = span ? span_passes : (int)(ev / 2);
     ctx->last_pre_ms = ctx->last_post_ms = 0;
     if (ev >= 2) {
         CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->force_events[0]));

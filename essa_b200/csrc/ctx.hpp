@@ -13,6 +13,7 @@
 namespace essa {
 
 constexpr int kTileJ = 256;       // j-records per shared-memory tile (8 KiB)
+constexpr int kChunkQ = 32;       // K1's j-chunks are cut at multiples of this many records
 constexpr int kStages = 4;        // bulk-copy pipeline depth
 constexpr int kForceThreads = 256;
 constexpr int kEnsembleMaxBodies = 320; // widest template one ensemble CTA takes
@@ -287,7 +288,7 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
 cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred, bool argmax_noop, bool save_old,
     bool argmax, unsigned long long const* akred, double eps2);
 int force_iblocks(essa_ctx const* c, int* R_out);
-void choose_split(essa_ctx const* c, int iblocks, int ntiles, int* S_out);
+void choose_split(essa_ctx const* c, int iblocks, int nquanta, int* S_out);
 
 cudaError_t launch_resident(essa_ctx* c, int steps, essa_step_opts const& o, bool forces_only, cudaStream_t st);
 cudaError_t launch_resident_warp(essa_ctx* c, int steps, essa_step_opts const& o, bool mask_may_change, cudaStream_t st,

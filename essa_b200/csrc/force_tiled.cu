@@ -78,9 +78,14 @@ __global__ void __launch_bounds__(kForceThreads, 2) k_force_tiled(ForceArgs cons
     int const tid = threadIdx.x;
     int const ib = blockIdx.x / A.S;
     int const sj = blockIdx.x - ib * A.S;
-    int const ntiles = (A.j1 - A.j0 + kTileJ - 1) / kTileJ;
-    int const t0 = (int)((long long)ntiles * sj / A.S);
-    int const t1 = (int)((long long)ntiles * (sj + 1) / A.S);
+    // this CTA's share of the sources, cut at multiples of kChunkQ records (a whole 256-record tile per CTA would leave a
+    // 2,048-body world with 64 CTAs of 18 us each), then streamed in tiles of up to kTileJ
+    int const nq = (A.j1 - A.j0 + kChunkQ - 1) / kChunkQ;
+    int const jlo = A.j0 + (int)((long long)nq * sj / A.S) * kChunkQ;
+    int const jhi_ = A.j0 + (int)((long long)nq * (sj + 1) / A.S) * kChunkQ;
+    int const jhi = jhi_ < A.j1 ? jhi_ : A.j1;
+    int const t0 = 0;
+    int const t1 = jhi > jlo ? (jhi - jlo + kTileJ - 1) / kTileJ : 0;
 
     double xi[R], yi[R], zi[R], gi[R], ax[R], ay[R], az[R], bm[R];
     int bj[R];
@@ -107,8 +112,8 @@ __global__ void __launch_bounds__(kForceThreads, 2) k_force_tiled(ForceArgs cons
     __syncthreads();
 
     auto issue = [&](int t, int s) {
-        int jb = A.j0 + t * kTileJ;
-        int cnt = min(kTileJ, A.j1 - jb);
+        int jb = jlo + t * kTileJ;
+        int cnt = min(kTileJ, jhi - jb);
         unsigned bytes = (unsigned)cnt * (unsigned)sizeof(double4);
         mbar_expect_tx(&full[s], bytes);
         bulk_g2s(&tile[s][0], A.w.pos_cur + jb, bytes, &full[s]);
@@ -123,8 +128,8 @@ __global__ void __launch_bounds__(kForceThreads, 2) k_force_tiled(ForceArgs cons
         int const k = t - t0;
         int const s = k % kStages;
         mbar_wait(&full[s], (unsigned)(k / kStages) & 1u);
-        int const jb = A.j0 + t * kTileJ;
-        int const cnt = min(kTileJ, A.j1 - jb);
+        int const jb = jlo + t * kTileJ;
+        int const cnt = min(kTileJ, jhi - jb);
         double4 const* tp = tile[s];
 #pragma unroll 4
         for (int jj = 0; jj < cnt; jj++) {
@@ -285,17 +290,17 @@ int force_iblocks(essa_ctx const* c, int* R_out) {
     return (ni + kForceThreads * R - 1) / (kForceThreads * R);
 }
 
-// j-chunks per launch: minimise (waves of 2 CTAs/SM) x (tiles of the longest chunk).
-void choose_split(essa_ctx const* c, int iblocks, int ntiles, int* S_out) {
+// j-chunks per launch: minimise (waves of 2 CTAs/SM) x (quanta of kChunkQ sources in the longest chunk).
+void choose_split(essa_ctx const* c, int iblocks, int nquanta, int* S_out) {
     long long slots = 2LL * c->sm_count;
-    int smax = ntiles < 48 ? ntiles : 48;
+    int smax = nquanta < 64 ? nquanta : 64;
     if (smax < 1)
         smax = 1;
     long long best = -1;
     int bestS = 1;
     for (int S = 1; S <= smax; S++) {
         long long waves = ((long long)iblocks * S + slots - 1) / slots;
-        long long cost = waves * ((ntiles + S - 1) / S) + waves; // + per-wave fixed cost
+        long long cost = waves * ((nquanta + S - 1) / S) + 3 * waves; // + per-wave fixed cost (launch ramp, first tile, ticket, ordered sum)
         if (best < 0 || cost < best) {
             best = cost;
             bestS = S;

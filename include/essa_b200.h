@@ -66,7 +66,7 @@ typedef enum essa_status {
 
 /* Which kernel essa_step runs. */
 typedef enum essa_kernel {
-    ESSA_KERNEL_AUTO = 0,     /* N <= ESSA_RESIDENT_MAX: resident; N >= 16384: paired (tracking: up to 2^21 bodies); else tiled */
+    ESSA_KERNEL_AUTO = 0,     /* N <= ESSA_RESIDENT_MAX: resident; N > 12288: paired (tracking: up to 2^21 bodies); else tiled */
     ESSA_KERNEL_TILED = 1,    /* K1: j-tiled FP64 force pass + fused kick/drift (any N) */
     ESSA_KERNEL_RESIDENT = 2, /* K3: one CTA keeps the world in shared memory for all steps */
     ESSA_KERNEL_PAIRED = 3    /* K1p: pair-shared force pass (each unordered pair once, both bodies updated) */

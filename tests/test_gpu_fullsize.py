@@ -16,7 +16,8 @@ def _rel_rows(a, b):
 
 
 @pytest.mark.parametrize("name,n,kernel", [("plummer", 16384, capi.KERNEL_AUTO), ("plummer", 16384, capi.KERNEL_TILED),
-                                           ("plummer", 16383, capi.KERNEL_AUTO),  # one below AUTO's switch to the pair-shared kernel
+                                           ("plummer", 16383, capi.KERNEL_AUTO),  # ragged last block of the pair-shared kernel
+                                           ("plummer", 12288, capi.KERNEL_AUTO), ("plummer", 12289, capi.KERNEL_AUTO),  # either side of AUTO's switch
                                            ("plummer", 262144, capi.KERNEL_AUTO), ("plummer", 262144, capi.KERNEL_TILED),
                                            ("galaxy", 1048576, capi.KERNEL_AUTO)])
 def test_full_size_force_pass_and_reversibility(name, n, kernel):
@@ -45,6 +46,28 @@ def test_full_size_force_pass_and_reversibility(name, n, kernel):
     rel = _rel_rows(pos, start)
     assert np.percentile(rel, 99) <= 1e-12 and rel.max() <= 1e-8, (np.percentile(rel, 99), rel.max())
     assert ctx.date == capi.START_DATE
+    ctx.close()
+
+
+def test_four_million_bodies_take_the_pair_shared_kernel_in_batches():
+    """4,194,304 bodies: the J-side slots of all 1,024 offsets would be 103 GB, so the pass runs in four batches of 256 offsets
+    against 26 GB of slots (force_paired.cu, k_pair_fold).  Sampled rows against the oracle's extended-precision sums, and
+    sum(m a) ~ 0 over all four million bodies -- a missed or doubled batch would show in either."""
+    n = 1 << 22
+    w = synth.plummer(n)
+    ctx = capi.Context(0, n)
+    ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
+    ctx.set_forces(kernel=capi.KERNEL_PAIRED)
+    got = ctx.download(("ax", "ay", "az"))
+    a = np.stack([got["ax"], got["ay"], got["az"]], axis=1)
+    rows = np.sort(np.random.default_rng(9).choice(n, 24, replace=False))
+    ld = oracle.forces_rows(w["x"], w["y"], w["z"], w["gf"], rows, mode="ld")
+    ref, _ = oracle.forces_rows(w["x"], w["y"], w["z"], w["gf"], rows, mode="omp")
+    err, err_ref = _rel_rows(a[rows], ld), _rel_rows(ref, ld)
+    assert err.max() <= max(1e-13, 4.0 * err_ref.max()), (err.max(), err_ref.max())
+    assert np.all(np.isfinite(a))
+    ma = a * w["gf"][:, None]
+    assert np.abs(ma.sum(axis=0)).max() <= 1e-11 * np.abs(ma).sum()
     ctx.close()
 
 
