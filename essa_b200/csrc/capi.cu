@@ -503,6 +503,9 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     cudaFree(c->pair_kslots);
     cudaFree(c->pair_kpart);
     cudaFree(c->pair_prior);
+    cudaFree(c->pair_perm);
+    cudaFree(c->pair_pos_s);
+    cudaFree(c->pair_sort_tmp);
     cudaFree(c->pair_kall);
     cudaFree(c->part);
     cudaFree(c->part_m);

@@ -185,6 +185,15 @@ struct essa_ctx {
     int pair_prior_npad = 0;
     bool pair_prior_valid = false;
     size_t pair_kpart_bytes = 0;
+    // mass-sorted layout of the tracked pair-shared pass (single GPU; force_paired.cu): slot s of the sorted domain holds body
+    // pair_perm[s]; records gathered into pair_pos_s before every pass; sort scratch
+    int* pair_perm = nullptr;
+    size_t pair_perm_n = 0;
+    double4* pair_pos_s = nullptr;
+    size_t pair_pos_s_n = 0;
+    void* pair_sort_tmp = nullptr;
+    size_t pair_sort_tmp_bytes = 0;
+    bool pair_sorted_pass = false; // the pass in flight (compute + finish) works in the sorted domain
 
     // recording
     int tracked = 0;

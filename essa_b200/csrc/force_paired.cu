@@ -25,8 +25,12 @@
 // double counted; it is 1 / (nb + 1) of the work.
 #include <cstdlib>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "ctx.hpp"
+
+#include <type_traits>
 
 namespace essa {
 
@@ -38,7 +42,7 @@ constexpr int kPHalf = 512;     // records per staged part of a J block
 constexpr int kPSub = 32 * kPRJ;
 constexpr int kPairMaxPeers = 8; // ranks whose slot buffers a kernel can address (one node)
 constexpr size_t kPSmem = 2 * kPHalf * sizeof(double4) + 8 * 3 * kPHalf * sizeof(double) + 64;
-constexpr size_t kPSmemKeys = 8 * kPHalf * sizeof(unsigned long long) + 2 * kPHalf * sizeof(unsigned); // + per-warp J-side candidate keys and the staged prior thresholds of the visitors (ARGMAX)
+constexpr size_t kPSmemKeys = 8 * kPHalf * sizeof(unsigned long long) + 2 * kPHalf * sizeof(unsigned) + 8 * kPThreads * sizeof(unsigned long long); // + per-warp J-side candidate keys and the staged prior thresholds of the visitors (ARGMAX)
 
 // Most-attracting candidates (src/Object.cpp:84-94) travel as sortable 64-bit keys: the bit pattern of the ranking
 // metric gf_p |d|^-3 y0 ~ gf_p / r^4 (positive doubles order like unsigned integers; y0 = rsqrt seed, relative
@@ -138,17 +142,32 @@ struct PairArgs {
     unsigned long long* part_k;  // [S][npad]              I-side candidate keys (ARGMAX)
     unsigned long long* slots_k; // writer-major fallback
     unsigned const* prior;       // [npad] filter thresholds left by the previous pass (ARGMAX)
+    // SORTED (mass-sorted layout, see k_force_paired): `pos`, `prior`, partials, slots and keys' homes are in the sorted domain;
+    // slot s holds body perm[s] (-1: padding) of pos_orig, and candidate keys carry ORIGINAL indices
+    int const* perm;
+    double4 const* pos_orig;
     double eps2;
 };
+
+// SORTED kernels keep MINUS the threshold of a target (what filter mode 2 adds to L(y0)); "nothing passes" becomes INT_MIN
+__device__ __forceinline__ unsigned thr_neg(unsigned t) { return t == kPriorNever ? 0x80000000u : 0u - t; }
+__device__ __forceinline__ unsigned thr_pos(unsigned x) { return x == 0x80000000u ? kPriorNever : 0u - x; }
 
 __device__ __forceinline__ double rot1(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // UNIFORM: every body of the world is live and has the same gravity factor g; the kernel then accumulates
 // sum |d|^-3 d and k_pair_finish multiplies by g once per body -- 18 instead of 20 FP64 instructions per pair.
-template<bool TWO_SIDED, bool ARGMAX, bool UNIFORM>
+// FILT: the candidate filter of most-attracting tracking.  0: none.  1: both sides, guarded by "partner not lighter" (any
+// layout).  2 / 3: mass-sorted layout, off-diagonal tile whose J block lies above / below the I block in the sorted order, so
+// that every visitor is at least / at most as heavy as every target: only the targets (2) / only the visitors (3) can gain a
+// candidate, no guard, and the test of the eight pairs of a rotation is a running maximum -- ONE fused integer add-max per pair
+// (SASS VIADDMNMX) and one compare per rotation:
+//   2:  lg_j + L(y0) >= thr_i   for some target   <=>   max_r (L(y0_r) - thr_i[r]) >= -lg_j      (thi holds -thr_i here)
+//   3:  lg_i + L(y0) >= thr_j   for some target   <=>   max_r (L(y0_r) + lg_i[r])  >=  thr_j
+template<bool TWO_SIDED, int FILT, bool UNIFORM>
 __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, double gi, double xj, double yj, double zj, double gj,
-    double eps2, double& aix, double& aiy, double& aiz, double& ajx, double& ajy, double& ajz, int iidx, int jidx,
-    unsigned long long& bi, unsigned long long& bj, unsigned lgi, unsigned lgj, unsigned thi, unsigned thj, bool& anyp) {
+    double eps2, double& aix, double& aiy, double& aiz, double& ajx, double& ajy, double& ajz,
+    unsigned lgi, unsigned lgj, unsigned thi, unsigned thj, bool& anyp, unsigned& mrun, bool first) {
     double dx = xj - xi, dy = yj - yi, dz = zj - zi;
     double r2 = fma(dx, dx, eps2);
     r2 = fma(dy, dy, r2);
@@ -182,7 +201,15 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
         ajy = fma(-sj, dy, ajy);
         ajz = fma(-sj, dz, ajz);
     }
-    if (ARGMAX) {
+    if (FILT == 2) {
+        int const ly = __double2hiint(y0);
+        mrun = first ? (unsigned)(ly + (int)thi) : (unsigned)__viaddmax_s32(ly, (int)thi, (int)mrun);
+    }
+    if (FILT == 3) {
+        unsigned const ly = (unsigned)__double2hiint(y0);
+        mrun = first ? ly + lgi : __viaddmax_u32(ly, lgi, mrun);
+    }
+    if (FILT == 1) {
         // candidate filter; the exact tests run after the 32 rotations of a visit, behind ONE warp-uniform branch
         // (pair_exact below): a branch per pair would make every pair its own basic block and serialise the
         // eight independent chains of a rotation, a branch per rotation still drains the pipeline every 8 pairs
@@ -200,9 +227,9 @@ __device__ __forceinline__ void pair_interact(double xi, double yi, double zi, d
 // with the very same operations (so the seed, and with it the key, are the ones the hot path saw) and applies
 // Object.cpp:84-94 -- strictly heavier partner, larger key -- to both bodies.
 template<bool TWO_SIDED>
-__device__ __forceinline__ void pair_exact(double4 const* __restrict__ pos, double xi, double yi, double zi, double gi, double xj, double yj,
-    double zj, double gj, double eps2, int iidx, int jidx, unsigned long long& bi, unsigned long long& bj, unsigned lgi, unsigned lgj,
-    unsigned& thi, unsigned& thj) {
+__device__ __forceinline__ void pair_exact(double4 const* __restrict__ pos, int const* __restrict__ perm, double xi, double yi, double zi,
+    double gi, double xj, double yj, double zj, double gj, double eps2, int iidx, int jidx, unsigned long long& bi, unsigned long long& bj,
+    unsigned lgi, unsigned lgj, unsigned& thi, unsigned& thj) {
     double dx = xj - xi, dy = yj - yi, dz = zj - zi;
     double r2 = fma(dx, dx, eps2);
     r2 = fma(dy, dy, r2);
@@ -228,6 +255,10 @@ __device__ __forceinline__ void pair_exact(double4 const* __restrict__ pos, doub
         // partners within 1e-6 of each other must not swap (the filter's margin covers the seed's error: it only decides
         // who gets here)
         double const yr = fma(y0 * e, fma(0.375, e, 0.5), y0);
+        if (perm) { // mass-sorted layout: keys name bodies by their ORIGINAL index (lowest index wins a tie; most[] is an index)
+            iidx = perm[iidx];
+            jidx = perm[jidx];
+        }
         if (pi) {
             double si = gj * u;
             unsigned long long const k = pack_key(si * yr, jidx);
@@ -248,8 +279,17 @@ __device__ __forceinline__ void pair_exact(double4 const* __restrict__ pos, doub
     }
 }
 
-template<int kPRI, bool ARGMAX, bool UNIFORM>
+// SORTED (only with ARGMAX; single GPU): the MASS-SORTED layout.  The pass runs on a copy of the records sorted by gravity
+// factor (ascending, equal ones by index; padding first), so "is the partner heavier" (src/Object.cpp:86,91) stops being a
+// question per pair and becomes a property of the TILE: in tile (I, J) with J above I every visitor is at least as heavy as
+// every target -- only targets can gain a candidate -- and below I it is the other way round.  The filter of such a tile is
+// pair_interact's mode 2 / 3: one VIADDMNMX per pair + one compare per rotation instead of 2 IADD + 2 VIMNMX + 2 ISETP per
+// pair, and only one of {lg_j, thr_j} travels with the visitor.  A unit whose heaviest possible partner is not heavier than its
+// lightest possible target (worlds with a few mass classes: whole tiles of one class) runs without any filter.  The diagonal
+// tile keeps the guarded filter.  Keys carry ORIGINAL indices (perm), so ties and most[] are unaffected by the layout.
+template<int kPRI, bool ARGMAX, bool UNIFORM, bool SORTED>
 __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A) {
+    static_assert(!SORTED || ARGMAX, "the sorted layout exists for the candidate filter");
     constexpr int kPB = kPThreads * kPRI;
     constexpr int kPParts = kPB / kPHalf;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -258,6 +298,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
     unsigned long long* full = reinterpret_cast<unsigned long long*>(accj + 8 * 3 * kPHalf); // [2]
     unsigned long long* acck = full + 8;                                                        // [8][kPHalf] (ARGMAX)
     unsigned* tprior = reinterpret_cast<unsigned*>(acck + 8 * kPHalf);                          // [2][kPHalf] (ARGMAX)
+    // best candidate key per target: touched by the cold path only, so it lives in shared memory ([r][thread]: conflict free)
+    unsigned long long* bis = reinterpret_cast<unsigned long long*>(tprior + 2 * kPHalf);       // [kPRI][kPThreads] (ARGMAX)
 
     int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int const ibl = blockIdx.x / A.S, chunk = blockIdx.x - ibl * A.S;
@@ -265,6 +307,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
     // work units of block I: (offset d = 0 .. dmax) x (kPParts parts of the J block), split into S chunks
     int const nunits = A.dn * kPParts;
     int const ulo = (int)((long long)nunits * chunk / A.S), uhi = (int)((long long)nunits * (chunk + 1) / A.S);
+    int const* const perm = SORTED ? A.perm : nullptr;
+    double4 const* const kpos = SORTED ? A.pos_orig : A.pos; // what candidate keys index
 
     double xi[kPRI], yi[kPRI], zi[kPRI], gi[kPRI], aix[kPRI], aiy[kPRI], aiz[kPRI];
 #pragma unroll
@@ -276,15 +320,23 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
         gi[r] = p.w;
         aix[r] = aiy[r] = aiz[r] = 0.0;
     }
-    unsigned long long bi[kPRI]; // best candidate key per target
-    unsigned lgi[kPRI], thi[kPRI]; // ... with the filter's view of the target's gf and of its best key
+    // the filter's view of the target's gf and of its best key; SORTED keeps MINUS the threshold (what mode 2 adds)
+    unsigned lgi[kPRI], thx[kPRI];
 #pragma unroll
     for (int r = 0; r < kPRI; r++) {
-        bi[r] = 0ull;
         lgi[r] = key_lg(gi[r]);
-        thi[r] = ARGMAX ? A.prior[(size_t)I * kPB + warp * (32 * kPRI) + r * 32 + lane] : 0u;
+        unsigned const t = ARGMAX ? A.prior[(size_t)I * kPB + warp * (32 * kPRI) + r * 32 + lane] : 0u;
+        thx[r] = SORTED ? thr_neg(t) : t;
+        if (ARGMAX)
+            bis[r * kPThreads + tid] = 0ull;
     }
     int const ibase = I * kPB + warp * (32 * kPRI) + lane; // + r * 32
+    // gravity factors at the two ends of the I block (sorted: the lightest and the heaviest target)
+    double gi_first = 0.0, gi_last = 0.0;
+    if (SORTED) {
+        gi_first = A.pos[(size_t)I * kPB].w;
+        gi_last = A.pos[(size_t)I * kPB + kPB - 1].w;
+    }
 
     if (tid == 0) {
         mbar_init(&full[0], 1);
@@ -334,125 +386,126 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
             mbar_wait(&full[buf], (unsigned)(seq >> 1) & 1u);
             double4 const* tp = tile + (size_t)buf * kPHalf;
             double* myacc = accj + (size_t)warp * 3 * kPHalf;
+            // which filter this unit runs (warp-uniform, one decision per 2048 x 512 pairs)
+            int mode = ARGMAX ? 1 : 0;
+            if (SORTED && d > 0) {
+                bool const above = J > I;
+                bool const cand = above ? tp[kPHalf - 1].w > gi_first : gi_last > tp[0].w;
+                mode = !cand ? 0 : (above ? 2 : 3);
+            }
 
             for (int s = 0; s < kPHalf / kPSub; s++) {
                 int const sub = (s + warp) & (kPHalf / kPSub - 1); // stagger shared-memory traffic between warps
-                double xj[kPRJ], yj[kPRJ], zj[kPRJ], gj[kPRJ], ajx[kPRJ], ajy[kPRJ], ajz[kPRJ];
-#pragma unroll
-                for (int q = 0; q < kPRJ; q++) {
-                    double4 p = tp[sub * kPSub + q * 32 + lane];
-                    xj[q] = p.x;
-                    yj[q] = p.y;
-                    zj[q] = p.z;
-                    gj[q] = p.w;
-                    ajx[q] = ajy[q] = ajz[q] = 0.0;
+                double xj, yj, zj, gj, ajx = 0.0, ajy = 0.0, ajz = 0.0;
+                {
+                    double4 p = tp[sub * kPSub + lane];
+                    xj = p.x;
+                    yj = p.y;
+                    zj = p.z;
+                    gj = p.w;
                 }
-                unsigned long long bjk[kPRJ]; // the visitors' own candidate keys travel with them
-                unsigned lgj[kPRJ], thj[kPRJ];
-#pragma unroll
-                for (int q = 0; q < kPRJ; q++) {
-                    bjk[q] = 0ull;
-                    lgj[q] = key_lg(gj[q]);
-                    thj[q] = ARGMAX ? tprior[(size_t)buf * kPHalf + sub * kPSub + q * 32 + lane] : 0u;
-                }
-                int const jbase = J * kPB + half * kPHalf + sub * kPSub; // + q * 32 + home lane of the visitor
+                unsigned long long bjk = 0ull; // the visitor's own candidate key (cold path only; travels with it there)
+                unsigned lgj = key_lg(gj);
+                unsigned thj = ARGMAX ? tprior[(size_t)buf * kPHalf + sub * kPSub + lane] : 0u;
+                int const jbase = J * kPB + half * kPHalf + sub * kPSub; // + home lane of the visitor
                 int const src = (lane + 31) & 31; // take from the previous lane = pass to the next
-                bool anyp = false;                // some pair of this rotation passed the candidate filter
+                // Rotations of this visit in which some pair of this lane passed the candidate filter (bit k = rotation k).  The
+                // exact tests run after the 32 rotations, behind ONE warp-uniform branch, and only for those rotations (rewalk):
+                // a pass is rare (a few per body and force pass), a branch per rotation would drain the pipeline every 8 pairs
+                // (ncu: FP64 pipe 64 % busy, "wait" stalls 1.5 per issue), and walking all 32 rotations again for one pass cost
+                // 12 % of the kernel (2.6 % of the visits at 4.5 x the instructions of a plain visit).
+                unsigned rmask = 0u;
+                // the exact tests of the flagged rotations.  The visitors are back in their home lanes; rotation k had lane L meet
+                // the visitor of home lane (L - k) mod 32, whose key and threshold are fetched from there and sent back after.
+                auto rewalk = [&](auto two_sided) {
+                    constexpr bool TWO = decltype(two_sided)::value;
+                    unsigned todo = __reduce_or_sync(0xffffffffu, rmask);
+                    while (todo) {
+                        int const rot = __ffs(todo) - 1;
+                        todo &= todo - 1u;
+                        int const from = (lane - rot) & 31, back = (lane + rot) & 31;
+                        double const xr = rot1(xj, from), yr = rot1(yj, from), zr = rot1(zj, from), gr = rot1(gj, from);
+                        unsigned long long br = __shfl_sync(0xffffffffu, bjk, from);
+                        unsigned tr = __shfl_sync(0xffffffffu, thj, from);
+                        unsigned const lr = key_lg(gr);
+#pragma unroll
+                        for (int r = 0; r < kPRI; r++) {
+                            unsigned th = SORTED ? thr_pos(thx[r]) : thx[r];
+                            pair_exact<TWO>(kpos, perm, xi[r], yi[r], zi[r], gi[r], xr, yr, zr, gr, A.eps2, ibase + r * 32, jbase + from,
+                                bis[r * kPThreads + tid], br, lgi[r], lr, th, tr);
+                            thx[r] = SORTED ? thr_neg(th) : th;
+                        }
+                        bjk = __shfl_sync(0xffffffffu, br, back);
+                        thj = __shfl_sync(0xffffffffu, tr, back);
+                    }
+                };
                 if (d == 0) {
                     for (int rot = 0; rot < 32; rot++) {
+                        unsigned mrun = 0u;
+                        bool prot = false;
 #pragma unroll
-                        for (int q = 0; q < kPRJ; q++)
-#pragma unroll
-                            for (int r = 0; r < kPRI; r++)
-                                pair_interact<false, ARGMAX, UNIFORM>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
-                                    aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q],
-                                    thi[r], thj[q], anyp);
-#pragma unroll
-                        for (int q = 0; q < kPRJ; q++) {
-                            xj[q] = rot1(xj[q], src);
-                            yj[q] = rot1(yj[q], src);
-                            zj[q] = rot1(zj[q], src);
-                            gj[q] = rot1(gj[q], src);
-                            if (ARGMAX)
-                                lgj[q] = __shfl_sync(0xffffffffu, lgj[q], src);
-                        }
-                    }
-                    // 32 rotations: every visitor is back in its home lane.  Did any pair pass the candidate filter?
-                    // Then walk the subset once more, exact tests only (see pair_exact).
-                    if (ARGMAX && __any_sync(0xffffffffu, anyp)) {
-                        for (int rot = 0; rot < 32; rot++) {
-#pragma unroll
-                            for (int q = 0; q < kPRJ; q++)
-#pragma unroll
-                                for (int r = 0; r < kPRI; r++)
-                                    pair_exact<false>(A.pos, xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
-                                        jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q], thi[r], thj[q]);
-#pragma unroll
-                            for (int q = 0; q < kPRJ; q++) {
-                                xj[q] = rot1(xj[q], src);
-                                yj[q] = rot1(yj[q], src);
-                                zj[q] = rot1(zj[q], src);
-                                gj[q] = rot1(gj[q], src);
-                                lgj[q] = __shfl_sync(0xffffffffu, lgj[q], src);
-                            }
-                        }
-                    }
-                } else {
-                    for (int rot = 0; rot < 32; rot++) {
-#pragma unroll
-                        for (int q = 0; q < kPRJ; q++)
-#pragma unroll
-                            for (int r = 0; r < kPRI; r++)
-                                pair_interact<true, ARGMAX, UNIFORM>(xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, aix[r], aiy[r],
-                                    aiz[r], ajx[q], ajy[q], ajz[q], ibase + r * 32, jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q],
-                                    thi[r], thj[q], anyp);
-#pragma unroll
-                        for (int q = 0; q < kPRJ; q++) {
-                            xj[q] = rot1(xj[q], src);
-                            yj[q] = rot1(yj[q], src);
-                            zj[q] = rot1(zj[q], src);
-                            gj[q] = rot1(gj[q], src);
-                            ajx[q] = rot1(ajx[q], src);
-                            ajy[q] = rot1(ajy[q], src);
-                            ajz[q] = rot1(ajz[q], src);
-                            if (ARGMAX) { // what the filter needs of the visitor; its key stays at home
-                                lgj[q] = __shfl_sync(0xffffffffu, lgj[q], src);
-                                thj[q] = __shfl_sync(0xffffffffu, thj[q], src);
-                            }
-                        }
-                    }
-                    // 32 rotations: every visitor is back in its home lane.  Did any pair pass the candidate filter?
-                    // Then walk the subset once more, exact tests only (see pair_exact); the branch sits here and not
-                    // in the rotation loop, where it would drain the pipeline eight pairs at a time (ncu: FP64 pipe
-                    // 64 % busy, "wait" stalls 1.5 per issue with the vote per rotation).
-                    if (ARGMAX && __any_sync(0xffffffffu, anyp)) {
-                        for (int rot = 0; rot < 32; rot++) {
-#pragma unroll
-                            for (int q = 0; q < kPRJ; q++)
-#pragma unroll
-                                for (int r = 0; r < kPRI; r++)
-                                    pair_exact<true>(A.pos, xi[r], yi[r], zi[r], gi[r], xj[q], yj[q], zj[q], gj[q], A.eps2, ibase + r * 32,
-                                        jbase + q * 32 + ((lane - rot) & 31), bi[r], bjk[q], lgi[r], lgj[q], thi[r], thj[q]);
-#pragma unroll
-                            for (int q = 0; q < kPRJ; q++) {
-                                xj[q] = rot1(xj[q], src);
-                                yj[q] = rot1(yj[q], src);
-                                zj[q] = rot1(zj[q], src);
-                                gj[q] = rot1(gj[q], src);
-                                bjk[q] = __shfl_sync(0xffffffffu, bjk[q], src);
-                                lgj[q] = __shfl_sync(0xffffffffu, lgj[q], src);
-                                thj[q] = __shfl_sync(0xffffffffu, thj[q], src);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < kPRJ; q++) {
-                        int j = sub * kPSub + q * 32 + lane;
-                        myacc[j] = ajx[q];
-                        myacc[kPHalf + j] = ajy[q];
-                        myacc[2 * kPHalf + j] = ajz[q];
+                        for (int r = 0; r < kPRI; r++)
+                            pair_interact<false, ARGMAX ? 1 : 0, UNIFORM>(xi[r], yi[r], zi[r], gi[r], xj, yj, zj, gj, A.eps2, aix[r], aiy[r], aiz[r],
+                                ajx, ajy, ajz, lgi[r], lgj, SORTED ? thr_pos(thx[r]) : thx[r], thj, prot, mrun, r == 0);
                         if (ARGMAX)
-                            acck[(size_t)warp * kPHalf + j] = bjk[q];
+                            rmask = (rmask >> 1) | (prot ? 0x80000000u : 0u);
+                        xj = rot1(xj, src);
+                        yj = rot1(yj, src);
+                        zj = rot1(zj, src);
+                        gj = rot1(gj, src);
+                        if (ARGMAX)
+                            lgj = __shfl_sync(0xffffffffu, lgj, src);
+                    }
+                    if (ARGMAX)
+                        rewalk(std::false_type {});
+                } else {
+                    // the 32 rotations of a visit, for one filter mode (a compile-time constant inside the loop)
+                    auto visit = [&](auto fc) {
+                        constexpr int FILT = decltype(fc)::value;
+                        for (int rot = 0; rot < 32; rot++) {
+                            unsigned mrun = 0u;
+                            bool prot = false;
+#pragma unroll
+                            for (int r = 0; r < kPRI; r++)
+                                pair_interact<true, FILT, UNIFORM>(xi[r], yi[r], zi[r], gi[r], xj, yj, zj, gj, A.eps2, aix[r], aiy[r], aiz[r], ajx,
+                                    ajy, ajz, lgi[r], lgj, thx[r], thj, prot, mrun, r == 0);
+                            if (FILT == 2)
+                                prot = (int)mrun >= -(int)lgj;
+                            if (FILT == 3)
+                                prot = mrun >= thj;
+                            if (FILT != 0)
+                                rmask = (rmask >> 1) | (prot ? 0x80000000u : 0u);
+                            xj = rot1(xj, src);
+                            yj = rot1(yj, src);
+                            zj = rot1(zj, src);
+                            gj = rot1(gj, src);
+                            ajx = rot1(ajx, src);
+                            ajy = rot1(ajy, src);
+                            ajz = rot1(ajz, src);
+                            // what the filter needs of the visitor; its key stays at home
+                            if (FILT == 1 || FILT == 2)
+                                lgj = __shfl_sync(0xffffffffu, lgj, src);
+                            if (FILT == 1 || FILT == 3)
+                                thj = __shfl_sync(0xffffffffu, thj, src);
+                        }
+                    };
+                    if (!ARGMAX || (SORTED && mode == 0))
+                        visit(std::integral_constant<int, 0> {});
+                    else if (!SORTED)
+                        visit(std::integral_constant<int, 1> {});
+                    else if (mode == 2)
+                        visit(std::integral_constant<int, SORTED ? 2 : 1> {});
+                    else
+                        visit(std::integral_constant<int, SORTED ? 3 : 1> {});
+                    if (ARGMAX)
+                        rewalk(std::true_type {});
+                    {
+                        int j = sub * kPSub + lane;
+                        myacc[j] = ajx;
+                        myacc[kPHalf + j] = ajy;
+                        myacc[2 * kPHalf + j] = ajz;
+                        if (ARGMAX)
+                            acck[(size_t)warp * kPHalf + j] = bjk;
                     }
                 }
             }
@@ -473,9 +526,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                     unsigned long long* slotk = (A.owner_major ? A.slotk_peer[owner] : A.slots_k) + tile * kPB + half * kPHalf;
                     for (int j = tid; j < kPHalf; j += kPThreads) {
                         unsigned long long k = 0ull;
+                        int const tgt = SORTED ? perm[J * kPB + half * kPHalf + j] : J * kPB + half * kPHalf + j;
 #pragma unroll
                         for (int w = 0; w < 8; w++)
-                            k = key_merge(A.pos, J * kPB + half * kPHalf + j, k, acck[(size_t)w * kPHalf + j], A.eps2);
+                            k = key_merge(kpos, tgt, k, acck[(size_t)w * kPHalf + j], A.eps2);
                         __stcg(slotk + j, k);
                     }
                 }
@@ -493,7 +547,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
         __stcg(p + A.npad, aiy[r]);
         __stcg(p + 2 * (size_t)A.npad, aiz[r]);
         if (ARGMAX)
-            __stcg(A.part_k + (size_t)chunk * A.npad + i, bi[r]);
+            __stcg(A.part_k + (size_t)chunk * A.npad + i, bis[r * kPThreads + tid]);
     }
 }
 
@@ -515,6 +569,7 @@ struct PairFinishArgs {
     int argmax_noop;     // most-attracting tracking requested on a world of equal gravity factors: clear_forces only
     int save_old;        // ... and Object::before_update's old_most = most
     unsigned* prior;     // ARGMAX: [npad] filter thresholds, read (what the pass used) and rewritten (for the next pass)
+    int const* perm;     // mass-sorted pass: thread s handles body perm[s] (-1: padding); partials, slots, priors are indexed by s
     double scale;        // UNIFORM worlds: the common gravity factor the sums still lack; otherwise 1
     double eps2;         // softening, for the repair of bodies that met an r = 0 pair in an unguarded tile
 };
@@ -537,9 +592,9 @@ __device__ __forceinline__ void slot_sum_owner(int g, int nb, int dmax, int ib0,
     }
 }
 template<int kPB>
-__device__ __forceinline__ unsigned long long slot_key_owner(int g, int nb, int dmax, int ib0, unsigned long long const* slots_k,
+__device__ __forceinline__ unsigned long long slot_key_owner(int s, int g, int nb, int dmax, int ib0, unsigned long long const* slots_k,
     double4 const* __restrict__ pos, double eps2) {
-    int const K = g / kPB, jl = g - K * kPB;
+    int const K = s / kPB, jl = s - K * kPB; // s: where the body's slots are (its place in the pass's layout); g: its index
     unsigned long long k = 0ull;
     for (int d = 1; d <= dmax; d++) {
         int I = K - d;
@@ -689,8 +744,15 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
     __shared__ double red[4][256];
     __shared__ int redj[256];
     __shared__ unsigned char sbad[256];
-    int g = A.i0 + blockIdx.x * blockDim.x + threadIdx.x;
-    bool const in = g < A.i1;
+    __shared__ int sg[256];
+    int const s = A.i0 + blockIdx.x * blockDim.x + threadIdx.x; // place in the layout of the pass
+    int g = s;                                                  // the body
+    bool in = s < A.i1;
+    if (A.perm) {
+        g = in ? A.perm[s] : -1;
+        in = g >= 0;
+    }
+    sg[threadIdx.x] = g;
     WorldPtrs const& W = A.w;
     KickArgs const& Kk = A.k;
     double ax = 0, ay = 0, az = 0;
@@ -699,17 +761,17 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
     double4 p = make_double4(0, 0, 0, 0);
     if (in) {
         for (int c = 0; c < A.S; c++) {
-            double const* q = A.part_i + (size_t)c * 3 * A.npad + g;
+            double const* q = A.part_i + (size_t)c * 3 * A.npad + s;
             ax = __dadd_rn(ax, __ldcg(q));
             ay = __dadd_rn(ay, __ldcg(q + A.npad));
             az = __dadd_rn(az, __ldcg(q + 2 * (size_t)A.npad));
         }
         if (A.ajred) {
-            ax = __dadd_rn(ax, __ldcg(A.ajred + g));
-            ay = __dadd_rn(ay, __ldcg(A.ajred + (size_t)A.npad + g));
-            az = __dadd_rn(az, __ldcg(A.ajred + 2 * (size_t)A.npad + g));
+            ax = __dadd_rn(ax, __ldcg(A.ajred + s));
+            ay = __dadd_rn(ay, __ldcg(A.ajred + (size_t)A.npad + s));
+            az = __dadd_rn(az, __ldcg(A.ajred + 2 * (size_t)A.npad + s));
         } else {
-            slot_sum_owner<kPB>(g, A.nb, A.dmax, A.ib0, A.slots, ax, ay, az);
+            slot_sum_owner<kPB>(s, A.nb, A.dmax, A.ib0, A.slots, ax, ay, az);
         }
         ax = __dmul_rn(ax, A.scale);
         ay = __dmul_rn(ay, A.scale);
@@ -721,10 +783,10 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
                 for (int r = 0; r < A.world; r++)
                     key = key_merge(W.pos_cur, g, key, __ldcg(A.akred + (size_t)r * (A.i1 - A.i0) + (g - A.i0)), A.eps2);
             } else {
-                key = slot_key_owner<kPB>(g, A.nb, A.dmax, A.ib0, A.slots_k, W.pos_cur, A.eps2);
+                key = slot_key_owner<kPB>(s, g, A.nb, A.dmax, A.ib0, A.slots_k, W.pos_cur, A.eps2);
             }
             for (int c = 0; c < A.S; c++)
-                key = key_merge(W.pos_cur, g, key, __ldcg(A.part_k + (size_t)c * A.npad + g), A.eps2);
+                key = key_merge(W.pos_cur, g, key, __ldcg(A.part_k + (size_t)c * A.npad + s), A.eps2);
         }
     }
     // ---- repair: bodies that met a coincident partner in an unguarded tile (see pair_interact), and bodies whose
@@ -733,7 +795,7 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
     bool const bad_acc = in && act && !(isfinite(ax) && isfinite(ay) && isfinite(az));
     bool bad = bad_acc;
     if (in && act && A.argmax) {
-        unsigned const P = A.prior[g];
+        unsigned const P = A.prior[s];
         bad = bad || !(P == kPriorNone || (key != 0ull && key_thr(key) > P));
     }
     if (__syncthreads_or(bad)) {
@@ -742,7 +804,7 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
         for (int t = 0; t < 256; t++) {
             if (!sbad[t])
                 continue; // uniform over the block
-            int const gt = A.i0 + blockIdx.x * blockDim.x + t;
+            int const gt = sg[t];
             double rx, ry, rz;
             unsigned long long rk;
             pair_repair_body(W.pos_cur, A.n, W.pos_cur[gt], A.eps2, A.argmax != 0, red, redj, rx, ry, rz, rk);
@@ -759,7 +821,7 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
     if (!in)
         return;
     if (A.argmax) // where the next pass starts its filters
-        A.prior[g] = !act ? kPriorNever : (key != 0ull ? key_thr(key) - kPriorSlack : kPriorNone);
+        A.prior[s] = !act ? kPriorNever : (key != 0ull ? key_thr(key) - kPriorSlack : kPriorNone);
     // ---- epilogue: identical to force_tiled.cu finish_body ----
     double vx = 0, vy = 0, vz = 0;
     if ((A.argmax_noop || A.argmax) && A.save_old)
@@ -822,6 +884,40 @@ __global__ void __launch_bounds__(256) k_pair_prior_reset(unsigned* prior, uint8
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < npad)
         prior[g] = g < n && active[g] ? kPriorNone : kPriorNever;
+}
+
+// ---- mass-sorted layout (SORTED kernels) ----
+// Sort key of a gravity factor: the IEEE bit pattern made monotone for the whole real line (negative values reversed).
+__global__ void __launch_bounds__(256) k_pair_sort_keys(double4 const* pos, int n, unsigned long long* keys, int* vals) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n)
+        return;
+    unsigned long long const b = (unsigned long long)__double_as_longlong(pos[g].w);
+    keys[g] = (b >> 63) ? ~b : b | 0x8000000000000000ull;
+    vals[g] = g;
+}
+__global__ void __launch_bounds__(256) k_pair_perm_pad(int* perm, int count) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < count)
+        perm[g] = -1;
+}
+// the records of a pass in sorted order; padding (lighter than everything, in front) far away as in the unsorted layout
+__global__ void __launch_bounds__(256) k_pair_gather_sorted(double4 const* pos, int const* perm, double4* out, int npad) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= npad)
+        return;
+    int const g = perm[s];
+    out[s] = g >= 0 ? pos[g] : make_double4(kPadCoord, kPadCoord, kPadCoord, 0.0);
+}
+__global__ void __launch_bounds__(256) k_pair_prior_reset_sorted(unsigned* prior, int const* perm, uint8_t const* active, int npad) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < npad)
+        prior[s] = perm[s] >= 0 && active[perm[s]] ? kPriorNone : kPriorNever;
+}
+// ESSA_PAIR_SORTED=0: the guarded filter on the unsorted layout (A/B measurements; what sharded worlds run)
+static bool pair_sorted_allowed() { // read per pass (not cached): the tests run both layouts in one process
+    char const* e = getenv("ESSA_PAIR_SORTED");
+    return e ? atoi(e) != 0 : true;
 }
 
 // Can this world go through the pair-shared kernel, and with which block size?  Whole blocks per
@@ -966,18 +1062,19 @@ static void pair_geometry(essa_ctx const* c, int nb, int* ib0, int* ib1) {
     *ib1 = (int)((long long)nb * (c->rank + 1) / c->world);
 }
 
-template<int RI, bool ARGMAX, bool UNIFORM>
+template<int RI, bool ARGMAX, bool UNIFORM, bool SORTED = false>
 static cudaError_t launch_pair_kernels(essa_ctx* c, PairArgs const& A, cudaStream_t st, double** acc, unsigned long long** kacc) {
     constexpr int PB = kPThreads * RI;
     constexpr size_t smem = kPSmem + (ARGMAX ? kPSmemKeys : 0);
-    bool& attr_set = c->attr_pair[(RI == 8 ? 0 : 1) + (ARGMAX ? 2 : 0) + (UNIFORM ? 4 : 0)]; // per context: the attribute is per device
+    // per context: the attribute is per device.  (UNIFORM and SORTED exclude each other: slots 4 and 5 vs 6 and 7)
+    bool& attr_set = c->attr_pair[(RI == 8 ? 0 : 1) + (ARGMAX ? 2 : 0) + (UNIFORM || SORTED ? 4 : 0)];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_force_paired<RI, ARGMAX, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_force_paired<RI, ARGMAX, UNIFORM, SORTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
         attr_set = true;
     }
-    k_force_paired<RI, ARGMAX, UNIFORM><<<(A.ib1 - A.ib0) * A.S, kPThreads, smem, st>>>(A);
+    k_force_paired<RI, ARGMAX, UNIFORM, SORTED><<<(A.ib1 - A.ib0) * A.S, kPThreads, smem, st>>>(A);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
@@ -1073,6 +1170,10 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
         if (e != cudaSuccess)
             return e;
     }
+    // mass-sorted layout: tracked passes of an unsharded world (a rank of a sharded world owns a contiguous range of ORIGINAL
+    // indices -- essa_upload_shard / essa_download_shard -- which a global sort by mass would scatter over the ranks)
+    bool const sorted = argmax && c->world == 1 && c->plan.batches == 1 && pair_sorted_allowed();
+    c->pair_sorted_pass = sorted;
     if (argmax) {
         size_t const want = (size_t)nb * kPThreads * ri;
         if (want > c->pair_prior_n) {
@@ -1085,16 +1186,55 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
                 return e;
             c->pair_prior_n = want;
         }
+        if (sorted) {
+            cudaError_t e = grow((void**)&c->pair_perm, &c->pair_perm_n, want * sizeof(int));
+            if (e == cudaSuccess)
+                e = grow((void**)&c->pair_pos_s, &c->pair_pos_s_n, want * sizeof(double4));
+            if (e != cudaSuccess)
+                return e;
+        }
         if (!c->pair_prior_valid || c->pair_prior_npad != (int)want) {
-            k_pair_prior_reset<<<(unsigned)((want + 255) / 256), 256, 0, st>>>(c->pair_prior, c->active, c->n, (int)want);
-            c->launches++;
+            if (sorted) {
+                // gravity factors or the active mask may have changed: sort again.  pos[cur].w = active ? gf : 0 is the key
+                // (stable radix sort: equal factors stay in index order); the n bodies go behind the npad - n padding slots
+                size_t const n = (size_t)c->n, kb = (n * sizeof(unsigned long long) + 255) / 256 * 256, vb = (n * sizeof(int) + 255) / 256 * 256;
+                size_t cub_bytes = 0;
+                cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (unsigned long long const*)nullptr, (unsigned long long*)nullptr,
+                    (int const*)nullptr, (int*)nullptr, (int)n, 0, 64, st);
+                if (e == cudaSuccess)
+                    e = grow(&c->pair_sort_tmp, &c->pair_sort_tmp_bytes, 2 * kb + vb + cub_bytes);
+                if (e != cudaSuccess)
+                    return e;
+                unsigned char* base = static_cast<unsigned char*>(c->pair_sort_tmp);
+                unsigned long long* k_in = reinterpret_cast<unsigned long long*>(base);
+                unsigned long long* k_out = reinterpret_cast<unsigned long long*>(base + kb);
+                int* v_in = reinterpret_cast<int*>(base + 2 * kb);
+                int const front = (int)(want - n);
+                k_pair_sort_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->pos[c->cur], (int)n, k_in, v_in);
+                if (front > 0)
+                    k_pair_perm_pad<<<(unsigned)((front + 255) / 256), 256, 0, st>>>(c->pair_perm, front);
+                e = cub::DeviceRadixSort::SortPairs(base + 2 * kb + vb, cub_bytes, k_in, k_out, v_in, c->pair_perm + front, (int)n, 0, 64, st);
+                if (e != cudaSuccess)
+                    return e;
+                k_pair_prior_reset_sorted<<<(unsigned)((want + 255) / 256), 256, 0, st>>>(c->pair_prior, c->pair_perm, c->active, (int)want);
+                c->launches += 4;
+            } else {
+                k_pair_prior_reset<<<(unsigned)((want + 255) / 256), 256, 0, st>>>(c->pair_prior, c->active, c->n, (int)want);
+                c->launches++;
+            }
             c->pair_prior_valid = true;
             c->pair_prior_npad = (int)want;
+        }
+        if (sorted) {
+            k_pair_gather_sorted<<<(unsigned)((want + 255) / 256), 256, 0, st>>>(c->pos[c->cur], c->pair_perm, c->pair_pos_s, (int)want);
+            c->launches++;
         }
     }
     PairArgs A;
     A.prior = c->pair_prior;
-    A.pos = c->pos[c->cur];
+    A.pos = sorted ? c->pair_pos_s : c->pos[c->cur];
+    A.pos_orig = c->pos[c->cur];
+    A.perm = sorted ? c->pair_perm : nullptr;
     A.nb = nb;
     A.dmax = nb / 2;
     A.S = S;
@@ -1126,7 +1266,9 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
         A.d0 = b == 0 ? 0 : b * db + 1; // the diagonal tile (d = 0, no slot) rides with the first batch
         A.dn = last - A.d0 + 1;
         A.dslot0 = b * db + 1;
-        if (ri == 8)
+        if (sorted)
+            e = ri == 8 ? launch_pair_kernels<8, true, false, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<4, true, false, true>(c, A, st, &acc, &kacc);
+        else if (ri == 8)
             e = argmax ? launch_pair_kernels<8, true, false>(c, A, st, &acc, &kacc)
                        : (uniform ? launch_pair_kernels<8, false, true>(c, A, st, &acc, &kacc) : launch_pair_kernels<8, false, false>(c, A, st, &acc, &kacc));
         else
@@ -1184,6 +1326,12 @@ cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStrea
     F.scale = pair_uniform(c) && !argmax ? c->gf_uniform_value : 1.0;
     F.slots = c->pair_slots;
     F.ajred = ajred;
+    F.perm = nullptr;
+    if (argmax && c->pair_sorted_pass) { // one thread per slot of the sorted layout (padding included: it returns at once)
+        F.perm = c->pair_perm;
+        F.i0 = 0;
+        F.i1 = F.npad;
+    }
     if (c->plan.batches > 1) { // the batches left their running sum behind the partials: nothing else to add
         F.ajred = c->pair_part + (size_t)S * 3 * F.npad;
         F.S = 0;

@@ -22,6 +22,14 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(params=["mass_sorted", "unsorted"])
+def layout(request, monkeypatch):
+    """Tracked passes of an unsharded world run on the mass-sorted layout (filter modes 2 / 3 of k_force_paired);
+    ESSA_PAIR_SORTED=0 keeps the guarded filter on the caller's order -- what the ranks of a sharded world run."""
+    monkeypatch.setenv("ESSA_PAIR_SORTED", "1" if request.param == "mass_sorted" else "0")
+    return request.param
+
+
 def _upload(ctx, w):
     ctx.date = capi.START_DATE
     ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"])
@@ -120,7 +128,7 @@ def test_paired_refuses_what_it_cannot_do(ctx):
 
 
 @pytest.mark.parametrize("n", [4096, 6000, 16384, 20000])
-def test_paired_most_attracting_links_match_tiled_and_oracle(ctx, n):
+def test_paired_most_attracting_links_match_tiled_and_oracle(ctx, n, layout):
     """Unequal masses: the pair-shared kernel carries the most-attracting candidates as sortable keys
     (src/Object.cpp:84-94: the heavier partner with the largest gf / r^4, lowest index on ties)."""
     w = synth.plummer(n, seed=31)
@@ -158,7 +166,7 @@ def test_paired_most_attracting_links_match_tiled_and_oracle(ctx, n):
 
 
 @pytest.mark.parametrize("track", [False, True])
-def test_paired_coincident_bodies_in_different_blocks(ctx, track):
+def test_paired_coincident_bodies_in_different_blocks(ctx, track, layout):
     """The off-diagonal tiles of the pair-shared kernel run without the r = 0 test; bodies that share a position
     across blocks (incl. a body at the origin next to ragged-block padding, and a masked body on top of a live one)
     are repaired in k_pair_finish: the pair contributes nothing, as on every other path (the reference yields NaN)."""
@@ -218,7 +226,7 @@ def test_paired_coincident_bodies_uniform_masses(ctx):
 
 
 @pytest.mark.parametrize("dt_scale", [1, 40])
-def test_paired_link_thresholds_survive_passes_and_large_moves(ctx, dt_scale):
+def test_paired_link_thresholds_survive_passes_and_large_moves(ctx, dt_scale, layout):
     """The pair-shared kernel filters candidates against thresholds left by the previous pass; a body whose
     most-attracting partner weakened by more than the slack (here: steps 40x too long, bodies move a lot) is
     re-ranked from scratch in k_pair_finish.  Links and max_attraction must stay those of the tiled kernel."""
@@ -286,7 +294,7 @@ def _near_tie_world(n, t, a, b, delta, seed=5):
 @pytest.mark.parametrize("kernel", [capi.KERNEL_PAIRED, capi.KERNEL_TILED])
 @pytest.mark.parametrize("delta", [1e-7, 1e-9, 1e-12, 0.0])
 @pytest.mark.parametrize("order", ["stronger_first", "stronger_last"])
-def test_most_attracting_near_ties_are_decided_as_the_reference_does(ctx, kernel, delta, order):
+def test_most_attracting_near_ties_are_decided_as_the_reference_does(ctx, kernel, delta, order, layout):
     """src/Object.cpp:84-94 decides in full binary64 with a strict '>' in ascending index order.  The pair-shared kernel
     ranks candidates by sortable keys that keep 31 mantissa bits of the metric: two heavier partners within 5e-10 of each
     other (or exactly tied) must be re-decided exactly, wherever in the reduction they meet -- here the three bodies sit
@@ -316,7 +324,7 @@ def test_most_attracting_near_ties_are_decided_as_the_reference_does(ctx, kernel
     assert np.array_equal(ctx.download(("most",))["most"], ost["most"])
 
 
-def test_most_attracting_near_tie_inside_one_block_and_one_warp_visit(ctx):
+def test_most_attracting_near_tie_inside_one_block_and_one_warp_visit(ctx, layout):
     """The same, with target and both partners inside one 32-body subset of one block (the candidates then meet in a
     lane's own running maximum, pair_exact) and in neighbouring subsets."""
     n = 4096
@@ -332,6 +340,73 @@ def test_most_attracting_near_tie_inside_one_block_and_one_warp_visit(ctx):
             ctx.set_forces(kernel=capi.KERNEL_PAIRED, track_most_attracting=True)
             got = ctx.download(("most",))
             assert np.array_equal(got["most"], ost["most"]), (t, a, b, delta, got["most"][t], ost["most"][t])
+
+
+@pytest.mark.parametrize("delta", [1e-7, 1e-9, 1e-12])
+@pytest.mark.parametrize("order", ["stronger_first", "stronger_last"])
+def test_most_attracting_near_ties_across_blocks_of_the_mass_sorted_layout(ctx, layout, delta, order):
+    """Near ties between partners of DIFFERENT masses: in the mass-sorted layout the target, the lighter partner and the
+    heavier partner land in different blocks (2,500 distant bodies of an intermediate mass lie between the two partners in
+    mass order), so the two candidates meet in the slot / chunk merges of k_pair_finish.  The oracle decides."""
+    n = 6144
+    rng = np.random.default_rng(77)
+    w = synth.plummer(n, seed=9)
+    x, y, z = w["x"] + 1e13, w["y"].copy(), w["z"].copy()
+    mass = 1e20 * rng.uniform(1.0, 2.0, n)
+    far = rng.choice(np.arange(200, n), 2500, replace=False)
+    mass[far] = 2e26  # heavier than partner a, lighter than partner b, ten thousand times farther away
+    free = np.setdiff1d(np.arange(200, n), far)
+    t, a, b = 100, int(free[10]), int(free[-10])
+    if order == "stronger_last":
+        a, b = b, a
+    d = 1.0e9
+    x[t], y[t], z[t] = 0.0, 0.0, 0.0
+    x[a], y[a], z[a] = d, 0.0, 0.0                                      # mass 1e26 at d: the stronger one by `delta`
+    x[b], y[b], z[b] = 0.0, d * np.sqrt(2.0) * (1.0 + delta / 4.0), 0.0  # mass 4e26 at sqrt(2) d (1 + delta / 4)
+    mass[a], mass[b] = 1e26, 4e26
+    ow = oracle.World()
+    ow.add_bodies(x, y, z, np.zeros(n), np.zeros(n), np.zeros(n), mass)
+    ow.set_forces()
+    ost = ow.state()
+    assert int(ost["most"][t]) in (a, b)
+    ctx.date = capi.START_DATE
+    ctx.upload(x, y, z, np.zeros(n), np.zeros(n), np.zeros(n), ost["gf"], most=np.full(n, -1, dtype=np.int32))
+    for _ in range(2):  # the second pass runs against the thresholds the first one left
+        ctx.set_forces(kernel=capi.KERNEL_PAIRED, track_most_attracting=True)
+        got = ctx.download(("most", "max_attraction"))
+        assert np.array_equal(got["most"], ost["most"])
+        assert np.allclose(got["max_attraction"], ost["maxattr"], rtol=1e-11, atol=0.0)
+
+
+def test_mass_sorted_layout_with_mass_classes_and_massless_bodies(ctx, layout):
+    """Worlds of a few mass classes (whole tiles of one class run without a filter), massless test particles and a ragged block: every link and
+    every acceleration as the tiled kernel and the oracle's rule give them; the layout follows a change of the masses and of
+    the active mask (a body created later joins, another upload with other masses)."""
+    n = 7000
+    w = synth.plummer(n, seed=21)
+    rng = np.random.default_rng(22)
+    gf = w["gf"] * rng.choice([1.0, 1.0, 1.0, 3.0, 10.0], n)
+    gf[rng.choice(n, 30, replace=False)] = 0.0
+    t0 = capi.START_DATE
+    dt = synth.default_dt(n)
+    cdate = np.full(n, t0, dtype=np.int64)
+    late = rng.choice(n, 25, replace=False)
+    cdate[late] = t0 + 2 * dt  # these join after two steps: the mask flips, the layout is sorted again
+    for round_ in range(2):
+        got = {}
+        for kern in (capi.KERNEL_TILED, capi.KERNEL_PAIRED):
+            ctx.date = t0
+            ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], gf, creation_date=cdate, most=np.full(n, -1, dtype=np.int32))
+            ctx.step(4, dt, kernel=kern, track_most_attracting=True)
+            got[kern] = ctx.download()
+        t, p = got[capi.KERNEL_TILED], got[capi.KERNEL_PAIRED]
+        assert np.array_equal(t["most"], p["most"])
+        assert (p["most"][late] >= 0).sum() >= 20  # the late bodies take part by now
+        for k in ("x", "y", "z", "vx", "vy", "vz"):
+            assert np.allclose(p[k], t[k], rtol=1e-10, atol=0.0), k
+        m_t, m_p = t["max_attraction"], p["max_attraction"]
+        assert np.all(np.abs(m_p - m_t) <= 1e-11 * np.abs(m_t))
+        gf = gf * rng.uniform(0.5, 2.0, n)  # second round: every mass different, another order
 
 
 @pytest.mark.parametrize("budget_mb", ["1", "4", None])
