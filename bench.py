@@ -355,6 +355,7 @@ def side_config(capi, synth, local_rank, rank, world_size, uid_fn, barrier, max_
         ms += ctx.last_step_ms
         fms += ctx.last_force_ms
         fp += ctx.last_force_passes
+    phases = ctx.last_pass_phases
     barrier()
     ms = max_over_ranks(ms)
     fms = max_over_ranks(fms)
@@ -368,7 +369,9 @@ def side_config(capi, synth, local_rank, rank, world_size, uid_fn, barrier, max_
     ipi = (9.0 if uniform else 10.0) if paired else 16.0
     tfl = (n // world_size) * float(n - 1) * FLOPS_PER_INTERACTION / (fms / max(1, fp) * 1e-3) / 1e12
     return {"n": n, "value": value, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "n_gpus": world_size,
-            "masses": "spread over a factor 4, most-attracting links tracked with candidate keys" if unequal else "equal",
+            "masses": ("spread over a factor 4, most-attracting links tracked with candidate keys on the %s" % (
+                "mass-sorted layout" if world_size == 1 else "caller's order (sharded ranks own ranges of original indices)")) if unequal else "equal",
+            "last_pass_phases_rank0": phases,
             "roofline_frac_20flop": tfl / peak if peak else None, "fp64_instructions_per_interaction": ipi,
             "fp64_pipe_frac": tfl / peak * (2.0 * ipi / FLOPS_PER_INTERACTION) if peak else None, "parity": par}
 
@@ -439,6 +442,7 @@ def run_ours(args):
         force_ms += ctx.last_force_ms
         force_passes += ctx.last_force_passes
         breakdown = ctx.last_step_breakdown
+        breakdown["pass_phases"] = ctx.last_pass_phases  # where the last force pass spent its time (sharded: the timeline of one rank)
     barrier()
     t_wall1 = time.time()
     launches = ctx.launches - launches0 - args.steps  # the L2 flush is a memset, not a kernel of ours... count kernels only

@@ -19,7 +19,7 @@ RESIDENT_MAX = 1024
 ENSEMBLE_MAX = 320
 NCCL_ID_BYTES = 128
 
-KERNEL_AUTO, KERNEL_TILED, KERNEL_RESIDENT, KERNEL_PAIRED = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_TILED, KERNEL_RESIDENT, KERNEL_PAIRED, KERNEL_GRID = 0, 1, 2, 3, 4
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -74,6 +74,7 @@ SYMBOLS = [
     ("essa_interaction_count", C.c_double, [_P]),
     ("essa_last_step_ms", C.c_double, [_P]),
     ("essa_last_force_ms", C.c_double, [_P]),
+    ("essa_last_pass_phases", C.c_int, [_P, C.POINTER(C.c_double)]),
     ("essa_last_force_passes", C.c_int, [_P]),
     ("essa_last_step_breakdown", C.c_int, [_P, _dp]),
     ("essa_sync", C.c_int, [_P]),
@@ -406,6 +407,13 @@ class Context:
     @property
     def last_force_passes(self):
         return self._L.essa_last_force_passes(self._h)
+
+    @property
+    def last_pass_phases(self):
+        """ms of the last pair-shared force pass that was timed by itself: before the kernel, kernel, exchange, finish."""
+        out = np.zeros(4)
+        self._L.essa_last_pass_phases(self._h, _ptr(out, _dp))
+        return dict(zip(("before_kernel_ms", "pair_kernel_ms", "exchange_ms", "finish_ms"), out.tolist()))
 
     @property
     def last_step_breakdown(self):

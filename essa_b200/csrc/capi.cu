@@ -506,6 +506,7 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     cudaFree(c->pair_perm);
     cudaFree(c->pair_pos_s);
     cudaFree(c->pair_sort_tmp);
+    cudaFree(c->grid_bar);
     cudaFree(c->pair_kall);
     cudaFree(c->part);
     cudaFree(c->part_m);
@@ -523,7 +524,7 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     cudaFree(c->l2_scratch);
     if (c->pinned)
         cudaFreeHost(c->pinned);
-    cudaEvent_t evs[] = { c->ev_begin, c->ev_end, c->ev_f0, c->ev_f1, c->ev_gather, c->ev_ready };
+    cudaEvent_t evs[] = { c->ev_begin, c->ev_end, c->ev_f0, c->ev_f1, c->ev_gather, c->ev_ready, c->ev_phase[0], c->ev_phase[1], c->ev_phase[2] };
     for (auto ev : evs)
         if (ev)
             cudaEventDestroy(ev);
@@ -564,6 +565,14 @@ extern "C" int essa_last_step_breakdown(const essa_ctx* c, double out[4]) {
     out[1] = c->last_force_ms;
     out[2] = c->last_pre_ms;
     out[3] = c->last_post_ms;
+    return ESSA_OK;
+}
+extern "C" int essa_last_pass_phases(const essa_ctx* c, double out[4]) {
+    if (!c || !out)
+        return ESSA_ERR_ARG;
+    settle_timing(c);
+    for (int i = 0; i < 4; i++)
+        out[i] = c->last_phase_ms[i];
     return ESSA_OK;
 }
 extern "C" int essa_body_count(const essa_ctx* c) { return c ? c->n : 0; }
@@ -1167,7 +1176,16 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
             if (prc != ESSA_OK)
                 return prc;
         }
+        bool const phases = e0 != nullptr; // a pass timed by itself: also where its time goes
+        if (phases) {
+            for (auto& pe : ctx->ev_phase)
+                if (!pe)
+                    CK(cudaEventCreate(&pe));
+            CK(cudaEventRecord(ctx->ev_phase[0], ctx->stream));
+        }
         CK(launch_force_paired_compute(ctx, eps2, ctx->stream, &acc, &npad, keys, &kacc));
+        if (phases)
+            CK(cudaEventRecord(ctx->ev_phase[1], ctx->stream));
         if (ctx->world > 1 && ctx->pair_peer_ok) {
             // the J-side partials went straight into their owners' slot buffers: wait until every rank's kernel is through
             int brc = shard_barrier(ctx);
@@ -1198,6 +1216,12 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
                 }
             }
             NK(nccl().GroupEnd());
+        }
+        if (phases) {
+            CK(cudaEventRecord(ctx->ev_phase[2], ctx->stream));
+            ctx->ev_phase_first = e0;
+            ctx->ev_phase_last = e1;
+            ctx->phases_recorded = true;
         }
         CK(launch_force_paired_finish(ctx, k, ctx->stream, acc, argmax && !keys, save_old, keys,
             keys && ctx->world > 1 && !ctx->pair_peer_ok ? ctx->pair_kall : nullptr, eps2));
@@ -1233,10 +1257,49 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
 
 constexpr int kPairedAutoMin = 12288; // AUTO takes the pair-shared kernel above this many bodies
 
+// K1g: a mid-size world's whole call in one cooperative launch (force_grid.cu).
+static int step_grid(essa_ctx* ctx, int steps, essa_step_opts const& o) {
+    int const K = std::abs(steps);
+    bool const argmax = o.track_most_attracting != 0;
+    bool const first_pass = !ctx->acc_valid || (argmax && !ctx->acc_has_most);
+    cudaEvent_t e0 = force_event(ctx, 0), e1 = force_event(ctx, 1);
+    if (!e0 || !e1) {
+        ctx->err = "cudaEventCreate failed";
+        return ESSA_ERR_CUDA;
+    }
+    if (!o.forward_simulated)
+        ctx->date += (int64_t)steps * o.dt_seconds; // no creation / deletion instant lies in between (the caller checked)
+    CK(cudaEventRecord(e0, ctx->stream));
+    CK(launch_force_grid(ctx, steps, o, first_pass, argmax, ctx->stream));
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->cur ^= K & 1;
+    ctx->acc_valid = true;
+    ctx->acc_has_most = argmax;
+    ctx->acc_exact = false;
+    int const passes = K + (first_pass ? 1 : 0);
+    ctx->passes += passes;
+    ctx->interactions += (double)passes * (double)ctx->n * (double)(ctx->n - 1);
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ctx->last_force_ms = ms;
+    ctx->last_force_passes = passes;
+    ctx->last_pre_ms = ctx->last_post_ms = 0;
+    return ESSA_OK;
+}
+
 static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool forces_only) {
     int const K = forces_only ? 0 : std::abs(steps);
     double const mul = steps >= 0 ? 1.0 : -1.0;
     bool const argmax = o.track_most_attracting || o.record;
+    if ((o.kernel == ESSA_KERNEL_AUTO || o.kernel == ESSA_KERNEL_GRID) && force_grid_applicable(ctx, o, forces_only)
+        && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds)))
+        return step_grid(ctx, steps, o);
+    if (o.kernel == ESSA_KERNEL_GRID) {
+        ctx->err = "grid kernel: 1,025 .. 5,120 bodies, unsharded, no recording, no two_pass, no creation / deletion instant inside the call";
+        return ESSA_ERR_ARG;
+    }
     {
         // pair-shared kernel: slots must fit comfortably.  Most-attracting tracking rides along as sortable candidate
         // keys (worlds of up to 2^21 bodies), or costs nothing where it is provably a no-op (all gravity factors
@@ -1358,6 +1421,14 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
         total += ms;
     }
     ctx->last_force_ms = total;
+    if (ctx->phases_recorded) {
+        cudaEvent_t const seq[5] = { ctx->ev_phase_first, ctx->ev_phase[0], ctx->ev_phase[1], ctx->ev_phase[2], ctx->ev_phase_last };
+        for (int i = 0; i < 4; i++) {
+            CK(cudaEventElapsedTime(&ms, seq[i], seq[i + 1]));
+            ctx->last_phase_ms[i] = ms;
+        }
+        ctx->phases_recorded = false;
+    }
     ctx->last_force_passes = span ? span_passes : (int)(ev / 2);
     ctx->last_pre_ms = ctx->last_post_ms = 0;
     if (ev >= 2) {
@@ -1380,6 +1451,7 @@ static int resident_finish(essa_ctx* ctx, int steps, essa_step_opts const& o, bo
 }
 
 constexpr int kResidentAutoMax = 320;
+constexpr int kGridAutoMin = 400; // AUTO prefers K1g to the resident cluster kernels from here on (calls without recording)
 
 static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, bool forces_only, bool async = false) {
     ARG(ctx, "ctx is null");
@@ -1428,8 +1500,13 @@ static int step_common(essa_ctx* ctx, int steps, const essa_step_opts* opts, boo
     bool const needs_resident = o.exact_order || (o.forward_simulated && ctx->closest && ctx->closest_n == ctx->n);
     bool const wide_ok = ctx->world == 1 && ctx->n > kResidentAutoMax && resident_cluster_wide_applicable(ctx, o, forces_only)
         && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds));
+    // ... except plain calls (no recording) on 400 .. 1,024 bodies: K1g spreads them over ALL SMs with one grid barrier per
+    // step (force_grid.cu; measured on B200, us per step, K1g vs K3xw: 384 bodies 3.3 vs 3.9, 512: 3.2 vs 6.1, 1,024: 4.2 vs
+    // 14.9; with most-attracting links 5.0 vs 4.9, 4.9 vs 6.8, 6.2 vs 18.8; below that the 16-SM cluster is ahead: 256: 2.9 vs 2.4)
+    bool const grid_better = o.kernel == ESSA_KERNEL_AUTO && ctx->n >= kGridAutoMin && !needs_resident && force_grid_applicable(ctx, o, forces_only)
+        && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds));
     bool resident = o.kernel == ESSA_KERNEL_RESIDENT
-        || (o.kernel == ESSA_KERNEL_AUTO && ctx->n <= ESSA_RESIDENT_MAX && (ctx->n <= kResidentAutoMax || needs_resident || wide_ok));
+        || (o.kernel == ESSA_KERNEL_AUTO && ctx->n <= ESSA_RESIDENT_MAX && !grid_better && (ctx->n <= kResidentAutoMax || needs_resident || wide_ok));
     if (ctx->world > 1)
         resident = false;
     if (resident && ctx->n > ESSA_RESIDENT_MAX) {

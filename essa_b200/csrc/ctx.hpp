@@ -17,6 +17,7 @@ constexpr int kChunkQ = 32;       // K1's j-chunks are cut at multiples of this 
 constexpr int kStages = 4;        // bulk-copy pipeline depth
 constexpr int kForceThreads = 256;
 constexpr int kEnsembleMaxBodies = 320; // widest template one ensemble CTA takes
+constexpr int kGridMaxBodies = 5120;     // K1g (force_grid.cu): every SM holds all positions in shared memory
 constexpr int kEnsembleSoloMax = 16;    // templates up to this size run one thread per copy (ensemble.cu k_ensemble_solo)
 
 // Arguments of the fused kick / drift epilogue (src/World.cpp:106-116,121-127).
@@ -194,6 +195,11 @@ struct essa_ctx {
     void* pair_sort_tmp = nullptr;
     size_t pair_sort_tmp_bytes = 0;
     bool pair_sorted_pass = false; // the pass in flight (compute + finish) works in the sorted domain
+    // K1g (force_grid.cu): grid-barrier counter {arrivals, timeout flag} and the host's copy of the arrivals so far
+    unsigned* grid_bar = nullptr;
+    unsigned grid_bar_count = 0;
+    bool attr_grid[2] = { false, false };
+    size_t grid_smem[2] = { 0, 0 };
 
     // recording
     int tracked = 0;
@@ -266,6 +272,13 @@ struct essa_ctx {
     double interactions = 0;
     double last_step_ms = 0;
     double last_force_ms = 0;
+    // phases of the LAST pair-shared force pass that was timed by itself: before the kernel (waits on the position gather, the
+    // threshold broadcast, the sort / gather of the mass-sorted layout), the pair kernel, the exchange after it (sharded: the
+    // one-word barrier, or the NCCL reduce-scatter fallback), k_pair_finish
+    cudaEvent_t ev_phase[3] = { nullptr, nullptr, nullptr };
+    cudaEvent_t ev_phase_first = nullptr, ev_phase_last = nullptr; // the pass's own e0 / e1 (owned by force_events)
+    bool phases_recorded = false;
+    double last_phase_ms[4] = { 0, 0, 0, 0 };
     double last_pre_ms = 0, last_post_ms = 0; // before the first / after the last force pass of the last essa_step
     std::string err;
 
@@ -296,6 +309,8 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
     unsigned long long** kacc_out);
 cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStream_t st, double const* ajred, bool argmax_noop, bool save_old,
     bool argmax, unsigned long long const* akred, double eps2);
+bool force_grid_applicable(essa_ctx const* c, essa_step_opts const& o, bool forces_only);
+cudaError_t launch_force_grid(essa_ctx* c, int steps, essa_step_opts const& o, bool first_pass, bool argmax, cudaStream_t st);
 int force_iblocks(essa_ctx const* c, int* R_out);
 void choose_split(essa_ctx const* c, int iblocks, int nquanta, int* S_out);
 

@@ -66,10 +66,11 @@ typedef enum essa_status {
 
 /* Which kernel essa_step runs. */
 typedef enum essa_kernel {
-    ESSA_KERNEL_AUTO = 0,     /* N <= ESSA_RESIDENT_MAX: resident; N > 12288: paired (tracking: up to 2^21 bodies); else tiled */
+    ESSA_KERNEL_AUTO = 0,     /* N <= ESSA_RESIDENT_MAX: resident; N <= 5120: grid (else tiled: recording, two_pass); N > 12288: paired (tracking: up to 2^21 bodies); else tiled */
     ESSA_KERNEL_TILED = 1,    /* K1: j-tiled FP64 force pass + fused kick/drift (any N) */
     ESSA_KERNEL_RESIDENT = 2, /* K3: one CTA keeps the world in shared memory for all steps */
-    ESSA_KERNEL_PAIRED = 3    /* K1p: pair-shared force pass (each unordered pair once, both bodies updated) */
+    ESSA_KERNEL_PAIRED = 3,   /* K1p: pair-shared force pass (each unordered pair once, both bodies updated) */
+    ESSA_KERNEL_GRID = 4      /* K1g: 1,025 .. 5,120 bodies, all steps of a call in one cooperative launch over all SMs */
 } essa_kernel;
 
 /* SoA view of the per-Object state (src/Object.hpp:152-191).  A null member is skipped.
@@ -121,6 +122,11 @@ double essa_last_force_ms(const essa_ctx* ctx);
 int essa_last_force_passes(const essa_ctx* ctx);
 /* out = {step ms, force-pass ms, ms before the first force pass, ms after the last} of the last essa_step. */
 int essa_last_step_breakdown(const essa_ctx* ctx, double out[4]);
+/* Phases of the last pair-shared force pass that was timed by itself (a single-step essa_step / essa_set_forces), in ms:
+ * out = {before the kernel: position gather wait, threshold exchange, mass sort; the pair kernel; the exchange behind it
+ * (sharded worlds: the barrier after the peer stores, or the NCCL reduce-scatter fallback); k_pair_finish}.
+ * New diagnostic (no reference counterpart): the per-kernel timeline of a sharded pass for bench.py. */
+int essa_last_pass_phases(const essa_ctx* ctx, double out[4]);
 int essa_sync(essa_ctx* ctx);
 
 /* ---- world state --------------------------------------------------------------------------- */
