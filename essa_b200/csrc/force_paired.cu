@@ -579,16 +579,36 @@ struct PairFinishArgs {
 template<int kPB>
 __device__ __forceinline__ void slot_sum_owner(int g, int nb, int dmax, int ib0, double const* slots, double& ax, double& ay, double& az) {
     int const K = g / kPB, jl = g - K * kPB;
-    for (int d = 1; d <= dmax; d++) {
-        int I = K - d;
-        if (I < 0)
-            I += nb;
-        if ((nb & 1) == 0 && d == nb / 2 && I >= nb / 2)
-            continue; // that tile belongs to the other half of the ring
-        double const* s = slots + ((size_t)(K - ib0) * dmax + (d - 1)) * 3 * kPB + jl;
-        ax = __dadd_rn(ax, __ldcg(s));
-        ay = __dadd_rn(ay, __ldcg(s + kPB));
-        az = __dadd_rn(az, __ldcg(s + 2 * kPB));
+    // eight offsets' loads in flight at a time (the additions stay in ascending d): one thread walks up to nb / 2 slots, and a
+    // load per addition made k_pair_finish latency-bound (10.7 us for 16,384 bodies, 7.7 ms with keys at 1,048,576)
+    for (int d0 = 1; d0 <= dmax; d0 += 8) {
+        double vx[8], vy[8], vz[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            int const d = d0 + u;
+            int I = K - d;
+            if (I < 0)
+                I += nb;
+            // d == nb / 2 of an even ring: that tile belongs to the other half of the ring
+            bool const on = d <= dmax && !((nb & 1) == 0 && d == nb / 2 && I >= nb / 2);
+            double const* s = slots + ((size_t)(K - ib0) * dmax + (d - 1)) * 3 * kPB + jl;
+            vx[u] = on ? __ldcg(s) : 0.0;
+            vy[u] = on ? __ldcg(s + kPB) : 0.0;
+            vz[u] = on ? __ldcg(s + 2 * kPB) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            int const d = d0 + u;
+            int I = K - d;
+            if (I < 0)
+                I += nb;
+            bool const on = d <= dmax && !((nb & 1) == 0 && d == nb / 2 && I >= nb / 2);
+            if (on) { // a skipped slot adds nothing, not +0.0 (-0.0 + 0.0 would flip a sign bit)
+                ax = __dadd_rn(ax, vx[u]);
+                ay = __dadd_rn(ay, vy[u]);
+                az = __dadd_rn(az, vz[u]);
+            }
+        }
     }
 }
 template<int kPB>
@@ -596,13 +616,20 @@ __device__ __forceinline__ unsigned long long slot_key_owner(int s, int g, int n
     double4 const* __restrict__ pos, double eps2) {
     int const K = s / kPB, jl = s - K * kPB; // s: where the body's slots are (its place in the pass's layout); g: its index
     unsigned long long k = 0ull;
-    for (int d = 1; d <= dmax; d++) {
-        int I = K - d;
-        if (I < 0)
-            I += nb;
-        if ((nb & 1) == 0 && d == nb / 2 && I >= nb / 2)
-            continue;
-        k = key_merge(pos, g, k, __ldcg(slots_k + ((size_t)(K - ib0) * dmax + (d - 1)) * kPB + jl), eps2);
+    for (int d0 = 1; d0 <= dmax; d0 += 8) {
+        unsigned long long v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            int const d = d0 + u;
+            int I = K - d;
+            if (I < 0)
+                I += nb;
+            bool const on = d <= dmax && !((nb & 1) == 0 && d == nb / 2 && I >= nb / 2);
+            v[u] = on ? __ldcg(slots_k + ((size_t)(K - ib0) * dmax + (d - 1)) * kPB + jl) : 0ull; // 0 = no candidate
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            k = key_merge(pos, g, k, v[u], eps2);
     }
     return k;
 }
@@ -740,7 +767,7 @@ __device__ __noinline__ void pair_repair_body(double4 const* __restrict__ pos, i
 }
 
 template<int kPB>
-__global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) {
+__global__ void __launch_bounds__(256, 2) k_pair_finish(PairFinishArgs const A) {
     __shared__ double red[4][256];
     __shared__ int redj[256];
     __shared__ unsigned char sbad[256];
@@ -760,11 +787,23 @@ __global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) 
     bool act = false;
     double4 p = make_double4(0, 0, 0, 0);
     if (in) {
-        for (int c = 0; c < A.S; c++) {
-            double const* q = A.part_i + (size_t)c * 3 * A.npad + s;
-            ax = __dadd_rn(ax, __ldcg(q));
-            ay = __dadd_rn(ay, __ldcg(q + A.npad));
-            az = __dadd_rn(az, __ldcg(q + 2 * (size_t)A.npad));
+        for (int c0 = 0; c0 < A.S; c0 += 8) { // eight chunks' loads in flight, additions in ascending chunk order
+            double vx[8], vy[8], vz[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                double const* q = A.part_i + (size_t)(c0 + u) * 3 * A.npad + s;
+                bool const on = c0 + u < A.S;
+                vx[u] = on ? __ldcg(q) : 0.0;
+                vy[u] = on ? __ldcg(q + A.npad) : 0.0;
+                vz[u] = on ? __ldcg(q + 2 * (size_t)A.npad) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (c0 + u < A.S) {
+                    ax = __dadd_rn(ax, vx[u]);
+                    ay = __dadd_rn(ay, vy[u]);
+                    az = __dadd_rn(az, vz[u]);
+                }
         }
         if (A.ajred) {
             ax = __dadd_rn(ax, __ldcg(A.ajred + s));
