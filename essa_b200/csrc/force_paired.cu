@@ -103,12 +103,15 @@ __device__ __forceinline__ unsigned long long key_merge(double4 const* __restric
 // halo bodies, so the weakest of eight passes nearly everything).
 constexpr unsigned kKeyMargin = 114688u; // > 0.0861 * 1.25 * 2^20 = 112,853, + slack for the truncations
 // Thresholds survive from one force pass to the next ("priors"): k_pair_finish leaves, for every body, the threshold
-// of its winning key lowered by kPriorSlack (a factor 2 in the metric: bodies move little in a step), and the next
+// of its winning key lowered by kPriorSlack (a factor 4 in the metric, 41 % in distance: bodies move little in a step), and the next
 // pass starts every filter there instead of at "anything goes" -- otherwise each CTA (I side) and each visit of a
 // 32-body subset (J side) would spend its first rotations in the cold block re-discovering the running maximum.
 // k_pair_finish accepts a winner only if  key_thr(winner) > prior  (then every better partner was above the prior
 // too and has been seen); otherwise that body is re-ranked from scratch by the repair path.
-constexpr unsigned kPriorSlack = 1u << 18;
+// Measured at 1,048,576 bodies (ms per pass: pair kernel + k_pair_finish with its re-ranks): slack 2^18 (a factor 2) 740.9 + 21.1,
+// 2^19 741.5 + 6.2, 2^20 744.2 + 4.8 -- a looser filter costs a few more re-walked rotations, a tighter one re-ranks (0.1 ms per
+// body) every body whose partner came 19 % closer or farther within one step.  ESSA_PAIR_PRIOR_SLACK_LOG2 overrides (diagnostics).
+constexpr unsigned kPriorSlack = 1u << 19;
 constexpr unsigned kPriorNone = 0x3FF00000u - kKeyMargin + 1u; // = key_thr(0): every real candidate passes
 constexpr unsigned kPriorNever = 0xFFFFFFFFu;              // padding and masked bodies: nothing passes
 __device__ __forceinline__ unsigned key_lg(double gf) { return (unsigned)__double2hiint(gf) >> 2; }
@@ -569,6 +572,7 @@ struct PairFinishArgs {
     int argmax_noop;     // most-attracting tracking requested on a world of equal gravity factors: clear_forces only
     int save_old;        // ... and Object::before_update's old_most = most
     unsigned* prior;     // ARGMAX: [npad] filter thresholds, read (what the pass used) and rewritten (for the next pass)
+    unsigned prior_slack; // how far below the winner's threshold the next pass starts its filter (kPriorSlack)
     int const* perm;     // mass-sorted pass: thread s handles body perm[s] (-1: padding); partials, slots, priors are indexed by s
     double scale;        // UNIFORM worlds: the common gravity factor the sums still lack; otherwise 1
     double eps2;         // softening, for the repair of bodies that met an r = 0 pair in an unguarded tile
@@ -579,36 +583,16 @@ struct PairFinishArgs {
 template<int kPB>
 __device__ __forceinline__ void slot_sum_owner(int g, int nb, int dmax, int ib0, double const* slots, double& ax, double& ay, double& az) {
     int const K = g / kPB, jl = g - K * kPB;
-    // eight offsets' loads in flight at a time (the additions stay in ascending d): one thread walks up to nb / 2 slots, and a
-    // load per addition made k_pair_finish latency-bound (10.7 us for 16,384 bodies, 7.7 ms with keys at 1,048,576)
-    for (int d0 = 1; d0 <= dmax; d0 += 8) {
-        double vx[8], vy[8], vz[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            int const d = d0 + u;
-            int I = K - d;
-            if (I < 0)
-                I += nb;
-            // d == nb / 2 of an even ring: that tile belongs to the other half of the ring
-            bool const on = d <= dmax && !((nb & 1) == 0 && d == nb / 2 && I >= nb / 2);
-            double const* s = slots + ((size_t)(K - ib0) * dmax + (d - 1)) * 3 * kPB + jl;
-            vx[u] = on ? __ldcg(s) : 0.0;
-            vy[u] = on ? __ldcg(s + kPB) : 0.0;
-            vz[u] = on ? __ldcg(s + 2 * kPB) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            int const d = d0 + u;
-            int I = K - d;
-            if (I < 0)
-                I += nb;
-            bool const on = d <= dmax && !((nb & 1) == 0 && d == nb / 2 && I >= nb / 2);
-            if (on) { // a skipped slot adds nothing, not +0.0 (-0.0 + 0.0 would flip a sign bit)
-                ax = __dadd_rn(ax, vx[u]);
-                ay = __dadd_rn(ay, vy[u]);
-                az = __dadd_rn(az, vz[u]);
-            }
-        }
+    for (int d = 1; d <= dmax; d++) {
+        int I = K - d;
+        if (I < 0)
+            I += nb;
+        if ((nb & 1) == 0 && d == nb / 2 && I >= nb / 2)
+            continue; // that tile belongs to the other half of the ring
+        double const* s = slots + ((size_t)(K - ib0) * dmax + (d - 1)) * 3 * kPB + jl;
+        ax = __dadd_rn(ax, __ldcg(s));
+        ay = __dadd_rn(ay, __ldcg(s + kPB));
+        az = __dadd_rn(az, __ldcg(s + 2 * kPB));
     }
 }
 template<int kPB>
@@ -616,20 +600,13 @@ __device__ __forceinline__ unsigned long long slot_key_owner(int s, int g, int n
     double4 const* __restrict__ pos, double eps2) {
     int const K = s / kPB, jl = s - K * kPB; // s: where the body's slots are (its place in the pass's layout); g: its index
     unsigned long long k = 0ull;
-    for (int d0 = 1; d0 <= dmax; d0 += 8) {
-        unsigned long long v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            int const d = d0 + u;
-            int I = K - d;
-            if (I < 0)
-                I += nb;
-            bool const on = d <= dmax && !((nb & 1) == 0 && d == nb / 2 && I >= nb / 2);
-            v[u] = on ? __ldcg(slots_k + ((size_t)(K - ib0) * dmax + (d - 1)) * kPB + jl) : 0ull; // 0 = no candidate
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++)
-            k = key_merge(pos, g, k, v[u], eps2);
+    for (int d = 1; d <= dmax; d++) {
+        int I = K - d;
+        if (I < 0)
+            I += nb;
+        if ((nb & 1) == 0 && d == nb / 2 && I >= nb / 2)
+            continue;
+        k = key_merge(pos, g, k, __ldcg(slots_k + ((size_t)(K - ib0) * dmax + (d - 1)) * kPB + jl), eps2);
     }
     return k;
 }
@@ -767,7 +744,7 @@ __device__ __noinline__ void pair_repair_body(double4 const* __restrict__ pos, i
 }
 
 template<int kPB>
-__global__ void __launch_bounds__(256, 2) k_pair_finish(PairFinishArgs const A) {
+__global__ void __launch_bounds__(256, 4) k_pair_finish(PairFinishArgs const A) {
     __shared__ double red[4][256];
     __shared__ int redj[256];
     __shared__ unsigned char sbad[256];
@@ -787,23 +764,11 @@ __global__ void __launch_bounds__(256, 2) k_pair_finish(PairFinishArgs const A) 
     bool act = false;
     double4 p = make_double4(0, 0, 0, 0);
     if (in) {
-        for (int c0 = 0; c0 < A.S; c0 += 8) { // eight chunks' loads in flight, additions in ascending chunk order
-            double vx[8], vy[8], vz[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                double const* q = A.part_i + (size_t)(c0 + u) * 3 * A.npad + s;
-                bool const on = c0 + u < A.S;
-                vx[u] = on ? __ldcg(q) : 0.0;
-                vy[u] = on ? __ldcg(q + A.npad) : 0.0;
-                vz[u] = on ? __ldcg(q + 2 * (size_t)A.npad) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++)
-                if (c0 + u < A.S) {
-                    ax = __dadd_rn(ax, vx[u]);
-                    ay = __dadd_rn(ay, vy[u]);
-                    az = __dadd_rn(az, vz[u]);
-                }
+        for (int c = 0; c < A.S; c++) {
+            double const* q = A.part_i + (size_t)c * 3 * A.npad + s;
+            ax = __dadd_rn(ax, __ldcg(q));
+            ay = __dadd_rn(ay, __ldcg(q + A.npad));
+            az = __dadd_rn(az, __ldcg(q + 2 * (size_t)A.npad));
         }
         if (A.ajred) {
             ax = __dadd_rn(ax, __ldcg(A.ajred + s));
@@ -860,7 +825,7 @@ __global__ void __launch_bounds__(256, 2) k_pair_finish(PairFinishArgs const A) 
     if (!in)
         return;
     if (A.argmax) // where the next pass starts its filters
-        A.prior[s] = !act ? kPriorNever : (key != 0ull ? key_thr(key) - kPriorSlack : kPriorNone);
+        A.prior[s] = !act ? kPriorNever : (key != 0ull ? key_thr(key) - A.prior_slack : kPriorNone);
     // ---- epilogue: identical to force_tiled.cu finish_body ----
     double vx = 0, vy = 0, vz = 0;
     if ((A.argmax_noop || A.argmax) && A.save_old)
@@ -1366,6 +1331,9 @@ cudaError_t launch_force_paired_finish(essa_ctx* c, KickArgs const& k, cudaStrea
     F.slots = c->pair_slots;
     F.ajred = ajred;
     F.perm = nullptr;
+    F.prior_slack = kPriorSlack;
+    if (char const* e = getenv("ESSA_PAIR_PRIOR_SLACK_LOG2")) // diagnostics: 18 = a factor 2 in the metric
+        F.prior_slack = 1u << atoi(e);
     if (argmax && c->pair_sorted_pass) { // one thread per slot of the sorted layout (padding included: it returns at once)
         F.perm = c->pair_perm;
         F.i0 = 0;

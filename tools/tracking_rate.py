@@ -27,4 +27,6 @@ for label, gf in (("equal masses", w["gf"]), ("unequal masses", w["gf"] * np.ran
         ms = c.last_step_ms / 3
         rate = n * (n - 1) / (ms * 1e-3)
         print("%-15s tracking=%d  %.3e interactions/s  %.2f ms/step  %.1f %% of FP64 peak" % (label, track, rate, ms, 100 * rate * 20 / (peak * 1e12)), flush=True)
+        c.step(1, dt, track_most_attracting=track)
+        print("    phases of one pass (ms): %s" % {k: round(v, 3) for k, v in c.last_pass_phases.items()}, flush=True)
 c.close()
