@@ -112,3 +112,84 @@ def test_the_filter_rejects_what_is_clearly_weaker():
     k_b = pack_key(m_b, np.zeros(n, dtype=np.int64))
     a_c = key_lg(gf_c) + hi(y_c)
     assert np.all(a_c < key_thr(k_b))
+
+
+# ---- the mass-sorted layout's filter modes (pair_interact FILT == 2 / 3) ---------------------------------------------
+def _i32(v):
+    """two's-complement wrap to int32, as the kernel's 32-bit registers do"""
+    return ((np.asarray(v, dtype=np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31).astype(np.int64)
+
+
+def _u32(v):
+    return np.asarray(v, dtype=np.int64) % 2 ** 32
+
+
+PRIOR_NEVER = 0xFFFFFFFF
+PRIOR_NONE = 0x3FF00000 - MARGIN + 1
+
+
+def thr_neg(t):
+    return np.where(t == PRIOR_NEVER, 0x80000000, _u32(-t))
+
+
+def test_source_has_the_sorted_filter_this_test_restates():
+    assert "mrun = first ? (unsigned)(ly + (int)thi) : (unsigned)__viaddmax_s32(ly, (int)thi, (int)mrun);" in SRC
+    assert "mrun = first ? ly + lgi : __viaddmax_u32(ly, lgi, mrun);" in SRC
+    assert "prot = (int)mrun >= -(int)lgj;" in SRC and "prot = mrun >= thj;" in SRC
+    assert "return t == kPriorNever ? 0x80000000u : 0u - t;" in SRC
+
+
+def test_sorted_filter_modes_decide_like_the_plain_comparison_and_never_wrap():
+    """Mode 2 keeps MINUS the target's threshold and takes a signed running maximum of L(y0) - thr_i over the eight
+    pairs of a rotation, compared once with -lg_j; mode 3 an unsigned running maximum of L(y0) + lg_i compared with
+    thr_j.  Both must flag a rotation exactly when some pair of it satisfies  lg + L(y0) >= thr  in plain unsigned
+    arithmetic, over the whole range the operands can take (any positive binary64 for y0 and gf, every threshold
+    k_pair_finish can leave, 'nothing passes')."""
+    rng = np.random.default_rng(11)
+    n, R = 40000, 8
+    # y0 over the whole positive range incl. the extremes; gf likewise
+    ly = hi(np.concatenate([10.0 ** rng.uniform(-300, 300, n - 4), [5e-324, 2.2e-308, 1.7e308, np.inf]]))[:, None] \
+        + rng.integers(-3, 4, (n, R))
+    ly = np.clip(ly, 0, 0x7FF00000)
+    lg_j = key_lg(10.0 ** rng.uniform(-300, 300, n))
+    lg_i = key_lg(10.0 ** rng.uniform(-300, 300, (n, R)))
+    # thresholds: key_thr of any key minus the slack, the no-prior value, and 'never'
+    khi = rng.integers(0, 0x7FF00000, (n, R))
+    thr = (khi >> 2) + PRIOR_NONE - SLACK * rng.integers(0, 2, (n, R))
+    thr = np.where(rng.random((n, R)) < 0.05, PRIOR_NEVER, thr)
+    thr = np.where(rng.random((n, R)) < 0.05, PRIOR_NONE, thr)
+    # make a good share of the rotations borderline: y0 within a few units of the threshold
+    border = rng.random((n, R)) < 0.3
+    ly = np.where(border & (thr != PRIOR_NEVER), np.clip(thr - lg_j[:, None] + rng.integers(-2, 3, (n, R)), 0, 0x7FF00000), ly)
+
+    # mode 2: targets can gain a candidate.  plain rule per pair: lg_j + ly >= thr_i (unsigned, no wrap: < 2^32)
+    plain2 = ((lg_j[:, None] + ly) >= thr).any(axis=1)
+    neg = thr_neg(thr)
+    terms = ly + _i32(neg)                      # the kernel's 32-bit signed add
+    assert np.all(np.abs(terms) < 2 ** 31)      # never wraps
+    mrun = terms.max(axis=1)
+    mode2 = mrun >= -lg_j
+    real = (thr != PRIOR_NEVER).all(axis=1)
+    assert np.array_equal(mode2[real], plain2[real])
+    # 'never' targets: cannot flag below y0 = 2^513 (r < 1e-154 m); a spurious flag would only cost a re-walk, a missed one a link
+    assert not np.any(plain2 & ~mode2)
+
+    # mode 3: visitors can gain a candidate.  plain rule per pair: lg_i + ly >= thr_j
+    thr_j = thr[:, 0]
+    plain3 = ((lg_i + ly) >= thr_j[:, None]).any(axis=1)
+    sums = lg_i + ly
+    assert np.all(sums < 2 ** 32)               # the unsigned add never wraps
+    mode3 = sums.max(axis=1) >= thr_j
+    assert np.array_equal(mode3, plain3)
+    assert 0.05 < plain2.mean() < 0.95 and 0.05 < plain3.mean() < 0.95  # both outcomes are exercised
+
+
+def test_sort_key_of_the_mass_sorted_layout_is_monotone_over_the_real_line():
+    """k_pair_sort_keys: the IEEE bit pattern with negative values reversed orders like the values themselves."""
+    assert "keys[g] = (b >> 63) ? ~b : b | 0x8000000000000000ull;" in SRC
+    rng = np.random.default_rng(3)
+    v = np.concatenate([rng.normal(0, 1, 2000) * 10.0 ** rng.uniform(-200, 200, 2000), [0.0, -0.0, 1e-320, -1e-320, np.inf, -np.inf]])
+    b = v.view(np.uint64)
+    key = np.where(b >> np.uint64(63), ~b, b | np.uint64(0x8000000000000000))
+    order = np.argsort(key, kind="stable")
+    assert np.all(np.diff(v[order]) >= 0)
