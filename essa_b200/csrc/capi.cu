@@ -507,6 +507,8 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     cudaFree(c->pair_pos_s);
     cudaFree(c->pair_sort_tmp);
     cudaFree(c->grid_bar);
+    if (c->grid_timed_out)
+        cudaFreeHost(c->grid_timed_out);
     cudaFree(c->pair_kall);
     cudaFree(c->part);
     cudaFree(c->part_m);
@@ -1276,6 +1278,12 @@ static int step_grid(essa_ctx* ctx, int steps, essa_step_opts const& o) {
     CK(cudaEventRecord(e1, ctx->stream));
     CK(cudaEventRecord(ctx->ev_end, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->grid_timed_out && *ctx->grid_timed_out) { // a CTA waited two seconds for the others: the state is not a step's result
+        *ctx->grid_timed_out = 0u;
+        ctx->acc_valid = false;
+        ctx->err = "grid kernel: a grid barrier timed out";
+        return ESSA_ERR_CUDA;
+    }
     ctx->cur ^= K & 1;
     ctx->acc_valid = true;
     ctx->acc_has_most = argmax;

@@ -195,8 +195,9 @@ struct essa_ctx {
     void* pair_sort_tmp = nullptr;
     size_t pair_sort_tmp_bytes = 0;
     bool pair_sorted_pass = false; // the pass in flight (compute + finish) works in the sorted domain
-    // K1g (force_grid.cu): grid-barrier counter {arrivals, timeout flag} and the host's copy of the arrivals so far
+    // K1g (force_grid.cu): grid-barrier arrival counter, its timeout flag and the host's copy of the arrivals so far
     unsigned* grid_bar = nullptr;
+    unsigned* grid_timed_out = nullptr; // mapped pinned host word
     unsigned grid_bar_count = 0;
     bool attr_grid[2] = { false, false };
     size_t grid_smem[2] = { 0, 0 };

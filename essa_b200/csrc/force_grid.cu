@@ -35,11 +35,12 @@ struct GridArgs {
     int first_pass;   // accelerations at the starting positions are not valid: evaluate them first (the step's first set_forces)
     int argmax;
     double h, dt, mul, eps2;
-    unsigned* bar;    // [0] arrivals (monotone over the life of the context), [1] set if a barrier timed out
+    unsigned* bar;    // arrivals (monotone over the life of the context)
+    unsigned* timed_out; // mapped host memory: set if a barrier gave up (the host checks it after the call, for free)
     unsigned bar_base; // value of bar[0] when this launch starts
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, unsigned* timed_out) {
     __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
@@ -50,7 +51,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
             if ((int)(v - target) >= 0)
                 break;
             if (clock64() - t0 > 4000000000ll) { // ~2 s: a CTA of the grid is gone; do not hang the device
-                bar[1] = 1u;
+                *(volatile unsigned*)timed_out = 1u;
                 break;
             }
         }
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_force_grid(GridArgs const A
             }
         }
         bar_target += gridDim.x;
-        grid_barrier(A.bar, bar_target);
+        grid_barrier(A.bar, bar_target, A.timed_out);
         cur ^= 1;
         load_all();
         if (s > 0 || !A.first_pass)
@@ -266,12 +267,21 @@ cudaError_t launch_force_grid(essa_ctx* c, int steps, essa_step_opts const& o, b
     A.mul = steps >= 0 ? 1.0 : -1.0;
     A.eps2 = o.eps2;
     if (!c->grid_bar) {
-        cudaError_t e = cudaMalloc(&c->grid_bar, 2 * sizeof(unsigned));
+        cudaError_t e = cudaMalloc(&c->grid_bar, sizeof(unsigned));
         if (e == cudaSuccess)
-            e = cudaMemsetAsync(c->grid_bar, 0, 2 * sizeof(unsigned), st);
+            e = cudaMemsetAsync(c->grid_bar, 0, sizeof(unsigned), st);
+        if (e == cudaSuccess)
+            e = cudaHostAlloc((void**)&c->grid_timed_out, sizeof(unsigned), cudaHostAllocMapped);
         if (e != cudaSuccess)
             return e;
+        *c->grid_timed_out = 0u;
         c->grid_bar_count = 0;
+    }
+    A.timed_out = nullptr;
+    {
+        cudaError_t e = cudaHostGetDevicePointer((void**)&A.timed_out, c->grid_timed_out, 0);
+        if (e != cudaSuccess)
+            return e;
     }
     int const blocks = (n + A.T - 1) / A.T; // <= G
     A.bar = c->grid_bar;
