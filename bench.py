@@ -299,6 +299,20 @@ def solar_leg():
             c.ensemble_step(esteps)
             out["solar_ensemble_1m_copies_copy_iters_per_s"] = big * esteps / (c.last_step_ms * 1e-3)
         c.close()
+    # mid-size worlds (no BASELINE configuration, but the sizes between the resident kernels and the pair-shared one): us per step of
+    # a 100-step call, one cooperative launch (K1g) vs one launch per step (K1), unequal masses with most-attracting links
+    from essa_b200 import synth
+    c = capi.Context(0)
+    for m in (1024, 2048, 4096):
+        w = synth.plummer(m, seed=m)
+        gf = w["gf"] * (1.0 + 1e-3 * (np.arange(m) % 7))
+        for label, kern in (("grid", capi.KERNEL_AUTO), ("tiled", capi.KERNEL_TILED)):
+            c.date = capi.START_DATE
+            c.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], gf)
+            c.step(5, 1000, kernel=kern, track_most_attracting=True)
+            c.step(100, 1000, kernel=kern, track_most_attracting=True)
+            out["mid_n%d_us_per_step_%s" % (m, label)] = c.last_step_ms * 1e3 / 100
+    c.close()
     out["note"] = ("dt=600 s, History + Trail + ap/pe recording on, offset trails, through the World facade (update(k) + read-back of every "
                    "object per call); *_iters_per_s_<mode> = one call of many steps, *_10_per_call = the GUI's cadence (10 iterations per "
                    "tick), where fast arithmetic is served by the persistent cluster kernel through its mailbox; a single trajectory is "

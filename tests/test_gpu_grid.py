@@ -190,3 +190,57 @@ def test_auto_takes_the_grid_kernel_and_leaves_what_it_cannot_do_to_the_tiled_on
     for k in ("x", "vx"):
         assert np.array_equal(c[k], d[k])
     assert c["x"][5] != w["x"][5]  # it did join
+
+
+def test_grid_softening_deleted_bodies_and_forward_simulation_agree_with_tiled(ctx):
+    """What else essa_step_opts can ask of the kernel: Plummer softening (eps2, the same for every pair), bodies whose deletion
+    date has passed (Object::deleted(), src/Object.cpp:60-62: neither attracted nor attracting nor moved), forward_simulated
+    (the date stands still, src/World.cpp:59-61) -- against K1 with the same options, and the date bookkeeping."""
+    n = 3000
+    w = synth.plummer(n, seed=13)
+    rng = np.random.default_rng(14)
+    t0 = capi.START_DATE
+    dt = synth.default_dt(n)
+    ddate = np.full(n, t0 - 1, dtype=np.int64)
+    deleted = np.zeros(n, dtype=np.uint8)
+    gone = rng.choice(n, 50, replace=False)
+    deleted[gone] = 1
+    eps2 = float(np.median(np.abs(w["x"])) * 1e-3) ** 2
+    for fwd in (False, True):
+        got = {}
+        for kern in (capi.KERNEL_TILED, capi.KERNEL_GRID):
+            ctx.date = t0
+            ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"], deletion_date=ddate, deleted=deleted)
+            ctx.step(4, dt, kernel=kern, eps2=eps2, forward_simulated=fwd)
+            got[kern] = ctx.download()
+            assert ctx.date == (t0 if fwd else t0 + 4 * dt)
+        t, g = got[capi.KERNEL_TILED], got[capi.KERNEL_GRID]
+        for k in ("x", "y", "z", "vx", "vy", "vz"):
+            assert np.allclose(g[k], t[k], rtol=1e-11, atol=0.0), k
+            assert np.array_equal(g[k][gone], w[k][gone])  # deleted bodies stay where they were
+        live = deleted == 0
+        assert np.abs(g["x"][live] - w["x"][live]).max() > 0
+
+
+@pytest.mark.parametrize("n", [64, 147, 148, 149, 400])
+def test_grid_small_worlds_one_body_per_cta_and_fewer_bodies_than_sms(ctx, n):
+    """T = 1 (fewer bodies than SMs: some CTAs own nothing but still take part in every barrier), T = 2 with a ragged last CTA,
+    AUTO's lower bound: trajectories against the oracle."""
+    w = synth.plummer(n, seed=n)
+    dt = synth.default_dt(n)
+    _upload(ctx, w)
+    ctx.step(7, dt, kernel=capi.KERNEL_GRID)
+    got = ctx.download()
+    (ox, oy, oz, ovx, ovy, ovz), _ = oracle.step_soa(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["gf"], 7, dt)
+    pos = np.stack([got["x"], got["y"], got["z"]], axis=1)
+    vel = np.stack([got["vx"], got["vy"], got["vz"]], axis=1)
+    assert _rel_rows(pos, np.stack([ox, oy, oz], axis=1)).max() <= 1e-10
+    assert _rel_rows(vel, np.stack([ovx, ovy, ovz], axis=1)).max() <= 1e-10
+
+
+def test_grid_refuses_worlds_outside_its_range(ctx):
+    for n in (32, 5121):
+        w = synth.plummer(n, seed=1)
+        _upload(ctx, w)
+        with pytest.raises(capi.EssaError):
+            ctx.step(1, 1000, kernel=capi.KERNEL_GRID)
