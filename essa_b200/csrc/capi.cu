@@ -1262,8 +1262,9 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
 constexpr int kPairedAutoMin = 12288; // AUTO takes the pair-shared kernel above this many bodies
 
 // K1g: a mid-size world's whole call in one cooperative launch (force_grid.cu).
-static int step_grid(essa_ctx* ctx, int steps, essa_step_opts const& o) {
+static int step_grid(essa_ctx* ctx, int steps, essa_step_opts const& o, bool* not_placed) {
     int const K = std::abs(steps);
+    *not_placed = false;
     bool const argmax = o.track_most_attracting != 0;
     bool const first_pass = !ctx->acc_valid || (argmax && !ctx->acc_has_most);
     cudaEvent_t e0 = force_event(ctx, 0), e1 = force_event(ctx, 1);
@@ -1271,10 +1272,20 @@ static int step_grid(essa_ctx* ctx, int steps, essa_step_opts const& o) {
         ctx->err = "cudaEventCreate failed";
         return ESSA_ERR_CUDA;
     }
+    CK(cudaEventRecord(e0, ctx->stream));
+    {
+        // the grid must be co-resident (one CTA per SM): another context's persistent kernel on this device, or a partitioned
+        // GPU, can make that impossible -- then the tiled kernel takes the call
+        cudaError_t const le = launch_force_grid(ctx, steps, o, first_pass, argmax, ctx->stream);
+        if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources) {
+            (void)cudaGetLastError();
+            *not_placed = true;
+            return ESSA_OK;
+        }
+        CK(le);
+    }
     if (!o.forward_simulated)
         ctx->date += (int64_t)steps * o.dt_seconds; // no creation / deletion instant lies in between (the caller checked)
-    CK(cudaEventRecord(e0, ctx->stream));
-    CK(launch_force_grid(ctx, steps, o, first_pass, argmax, ctx->stream));
     CK(cudaEventRecord(e1, ctx->stream));
     CK(cudaEventRecord(ctx->ev_end, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1304,9 +1315,16 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
     double const mul = steps >= 0 ? 1.0 : -1.0;
     bool const argmax = o.track_most_attracting || o.record;
     if ((o.kernel == ESSA_KERNEL_AUTO || o.kernel == ESSA_KERNEL_GRID) && force_grid_applicable(ctx, o, forces_only)
-        && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds)))
-        return step_grid(ctx, steps, o);
-    if (o.kernel == ESSA_KERNEL_GRID) {
+        && (o.forward_simulated || !mask_changes(ctx, ctx->date, ctx->date + (int64_t)steps * o.dt_seconds))) {
+        bool not_placed = false;
+        int const rc = step_grid(ctx, steps, o, &not_placed);
+        if (rc != ESSA_OK || !not_placed)
+            return rc;
+        if (o.kernel == ESSA_KERNEL_GRID) {
+            ctx->err = "grid kernel: the device cannot hold one CTA per SM at once (another resident kernel is running)";
+            return ESSA_ERR_CUDA;
+        }
+    } else if (o.kernel == ESSA_KERNEL_GRID) {
         ctx->err = "grid kernel: 1,025 .. 5,120 bodies, unsharded, no recording, no two_pass, no creation / deletion instant inside the call";
         return ESSA_ERR_ARG;
     }

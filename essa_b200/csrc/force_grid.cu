@@ -286,7 +286,6 @@ cudaError_t launch_force_grid(essa_ctx* c, int steps, essa_step_opts const& o, b
     int const blocks = (n + A.T - 1) / A.T; // <= G
     A.bar = c->grid_bar;
     A.bar_base = c->grid_bar_count;
-    c->grid_bar_count += (unsigned)blocks * (unsigned)A.steps;
     size_t const smem = (size_t)n * sizeof(double4) + 2 * kGridThreads * (4 * sizeof(double) + sizeof(int));
     void const* fn = argmax ? (void const*)k_force_grid<true> : (void const*)k_force_grid<false>;
     bool& attr = c->attr_grid[argmax ? 1 : 0];
@@ -299,7 +298,10 @@ cudaError_t launch_force_grid(essa_ctx* c, int steps, essa_step_opts const& o, b
     }
     void* args[] = { (void*)&A };
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(kGridThreads), args, smem, st);
-    c->launches++;
+    if (e == cudaSuccess) {
+        c->launches++;
+        c->grid_bar_count += (unsigned)blocks * (unsigned)A.steps; // what the device counter will read when this launch is through
+    }
     return e;
 }
 

@@ -83,3 +83,42 @@ def test_energy_diagnostic_on_a_subproblem():
     assert ke == pytest.approx(oke, rel=1e-12) and pe == pytest.approx(ope, rel=1e-12)
     assert np.allclose(mom, omom, rtol=1e-10, atol=1e-12 * np.abs(sub["vx"]).sum() * synth.BODY_MASS)
     ctx.close()
+
+
+@pytest.mark.parametrize("n", [262144, 1048576])
+def test_full_size_most_attracting_links_on_unequal_masses(n, monkeypatch):
+    """BASELINE's large worlds with unequal masses, most-attracting links tracked (what every real .essa world asks for):
+    the mass-sorted tracked pass against (i) a direct evaluation of src/Object.cpp:84-94 over ALL partners for sampled bodies,
+    (ii) the same pass on the caller's order (the two layouts share nothing but the exact tests), link for link over the whole
+    world, after two steps (so that the second pass filters against the thresholds the first one left), and (iii) the
+    accelerations of sampled rows against the oracle's extended-precision sums."""
+    w = synth.plummer(n) if n < (1 << 20) else synth.galaxy_collision(n)
+    rng = np.random.default_rng(n)
+    gf = w["gf"] * (1.0 + 3.0 * rng.random(n))
+    dt = synth.default_dt(n)
+    got = {}
+    for layout in ("1", "0"):
+        monkeypatch.setenv("ESSA_PAIR_SORTED", layout)
+        ctx = capi.Context(0, n)
+        ctx.upload(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], gf, most=np.full(n, -1, dtype=np.int32))
+        ctx.step(2, dt, track_most_attracting=True)
+        got[layout] = ctx.download(("x", "y", "z", "ax", "ay", "az", "most", "max_attraction"))
+        ctx.close()
+    s, u = got["1"], got["0"]
+    assert np.array_equal(s["most"], u["most"])
+    assert (s["most"] >= 0).sum() >= n - 1  # everybody but the heaviest has a link
+    assert np.all(np.abs(s["max_attraction"] - u["max_attraction"]) <= 1e-12 * np.abs(u["max_attraction"]))
+    for k in ("x", "y", "z"):
+        assert np.allclose(s[k], u[k], rtol=1e-13, atol=0.0)
+    x, y, z = s["x"], s["y"], s["z"]
+    for i in rng.choice(n, 24, replace=False):
+        r2 = (x - x[i]) ** 2 + (y - y[i]) ** 2 + (z - z[i]) ** 2
+        r2[i] = np.inf
+        metric = np.where(gf > gf[i], gf / r2 ** 2, 0.0)
+        if metric.max() > 0:
+            assert s["most"][i] == int(np.argmax(metric)), i
+            assert s["max_attraction"][i] == pytest.approx(metric.max(), rel=1e-9)
+    rows = np.sort(rng.choice(n, 16, replace=False))
+    ld = oracle.forces_rows(x, y, z, gf, rows, mode="ld")
+    a = np.stack([s["ax"], s["ay"], s["az"]], axis=1)
+    assert _rel_rows(a[rows], ld).max() <= 1e-12
