@@ -17,6 +17,11 @@
 // drift never mix components), thread (t, 3) the body's gravity factor, active flag and most-attracting link
 // (src/Object.cpp:84-94: strictly heavier partner, largest gf / r^4, lowest index on ties -- as K1's ARGMAX variant).
 //
+// Measured and rejected: a barrier-free exchange in which the positions travel as self-validating 64-bit words {step tag, 32 bits
+// of payload} that every CTA polls (what the persistent kernels do towards the host): bit-identical results, but 48 instead of
+// 32 bytes per body in 8-byte loads and the re-polls of 148 x 512 threads cost more than the barrier saves -- 2,048 bodies 9.1
+// vs 8.1 us per step, 4,096: 25.9 vs 23.1; only 400 bodies gained (2.9 vs 3.1).
+//
 // Not taken (falls to K1): recording (History / Trail of a tracked prefix), two_pass, a call during which the active mask
 // flips, sharded worlds.
 #include <cstdlib>
