@@ -549,7 +549,10 @@ static cudaError_t launch_solo(essa_ctx* c, EnsembleArgs const& A, cudaStream_t 
     int const blocks = (int)(((long long)A.copies + kSoloThreads - 1) / kSoloThreads);
     // Registers: 6 N doubles of state + the pairs in flight: 8 warps per SM, two per scheduler, whose unrolled pairs keep the
     // FP64 pipe fed.  (A 65,536-copy ensemble is 2,048 warps on 592 schedulers: 3.46 each, so 4 on the busiest whichever way
-    // they are packed -- two waves of 8 warps per SM cost what one wave of 14 would, without its register spills.)
+    // they are packed -- two waves of 8 warps per SM cost what one wave of 14 would, without its register spills.  Also measured
+    // (round 2) and rejected: a persistent grid of 1,184 CTAs walking (quarter of the steps, CTA) items part-major, so that the
+    // tail of one part's last wave is filled with the next part's first items (8,192 items = 6.92 per place): 1.175e10 against
+    // 1.189e10 copy-iterations/s -- the second wave's warps have the FP64 pipes more to themselves and finish sooner anyway.)
 #ifndef SOLO_MINB
 #define SOLO_MINB 8
 #endif
