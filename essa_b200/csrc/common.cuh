@@ -13,6 +13,21 @@
 
 #include "../../include/essa_b200.h"
 
+// Bounds / index assertions of our own (compute-sanitizer is not available on the GPU pool): compiled in with -DESSA_BOUNDS
+// (tools/bounds_check.sh builds that variant and runs the kernels' GPU tests under it), absent from the product build.
+#ifdef ESSA_BOUNDS
+#include <cstdio>
+#define ESSA_CHECK(cond) \
+    do { \
+        if (!(cond)) { \
+            printf("ESSA_BOUNDS: %s:%d: %s (block %d thread %d)\n", __FILE__, __LINE__, #cond, (int)blockIdx.x, (int)threadIdx.x); \
+            __trap(); \
+        } \
+    } while (0)
+#else
+#define ESSA_CHECK(cond) ((void)0)
+#endif
+
 namespace essa {
 
 // ------------------------------------------------------------------------------------------

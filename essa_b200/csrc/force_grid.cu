@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_force_grid(GridArgs const A
         // (a plain loop: the compiler keeps four loads in flight; eight explicit ones measured 0.7 us slower per 64 KB)
         for (int i = tid; i < 2 * n; i += kGridThreads)
             dst[i] = __ldcg(src + i);
+        ESSA_CHECK(T * L <= kGridThreads && L >= 4 && A.R >= 4 && A.R <= L && (int)gridDim.x * T >= n);
         __syncthreads();
     };
     // one set_forces(): partial sums by the workers, ordered sums by the owners
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_force_grid(GridArgs const A
             double4 const p = spos[g];
 #pragma unroll 4
             for (int j = l; j < n; j += L) {
+                ESSA_CHECK(j >= 0 && j < n && g < n);
                 if (ARGMAX)
                     fast_interact_argmax(p.x, p.y, p.z, p.w, spos[j], j, A.eps2, ax, ay, az, best, bj);
                 else
@@ -148,6 +150,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_force_grid(GridArgs const A
             int mj = -1;
             for (int k = l; k < L; k += R) {
                 int const e = k * T + t;
+                ESSA_CHECK(e >= 0 && e < kGridThreads);
                 s0 = __dadd_rn(s0, red[e]);
                 s1 = __dadd_rn(s1, red[kGridThreads + e]);
                 s2 = __dadd_rn(s2, red[2 * kGridThreads + e]);
@@ -171,8 +174,10 @@ __global__ void __launch_bounds__(kGridThreads, 1) k_force_grid(GridArgs const A
         __syncthreads();
         if (owner && l < 3) {
             double s = 0.0;
-            for (int k = 0; k < R; k++)
+            for (int k = 0; k < R; k++) {
+                ESSA_CHECK(k * T + t < kGridThreads && l < 3);
                 s = __dadd_rn(s, red2[l * kGridThreads + k * T + t]);
+            }
             if (act)
                 ac = s;
         }

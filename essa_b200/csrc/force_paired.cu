@@ -150,6 +150,9 @@ struct PairArgs {
     int const* perm;
     double4 const* pos_orig;
     double eps2;
+    // extents of the buffers above, in elements (ESSA_BOUNDS builds check every computed address against them)
+    size_t n_part_i, n_slots, n_part_k, n_slots_k;
+    int n_world; // bodies (what a key's index and perm[] entries must stay below)
 };
 
 // SORTED kernels keep MINUS the threshold of a target (what filter mode 2 adds to L(y0)); "nothing passes" becomes INT_MIN
@@ -261,6 +264,7 @@ __device__ __forceinline__ void pair_exact(double4 const* __restrict__ pos, int 
         if (perm) { // mass-sorted layout: keys name bodies by their ORIGINAL index (lowest index wins a tie; most[] is an index)
             iidx = perm[iidx];
             jidx = perm[jidx];
+            ESSA_CHECK(iidx >= 0 && jidx >= 0); // a padding slot (-1) has gf 0: it can be neither heavier nor lighter-with-a-candidate
         }
         if (pi) {
             double si = gj * u;
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
     double xi[kPRI], yi[kPRI], zi[kPRI], gi[kPRI], aix[kPRI], aiy[kPRI], aiz[kPRI];
 #pragma unroll
     for (int r = 0; r < kPRI; r++) {
+        ESSA_CHECK(I >= 0 && I < A.nb && (size_t)I * kPB + warp * (32 * kPRI) + r * 32 + lane < (size_t)A.npad);
         double4 p = A.pos[(size_t)I * kPB + warp * (32 * kPRI) + r * 32 + lane];
         xi[r] = p.x;
         yi[r] = p.y;
@@ -354,6 +359,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
         int J = I + d;
         if (J >= A.nb)
             J -= A.nb;
+        ESSA_CHECK(J >= 0 && J < A.nb && half >= 0 && half < kPParts && (size_t)J * kPB + (size_t)(half + 1) * kPHalf <= (size_t)A.npad);
         unsigned bytes = kPHalf * (unsigned)sizeof(double4);
         mbar_expect_tx(&full[buf], bytes + (ARGMAX ? kPHalf * (unsigned)sizeof(unsigned) : 0u));
         bulk_g2s(tile + (size_t)buf * kPHalf, A.pos + (size_t)J * kPB + half * kPHalf, bytes, &full[buf]);
@@ -517,6 +523,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                 int const owner = A.owner_major ? J / A.bpr : 0;
                 size_t const tile = A.owner_major ? (size_t)(J - owner * A.bpr) * A.dslots + (d - A.dslot0) : (size_t)ibl * A.dslots + (d - A.dslot0);
                 double* slot = (A.owner_major ? A.slot_peer[owner] : A.slots) + tile * 3 * kPB;
+                ESSA_CHECK(d >= A.dslot0 && d - A.dslot0 < A.dslots && owner >= 0 && owner < kPairMaxPeers && (tile + 1) * 3 * kPB <= A.n_slots);
                 for (int e = tid; e < 3 * kPHalf; e += kPThreads) {
                     int c = e / kPHalf, j = e - c * kPHalf;
                     double sum = 0.0;
@@ -527,9 +534,11 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
                 }
                 if (ARGMAX) {
                     unsigned long long* slotk = (A.owner_major ? A.slotk_peer[owner] : A.slots_k) + tile * kPB + half * kPHalf;
+                    ESSA_CHECK((tile + 1) * kPB <= A.n_slots_k);
                     for (int j = tid; j < kPHalf; j += kPThreads) {
                         unsigned long long k = 0ull;
                         int const tgt = SORTED ? perm[J * kPB + half * kPHalf + j] : J * kPB + half * kPHalf + j;
+                        ESSA_CHECK(tgt >= -1 && tgt < (SORTED ? A.n_world : A.npad));
 #pragma unroll
                         for (int w = 0; w < 8; w++)
                             k = key_merge(kpos, tgt, k, acck[(size_t)w * kPHalf + j], A.eps2);
@@ -546,6 +555,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
     for (int r = 0; r < kPRI; r++) {
         size_t i = (size_t)I * kPB + warp * (32 * kPRI) + r * 32 + lane;
         double* p = A.part_i + (size_t)chunk * 3 * A.npad + i;
+        ESSA_CHECK(chunk >= 0 && chunk < A.S && i < (size_t)A.npad && (size_t)(chunk + 1) * 3 * A.npad <= A.n_part_i);
+        ESSA_CHECK(!ARGMAX || (size_t)(chunk + 1) * A.npad <= A.n_part_k);
         __stcg(p, aix[r]);
         __stcg(p + A.npad, aiy[r]);
         __stcg(p + 2 * (size_t)A.npad, aiz[r]);
@@ -1249,6 +1260,11 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
     A.part_k = c->pair_kpart;
     A.slots_k = c->pair_kslots;
     A.eps2 = eps2;
+    A.n_part_i = c->pair_part_n;
+    A.n_slots = c->pair_slots_n;
+    A.n_part_k = c->pair_kpart_bytes / sizeof(unsigned long long);
+    A.n_slots_k = c->pair_kslots_bytes / sizeof(unsigned long long);
+    A.n_world = c->n;
     // J-side slots live with the owner of the J block: own memory on one GPU, peer-mapped memory when sharded (capi.cu set the
     // table up); without peer access the writer-major fallback + NCCL reduce-scatter
     A.owner_major = c->world == 1 || c->pair_peer_ok;
