@@ -118,6 +118,7 @@ __device__ __forceinline__ float to_vertex1(double p) {
 }
 
 __device__ __forceinline__ void vert_write(RecordPtrs const& R, BodyRec const& b, int slot, float x, float y, float z) {
+    ESSA_CHECK(slot >= 0 && slot < b.cap && b.cap >= 3);
     float* v = R.verts + (b.voff + slot) * 3;
     v[0] = x;
     v[1] = y;
@@ -196,6 +197,7 @@ __device__ __forceinline__ void history_push(RecordPtrs const& R, int k, BodyRec
     b.hist_len = grow ? b.hist_len + 1 : b.hist_len;
     b.hist_start = grow ? b.hist_start : next;
     // 48-byte entries in a 256-byte aligned ring: three 16-byte stores
+    ESSA_CHECK(k >= 0 && k < R.tracked && slot >= 0 && slot < ESSA_HISTORY_SEGMENTS && b.hist_len <= ESSA_HISTORY_SEGMENTS);
     double2* e = reinterpret_cast<double2*>(R.hist + ((size_t)k * ESSA_HISTORY_SEGMENTS + slot) * 6);
     e[0] = make_double2(px, py);
     e[1] = make_double2(pz, vx);
@@ -209,6 +211,7 @@ __device__ __forceinline__ void trail_recalculate(RecordPtrs const& R, BodyRec& 
     trail_flush_vertex(R, b);
     float ax = to_vertex1(b.offx), ay = to_vertex1(b.offy), az = to_vertex1(b.offz);
     float bx = to_vertex1(ox), by = to_vertex1(oy), bz = to_vertex1(oz);
+    ESSA_CHECK(b.length >= 0 && b.length <= b.cap);
     float* v = R.verts + b.voff * 3;
     for (int s = 0; s < b.length; s++) {
         v[3 * s] = __fsub_rn(__fadd_rn(v[3 * s], ax), bx);
@@ -268,6 +271,7 @@ __device__ __forceinline__ void trail_append(RecordPtrs const& R, BodyRec& b, fl
         vert_write(R, b, b.append_off - 1, v[0], v[1], v[2]);
         b.vpend = 0;
     }
+    ESSA_CHECK(b.append_off >= 0 && b.append_off < b.cap && (!b.vpend || b.append_off >= 1));
     vert_write(R, b, b.append_off, v[3], v[4], v[5]);
     b.append_off++;
     if (b.length < b.cap)

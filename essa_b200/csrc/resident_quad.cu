@@ -327,6 +327,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kQuadThreads, 1) k_r
                 QSnap const& sn = ring[slot];
                 bool const act = body && ((sn.mask >> lane) & 1ull);
                 int const winner = body ? sn.win[lane] : -1;
+                ESSA_CHECK(slot >= 0 && slot < kRing && winner >= -1 && winner < n && most >= -1 && most < n);
                 old_most = most; // Object::before_update (every object)
                 if (act && winner >= 0)
                     most = winner;
