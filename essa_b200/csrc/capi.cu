@@ -319,10 +319,15 @@ static void persist_post(essa_ctx* ctx, int steps) {
 // context
 // ---------------------------------------------------------------------------------------------
 static void pair_peer_close(essa_ctx* ctx);
+constexpr int kXchgWords = 64; // words per rank of the handle exchange (pair_peer_setup)
 
 static void free_world(essa_ctx* c) {
-    cudaFree(c->pos[0]);
-    cudaFree(c->pos[1]);
+    for (int k = 0; k < 2; k++) {
+        if (c->pos[k] && c->pos[k] == c->pair_pos_exported[k])
+            c->pos_graveyard.push_back(c->pos[k]); // other ranks may still have it mapped: lives until the context goes
+        else
+            cudaFree(c->pos[k]);
+    }
     cudaFree(c->vel);
     cudaFree(c->velh);
     cudaFree(c->acc);
@@ -490,6 +495,10 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
             cudaStreamSynchronize(c->stream);
     }
     cudaFree(c->peer_xchg);
+    cudaFree(c->pair_flags);
+    for (void* g : c->pos_graveyard)
+        cudaFree(g);
+    c->pos_graveyard.clear();
     if (c->persist.mailbox)
         cudaFreeHost(c->persist.mailbox);
     if (c->stream)
@@ -1012,6 +1021,11 @@ static cudaEvent_t force_event(essa_ctx* c, size_t idx) {
 static void pair_peer_close(essa_ctx* ctx) {
     for (int r = 0; r < essa_ctx::kMaxPeers; r++) {
         if (r != ctx->rank) {
+            for (int k = 0; k < 2; k++)
+                if (ctx->pair_pos_peer[k][r])
+                    cudaIpcCloseMemHandle(ctx->pair_pos_peer[k][r]);
+            if (ctx->pair_flags_peer[r])
+                cudaIpcCloseMemHandle(ctx->pair_flags_peer[r]);
             if (ctx->pair_slot_peer[r])
                 cudaIpcCloseMemHandle(ctx->pair_slot_peer[r]);
             if (ctx->pair_kslot_peer[r])
@@ -1019,14 +1033,51 @@ static void pair_peer_close(essa_ctx* ctx) {
         }
         ctx->pair_slot_peer[r] = nullptr;
         ctx->pair_kslot_peer[r] = nullptr;
+        ctx->pair_pos_peer[0][r] = ctx->pair_pos_peer[1][r] = nullptr;
+        ctx->pair_flags_peer[r] = nullptr;
     }
     ctx->pair_peer_ok = false;
+    ctx->pair_pospeer_ok = false;
+}
+
+// Barrier over the peer mappings, without NCCL: every rank announces an epoch in each peer's flag array (one word per sender),
+// then waits until its own array shows that epoch from everybody.  Stream-ordered behind the kernel whose results it announces.
+__global__ void k_peer_wait(unsigned long long const* flags, int world, unsigned long long epoch) {
+    int const r = threadIdx.x;
+    if (r < world) {
+        long long const t0 = clock64();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+        } while (v < epoch && clock64() - t0 < 20000000000ll); // (~10 s: a rank that died must not hang the others' GPUs)
+    }
+}
+struct PeerFlagTable {
+    unsigned long long* p[essa_ctx::kMaxPeers];
+};
+__global__ void k_peer_signal_t(PeerFlagTable const T, int rank, int world, unsigned long long epoch) {
+    int const r = threadIdx.x;
+    if (r < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(T.p[r] + rank), "l"(epoch) : "memory");
+    }
+}
+static int peer_flag_barrier(essa_ctx* ctx) {
+    PeerFlagTable T;
+    for (int r = 0; r < essa_ctx::kMaxPeers; r++)
+        T.p[r] = ctx->pair_flags_peer[r];
+    unsigned long long const epoch = ++ctx->pair_epoch;
+    k_peer_signal_t<<<1, 32, 0, ctx->stream>>>(T, ctx->rank, ctx->world, epoch);
+    k_peer_wait<<<1, 32, 0, ctx->stream>>>(ctx->pair_flags, ctx->world, epoch);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return ESSA_OK;
 }
 
 // every rank's kernels issued so far on the context's stream have finished (device-side: one word through NCCL)
 static int shard_barrier(essa_ctx* ctx) {
     if (!ctx->peer_xchg)
-        CK(cudaMalloc(&ctx->peer_xchg, (size_t)essa_ctx::kMaxPeers * 32 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->peer_xchg, (size_t)essa_ctx::kMaxPeers * kXchgWords * sizeof(unsigned long long)));
     NK(nccl().AllReduce(ctx->peer_xchg, ctx->peer_xchg, 1, kNcclUint32, kNcclSum, ctx->comm, ctx->stream));
     return ESSA_OK;
 }
@@ -1043,7 +1094,8 @@ static int pair_peer_setup(essa_ctx* ctx, bool keys) {
         ctx->pair_peer_failed = true;
         return ESSA_OK;
     }
-    bool const will_change = pair_reserve_would_change(ctx, keys);
+    bool const will_change = pair_reserve_would_change(ctx, keys) || ctx->pos[0] != ctx->pair_pos_exported[0]
+        || ctx->pos[1] != ctx->pair_pos_exported[1]; // (a grown world has new position buffers: on every rank, uploads are collective)
     if (ctx->pair_peer_ok && !will_change)
         return ESSA_OK;
     if (ctx->pair_peer_ok) { // the buffers the peers have mapped are about to be freed: everybody lets go first
@@ -1055,11 +1107,25 @@ static int pair_peer_setup(essa_ctx* ctx, bool keys) {
     }
     CK(pair_reserve(ctx, keys, nullptr));
     if (!ctx->peer_xchg)
-        CK(cudaMalloc(&ctx->peer_xchg, (size_t)essa_ctx::kMaxPeers * 32 * sizeof(unsigned long long)));
-    // 32 words per rank: [0] ok flag, [1] has keys, [8..16) handle of the slots, [16..24) handle of the key slots
+        CK(cudaMalloc(&ctx->peer_xchg, (size_t)essa_ctx::kMaxPeers * kXchgWords * sizeof(unsigned long long)));
+    // 64 words per rank: [0] ok flag, [1] has keys, [2] position buffers exported, [8..16) handle of the slots, [16..24) handle of
+    // the key slots, [24..32) / [32..40) handles of the two position buffers
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    unsigned long long mine[32] = {};
-    cudaIpcMemHandle_t hs, hk;
+    unsigned long long mine[kXchgWords] = {};
+    cudaIpcMemHandle_t hs, hk, hp[2];
+    if (!ctx->pair_flags) { // (never freed before the context: the epochs only grow)
+        CK(cudaMalloc(&ctx->pair_flags, (size_t)2 << 20)); // a whole 2 MiB page of its own: what an IPC handle exposes
+        CK(cudaMemsetAsync(ctx->pair_flags, 0, essa_ctx::kMaxPeers * sizeof(unsigned long long), ctx->stream));
+    }
+    cudaIpcMemHandle_t hf;
+    bool const pos_ok = cudaIpcGetMemHandle(&hp[0], ctx->pos[0]) == cudaSuccess && cudaIpcGetMemHandle(&hp[1], ctx->pos[1]) == cudaSuccess
+        && cudaIpcGetMemHandle(&hf, ctx->pair_flags) == cudaSuccess;
+    mine[2] = pos_ok ? 1 : 0;
+    if (pos_ok) {
+        memcpy(&mine[24], &hp[0], 64);
+        memcpy(&mine[32], &hp[1], 64);
+        memcpy(&mine[40], &hf, 64);
+    }
     bool ok = cudaIpcGetMemHandle(&hs, ctx->pair_slots) == cudaSuccess;
     bool const have_k = ctx->pair_kslots != nullptr;
     if (ok && have_k)
@@ -1072,14 +1138,16 @@ static int pair_peer_setup(essa_ctx* ctx, bool keys) {
         if (have_k)
             memcpy(&mine[16], &hk, 64);
     }
-    CK(cudaMemcpyAsync(ctx->peer_xchg + (size_t)ctx->rank * 32, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
-    NK(nccl().AllGather(ctx->peer_xchg + (size_t)ctx->rank * 32, ctx->peer_xchg, 32, kNcclUint64, ctx->comm, ctx->stream));
-    std::vector<unsigned long long> all((size_t)ctx->world * 32);
+    CK(cudaMemcpyAsync(ctx->peer_xchg + (size_t)ctx->rank * kXchgWords, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+    NK(nccl().AllGather(ctx->peer_xchg + (size_t)ctx->rank * kXchgWords, ctx->peer_xchg, kXchgWords, kNcclUint64, ctx->comm, ctx->stream));
+    std::vector<unsigned long long> all((size_t)ctx->world * kXchgWords);
     CK(cudaMemcpyAsync(all.data(), ctx->peer_xchg, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    bool all_ok = true;
-    for (int r = 0; r < ctx->world; r++)
-        all_ok = all_ok && all[(size_t)r * 32] == 1 && all[(size_t)r * 32 + 1] == (have_k ? 1u : 0u);
+    bool all_ok = true, all_pos = true;
+    for (int r = 0; r < ctx->world; r++) {
+        all_ok = all_ok && all[(size_t)r * kXchgWords] == 1 && all[(size_t)r * kXchgWords + 1] == (have_k ? 1u : 0u);
+        all_pos = all_pos && all[(size_t)r * kXchgWords + 2] == 1;
+    }
     if (all_ok) {
         for (int r = 0; r < ctx->world && all_ok; r++) {
             if (r == ctx->rank) {
@@ -1089,26 +1157,51 @@ static int pair_peer_setup(essa_ctx* ctx, bool keys) {
             }
             cudaIpcMemHandle_t h;
             void* ptr = nullptr;
-            memcpy(&h, &all[(size_t)r * 32 + 8], 64);
+            memcpy(&h, &all[(size_t)r * kXchgWords + 8], 64);
             all_ok = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
             ctx->pair_slot_peer[r] = static_cast<double*>(ptr);
             if (all_ok && have_k) {
-                memcpy(&h, &all[(size_t)r * 32 + 16], 64);
+                memcpy(&h, &all[(size_t)r * kXchgWords + 16], 64);
                 ptr = nullptr;
                 all_ok = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
                 ctx->pair_kslot_peer[r] = static_cast<unsigned long long*>(ptr);
             }
+            for (int k = 0; k < 2 && all_ok && all_pos; k++) {
+                memcpy(&h, &all[(size_t)r * kXchgWords + 24 + 8 * k], 64);
+                ptr = nullptr;
+                all_pos = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                ctx->pair_pos_peer[k][r] = static_cast<double4*>(ptr);
+            }
+            if (all_ok && all_pos) {
+                memcpy(&h, &all[(size_t)r * kXchgWords + 40], 64);
+                ptr = nullptr;
+                all_pos = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                ctx->pair_flags_peer[r] = static_cast<unsigned long long*>(ptr);
+            }
         }
         (void)cudaGetLastError();
     }
-    // the decision must be the same everywhere: one more word around
-    unsigned long long flag = all_ok ? 1 : 0;
+    if (all_ok && all_pos) {
+        ctx->pair_pos_peer[0][ctx->rank] = ctx->pos[0];
+        ctx->pair_pos_peer[1][ctx->rank] = ctx->pos[1];
+        ctx->pair_flags_peer[ctx->rank] = ctx->pair_flags;
+    }
+    // whatever came of it, the peers were handed these two buffers: they must outlive a grown world (free_world)
+    ctx->pair_pos_exported[0] = ctx->pos[0];
+    ctx->pair_pos_exported[1] = ctx->pos[1];
+    // the decision must be the same everywhere: one more word around (low half: slots, high half: positions too)
+    unsigned long long flag = (all_ok ? 1ull : 0ull) | (all_ok && all_pos ? 1ull << 32 : 0ull);
     CK(cudaMemcpyAsync(ctx->peer_xchg, &flag, sizeof(flag), cudaMemcpyHostToDevice, ctx->stream));
     NK(nccl().AllReduce(ctx->peer_xchg, ctx->peer_xchg, 1, kNcclUint64, kNcclSum, ctx->comm, ctx->stream));
     CK(cudaMemcpyAsync(&flag, ctx->peer_xchg, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (flag == (unsigned long long)ctx->world) {
+    if ((flag & 0xffffffffull) == (unsigned long long)ctx->world) {
         ctx->pair_peer_ok = true;
+        static bool const pos_allowed = [] {
+            char const* e = getenv("ESSA_PAIR_PEER_POS"); // diagnostics: 0 = wait for the gathered positions instead
+            return !(e && atoi(e) == 0);
+        }();
+        ctx->pair_pospeer_ok = pos_allowed && (flag >> 32) == (unsigned long long)ctx->world;
     } else {
         pair_peer_close(ctx);
         ctx->pair_peer_failed = true;
@@ -1156,15 +1249,34 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
         CK(cudaEventRecord(e0, ctx->stream));
     }
     if (ctx->use_paired) {
-        if (ctx->gather_pending) { // the pair kernel walks the whole ring of blocks: all positions must be in
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
-            ctx->gather_pending = false;
+        // most-attracting tracking: real candidate keys, unless every gravity factor is equal (then it is a no-op)
+        bool const keys = argmax && !ctx->gf_uniform;
+        if (ctx->world > 1) {
+            int prc = pair_peer_setup(ctx, keys);
+            if (prc != ESSA_OK)
+                return prc;
         }
+        // The pair kernel walks the whole ring of blocks.  With peer-mapped position buffers it reads a remote block from the
+        // rank that owns it, so all it needs is that every rank's previous kernel (the one that wrote its shard of these
+        // positions) is through: a one-word barrier instead of the wait for the gathered copy, which lands in the background
+        // and is waited for only in front of k_pair_finish (whose rare repair path reads all positions from local memory).
+        bool const peer_pos = ctx->world > 1 && ctx->pair_peer_ok && ctx->pair_pospeer_ok && !keys;
+        bool gather_late = false;
+        if (ctx->gather_pending) {
+            if (peer_pos) {
+                int brc = peer_flag_barrier(ctx);
+                if (brc != ESSA_OK)
+                    return brc;
+                gather_late = true;
+            } else {
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
+                ctx->gather_pending = false;
+            }
+        }
+        ctx->pair_peer_pos_pass = gather_late; // without a pending gather the local copy is complete: nothing to fetch from peers
         double* acc = nullptr;
         unsigned long long* kacc = nullptr;
         int npad = 0;
-        // most-attracting tracking: real candidate keys, unless every gravity factor is equal (then it is a no-op)
-        bool const keys = argmax && !ctx->gf_uniform;
         if (keys && ctx->world > 1 && ctx->pair_prior_valid) {
             // every rank's k_pair_finish rewrote the filter thresholds of its own targets: all ranks need all of them
             size_t cnt = (size_t)n / ctx->world;
@@ -1172,11 +1284,6 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
             for (int r = 0; r < ctx->world; r++)
                 NK(nccl().Broadcast(ctx->pair_prior + r * cnt, ctx->pair_prior + r * cnt, cnt, kNcclUint32, r, ctx->comm, ctx->stream));
             NK(nccl().GroupEnd());
-        }
-        if (ctx->world > 1) {
-            int prc = pair_peer_setup(ctx, keys);
-            if (prc != ESSA_OK)
-                return prc;
         }
         // a pass timed by itself: also where its time goes (three more event records; not for small worlds, whose steps are
         // bounded by how fast the host enqueues work: 16,384 bodies 210 -> 217 us per step with them)
@@ -1220,6 +1327,10 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
                 }
             }
             NK(nccl().GroupEnd());
+        }
+        if (gather_late) { // by now a formality
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
+            ctx->gather_pending = false;
         }
         if (phases) {
             CK(cudaEventRecord(ctx->ev_phase[2], ctx->stream));

@@ -177,6 +177,18 @@ struct essa_ctx {
     double* pair_slot_peer[kMaxPeers] = {};
     unsigned long long* pair_kslot_peer[kMaxPeers] = {};
     bool pair_peer_ok = false;      // the tables above are valid
+    // ... and both position buffers of every rank (same exchange): the sharded pair kernel then takes the J tiles of remote
+    // blocks straight from their owner over NVLink and does not wait for the gather of the next positions (capi.cu force_pass)
+    double4* pair_pos_peer[2][kMaxPeers] = {};
+    double4* pair_pos_exported[2] = { nullptr, nullptr }; // this rank's buffers as the peers have them mapped
+    bool pair_pospeer_ok = false;
+    // ... and a word per peer for the barrier in front of such a pass ("every rank's shard of these positions is written"): a
+    // device-side flag exchange over the same mappings -- an NCCL collective would queue behind the gather on the communicator
+    unsigned long long* pair_flags = nullptr;               // [kMaxPeers] epochs announced TO this rank, one word per sender
+    unsigned long long* pair_flags_peer[kMaxPeers] = {};
+    unsigned long long pair_epoch = 0;
+    bool pair_peer_pos_pass = false; // the pass being launched reads remote blocks from their owners
+    std::vector<void*> pos_graveyard; // exported buffers that a grown world replaced: freed with the context (peers may map them)
     bool pair_peer_failed = false;  // peer mapping is not available here: NCCL reduce-scatter fallback
     unsigned long long* peer_xchg = nullptr; // device scratch for the handle exchange / the per-pass barrier
     unsigned long long* pair_kall = nullptr; // sharded: every rank's candidate key for each of this rank's bodies [world][n / world]

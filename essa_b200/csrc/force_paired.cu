@@ -149,6 +149,10 @@ struct PairArgs {
     // slot s holds body perm[s] (-1: padding) of pos_orig, and candidate keys carry ORIGINAL indices
     int const* perm;
     double4 const* pos_orig;
+    // sharded, peer-mapped position buffers (peer_pos != 0): the records of block J are read from the rank that owns it
+    // (pos_peer[J / bpr]: its copy is final when the per-pass barrier has passed), not from this rank's gathered copy
+    double4 const* pos_peer[kPairMaxPeers];
+    int peer_pos;
     double eps2;
     // extents of the buffers above, in elements (ESSA_BOUNDS builds check every computed address against them)
     size_t n_part_i, n_slots, n_part_k, n_slots_k;
@@ -362,7 +366,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_force_paired(PairArgs const A)
         ESSA_CHECK(J >= 0 && J < A.nb && half >= 0 && half < kPParts && (size_t)J * kPB + (size_t)(half + 1) * kPHalf <= (size_t)A.npad);
         unsigned bytes = kPHalf * (unsigned)sizeof(double4);
         mbar_expect_tx(&full[buf], bytes + (ARGMAX ? kPHalf * (unsigned)sizeof(unsigned) : 0u));
-        bulk_g2s(tile + (size_t)buf * kPHalf, A.pos + (size_t)J * kPB + half * kPHalf, bytes, &full[buf]);
+        double4 const* const from = A.peer_pos ? A.pos_peer[J / A.bpr] : A.pos;
+        bulk_g2s(tile + (size_t)buf * kPHalf, from + (size_t)J * kPB + half * kPHalf, bytes, &full[buf]);
         if (ARGMAX)
             bulk_g2s(tprior + (size_t)buf * kPHalf, A.prior + (size_t)J * kPB + half * kPHalf, kPHalf * (unsigned)sizeof(unsigned), &full[buf]);
     };
@@ -1273,6 +1278,11 @@ cudaError_t launch_force_paired_compute(essa_ctx* c, double eps2, cudaStream_t s
         A.slot_peer[r] = c->world == 1 ? c->pair_slots : (r < c->world ? c->pair_slot_peer[r] : nullptr);
         A.slotk_peer[r] = c->world == 1 ? c->pair_kslots : (r < c->world ? c->pair_kslot_peer[r] : nullptr);
     }
+    // remote J tiles straight from their owners (the caller has put the barrier in front of this launch): untracked passes only
+    // -- the tracked one also stages the owners' filter thresholds, which arrive with their own broadcast
+    A.peer_pos = c->world > 1 && c->pair_peer_ok && c->pair_pospeer_ok && c->pair_peer_pos_pass && !argmax ? 1 : 0;
+    for (int r = 0; r < kPairMaxPeers; r++)
+        A.pos_peer[r] = A.peer_pos && r < c->world ? c->pair_pos_peer[c->cur][r] : nullptr;
     double* acc = nullptr;
     unsigned long long* kacc = nullptr;
     bool const uniform = pair_uniform(c) && !argmax;
