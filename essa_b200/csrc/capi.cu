@@ -1212,12 +1212,26 @@ static int pair_peer_setup(essa_ctx* ctx, bool keys) {
 // In a sharded context every rank has just written its own targets' records into the `next`
 // position buffer: gather the other ranks' shards (ragged shards -> one broadcast per rank,
 // grouped).  Runs on the comm stream so that the force pass can start on the local shard.
+static int gather_issue(essa_ctx* ctx);
 static int gather_next(essa_ctx* ctx) {
     if (ctx->world == 1)
         return ESSA_OK;
     CK(cudaEventRecord(ctx->ev_ready, ctx->stream));
+    ctx->gather_buf = ctx->pos[ctx->cur ^ 1];
+    ctx->gather_deferred = true;
+    ctx->gather_pending = true;
+    // Issued at once.  (Measured and rejected: issuing the NCCL calls only behind the launch of a force kernel that reads its
+    // remote tiles from their owners, so that the host's ~0.1 ms in the group call does not hold that launch back -- the
+    // gather's own kernel then finds every SM taken and runs at the force kernel's tail, in front of the barrier that follows
+    // it: 16,384 bodies on 2 GPUs 156 -> 166 us per step.)
+    return gather_issue(ctx);
+}
+static int gather_issue(essa_ctx* ctx) {
+    if (!ctx->gather_deferred)
+        return ESSA_OK;
+    ctx->gather_deferred = false;
     CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0));
-    double4* buf = ctx->pos[ctx->cur ^ 1];
+    double4* buf = ctx->gather_buf;
     NK(nccl().GroupStart());
     for (int r = 0; r < ctx->world; r++) {
         long long a = (long long)ctx->n * r / ctx->world, b = (long long)ctx->n * (r + 1) / ctx->world;
@@ -1226,7 +1240,17 @@ static int gather_next(essa_ctx* ctx) {
     }
     NK(nccl().GroupEnd());
     CK(cudaEventRecord(ctx->ev_gather, ctx->comm_stream));
-    ctx->gather_pending = true;
+    return ESSA_OK;
+}
+// ... and the wait for it on the context's stream
+static int gather_wait(essa_ctx* ctx) {
+    if (!ctx->gather_pending)
+        return ESSA_OK;
+    int rc = gather_issue(ctx);
+    if (rc != ESSA_OK)
+        return rc;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
+    ctx->gather_pending = false;
     return ESSA_OK;
 }
 
@@ -1269,8 +1293,9 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
                     return brc;
                 gather_late = true;
             } else {
-                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
-                ctx->gather_pending = false;
+                int grc = gather_wait(ctx);
+                if (grc != ESSA_OK)
+                    return grc;
             }
         }
         ctx->pair_peer_pos_pass = gather_late; // without a pending gather the local copy is complete: nothing to fetch from peers
@@ -1328,9 +1353,10 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
             }
             NK(nccl().GroupEnd());
         }
-        if (gather_late) { // by now a formality
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
-            ctx->gather_pending = false;
+        if (gather_late) { // the gather's NCCL calls go out behind the force kernel's launch; the wait is a formality by then
+            int grc = gather_wait(ctx);
+            if (grc != ESSA_OK)
+                return grc;
         }
         if (phases) {
             CK(cudaEventRecord(ctx->ev_phase[2], ctx->stream));
@@ -1355,8 +1381,11 @@ static int force_pass(essa_ctx* ctx, bool argmax, bool save_old, KickArgs const&
         int total = SA + SB0 + SB1;
         // slot order follows source index so that the ordered reduction is the same on every rank count
         CK(launch_force_pass(ctx, i0, i1, SA, SB0, total, argmax, save_old, k, eps2, ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
-        ctx->gather_pending = false;
+        {
+            int grc = gather_wait(ctx); // (the NCCL calls go out behind the local-shard launch)
+            if (grc != ESSA_OK)
+                return grc;
+        }
         if (SB0)
             CK(launch_force_pass(ctx, 0, i0, SB0, 0, total, argmax, save_old, k, eps2, ctx->stream));
         if (SB1)
@@ -1482,8 +1511,9 @@ static int step_tiled(essa_ctx* ctx, int steps, essa_step_opts const& o, bool fo
         CK(cudaEventRecord(e0, ctx->stream));
     }
     if (ctx->gather_pending) { // never left pending between calls, defensive
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gather, 0));
-        ctx->gather_pending = false;
+        int grc = gather_wait(ctx);
+        if (grc != ESSA_OK)
+            return grc;
     }
     if (forces_only) {
         int rc = force_pass(ctx, argmax, false, base, o.eps2, &ev);

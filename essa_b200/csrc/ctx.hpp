@@ -187,6 +187,8 @@ struct essa_ctx {
     unsigned long long* pair_flags = nullptr;               // [kMaxPeers] epochs announced TO this rank, one word per sender
     unsigned long long* pair_flags_peer[kMaxPeers] = {};
     unsigned long long pair_epoch = 0;
+    bool gather_deferred = false;   // gather_next has marked the buffer; the NCCL calls are still to be issued (gather_issue)
+    double4* gather_buf = nullptr;
     bool pair_peer_pos_pass = false; // the pass being launched reads remote blocks from their owners
     std::vector<void*> pos_graveyard; // exported buffers that a grown world replaced: freed with the context (peers may map them)
     bool pair_peer_failed = false;  // peer mapping is not available here: NCCL reduce-scatter fallback
