@@ -499,6 +499,7 @@ extern "C" void essa_ctx_destroy(essa_ctx* c) {
     for (void* g : c->pos_graveyard)
         cudaFree(g);
     c->pos_graveyard.clear();
+    c->pair_pos_exported[0] = c->pair_pos_exported[1] = nullptr; // the peers have let go: free_world below frees for real
     if (c->persist.mailbox)
         cudaFreeHost(c->persist.mailbox);
     if (c->stream)
