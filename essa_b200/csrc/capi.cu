@@ -157,6 +157,11 @@ static int persist_wait_ack(essa_ctx* ctx) {
         for (int w = kPersistRecWords * n + 1; w >= kPersistRecWords * n; w--)
             if ((unsigned)(__atomic_load_n(&mb->ll[w], __ATOMIC_RELAXED) >> 32) != p.seq)
                 return false;
+        // the time words are the last the kernel writes: the records (256 bytes per body, fresh from the PCIe DMA and in no
+        // cache of this core) are here or about to be -- have all their lines on the way before the first one is looked at
+        for (int k = 0; k < n; k++)
+            for (int line = 0; line < kPersistRecWords * 8; line += 64)
+                __builtin_prefetch(reinterpret_cast<char const*>(mb->ll + kPersistRecWords * k) + line, 0, 3);
         for (int k = n - 1; k >= 0; k--)
             for (int w = kPersistRecUsed - 1; w >= 0; w--)
                 if ((unsigned)(__atomic_load_n(&mb->ll[kPersistRecWords * k + w], __ATOMIC_RELAXED) >> 32) != p.seq)
